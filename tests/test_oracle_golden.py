@@ -1,0 +1,54 @@
+"""CPU: the C oracle (oracle/arah_oracle.c) against fixtures produced by the unmodified reference
+(oracle/gen_golden.py).  This is what pins the oracle; the GPU tests then compare the CUDA path with both."""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_CASES, check_render, load_golden
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_oracle_matches_reference(name):
+    from oracle import oracle as orc
+    fr, ref, meta = load_golden(name)
+    out = orc.render(fr, threads=0)
+    st = check_render(out, ref, label=name)
+    # iteration counters agree with the reference's own (wrapped broyden) to within borderline cases
+    iso_ref = meta['iso_calls'][0]['g_evals']
+    corr_ref = meta['corr_calls'][0]['g_evals']
+    n_pts = meta['corr_calls'][0]['n']
+    assert abs(int(out['n_iso_evals'].sum()) - iso_ref) <= max(8, 0.05 * iso_ref)   # non-converging rays iterate chaotically
+    corr_ours = int(out['n_corr_evals'].sum()) - n_pts          # ours also counts the J-init evaluation
+    assert abs(corr_ours - corr_ref) <= 0.02 * corr_ref
+    print(name, st)
+
+
+def test_degenerate_rays_are_background():
+    from oracle import oracle as orc
+    fr, ref, meta = load_golden('n32_16x16_s2')
+    nd = meta['n_degenerate']
+    out = orc.render(fr)
+    assert not out['trace.network_body_mask'][-nd:].any()
+    np.testing.assert_allclose(out['trace.dists'][-nd:], fr.near_far[-nd:, 0])
+
+
+def test_oracle_unit_functions_selfconsistent():
+    """finite-difference checks of the analytic derivatives the oracle (and the kernels) rely on."""
+    from oracle import oracle as orc
+    fr, _, _ = load_golden('n32_16x16_s2')
+    rng = np.random.default_rng(0)
+    xn = rng.uniform(-0.5, 0.5, size=(64, 3)).astype(np.float32)
+    s, g, _ = orc.sdf(fr, xn)
+    h = 1e-3
+    for k in range(3):
+        e = np.zeros(3, np.float32); e[k] = h
+        sp, _, _ = orc.sdf(fr, xn + e, grad=False)
+        sm, _, _ = orc.sdf(fr, xn - e, grad=False)
+        np.testing.assert_allclose((sp - sm) / (2 * h), g[:, k], atol=2e-2, rtol=5e-2)
+    xh = rng.uniform(-0.4, 0.4, size=(64, 3)).astype(np.float32)
+    w, xb, J = orc.skin(fr, xh)
+    np.testing.assert_allclose(w.sum(1), 1.0, atol=1e-5)
+    for k in range(3):
+        e = np.zeros(3, np.float32); e[k] = h
+        _, xp, _ = orc.skin(fr, xh + e, jac=False)
+        _, xm, _ = orc.skin(fr, xh - e, jac=False)
+        np.testing.assert_allclose((xp - xm) / (2 * h), J[:, :, k], atol=3e-2, rtol=5e-2)
