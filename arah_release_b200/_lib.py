@@ -1,0 +1,67 @@
+"""ctypes binding of libarah_b200.so (include/arah_b200.h).  No fallback: a missing library is an error."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, 'libarah_b200.so')
+FP = C.c_void_p
+
+
+class ArahConfig(C.Structure):
+    _fields_ = [('device', C.c_int32), ('n_steps', C.c_int32), ('near_samples', C.c_int32), ('far_samples', C.c_int32),
+                ('cano_view_dirs', C.c_int32), ('latent_dim', C.c_int32), ('n_verts', C.c_int32), ('max_rays', C.c_int32)]
+
+
+class ArahFrame(C.Structure):
+    _fields_ = [('sdf_W', FP * 7), ('sdf_b', FP * 7), ('sdf_freq', FP), ('sdf_phase', FP),
+                ('skin_W', FP * 5), ('skin_b', FP * 5), ('col_W', FP * 6), ('col_b', FP * 6),
+                ('latent', FP), ('beta', C.c_float),
+                ('bone_transforms', FP), ('smpl_verts', FP), ('smpl_weights', FP), ('pose_on_host', C.c_int32),
+                ('trans', C.c_float * 3), ('coord_min', C.c_float), ('coord_max', C.c_float), ('center', C.c_float * 3),
+                ('cam_loc', C.c_float * 3), ('pose', C.c_float * 16)]
+
+
+class ArahStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ('rays', 'trace_sdf_evals', 'iso_rays', 'iso_g_evals', 'on_samples',
+                                         'corr_skin_evals', 'shaded_samples', 'hit_rays', 'vol_rays', 'kernel_launches')]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'arah_set_frame', 'arah_render',
+           'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin']
+
+_lib = None
+
+
+class ArahError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library.  Raises if it has not been built (python -m arah_release_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise ArahError(f'{SO} is missing: build it with `python -m arah_release_b200.build` '
+                        f'(__graft_entry__.build()); there is no CPU fallback')
+    L = C.CDLL(SO)
+    L.arah_last_error.restype = C.c_char_p
+    L.arah_create.argtypes = [C.POINTER(ArahConfig), C.POINTER(C.c_void_p)]
+    L.arah_destroy.argtypes = [C.c_void_p]
+    L.arah_set_frame.argtypes = [C.c_void_p, C.POINTER(ArahFrame), C.c_void_p]
+    L.arah_render.argtypes = [C.c_void_p, FP, FP, C.c_int32, FP, FP, FP, FP, C.c_void_p]
+    L.arah_render_host.argtypes = [C.c_void_p, FP, FP, C.c_int32, FP, FP, FP, C.c_void_p]
+    L.arah_get_trace.argtypes = [C.c_void_p, FP, FP, FP, FP, FP, FP, FP, C.c_void_p]
+    L.arah_get_stats.argtypes = [C.c_void_p, C.POINTER(ArahStats), C.c_void_p]
+    L.arah_eval_sdf.argtypes = [C.c_void_p, FP, C.c_int32, FP, FP, FP, C.c_void_p]
+    L.arah_eval_skin.argtypes = [C.c_void_p, FP, C.c_int32, FP, FP, C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise ArahError(f'arah_b200 error {rc}: {lib().arah_last_error().decode()}')

@@ -1,0 +1,474 @@
+// arah_api.cu — C ABI (include/arah_b200.h), workspace management, weight packing and the launch sequence.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/arah_b200.h"
+#include "arah_kernels.cuh"
+
+using namespace arah;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(ARAH_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+extern "C" const char* arah_last_error(void) { return g_err.c_str(); }
+extern "C" int arah_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------ pack kernels
+// dst[k][n] = (k < K && n < N) ? src[n][col(k)] : 0   with col(k) = (k < split) ? k + off_lo : k - split + off_hi
+__global__ void k_pack_transpose(const float* __restrict__ src, int src_ld, float* __restrict__ dst, int K, int N,
+                                 int Kpad, int Npad, int split, int off_lo, int off_hi) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Kpad * Npad) return;
+    const int k = idx / Npad, n = idx % Npad;
+    float v = 0.f;
+    if (k < K && n < N) {
+        const int col = (k < split) ? (k + off_lo) : (k - split + off_hi);
+        v = src[(size_t)n * src_ld + col];
+    }
+    dst[idx] = v;
+}
+// b'[o] = b[o] + sum_j W[o][col0 + j] * latent[j]   (sequential j; folds the per-frame-constant latent)
+__global__ void k_fold_latent(const float* __restrict__ W, int ld, int col0, const float* __restrict__ latent, int L,
+                              const float* __restrict__ b, float* __restrict__ out, int n_out) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    float acc = 0.f;
+    for (int j = 0; j < L; ++j) acc = fmaf(W[(size_t)o * ld + col0 + j], latent[j], acc);
+    out[o] = b[o] + acc;
+}
+__global__ void k_copy_pad(const float* __restrict__ src, float* __restrict__ dst, int n, int npad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npad) dst[i] = (i < n) ? src[i] : 0.f;
+}
+__global__ void k_verts4(const float* __restrict__ v3, float4* __restrict__ v4, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v4[i] = make_float4(v3[3 * i], v3[3 * i + 1], v3[3 * i + 2], 0.f);
+}
+__global__ void k_read_b6(const float* __restrict__ b6, float* __restrict__ dst) { dst[0] = b6[0]; }
+
+// ------------------------------------------------------------------------------------------------ unit kernels
+__global__ void __launch_bounds__(256, 1) k_eval_sdf(FrameParams fp, const float* xn, int n, float* sdf, float* grad, float* feat_out, float* scratch) {
+    extern __shared__ __align__(128) float smem[];
+    if ((int)blockIdx.x * TM >= n) return;
+    TileSmem s = carve(smem, LDA_SDF);
+    WPipe wp;
+    wpipe_init(wp, s.wbuf, s.bars);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* cf = scratch + (size_t)blockIdx.x * 7 * TM * SDF_H;
+    float (*g)[4] = reinterpret_cast<float (*)[4]>(s.logits);
+    for (int tile = blockIdx.x; tile * TM < n; tile += gridDim.x) {
+        if (tid < TM) {
+            const int i = tile * TM + tid;
+            for (int k = 0; k < 3; ++k) s.xs[tid][k] = (i < n) ? xn[3 * i + k] : 0.f;
+            s.xs[tid][3] = 0.f;
+        }
+        __syncthreads();
+        sdf_tile_forward<PLAIN>(fp, s.xs, s.A, LDA_SDF, wp, s.sdfo, cf, 0.f);
+        if (feat_out) {
+            for (int r = 0; r < 8; ++r) {
+                const int i = tile * TM + warp * 8 + r;
+                if (i < n) for (int c = lane; c < SDF_H; c += 32) feat_out[(size_t)i * SDF_H + c] = s.A[(warp * 8 + r) * LDA_SDF + c];
+            }
+        }
+        __syncwarp();
+        sdf_tile_backward(fp, s.A, LDA_SDF, wp, cf, g);
+        __syncthreads();
+        if (tid < TM) {
+            const int i = tile * TM + tid;
+            if (i < n) {
+                sdf[i] = s.sdfo[tid];
+                if (grad) for (int k = 0; k < 3; ++k) grad[3 * i + k] = g[tid][k];
+            }
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256, 2) k_eval_skin(FrameParams fp, const float* x_hat, int n, float* weights, float* x_bar) {
+    extern __shared__ __align__(128) float smem[];
+    if ((int)blockIdx.x * TM >= n) return;
+    TileSmem s = carve(smem, LDA_SKIN);
+    WPipe wp;
+    wpipe_init(wp, s.wbuf, s.bars);
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile * TM < n; tile += gridDim.x) {
+        float xh[3] = {0.f, 0.f, 0.f};
+        const int i = tile * TM + tid;
+        if (tid < TM) {
+            float xn[3] = {0.f, 0.f, 0.f};
+            if (i < n) { xh[0] = x_hat[3 * i]; xh[1] = x_hat[3 * i + 1]; xh[2] = x_hat[3 * i + 2]; normalize3(fp, xh, xn); }
+            s.xs[tid][0] = xn[0]; s.xs[tid][1] = xn[1]; s.xs[tid][2] = xn[2]; s.xs[tid][3] = 0.f;
+        }
+        __syncthreads();
+        skin_tile_forward<PLAIN>(fp, s.xs, s.A, LDA_SKIN, wp, s.logits, 0.f);
+        __syncthreads();
+        if (tid < TM && i < n) {
+            float lg[25], wj[NJ], T12[12], xb[3];
+            for (int k = 0; k < 25; ++k) lg[k] = s.logits[tid][k] * 20.0f;
+            hierarchical_softmax(lg, wj);
+            blend_T(wj, fp.bone_T, T12, nullptr);
+            apply_T(T12, xh, xb);
+            for (int k = 0; k < NJ; ++k) weights[(size_t)i * NJ + k] = wj[k];
+            for (int k = 0; k < 3; ++k) x_bar[3 * i + k] = xb[k];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ handle
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n) {
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        if (cudaMalloc(&p, n) != cudaSuccess) return -1;
+        bytes = n;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct ArahHandle {
+    ArahConfig cfg;
+    int n_sms = 148;
+    bool frame_set = false, rendered = false, have_smpl_w = false;
+    FrameParams fp;
+    // packed weights (one arena)
+    DevBuf arena;
+    float* sdf_Wt[6]; float* sdf_W[6]; float* sdf_b[6]; float* sdf_w6; float* sdf_freq; float* sdf_phase; float* d_b6;
+    float* skin_Wt[5]; float* skin_b[5];
+    float* col_Wt0; float* col_Wt1; float* col_Wt2; float* col_Wt3a; float* col_Wt3b; float* col_Wt4; float* col_W5; float* col_b[6];
+    float* bone_T; float4* verts4; float* verts3; float* smpl_w;
+    // workspace
+    DevBuf ws, scratch, io_in, io_out;
+    Work w;
+    int cap_rays = 0;
+    int64_t launches = 0;
+    int last_P = 0;
+    float* pinned_b6 = nullptr;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int alloc_arena(ArahHandle* h) {
+    const int L = h->cfg.latent_dim;
+    (void)L;
+    size_t off = 0;
+    auto take = [&](size_t floats) { size_t o = off; off += align_up(floats * 4, 256); return o; };
+    std::vector<std::pair<float**, size_t>> slots;
+    auto reg = [&](float** p, size_t floats) { slots.push_back({p, take(floats)}); };
+    reg(&h->sdf_Wt[0], 3 * 256); reg(&h->sdf_W[0], 256 * 3); reg(&h->sdf_b[0], 256);
+    for (int l = 1; l < 6; ++l) { reg(&h->sdf_Wt[l], 256 * 256); reg(&h->sdf_W[l], 256 * 256); reg(&h->sdf_b[l], 256); }
+    reg(&h->sdf_w6, 256); reg(&h->sdf_freq, 6 * 256); reg(&h->sdf_phase, 6 * 256); reg(&h->d_b6, 64);
+    reg(&h->skin_Wt[0], 3 * 128); reg(&h->skin_b[0], 128);
+    for (int l = 1; l < 4; ++l) { reg(&h->skin_Wt[l], 128 * 128); reg(&h->skin_b[l], 128); }
+    reg(&h->skin_Wt[4], 128 * 32); reg(&h->skin_b[4], 32);
+    reg(&h->col_Wt0, COL_IN_PAD * 256); reg(&h->col_Wt1, 256 * 256); reg(&h->col_Wt2, 256 * 128);
+    reg(&h->col_Wt3a, COL_IN_PAD * 256); reg(&h->col_Wt3b, 128 * 256); reg(&h->col_Wt4, 256 * 256); reg(&h->col_W5, 3 * 256);
+    reg(&h->col_b[0], 256); reg(&h->col_b[1], 256); reg(&h->col_b[2], 128); reg(&h->col_b[3], 256); reg(&h->col_b[4], 256); reg(&h->col_b[5], 64);
+    reg(&h->bone_T, 24 * 16);
+    float* v4 = nullptr;
+    reg(&v4, (size_t)h->cfg.n_verts * 4);
+    reg(&h->verts3, (size_t)h->cfg.n_verts * 3);
+    reg(&h->smpl_w, (size_t)h->cfg.n_verts * 24);
+    if (h->arena.ensure(off) != 0) return -1;
+    for (auto& s : slots) *s.first = reinterpret_cast<float*>(static_cast<char*>(h->arena.p) + s.second);
+    h->verts4 = reinterpret_cast<float4*>(static_cast<char*>(h->arena.p) + slots[slots.size() - 3].second);
+    return 0;
+}
+
+static int ensure_workspace(ArahHandle* h, int P) {
+    if (P <= h->cap_rays) return 0;
+    const int cap = (int)align_up((size_t)P, 1024);
+    const size_t S = h->cfg.n_steps, PS = (size_t)cap * S;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_t = take(cap * 4), o_fl = take(cap), o_cur = take(cap * sizeof(RayCur)), o_iso = take(cap * sizeof(BroydenState<4>));
+    const size_t o_conv = take(cap), o_dist = take(cap * 4), o_pn = take(cap * 12);
+    const size_t o_z = take(PS * 4), o_xn = take(PS * 12), o_T = take(PS * 48), o_sc = take(PS), o_sdf = take(PS * 4), o_rgb = take(PS * 12);
+    const size_t o_cs = take(PS * sizeof(BroydenState<3>));
+    const size_t o_la = take(PS * 4), o_lb = take(PS * 4), o_on = take(PS * 4), o_sh = take(PS * 4), o_ctr = take(C_COUNT * 4 + 64);
+    if (h->ws.ensure(off) != 0) return -1;
+    char* b = static_cast<char*>(h->ws.p);
+    Work& w = h->w;
+    w.S = (int)S;
+    w.ray_t = (float*)(b + o_t); w.ray_flags = (uint8_t*)(b + o_fl); w.ray_cur = (RayCur*)(b + o_cur);
+    w.iso_state = (BroydenState<4>*)(b + o_iso); w.ray_conv = (uint8_t*)(b + o_conv); w.ray_dist = (float*)(b + o_dist);
+    w.ray_pnorm = (float*)(b + o_pn); w.z_vals = (float*)(b + o_z); w.smp_xn = (float*)(b + o_xn); w.smp_T = (float*)(b + o_T);
+    w.smp_conv = (uint8_t*)(b + o_sc); w.smp_sdf = (float*)(b + o_sdf); w.smp_rgb = (float*)(b + o_rgb);
+    w.corr_state = (BroydenState<3>*)(b + o_cs); w.listA = (int*)(b + o_la); w.listB = (int*)(b + o_lb);
+    w.on_list = (int*)(b + o_on); w.shade_list = (int*)(b + o_sh); w.counters = (int*)(b + o_ctr);
+    h->cap_rays = cap;
+    return 0;
+}
+
+extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
+    if (!cfg || !out) return fail(ARAH_EINVAL, "null argument");
+    if (cfg->n_steps <= 0 || cfg->n_steps > MAX_STEPS) return fail(ARAH_EINVAL, "n_steps must be in [1,256]");
+    if (cfg->near_samples + 1 + cfg->far_samples > cfg->n_steps)
+        return fail(ARAH_EINVAL, "near_samples + 1 + far_samples must be <= n_steps (ray_tracing.py:336,346)");
+    if (cfg->near_samples < 0 || cfg->far_samples < 0 || (cfg->near_samples == 0 && cfg->far_samples == 0))
+        return fail(ARAH_EINVAL, "need near_samples > 0 or far_samples > 0 (ray_tracing.py:107)");
+    if (cfg->latent_dim < 0 || cfg->latent_dim > 512) return fail(ARAH_EINVAL, "latent_dim must be in [0,512]");
+    if (cfg->n_verts <= 0 || (size_t)cfg->n_verts * 16 > 200 * 1024) return fail(ARAH_EINVAL, "n_verts must fit 200 KB of shared memory (<= 12800)");
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(ARAH_EINVAL, "arah_b200 needs an sm_100-class GPU");
+    ArahHandle* h = new ArahHandle();
+    h->cfg = *cfg;
+    h->n_sms = prop.multiProcessorCount;
+    memset(&h->w, 0, sizeof(h->w));
+    if (alloc_arena(h) != 0) { delete h; return fail(ARAH_ENOMEM, "weight arena allocation failed"); }
+    if (ensure_workspace(h, cfg->max_rays > 0 ? cfg->max_rays : 4096) != 0) { h->arena.release(); delete h; return fail(ARAH_ENOMEM, "workspace allocation failed"); }
+    if (h->scratch.ensure((size_t)h->n_sms * 7 * TM * SDF_H * 4) != 0) { delete h; return fail(ARAH_ENOMEM, "scratch allocation failed"); }
+    h->w.scratch = (float*)h->scratch.p;
+    CU(cudaFuncSetAttribute(k_trace_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SDF)));
+    CU(cudaFuncSetAttribute(k_iso_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SDF)));
+    CU(cudaFuncSetAttribute(k_iso_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SDF)));
+    CU(cudaFuncSetAttribute(k_eval_sdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SDF)));
+    CU(cudaFuncSetAttribute(k_corr_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SKIN)));
+    CU(cudaFuncSetAttribute(k_eval_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SKIN)));
+    CU(cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->n_verts * 16));
+    CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->n_verts * 16));
+    *out = h;
+    return ARAH_OK;
+}
+
+extern "C" int arah_destroy(ArahHandle* h) {
+    if (!h) return ARAH_OK;
+    h->arena.release(); h->ws.release(); h->scratch.release(); h->io_in.release(); h->io_out.release();
+    delete h;
+    return ARAH_OK;
+}
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+static inline unsigned grid_min(size_t a, size_t b) { return (unsigned)(a < b ? a : b); }
+
+extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) {
+    if (!h || !f) return fail(ARAH_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream_;
+    CU(cudaSetDevice(h->cfg.device));
+    for (int l = 0; l < 7; ++l) if (!f->sdf_W[l] || !f->sdf_b[l]) return fail(ARAH_EINVAL, "sdf weights missing");
+    for (int l = 0; l < 5; ++l) if (!f->skin_W[l] || !f->skin_b[l]) return fail(ARAH_EINVAL, "skinning weights missing");
+    for (int l = 0; l < 6; ++l) if (!f->col_W[l] || !f->col_b[l]) return fail(ARAH_EINVAL, "colour weights missing");
+    if (!f->sdf_freq || !f->sdf_phase || !f->bone_transforms || !f->smpl_verts) return fail(ARAH_EINVAL, "frame buffers missing");
+    if (h->cfg.latent_dim > 0 && !f->latent) return fail(ARAH_EINVAL, "latent missing");
+    if (!f->smpl_weights && !h->have_smpl_w) return fail(ARAH_EINVAL, "smpl_weights required on the first frame");
+    const int L = h->cfg.latent_dim;
+    const int din = 3 + 27 + 3 + 256 + L;     // colour-net input width in the reference's order [x|PE|n|feat|latent]
+    auto tp = [&](const float* src, int ld, float* dst, int K, int N, int Kp, int Np, int split, int lo, int hi) {
+        k_pack_transpose<<<cdiv((size_t)Kp * Np, 256), 256, 0, st>>>(src, ld, dst, K, N, Kp, Np, split, lo, hi);
+    };
+    // SDF
+    tp(f->sdf_W[0], 3, h->sdf_Wt[0], 3, 256, 3, 256, 3, 0, 0);
+    CU(cudaMemcpyAsync(h->sdf_W[0], f->sdf_W[0], 256 * 3 * 4, cudaMemcpyDeviceToDevice, st));
+    for (int l = 1; l < 6; ++l) {
+        tp(f->sdf_W[l], 256, h->sdf_Wt[l], 256, 256, 256, 256, 256, 0, 0);
+        CU(cudaMemcpyAsync(h->sdf_W[l], f->sdf_W[l], 256 * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    for (int l = 0; l < 6; ++l) CU(cudaMemcpyAsync(h->sdf_b[l], f->sdf_b[l], 256 * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->sdf_w6, f->sdf_W[6], 256 * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->sdf_freq, f->sdf_freq, 6 * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->sdf_phase, f->sdf_phase, 6 * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    // the scalar output bias travels as a kernel parameter: fetch it (4 bytes, the only D2H of set_frame)
+    float b6 = 0.f;
+    CU(cudaMemcpyAsync(&b6, f->sdf_b[6], 4, cudaMemcpyDeviceToHost, st));
+    // skinning
+    tp(f->skin_W[0], 3, h->skin_Wt[0], 3, 128, 3, 128, 3, 0, 0);
+    for (int l = 1; l < 4; ++l) tp(f->skin_W[l], 128, h->skin_Wt[l], 128, 128, 128, 128, 128, 0, 0);
+    tp(f->skin_W[4], 128, h->skin_Wt[4], 128, 25, 128, 32, 128, 0, 0);
+    for (int l = 0; l < 4; ++l) CU(cudaMemcpyAsync(h->skin_b[l], f->skin_b[l], 128 * 4, cudaMemcpyDeviceToDevice, st));
+    k_copy_pad<<<1, 32, 0, st>>>(f->skin_b[4], h->skin_b[4], 25, 32);
+    // colour: reference input order [x 3 | PE 27 | n 3 | feat 256 | latent L]; ours [feat | x | PE | n]
+    tp(f->col_W[0], din, h->col_Wt0, COL_IN, 256, COL_IN_PAD, 256, 256, 33, 0);
+    tp(f->col_W[1], 256, h->col_Wt1, 256, 256, 256, 256, 256, 0, 0);
+    tp(f->col_W[2], 256, h->col_Wt2, 256, 128, 256, 128, 256, 0, 0);
+    tp(f->col_W[3], din + 128, h->col_Wt3a, COL_IN, 256, COL_IN_PAD, 256, 256, 33, 0);
+    tp(f->col_W[3], din + 128, h->col_Wt3b, 128, 256, 128, 256, 128, din, 0);
+    tp(f->col_W[4], 256, h->col_Wt4, 256, 256, 256, 256, 256, 0, 0);
+    CU(cudaMemcpyAsync(h->col_W5, f->col_W[5], 3 * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    if (L > 0) {
+        k_fold_latent<<<1, 256, 0, st>>>(f->col_W[0], din, 289, f->latent, L, f->col_b[0], h->col_b[0], 256);
+        k_fold_latent<<<1, 256, 0, st>>>(f->col_W[3], din + 128, 289, f->latent, L, f->col_b[3], h->col_b[3], 256);
+    } else {
+        CU(cudaMemcpyAsync(h->col_b[0], f->col_b[0], 256 * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(h->col_b[3], f->col_b[3], 256 * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CU(cudaMemcpyAsync(h->col_b[1], f->col_b[1], 256 * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->col_b[2], f->col_b[2], 128 * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->col_b[4], f->col_b[4], 256 * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->col_b[5], f->col_b[5], 3 * 4, cudaMemcpyDeviceToDevice, st));
+    // pose buffers
+    const cudaMemcpyKind kind = f->pose_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CU(cudaMemcpyAsync(h->bone_T, f->bone_transforms, 24 * 16 * 4, kind, st));
+    CU(cudaMemcpyAsync(h->verts3, f->smpl_verts, (size_t)h->cfg.n_verts * 12, kind, st));
+    k_verts4<<<cdiv(h->cfg.n_verts, 256), 256, 0, st>>>(h->verts3, h->verts4, h->cfg.n_verts);
+    if (f->smpl_weights) {
+        CU(cudaMemcpyAsync(h->smpl_w, f->smpl_weights, (size_t)h->cfg.n_verts * 24 * 4, kind, st));
+        h->have_smpl_w = true;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));       // b6 has landed; packing done (set_frame is once per frame, not per ray batch)
+    FrameParams& fp = h->fp;
+    for (int l = 0; l < 6; ++l) { fp.sdf_Wt[l] = h->sdf_Wt[l]; fp.sdf_W[l] = h->sdf_W[l]; fp.sdf_b[l] = h->sdf_b[l]; }
+    fp.sdf_w6 = h->sdf_w6; fp.sdf_b6 = b6; fp.sdf_freq = h->sdf_freq; fp.sdf_phase = h->sdf_phase;
+    for (int l = 0; l < 5; ++l) { fp.skin_Wt[l] = h->skin_Wt[l]; fp.skin_b[l] = h->skin_b[l]; }
+    fp.col_Wt0 = h->col_Wt0; fp.col_Wt1 = h->col_Wt1; fp.col_Wt2 = h->col_Wt2; fp.col_Wt3a = h->col_Wt3a;
+    fp.col_Wt3b = h->col_Wt3b; fp.col_Wt4 = h->col_Wt4; fp.col_W5 = h->col_W5;
+    for (int l = 0; l < 6; ++l) fp.col_b[l] = h->col_b[l];
+    fp.bone_T = h->bone_T; fp.verts4 = h->verts4; fp.smpl_w = h->smpl_w; fp.n_verts = h->cfg.n_verts;
+    for (int k = 0; k < 3; ++k) { fp.trans[k] = f->trans[k]; fp.center[k] = f->center[k]; fp.cam_loc[k] = f->cam_loc[k]; }
+    fp.cmin = f->coord_min; fp.cmax = f->coord_max;
+    for (int k = 0; k < 16; ++k) fp.pose[k] = f->pose[k];
+    fp.beta = f->beta;
+    fp.n_steps = h->cfg.n_steps; fp.near_samples = h->cfg.near_samples; fp.far_samples = h->cfg.far_samples;
+    fp.cano_view_dirs = h->cfg.cano_view_dirs;
+    if (!(fp.cmax > fp.cmin)) return fail(ARAH_EINVAL, "coord_max must exceed coord_min");
+    h->frame_set = true;
+    return ARAH_OK;
+}
+
+static int render_device(ArahHandle* h, const float* ray_dirs, const float* near_far, int P, float* rgb, uint8_t* mask,
+                         float* points_cam, float* wsum, cudaStream_t st) {
+    if (!h->frame_set) return fail(ARAH_ESTATE, "arah_set_frame must be called before arah_render");
+    if (P < 0) return fail(ARAH_EINVAL, "P < 0");
+    h->launches = 0;
+    h->last_P = P;
+    h->rendered = true;
+    if (P == 0) return ARAH_OK;
+    if (!ray_dirs || !near_far || !rgb || !mask) return fail(ARAH_EINVAL, "null buffer");
+    CU(cudaSetDevice(h->cfg.device));
+    if (ensure_workspace(h, P) != 0) return fail(ARAH_ENOMEM, "workspace allocation failed");
+    Work& w = h->w;
+    w.P = P; w.ray_dirs = ray_dirs; w.near_far = near_far;
+    w.out_rgb = rgb; w.out_mask = mask; w.out_points_cam = points_cam; w.out_wsum = wsum;
+    const FrameParams& fp = h->fp;
+    const int S = w.S;
+    const size_t PS = (size_t)P * S;
+    const int nsm = h->n_sms;
+    const size_t sm_sdf = tile_smem_bytes(LDA_SDF), sm_skin = tile_smem_bytes(LDA_SKIN), sm_knn = (size_t)fp.n_verts * 16;
+    auto L = [&]() { h->launches++; };
+    CU(cudaMemsetAsync(w.counters, 0, C_COUNT * 4, st));
+    k_trace_begin<<<cdiv(P, 256), 256, 0, st>>>(w); L();
+    const unsigned g_ray_tiles = grid_min(cdiv(P, TM), (size_t)nsm);
+    const unsigned g_knn_rays = grid_min(cdiv(P, 256), (size_t)2 * nsm);
+    for (int it = 0; it < TRACE_ITERS; ++it) {
+        k_knn_rays<<<g_knn_rays, 256, sm_knn, st>>>(fp, w, it); L();
+        k_trace_iter<<<g_ray_tiles, 256, sm_sdf, st>>>(fp, w, it); L();
+    }
+    k_iso_prepare<<<cdiv(P, 256), 256, 0, st>>>(w); L();
+    k_iso_init<<<grid_min(cdiv(P, TM / 4), (size_t)nsm), 256, sm_sdf, st>>>(fp, w); L();
+    for (int it = 0; it < BROYDEN_ITERS; ++it) { k_iso_iter<<<g_ray_tiles, 256, sm_sdf, st>>>(fp, w, it); L(); }
+    k_trace_finish<<<cdiv(P, 128), 128, 0, st>>>(fp, w); L();
+    const unsigned g_knn_s = grid_min(cdiv(PS, 256), (size_t)2 * nsm);
+    k_knn_samples<<<g_knn_s, 256, sm_knn, st>>>(fp, w); L();
+    const unsigned g_smp_tiles = grid_min(cdiv(PS, TM), (size_t)2 * nsm);
+    for (int it = -1; it < BROYDEN_ITERS; ++it) { k_corr_step<<<g_smp_tiles, 256, sm_skin, st>>>(fp, w, it); L(); }
+    k_shade<<<grid_min(cdiv(PS, TM), (size_t)nsm), 256, shade_smem_bytes(), st>>>(fp, w); L();
+    k_composite<<<cdiv(P, COMP_WARPS), 32 * COMP_WARPS, 0, st>>>(fp, w); L();
+    CU(cudaGetLastError());
+    return ARAH_OK;
+}
+
+extern "C" int arah_render(ArahHandle* h, const float* ray_dirs, const float* near_far, int32_t P, float* rgb, uint8_t* mask,
+                           float* points_cam, float* weights_sum, void* stream) {
+    if (!h) return fail(ARAH_EINVAL, "null handle");
+    return render_device(h, ray_dirs, near_far, P, rgb, mask, points_cam, weights_sum, (cudaStream_t)stream);
+}
+
+extern "C" int arah_render_host(ArahHandle* h, const float* ray_dirs, const float* near_far, int32_t P, float* rgb, uint8_t* mask,
+                                float* points_cam, void* stream) {
+    if (!h) return fail(ARAH_EINVAL, "null handle");
+    if (P < 0) return fail(ARAH_EINVAL, "P < 0");
+    if (P == 0) { h->launches = 0; h->last_P = 0; return ARAH_OK; }
+    if (!ray_dirs || !near_far || !rgb || !mask) return fail(ARAH_EINVAL, "null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)P;
+    if (h->io_in.ensure(n * 20 + 256) != 0 || h->io_out.ensure(n * 28 + 512) != 0) return fail(ARAH_ENOMEM, "io buffers");
+    float* d_dirs = (float*)h->io_in.p;
+    float* d_nf = d_dirs + n * 3;
+    float* d_rgb = (float*)h->io_out.p;
+    float* d_pc = d_rgb + n * 3;
+    uint8_t* d_mask = (uint8_t*)(d_pc + n * 3);
+    CU(cudaMemcpyAsync(d_dirs, ray_dirs, n * 12, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_nf, near_far, n * 8, cudaMemcpyHostToDevice, st));
+    int rc = render_device(h, d_dirs, d_nf, P, d_rgb, d_mask, d_pc, nullptr, st);
+    if (rc != ARAH_OK) return rc;
+    CU(cudaMemcpyAsync(rgb, d_rgb, n * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(mask, d_mask, n, cudaMemcpyDeviceToHost, st));
+    if (points_cam) CU(cudaMemcpyAsync(points_cam, d_pc, n * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ARAH_OK;
+}
+
+extern "C" int arah_get_trace(ArahHandle* h, float* points_hat_norm, uint8_t* network_body_mask, float* dists, float* sampled_pts,
+                              float* sampled_dists, float* sampled_transforms, uint8_t* sampler_converge_mask, void* stream) {
+    if (!h) return fail(ARAH_EINVAL, "null handle");
+    if (!h->rendered) return fail(ARAH_ESTATE, "arah_get_trace needs a preceding arah_render");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = h->last_P;
+    if (P == 0) return ARAH_OK;
+    const Work& w = h->w;
+    if (points_hat_norm) CU(cudaMemcpyAsync(points_hat_norm, w.ray_pnorm, (size_t)P * 12, cudaMemcpyDeviceToDevice, st));
+    if (network_body_mask) CU(cudaMemcpyAsync(network_body_mask, w.ray_conv, (size_t)P, cudaMemcpyDeviceToDevice, st));
+    if (dists) CU(cudaMemcpyAsync(dists, w.ray_dist, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
+    if (sampled_pts || sampled_dists || sampled_transforms || sampler_converge_mask) {
+        const size_t PS = (size_t)P * w.S;
+        k_export_samples<<<cdiv(PS, 256), 256, 0, st>>>(w, h->cfg.near_samples + 1 + h->cfg.far_samples, sampled_pts, sampled_dists,
+                                                        sampled_transforms, sampler_converge_mask);
+        CU(cudaGetLastError());
+    }
+    return ARAH_OK;
+}
+
+extern "C" int arah_get_stats(ArahHandle* h, ArahStats* s, void* stream) {
+    if (!h || !s) return fail(ARAH_EINVAL, "null argument");
+    memset(s, 0, sizeof(*s));
+    s->rays = h->last_P;
+    s->kernel_launches = h->launches;
+    if (!h->rendered || h->last_P == 0) return ARAH_OK;
+    int c[C_COUNT];
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    CU(cudaMemcpy(c, h->w.counters, sizeof(c), cudaMemcpyDeviceToHost));
+    s->trace_sdf_evals = c[C_STAT_TRACE_EVALS];
+    s->iso_rays = c[C_ISO];
+    s->iso_g_evals = c[C_STAT_ISO_EVALS];
+    s->on_samples = c[C_ON];
+    s->corr_skin_evals = c[C_STAT_CORR_EVALS];
+    s->shaded_samples = c[C_SHADE];
+    s->hit_rays = c[C_STAT_HIT_RAYS];
+    s->vol_rays = c[C_STAT_VOL_RAYS];
+    return ARAH_OK;
+}
+
+extern "C" int arah_eval_sdf(ArahHandle* h, const float* xn, int32_t n, float* sdf, float* grad, float* feat, void* stream) {
+    if (!h || !h->frame_set) return fail(ARAH_ESTATE, "arah_set_frame first");
+    if (n <= 0) return ARAH_OK;
+    if (!xn || !sdf) return fail(ARAH_EINVAL, "null buffer");
+    const unsigned g = grid_min(cdiv(n, TM), (size_t)h->n_sms);
+    k_eval_sdf<<<g, 256, tile_smem_bytes(LDA_SDF), (cudaStream_t)stream>>>(h->fp, xn, n, sdf, grad, feat, (float*)h->scratch.p);
+    CU(cudaGetLastError());
+    return ARAH_OK;
+}
+extern "C" int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, float* weights, float* x_bar, void* stream) {
+    if (!h || !h->frame_set) return fail(ARAH_ESTATE, "arah_set_frame first");
+    if (n <= 0) return ARAH_OK;
+    if (!x_hat || !weights || !x_bar) return fail(ARAH_EINVAL, "null buffer");
+    const unsigned g = grid_min(cdiv(n, TM), (size_t)2 * h->n_sms);
+    k_eval_skin<<<g, 256, tile_smem_bytes(LDA_SKIN), (cudaStream_t)stream>>>(h->fp, x_hat, n, weights, x_bar);
+    CU(cudaGetLastError());
+    return ARAH_OK;
+}

@@ -1,0 +1,783 @@
+// arah_kernels.cuh — the stage kernels of the ARAH hot path (sm_100a).
+//
+// Stage map (reference file:line each kernel replaces; all under /root/reference/im2mesh):
+//   k_trace_begin        ray_tracing.py:178-196            per-ray init, active list
+//   k_knn_rays/_samples  ray_tracing.py:382-400, 403-421   brute-force 1-NN over the posed SMPL verts + NN-skinning inverse
+//   k_trace_iter         ray_tracing.py:198-241            one sphere-tracing step for the still-active rays
+//   k_iso_prepare/_init  utils/root_finding_utils.py:365-418  joint-search Jacobian (full LBS jac + grad sdf), J^-1, g(u0)
+//   k_iso_iter           utils/root_finding_utils.py:426-461 + utils/broyden.py:47-76   4-D Broyden step
+//   k_trace_finish       ray_tracing.py:266-294, 313-350   accept/reject, z-sample placement (merge of 2 sorted runs)
+//   k_corr_init/_iter    utils/root_finding_utils.py:267-362 + utils/broyden.py   3-D Broyden per sample
+//   k_shade              renderer/implicit_differentiable_renderer.py:284-361    SDF fwd + grad, colour MLP
+//   k_composite          renderer/implicit_differentiable_renderer.py:366-394, 225-257
+// Iterations are separate launches over a compacted active list that lives in HBM (the reference compacts with
+// boolean masks too); no host synchronisation anywhere — list sizes are read from device counters.
+#pragma once
+#include "arah_tile.cuh"
+
+namespace arah {
+
+constexpr int TRACE_ITERS = 50;
+constexpr int BROYDEN_ITERS = 50;
+constexpr int MAX_STEPS = 256;
+
+// counter slots (int32) in Work::counters
+enum Ctr {
+    C_TRACE = 0,                         // [0..50] active rays entering sphere-tracing step i
+    C_ISO = C_TRACE + TRACE_ITERS + 1,   // [0..50] active rays entering joint-search step i
+    C_CORR = C_ISO + BROYDEN_ITERS + 1,  // [0..50] active samples entering correspondence step i
+    C_ON = C_CORR + BROYDEN_ITERS + 1,   // number of "on" samples
+    C_SHADE,                             // number of converged samples to shade
+    C_STAT_TRACE_EVALS, C_STAT_ISO_EVALS, C_STAT_CORR_EVALS, C_STAT_HIT_RAYS, C_STAT_VOL_RAYS,
+    C_COUNT
+};
+
+struct RayCur { float xn[3]; float s; float T[12]; };   // 64 B: last sphere-tracing evaluation of a ray
+
+struct Work {
+    int P, S;
+    const float* ray_dirs;    // [P][3]
+    const float* near_far;    // [P][2]
+    float* ray_t;             // [P]
+    uint8_t* ray_flags;       // [P] bit0 unfinished, bit1 diverged
+    RayCur* ray_cur;          // [P]
+    BroydenState<4>* iso_state;   // [P]
+    uint8_t* ray_conv;        // [P]   BodyRayTracing network_body_mask
+    float* ray_dist;          // [P]   dists
+    float* ray_pnorm;         // [P][3] points_hat_norm
+    float* z_vals;            // [P][S]
+    float* smp_xn;            // [P*S][3]
+    float* smp_T;             // [P*S][12]
+    uint8_t* smp_conv;        // [P*S]
+    float* smp_sdf;           // [P*S]   metres
+    float* smp_rgb;           // [P*S][3]
+    BroydenState<3>* corr_state;  // [P*S]
+    int* listA; int* listB;   // [P*S]
+    int* on_list;             // [P*S] sample slot index of the k-th on-sample
+    int* shade_list;          // [P*S]
+    int* counters;            // [C_COUNT]
+    float* scratch;           // shade kernel: per-CTA [7][TM][256]
+    float* out_rgb;           // [P][3]
+    uint8_t* out_mask;        // [P]
+    float* out_points_cam;    // [P][3]
+    float* out_wsum;          // [P]
+};
+
+// warp-aggregated append of `value` to list (returns nothing); all 32 lanes must call
+__device__ __forceinline__ void warp_append(bool pred, int value, int* list, int* counter) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == (__ffs(m) - 1)) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+__device__ __forceinline__ void warp_stat_add(int v, int* counter) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, v);
+}
+
+// ================================================================================================ tracing
+__global__ void k_trace_begin(Work w) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    bool unfinished = false;
+    if (r < w.P) {
+        const float nr = w.near_far[2 * r], fr = w.near_far[2 * r + 1];
+        unfinished = nr < fr;
+        w.ray_t[r] = nr;
+        w.ray_flags[r] = unfinished ? 1 : 2;
+        RayCur c;
+        c.xn[0] = c.xn[1] = c.xn[2] = 0.0f; c.s = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 12; ++e) c.T[e] = 0.0f;
+        w.ray_cur[r] = c;
+    }
+    warp_append(unfinished, r, w.listA, &w.counters[C_TRACE]);
+}
+
+// nearest posed SMPL vertex by exhaustive search; verts broadcast from shared memory (1 LDS.128 per vertex per warp)
+__device__ __forceinline__ int knn_scan(const float4* sv, int n_verts, float x, float y, float z) {
+    float bd = INFINITY;
+    int bi = 0;
+#pragma unroll 4
+    for (int v = 0; v < n_verts; ++v) {
+        const float4 p = sv[v];
+        const float dx = x - p.x, dy = y - p.y, dz = z - p.z;
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d < bd) { bd = d; bi = v; }
+    }
+    return bi;
+}
+__device__ __forceinline__ void load_verts(float4* sv, const FrameParams& fp) {
+    for (int v = threadIdx.x; v < fp.n_verts; v += blockDim.x) sv[v] = __ldg(fp.verts4 + v);
+    __syncthreads();
+}
+// NN-skinning inverse of one posed point x (incl. trans): T = sum_j W[idx][j] B_j, x_hat = T^-1 (x - trans)
+__device__ __forceinline__ void nn_inverse_skinning(const FrameParams& fp, int idx, const float* x, float* T12, float* s, float* x_hat) {
+    float wj[NJ];
+    const float4* wp = reinterpret_cast<const float4*>(fp.smpl_w + (size_t)idx * NJ);
+#pragma unroll
+    for (int q = 0; q < NJ / 4; ++q) { const float4 t = __ldg(wp + q); wj[4 * q] = t.x; wj[4 * q + 1] = t.y; wj[4 * q + 2] = t.z; wj[4 * q + 3] = t.w; }
+    blend_T(wj, fp.bone_T, T12, s);
+    const float xl[3] = {x[0] - fp.trans[0], x[1] - fp.trans[1], x[2] - fp.trans[2]};
+    affine_inverse_apply(T12, *s, xl, x_hat);
+}
+
+__global__ void __launch_bounds__(256) k_knn_rays(FrameParams fp, Work w, int iter) {
+    extern __shared__ float4 sv[];
+    const int n = w.counters[C_TRACE + iter];
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    load_verts(sv, fp);
+    const int* list = (iter & 1) ? w.listB : w.listA;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = list[i];
+        const float t = w.ray_t[r];
+        float x[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) x[k] = w.ray_dirs[3 * r + k] * t + fp.cam_loc[k];
+        const int idx = knn_scan(sv, fp.n_verts, x[0], x[1], x[2]);
+        RayCur c;
+        float xh[3];
+        nn_inverse_skinning(fp, idx, x, c.T, &c.s, xh);
+        normalize3(fp, xh, c.xn);
+        w.ray_cur[r] = c;
+    }
+}
+
+// smem layout helpers -------------------------------------------------------------------------------------------
+struct TileSmem {
+    float* A; float* wbuf; float (*xs)[4]; float (*logits)[32]; float* sdfo; uint64_t* bars;
+};
+constexpr int LDA_SDF = 260;      // 256 + 4
+constexpr int LDA_SHADE = 308;    // 304 + 4
+__host__ __device__ constexpr size_t tile_smem_bytes(int lda) {
+    return (size_t)(TM * lda + WBUF_FLOATS + TM * 4 + TM * 32 + TM) * 4 + 64;
+}
+__device__ __forceinline__ TileSmem carve(float* base, int lda) {
+    TileSmem s;
+    s.wbuf = base;                               // 128-byte aligned start (dynamic smem base)
+    s.A = base + WBUF_FLOATS;
+    float* p = s.A + TM * lda;
+    s.xs = reinterpret_cast<float (*)[4]>(p); p += TM * 4;
+    s.logits = reinterpret_cast<float (*)[32]>(p); p += TM * 32;
+    s.sdfo = p; p += TM;
+    s.bars = reinterpret_cast<uint64_t*>(p);
+    return s;
+}
+
+__global__ void __launch_bounds__(256, 1) k_trace_iter(FrameParams fp, Work w, int iter) {
+    extern __shared__ __align__(128) float smem[];
+    const int n = w.counters[C_TRACE + iter];
+    if ((int)blockIdx.x * TM >= n) return;
+    TileSmem s = carve(smem, LDA_SDF);
+    WPipe wp;
+    wpipe_init(wp, s.wbuf, s.bars);
+    const int* list = (iter & 1) ? w.listB : w.listA;
+    int* next = (iter & 1) ? w.listA : w.listB;
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile * TM < n; tile += gridDim.x) {
+        int r = -1;
+        if (tid < TM) {
+            const int i = tile * TM + tid;
+            float xn[3] = {0.f, 0.f, 0.f};
+            if (i < n) { r = list[i]; const RayCur& c = w.ray_cur[r]; xn[0] = c.xn[0]; xn[1] = c.xn[1]; xn[2] = c.xn[2]; }
+            s.xs[tid][0] = xn[0]; s.xs[tid][1] = xn[1]; s.xs[tid][2] = xn[2]; s.xs[tid][3] = 0.f;
+        }
+        __syncthreads();
+        sdf_tile_forward<PLAIN>(fp, s.xs, s.A, LDA_SDF, wp, s.sdfo, nullptr, 0.f);
+        __syncthreads();
+        if (tid < TM) {       // warps 0,1: marching logic (ray_tracing.py:228-241)
+            bool still = false;
+            if (r >= 0) {
+                const float sdf = sdf_to_metres(s.sdfo[tid], fp.cmin, fp.cmax);
+                float t = w.ray_t[r];
+                const float far_ = w.near_far[2 * r + 1];
+                const float sm = fminf(fmaxf(sdf, -0.1f), 0.1f);
+                bool diverge = false;
+                if (fabsf(sm) > CVG_THRESH && fabsf(sdf) < 1e6f) { t = t + sm; diverge = t >= far_; w.ray_t[r] = t; }
+                still = !(fabsf(sdf) <= CVG_THRESH || diverge);
+                w.ray_flags[r] = (still ? 1 : 0) | (diverge ? 2 : 0);
+            }
+            if (iter + 1 < TRACE_ITERS) warp_append(still, r, next, &w.counters[C_TRACE + iter + 1]);
+            warp_stat_add(r >= 0 ? 1 : 0, &w.counters[C_STAT_TRACE_EVALS]);
+        }
+        __syncthreads();
+    }
+}
+
+// ================================================================================================ joint iso search
+__global__ void k_iso_prepare(Work w) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool go = (r < w.P) && !(w.ray_flags[r] & 2);        // eval mode: non-diverged rays (ray_tracing.py:249)
+    warp_append(go, r, w.listA, &w.counters[C_ISO]);
+}
+
+__device__ __forceinline__ void iso_residual(const FrameParams& fp, const Work& w, int r, const float* u, const float* lg32,
+                                             float sdf_raw, float* g, float* T12) {
+    float xb[3];
+    skin_point(fp, lg32, u, T12, xb);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float xbar = w.ray_dirs[3 * r + k] * u[3] + fp.cam_loc[k];
+        g[1 + k] = xb[k] - (xbar - fp.trans[k]);
+    }
+    g[0] = sdf_to_metres(sdf_raw, fp.cmin, fp.cmax);
+}
+
+// 16 rays per tile (value + 3 tangent rows each): full LBS Jacobian, grad sdf, 4x4 inverse, g(u0)
+__global__ void __launch_bounds__(256, 1) k_iso_init(FrameParams fp, Work w) {
+    extern __shared__ __align__(128) float smem[];
+    const int n = w.counters[C_ISO];
+    constexpr int PTS = TM / 4;
+    if ((int)blockIdx.x * PTS >= n) return;
+    TileSmem s = carve(smem, LDA_SDF);
+    WPipe wp;
+    wpipe_init(wp, s.wbuf, s.bars);
+    const int tid = threadIdx.x;
+    const float dn = 2.0f / (fp.cmax - fp.cmin) / 1.1f;
+    for (int tile = blockIdx.x; tile * PTS < n; tile += gridDim.x) {
+        int r = -1;
+        float x0[3] = {0.f, 0.f, 0.f};
+        if (tid < PTS) {
+            const int i = tile * PTS + tid;
+            float xn[3] = {0.f, 0.f, 0.f};
+            if (i < n) {
+                r = w.listA[i];
+                const RayCur& c = w.ray_cur[r];
+                unnormalize3(fp, c.xn, x0);              // ray_tracing.py:245
+                normalize3(fp, x0, xn);                  // root_finding_utils.py:75 (inside query_weights)
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s.xs[4 * tid + q][0] = xn[0]; s.xs[4 * tid + q][1] = xn[1]; s.xs[4 * tid + q][2] = xn[2]; s.xs[4 * tid + q][3] = 0.f; }
+        }
+        __syncthreads();
+        skin_tile_forward<DUAL>(fp, s.xs, s.A, LDA_SDF, wp, s.logits, dn);
+        __syncthreads();
+        sdf_tile_forward<DUAL>(fp, s.xs, s.A, LDA_SDF, wp, s.sdfo, nullptr, dn);
+        __syncthreads();
+        if (r >= 0) {
+            Dual3 lx[25], pw[NJ];
+#pragma unroll
+            for (int c = 0; c < 25; ++c) {
+                lx[c].v = s.logits[4 * tid][c] * 20.0f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) lx[c].d[k] = s.logits[4 * tid + 1 + k][c] * 20.0f;
+            }
+            hierarchical_softmax_dual(lx, pw);
+            float J[16], T12[12], xb[3];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) J[e] = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 12; ++e) T12[e] = 0.0f;
+            for (int j = 0; j < NJ; ++j) {
+                const float* B = fp.bone_T + j * 16;
+                float bx[3];
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) bx[rr] = B[rr * 4] * x0[0] + B[rr * 4 + 1] * x0[1] + B[rr * 4 + 2] * x0[2] + B[rr * 4 + 3];
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) J[(rr + 1) * 4 + c] += pw[j].v * B[rr * 4 + c] + bx[rr] * pw[j].d[c];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) T12[rr * 4 + c] += pw[j].v * B[rr * 4 + c];
+                }
+            }
+            apply_T(T12, x0, xb);
+            const float so = 1.0f / 2.0f * 1.1f * (fp.cmax - fp.cmin);        // d(sdf metres)/d(sdf raw)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) J[c] = s.sdfo[4 * tid + 1 + c] * so;
+            J[3] = 0.0f;
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) J[(rr + 1) * 4 + 3] = -w.ray_dirs[3 * r + rr];
+            float Ji[16];
+            invert_gj<4>(J, Ji);
+            const float z0 = w.ray_t[r];
+            const float u0[4] = {x0[0], x0[1], x0[2], z0};
+            float g0[4];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g0[1 + k] = xb[k] - ((w.ray_dirs[3 * r + k] * z0 + fp.cam_loc[k]) - fp.trans[k]);
+            g0[0] = sdf_to_metres(s.sdfo[4 * tid], fp.cmin, fp.cmax);
+            BroydenState<4> st;
+            broyden_begin<4>(st, u0, g0, Ji, w.ray_cur[r].T);
+            st.owner = r;
+            st.tgt[0] = st.tgt[1] = st.tgt[2] = 0.f;
+            w.iso_state[r] = st;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) k_iso_iter(FrameParams fp, Work w, int iter) {
+    extern __shared__ __align__(128) float smem[];
+    const int n = w.counters[C_ISO + iter];
+    if ((int)blockIdx.x * TM >= n) return;
+    TileSmem s = carve(smem, LDA_SDF);
+    WPipe wp;
+    wpipe_init(wp, s.wbuf, s.bars);
+    const int* list = (iter & 1) ? w.listB : w.listA;
+    int* next = (iter & 1) ? w.listA : w.listB;
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile * TM < n; tile += gridDim.x) {
+        int r = -1;
+        BroydenState<4> st;
+        float dx[4];
+        if (tid < TM) {
+            const int i = tile * TM + tid;
+            float xn[3] = {0.f, 0.f, 0.f};
+            if (i < n) {
+                r = list[i];
+                st = w.iso_state[r];
+                broyden_advance<4>(st, dx);
+                normalize3(fp, st.x, xn);
+            }
+            s.xs[tid][0] = xn[0]; s.xs[tid][1] = xn[1]; s.xs[tid][2] = xn[2]; s.xs[tid][3] = 0.f;
+        }
+        __syncthreads();
+        skin_tile_forward<PLAIN>(fp, s.xs, s.A, LDA_SDF, wp, s.logits, 0.f);
+        __syncthreads();
+        sdf_tile_forward<PLAIN>(fp, s.xs, s.A, LDA_SDF, wp, s.sdfo, nullptr, 0.f);
+        __syncthreads();
+        if (tid < TM) {
+            bool active = false;
+            if (r >= 0) {
+                float g[4], T12[12];
+                iso_residual(fp, w, r, st.x, s.logits[tid], s.sdfo[tid], g, T12);
+                active = broyden_update<4>(st, dx, g, T12);
+                if (iter + 1 >= BROYDEN_ITERS) active = false;
+                w.iso_state[r] = st;
+            }
+            if (iter + 1 < BROYDEN_ITERS) warp_append(active, r, next, &w.counters[C_ISO + iter + 1]);
+            warp_stat_add(r >= 0 ? 1 : 0, &w.counters[C_STAT_ISO_EVALS]);
+        }
+        __syncthreads();
+    }
+}
+
+// accept/reject the joint-search result, emit the tracer outputs, place the z samples and enqueue the on-samples
+__global__ void k_trace_finish(FrameParams fp, Work w) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int count = 0;
+    if (r < w.P) {
+        const int S = w.S;
+        const float nr = w.near_far[2 * r], fr = w.near_far[2 * r + 1];
+        const uint8_t fl = w.ray_flags[r];
+        float xopt[3], zopt;
+        bool conv = false;
+        if (!(fl & 2)) {
+            const BroydenState<4>& st = w.iso_state[r];
+            xopt[0] = st.best_x[0]; xopt[1] = st.best_x[1]; xopt[2] = st.best_x[2]; zopt = st.best_x[3];
+            conv = st.best_n < CVG_THRESH;
+        } else {
+            unnormalize3(fp, w.ray_cur[r].xn, xopt);
+            zopt = w.ray_t[r];
+        }
+        conv = conv && (zopt >= nr) && (zopt <= fr);                      // ray_tracing.py:266
+        float pn[3];
+        normalize3(fp, xopt, pn);
+        const float dist = conv ? zopt : nr;                              // :274-278
+        w.ray_conv[r] = conv ? 1 : 0;
+        w.ray_dist[r] = dist;
+        w.ray_pnorm[3 * r] = pn[0]; w.ray_pnorm[3 * r + 1] = pn[1]; w.ray_pnorm[3 * r + 2] = pn[2];
+        if (w.out_points_cam) {                                           // implicit_differentiable_renderer.py:114-115,142-143,251
+            const bool surf = conv && fabsf(pn[0]) <= 1.0f && fabsf(pn[1]) <= 1.0f && fabsf(pn[2]) <= 1.0f;
+            float pc[3] = {0.f, 0.f, 0.f};
+            if (surf) {
+                float pw[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pw[k] = ((fp.cam_loc[k] + dist * w.ray_dirs[3 * r + k]) - fp.trans[k]) + fp.trans[k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pc[k] = pw[0] * fp.pose[k * 4] + pw[1] * fp.pose[k * 4 + 1] + pw[2] * fp.pose[k * 4 + 2] + fp.pose[k * 4 + 3];
+            }
+            w.out_points_cam[3 * r] = pc[0]; w.out_points_cam[3 * r + 1] = pc[1]; w.out_points_cam[3 * r + 2] = pc[2];
+        }
+        // ---- z placement (ray_sampler, ray_tracing.py:317-350)
+        float* z = w.z_vals + (size_t)r * S;
+        const int nn = fp.near_samples + 1, nf = fp.far_samples;
+        if (!conv) {
+            for (int i = 0; i < S; ++i) z[i] = dist + (fr - dist) * linspace01(i, S);
+            count = S;
+        } else {
+            count = nn + nf;
+            for (int i = count; i < S; ++i) z[i] = dist + (fr - dist) * linspace01(i, S);
+            // merge of two ascending runs == torch.sort of their concatenation (:348)
+            const float zs0 = dist - 0.05f;
+            const float span = fmaxf(dist - 0.05f - nr, 1e-5f);
+            int a = 0, b = 0;
+            float va = zs0 + 0.1f * linspace01(0, nn);
+            float vb = (nf > 0) ? (nr + span * linspace01(0, nf)) : INFINITY;
+            for (int k = 0; k < count; ++k) {
+                if (b >= nf || (a < nn && va <= vb)) { z[k] = va; ++a; va = (a < nn) ? (zs0 + 0.1f * linspace01(a, nn)) : INFINITY; }
+                else { z[k] = vb; ++b; vb = (b < nf) ? (nr + span * linspace01(b, nf)) : INFINITY; }
+            }
+        }
+        // slots that are off keep zeros / false (generate_point_samples_opt scatters into zeros, :549-555)
+        for (int i = count; i < S; ++i) {
+            const size_t sl = (size_t)r * S + i;
+            w.smp_conv[sl] = 0;
+            w.smp_xn[3 * sl] = 0.f; w.smp_xn[3 * sl + 1] = 0.f; w.smp_xn[3 * sl + 2] = 0.f;
+        }
+        if (conv) atomicAdd(&w.counters[C_STAT_HIT_RAYS], 1);
+    }
+    // enqueue on-samples: the first `count` slots of the ray; one warp-aggregated reservation per warp
+    const int lane = threadIdx.x & 31;
+    int incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 0 && total) base = atomicAdd(&w.counters[C_ON], total);
+    base = __shfl_sync(0xffffffffu, base, 0) + incl - count;
+    for (int i = 0; i < count; ++i) w.on_list[base + i] = r * w.S + i;
+}
+
+// ================================================================================================ correspondences
+__global__ void __launch_bounds__(256) k_knn_samples(FrameParams fp, Work w) {
+    extern __shared__ float4 sv[];
+    const int n = w.counters[C_ON];
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    load_verts(sv, fp);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int sl = w.on_list[i];
+        const int r = sl / w.S;
+        const float z = w.z_vals[sl];
+        float x[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) x[k] = w.ray_dirs[3 * r + k] * z + fp.cam_loc[k];
+        const int idx = knn_scan(sv, fp.n_verts, x[0], x[1], x[2]);
+        BroydenState<3> st;
+        float s_, xh[3];
+        nn_inverse_skinning(fp, idx, x, st.best_T, &s_, xh);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { st.x[k] = xh[k]; st.best_x[k] = xh[k]; st.tgt[k] = x[k] - fp.trans[k]; st.gx[k] = 0.f; st.upd[k] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) st.Jinv[k] = 0.f;
+        st.best_n = 0.f; st.owner = sl; st.g_evals = 0;
+        w.corr_state[i] = st;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.counters[C_CORR] = n;
+}
+
+constexpr int LDA_SKIN = 132;
+__device__ __forceinline__ void corr_finalize(const FrameParams& fp, const Work& w, const BroydenState<3>& st) {
+    const size_t sl = (size_t)st.owner;
+    float xn[3];
+    normalize3(fp, st.best_x, xn);
+    w.smp_xn[3 * sl] = xn[0]; w.smp_xn[3 * sl + 1] = xn[1]; w.smp_xn[3 * sl + 2] = xn[2];
+    float4* Tp = reinterpret_cast<float4*>(w.smp_T + 12 * sl);
+    Tp[0] = make_float4(st.best_T[0], st.best_T[1], st.best_T[2], st.best_T[3]);
+    Tp[1] = make_float4(st.best_T[4], st.best_T[5], st.best_T[6], st.best_T[7]);
+    Tp[2] = make_float4(st.best_T[8], st.best_T[9], st.best_T[10], st.best_T[11]);
+    w.smp_conv[sl] = (st.best_n < CVG_THRESH) ? 1 : 0;
+}
+
+// iter == -1: initial evaluation g(x0) + J^-1 init (root_finding_utils.py:327-328) over all on-samples;
+// iter >= 0 : Broyden step `iter` over the active list.
+__global__ void __launch_bounds__(256, 2) k_corr_step(FrameParams fp, Work w, int iter) {
+    extern __shared__ __align__(128) float smem[];
+    const int n = (iter < 0) ? w.counters[C_ON] : w.counters[C_CORR + iter];
+    if ((int)blockIdx.x * TM >= n) return;
+    TileSmem s = carve(smem, LDA_SKIN);
+    WPipe wp;
+    wpipe_init(wp, s.wbuf, s.bars);
+    const int* list = (iter <= 0) ? nullptr : ((iter & 1) ? w.listB : w.listA);     // step 0 runs on every on-sample
+    int* next = (iter & 1) ? w.listA : w.listB;
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile * TM < n; tile += gridDim.x) {
+        int id = -1;
+        BroydenState<3> st;
+        float dx[3];
+        if (tid < TM) {
+            const int i = tile * TM + tid;
+            float xn[3] = {0.f, 0.f, 0.f};
+            if (i < n) {
+                id = list ? list[i] : i;
+                st = w.corr_state[id];
+                if (iter >= 0) broyden_advance<3>(st, dx);
+                normalize3(fp, st.x, xn);
+            }
+            s.xs[tid][0] = xn[0]; s.xs[tid][1] = xn[1]; s.xs[tid][2] = xn[2]; s.xs[tid][3] = 0.f;
+        }
+        __syncthreads();
+        skin_tile_forward<PLAIN>(fp, s.xs, s.A, LDA_SKIN, wp, s.logits, 0.f);
+        __syncthreads();
+        if (tid < TM) {
+            bool active = false;
+            if (id >= 0) {
+                float T12[12], xb[3], g[3];
+                skin_point(fp, s.logits[tid], st.x, T12, xb);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g[k] = xb[k] - st.tgt[k];
+                if (iter < 0) {
+                    float A3[9], Ai[9], Tinit[12];
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) A3[rr * 3 + c] = T12[rr * 4 + c];
+                    invert3(A3, Ai);
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) Tinit[e] = st.best_T[e];
+                    const float x0[3] = {st.x[0], st.x[1], st.x[2]};
+                    const int owner = st.owner;
+                    const float tg[3] = {st.tgt[0], st.tgt[1], st.tgt[2]};
+                    broyden_begin<3>(st, x0, g, Ai, Tinit);
+                    st.owner = owner; st.tgt[0] = tg[0]; st.tgt[1] = tg[1]; st.tgt[2] = tg[2];
+                    st.g_evals = 2;                         // J-init evaluation + g(x0) (the reference evaluates twice)
+                    w.corr_state[id] = st;
+                } else {
+                    active = broyden_update<3>(st, dx, g, T12);
+                    if (iter + 1 >= BROYDEN_ITERS) active = false;
+                    if (active) w.corr_state[id] = st;
+                    else corr_finalize(fp, w, st);
+                }
+            }
+            if (iter >= 0) {
+                if (iter + 1 < BROYDEN_ITERS) warp_append(active, id, next, &w.counters[C_CORR + iter + 1]);
+                const bool done = (id >= 0) && !active;
+                warp_append(done && st.best_n < CVG_THRESH, done ? st.owner : 0, w.shade_list, &w.counters[C_SHADE]);
+                warp_stat_add(done ? st.g_evals : 0, &w.counters[C_STAT_CORR_EVALS]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ================================================================================================ shading
+// smem: wbuf | A[TM][308] | xs[TM][4] | cin[TM][36] | grad[TM][4] | sdfo[TM] | bars
+__host__ __device__ constexpr size_t shade_smem_bytes() {
+    return (size_t)(WBUF_FLOATS + TM * LDA_SHADE + TM * 4 + TM * 36 + TM * 4 + TM) * 4 + 64;
+}
+
+__global__ void __launch_bounds__(256, 1) k_shade(FrameParams fp, Work w) {
+    extern __shared__ __align__(128) float smem[];
+    const int n = w.counters[C_SHADE];
+    if ((int)blockIdx.x * TM >= n) return;
+    float* wbuf = smem;
+    float* A = smem + WBUF_FLOATS;
+    float* p = A + TM * LDA_SHADE;
+    float (*xs)[4] = reinterpret_cast<float (*)[4]>(p); p += TM * 4;
+    float (*cin)[36] = reinterpret_cast<float (*)[36]>(p); p += TM * 36;
+    float (*grad)[4] = reinterpret_cast<float (*)[4]>(p); p += TM * 4;
+    float* sdfo = p; p += TM;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p);
+    WPipe wp;
+    wpipe_init(wp, wbuf, bars);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* cf = w.scratch + (size_t)blockIdx.x * 7 * TM * SDF_H;      // [6][TM][256] cos factors + [TM][256] features
+    float* feat = cf + (size_t)6 * TM * SDF_H;
+    float* Arow = A + warp * 8 * LDA_SHADE;
+    for (int tile = blockIdx.x; tile * TM < n; tile += gridDim.x) {
+        int sl = -1;
+        if (tid < TM) {
+            const int i = tile * TM + tid;
+            float xn[3] = {0.f, 0.f, 0.f};
+            if (i < n) { sl = w.shade_list[i]; xn[0] = w.smp_xn[3 * (size_t)sl]; xn[1] = w.smp_xn[3 * (size_t)sl + 1]; xn[2] = w.smp_xn[3 * (size_t)sl + 2]; }
+            xs[tid][0] = xn[0]; xs[tid][1] = xn[1]; xs[tid][2] = xn[2]; xs[tid][3] = 0.f;
+        }
+        __syncthreads();
+        // ---- SDF forward (keeps 30 f cos(arg) per layer) and the 256-d feature (implicit_differentiable_renderer.py:336-337)
+        sdf_tile_forward<PLAIN>(fp, xs, A, LDA_SHADE, wp, sdfo, cf, 0.f);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float h[8];
+            const float* row = Arow + r * LDA_SHADE;
+            const float4 a = *reinterpret_cast<const float4*>(row + 4 * lane), b = *reinterpret_cast<const float4*>(row + 128 + 4 * lane);
+            h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+            store_row<256>(feat + (size_t)(warp * 8 + r) * SDF_H, h, lane);
+        }
+        __syncwarp();
+        // ---- gradient wrt the normalised point (autograd in the reference, :338)
+        sdf_tile_backward(fp, A, LDA_SHADE, wp, cf, grad);
+        __syncthreads();
+        // ---- per-sample colour inputs: xn, PE(view), normal (rotated to posed space unless cano_view_dirs)
+        if (tid < TM) {
+            float v[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
+            if (sl >= 0) {
+                const int r = sl / w.S;
+                const float* T = w.smp_T + 12 * (size_t)sl;
+                const float d[3] = {w.ray_dirs[3 * r], w.ray_dirs[3 * r + 1], w.ray_dirs[3 * r + 2]};
+                const float g[3] = {grad[tid][0], grad[tid][1], grad[tid][2]};
+                if (fp.cano_view_dirs) {
+                    float A3[9], Ai[9];
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) A3[rr * 3 + c] = T[rr * 4 + c];
+                    invert3(A3, Ai);
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr) { v[rr] = Ai[rr * 3] * -d[0] + Ai[rr * 3 + 1] * -d[1] + Ai[rr * 3 + 2] * -d[2]; nrm[rr] = g[rr]; }
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr) { v[rr] = -d[rr]; nrm[rr] = T[rr * 4] * g[0] + T[rr * 4 + 1] * g[1] + T[rr * 4 + 2] * g[2]; }
+                }
+                w.smp_sdf[sl] = sdf_to_metres(sdfo[tid], fp.cmin, fp.cmax);
+            }
+            float* c = cin[tid];
+            c[0] = xs[tid][0]; c[1] = xs[tid][1]; c[2] = xs[tid][2];
+            c[3] = v[0]; c[4] = v[1]; c[5] = v[2];
+            int q = 6;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {                      // embedder.py:11-36, multires_view = 4
+                const float fr = (float)(1 << l);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) c[q++] = sinf(v[k] * fr);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) c[q++] = cosf(v[k] * fr);
+            }
+            c[30] = nrm[0]; c[31] = nrm[1]; c[32] = nrm[2]; c[33] = 0.f; c[34] = 0.f; c[35] = 0.f;
+        }
+        __syncthreads();
+        // ---- colour MLP (decoder.py:69-124); A[row] = [feat | cin(33) | 0...]
+        auto fill_input = [&]() {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float h[8];
+                load_cols_rw<256>(h, feat + (size_t)(warp * 8 + r) * SDF_H, lane);   // same thread wrote these values
+                float* row = Arow + r * LDA_SHADE;
+                store_row<256>(row, h, lane);
+                for (int k = lane; k < COL_IN_PAD - 256; k += 32) row[256 + k] = (k < 33) ? cin[warp * 8 + r][k] : 0.f;
+            }
+            __syncwarp();
+        };
+        fill_input();
+        float acc[8][8];
+        auto relu_store = [&](const float* bias) {
+            float b[8];
+            load_cols<256>(b, bias, lane);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float h[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) h[c] = fmaxf(acc[r][c] + b[c], 0.f);
+                store_row<256>(Arow + r * LDA_SHADE, h, lane);
+            }
+            __syncwarp();
+        };
+        tile_gemm<256>(acc, Arow, LDA_SHADE, COL_IN_PAD, fp.col_Wt0, wp);
+        relu_store(fp.col_b[0]);
+        tile_gemm<256>(acc, Arow, LDA_SHADE, 256, fp.col_Wt1, wp);
+        relu_store(fp.col_b[1]);
+        {
+            float acc2[8][4], b[4];
+            tile_gemm<128>(acc2, Arow, LDA_SHADE, 256, fp.col_Wt2, wp);
+            load_cols<128>(b, fp.col_b[2], lane);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float h[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) h[c] = fmaxf(acc2[r][c] + b[c], 0.f);
+                store_row<128>(Arow + r * LDA_SHADE, h, lane);
+            }
+            __syncwarp();
+        }
+        tile_gemm<256>(acc, Arow, LDA_SHADE, 128, fp.col_Wt3b, wp);             // skip connection, lin2 part ...
+        fill_input();
+        tile_gemm<256, true>(acc, Arow, LDA_SHADE, COL_IN_PAD, fp.col_Wt3a, wp);  // ... + network-input part (:113-115)
+        relu_store(fp.col_b[3]);
+        tile_gemm<256>(acc, Arow, LDA_SHADE, 256, fp.col_Wt4, wp);
+        relu_store(fp.col_b[4]);
+        float rgb[3][8];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) warp_rows_dot(Arow, LDA_SHADE, 256, fp.col_W5 + j * 256, rgb[j], lane);
+        if (lane < 8) {
+            const int row = warp * 8 + lane;
+            const int i = tile * TM + row;
+            if (i < n) {
+                const int sl2 = w.shade_list[i];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    float v = rgb[j][0];
+#pragma unroll
+                    for (int r = 1; r < 8; ++r) if (lane == r) v = rgb[j][r];
+                    w.smp_rgb[3 * (size_t)sl2 + j] = sigmoid_(v + __ldg(fp.col_b[5] + j));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ================================================================================================ compositing
+// one warp per ray: converged samples are compacted in slot order into a per-warp shared-memory strip
+// (ballot/popc ranks), then alpha, the transmittance product (warp shuffle scan) and the weighted colour sum run
+// 32 samples at a time (implicit_differentiable_renderer.py:366-394).
+constexpr int COMP_WARPS = 4;
+__global__ void __launch_bounds__(32 * COMP_WARPS) k_composite(FrameParams fp, Work w) {
+    __shared__ float strip[COMP_WARPS][5][MAX_STEPS];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * COMP_WARPS + wib;
+    if (r >= w.P) return;
+    const int S = w.S;
+    float beta = fabsf(fp.beta);
+    beta = fminf(fmaxf(beta, 1e-6f), 1e6f);
+    const float inv_beta = 1.0f / beta;
+    float* cz = strip[wib][0]; float* cd = strip[wib][1];
+    float* cr = strip[wib][2]; float* cg = strip[wib][3]; float* cb = strip[wib][4];
+    int len = 0;
+    for (int base = 0; base < S; base += 32) {
+        const int i = base + lane;
+        const size_t sl = (size_t)r * S + i;
+        const bool valid = (i < S) && w.smp_conv[sl];
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const int k = len + __popc(m & ((1u << lane) - 1u));
+            cz[k] = w.z_vals[sl];
+            cd[k] = laplace_density(w.smp_sdf[sl], inv_beta);
+            cr[k] = w.smp_rgb[3 * sl]; cg[k] = w.smp_rgb[3 * sl + 1]; cb[k] = w.smp_rgb[3 * sl + 2];
+        }
+        len += __popc(m);
+    }
+    __syncwarp();
+    float Tr = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_w = 0.f;
+    for (int base = 0; base < len; base += 32) {
+        const int e = base + lane;
+        const bool in = e < len;
+        float alpha = 0.f;
+        if (in) {
+            const float dz = (e + 1 < len) ? (cz[e + 1] - cz[e]) : (1.0f / (float)S);     // :379-385
+            alpha = 1.0f - expf(-cd[e] * dz);
+        }
+        const float fac = in ? (1.0f - alpha + 1e-7f) : 1.0f;
+        float incl = fac;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl *= t; }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float wgt = in ? alpha * (Tr * excl) : 0.f;
+        float sr = in ? wgt * cr[e] : 0.f, sg = in ? wgt * cg[e] : 0.f, sb = in ? wgt * cb[e] : 0.f, sw = wgt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sr += __shfl_xor_sync(0xffffffffu, sr, o); sg += __shfl_xor_sync(0xffffffffu, sg, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o); sw += __shfl_xor_sync(0xffffffffu, sw, o);
+        }
+        acc_r += sr; acc_g += sg; acc_b += sb; acc_w += sw;
+        Tr *= __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+        w.out_rgb[3 * r] = acc_r; w.out_rgb[3 * r + 1] = acc_g; w.out_rgb[3 * r + 2] = acc_b;
+        w.out_mask[r] = len > 0 ? 1 : 0;
+        if (w.out_wsum) w.out_wsum[r] = fminf(fmaxf(acc_w, 0.f), 1.f);
+        if (len > 0) atomicAdd(&w.counters[C_STAT_VOL_RAYS], 1);
+    }
+}
+
+// stage export for the BodyRayTracing.forward sub-boundary (ray_tracing.py:166-172): 4x4 transforms, zeros where off
+__global__ void k_export_samples(Work w, int n_on_hit, float* pts, float* dists, float* T16, uint8_t* conv) {
+    const size_t sl = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sl >= (size_t)w.P * w.S) return;
+    const int r = (int)(sl / w.S), i = (int)(sl % w.S);
+    const int n_on = w.ray_conv[r] ? n_on_hit : w.S;
+    const bool on = i < n_on;
+    if (pts) { pts[3 * sl] = w.smp_xn[3 * sl]; pts[3 * sl + 1] = w.smp_xn[3 * sl + 1]; pts[3 * sl + 2] = w.smp_xn[3 * sl + 2]; }
+    if (dists) dists[sl] = w.z_vals[sl];
+    if (conv) conv[sl] = w.smp_conv[sl];
+    if (T16) {
+        float* o = T16 + 16 * sl;
+#pragma unroll
+        for (int e = 0; e < 12; ++e) o[e] = on ? w.smp_T[12 * sl + e] : 0.f;
+        o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = on ? 1.f : 0.f;
+    }
+}
+
+}  // namespace arah

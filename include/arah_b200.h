@@ -1,0 +1,129 @@
+/*
+ * arah_b200.h — C ABI of the B200-native ARAH hot path (libarah_b200.so).
+ *
+ * The reference (taconite/arah-release) is pure Python/PyTorch and has no FFI of its own; the entry points below are
+ * what a binding for its renderer modules would call.  Each one names the reference interface it replaces
+ * (paths relative to /root/reference/im2mesh).  All pointers are plain fp32 / uint8 / int32 buffers; nothing in this
+ * header depends on torch.  Unless stated otherwise pointers are DEVICE pointers borrowed from the caller, must be
+ * contiguous and stay alive until the stream has been synchronised; every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*) and performs no host synchronisation.
+ *
+ * Error model: every function returns 0 on success or a negative ARAH_E* code; arah_last_error() returns a
+ * thread-local message.  No C++ exception crosses the boundary.  A handle is not thread-safe; use one per stream.
+ */
+#ifndef ARAH_B200_H
+#define ARAH_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARAH_OK 0
+#define ARAH_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define ARAH_ECUDA (-2)    /* CUDA runtime error (message has the CUDA string) */
+#define ARAH_ENOMEM (-3)
+#define ARAH_ESTATE (-4)   /* call order violated (e.g. render before set_frame) */
+
+typedef struct ArahHandle ArahHandle;
+
+/* Static configuration == constructor arguments of BodyRayTracing / IDHRNetwork
+ * (metaavatar_render/renderer/ray_tracing.py:16-49, renderer/implicit_differentiable_renderer.py:18-40)
+ * and the network shapes of configs/arah-zju/ZJUMOCAP-377_4gpus.yaml:34-43. */
+typedef struct ArahConfig {
+    int32_t device;               /* CUDA device ordinal */
+    int32_t n_steps;              /* model.n_steps (64) */
+    int32_t near_samples;         /* model.near_surface_samples (16) */
+    int32_t far_samples;          /* model.far_surface_samples (16) */
+    int32_t cano_view_dirs;       /* model.cano_view_dirs */
+    int32_t latent_dim;           /* colour-net per-frame latent (128; 0 = none) */
+    int32_t n_verts;              /* SMPL vertices (6890) */
+    int32_t max_rays;             /* initial workspace size in rays (grown on demand) */
+} ArahConfig;
+
+/* Per-frame inputs == what IDHRNetwork.forward reads from its `input` dict
+ * (renderer/implicit_differentiable_renderer.py:52-71) plus the weights of the modules it owns.
+ * Weight matrices are dense fp32 in the reference's own layout [out][in] (weight-norm already applied:
+ * w = g * v / ||v||, i.e. what `lin.weight` holds after the forward pre-hook). */
+typedef struct ArahFrame {
+    /* per-frame SDF FiLM-SIREN produced by the hypernetwork: sdf_network[l][0].weights / .biases / .freq / .phase_shift
+     * (hyperlayers.py:391-415); l = 6 is the final BatchLinear (hyperlayers.py:368-388) */
+    const float* sdf_W[7];        /* [256][3], 5 x [256][256], [1][256] */
+    const float* sdf_b[7];        /* [256] x 6, [1] */
+    const float* sdf_freq;        /* [6][256] */
+    const float* sdf_phase;       /* [6][256] */
+    /* skinning_model.skinning_decoder_fwd.lin0..lin4 (metaavatar/models/decoder.py:133-233) */
+    const float* skin_W[5];       /* [128][3], 3 x [128][128], [25][128] */
+    const float* skin_b[5];
+    /* rendering_network.lin0..lin5 (metaavatar_render/models/decoder.py:10-124), mode 'idr', multires_view 4, skips [3] */
+    const float* col_W[6];        /* [256][417], [256][256], [128][256], [256][545], [256][256], [3][256] */
+    const float* col_b[6];
+    const float* latent;          /* [latent_dim] pose_cond['latent_code'] */
+    float beta;                   /* deviation_network.variance (metaavatar_render/models/decoder.py:127-133) */
+    /* body / pose buffers; HOST pointers if pose_on_host != 0 (copied with cudaMemcpyAsync), else device pointers */
+    const float* bone_transforms; /* [24][4][4] */
+    const float* smpl_verts;      /* [n_verts][3]  posed, including trans */
+    const float* smpl_weights;    /* [n_verts][24]; may be NULL after the first frame (kept from the previous call) */
+    int32_t pose_on_host;
+    float trans[3];
+    float coord_min, coord_max;   /* scalars (data/zju_mocap_odp.py:326-331) */
+    float center[3];
+    float cam_loc[3];
+    float pose[16];               /* world->camera [R|T], row-major 4x4 */
+} ArahFrame;
+
+/* Iteration counters of the last render (algorithmic work is defined through these). */
+typedef struct ArahStats {
+    int64_t rays;
+    int64_t trace_sdf_evals;      /* sphere-tracing SDF evaluations */
+    int64_t iso_rays;             /* rays that entered the joint search */
+    int64_t iso_g_evals;          /* joint-search g evaluations (excluding the Jacobian init) */
+    int64_t on_samples;           /* samples that entered the correspondence search */
+    int64_t corr_skin_evals;      /* skinning-net evaluations in the correspondence search (incl. J init + g(x0)) */
+    int64_t shaded_samples;       /* converged samples shaded (SDF fwd + grad + colour) */
+    int64_t hit_rays;             /* rays with a converged surface point */
+    int64_t vol_rays;             /* rays with >= 1 converged sample (rendered) */
+    int64_t kernel_launches;      /* CUDA kernels launched by the last render call */
+} ArahStats;
+
+const char* arah_last_error(void);
+int arah_version(void);
+
+int arah_create(const ArahConfig* cfg, ArahHandle** out);
+int arah_destroy(ArahHandle* h);
+
+/* Pack the frame's weights for the kernels (transpose, pad, fold the latent into the colour biases) and stage the
+ * pose buffers.  Replaces nothing in the reference one-to-one; it is the boundary crossing that
+ * MetaAvatarRender.forward performs by handing modules to idhr_network (metaavatar_render/models/__init__.py:186-200). */
+int arah_set_frame(ArahHandle* h, const ArahFrame* frame, void* stream);
+
+/* IDHRNetwork.forward, eval branch (renderer/implicit_differentiable_renderer.py:42-112,141-148,180-259):
+ *   ray_dirs [P][3], near_far [P][2] (input['ray_dirs'], input['body_bounds_intersections'])
+ *   -> rgb [P][3] ('rgb_values'), mask [P] ('network_body_mask'), points_cam [P][3] ('points_cam'); weights_sum may be NULL. */
+int arah_render(ArahHandle* h, const float* ray_dirs, const float* near_far, int32_t P,
+                float* rgb, uint8_t* mask, float* points_cam, float* weights_sum, void* stream);
+
+/* Same call with HOST buffers: inputs are copied host->device and results device->host inside the call
+ * (pinned buffers recommended); the stream is synchronised before returning. */
+int arah_render_host(ArahHandle* h, const float* ray_dirs, const float* near_far, int32_t P,
+                     float* rgb, uint8_t* mask, float* points_cam, void* stream);
+
+/* BodyRayTracing.forward (renderer/ray_tracing.py:51-172) outputs of the LAST arah_render call, any pointer may be NULL:
+ *   points_hat_norm [P][3], network_body_mask [P], dists [P], sampled_pts [P][S][3], sampled_dists [P][S],
+ *   sampled_transforms [P][S][4][4], sampler_converge_mask [P][S]. */
+int arah_get_trace(ArahHandle* h, float* points_hat_norm, uint8_t* network_body_mask, float* dists,
+                   float* sampled_pts, float* sampled_dists, float* sampled_transforms,
+                   uint8_t* sampler_converge_mask, void* stream);
+
+/* Synchronises `stream` and reads the device counters of the last render. */
+int arah_get_stats(ArahHandle* h, ArahStats* stats, void* stream);
+
+/* Unit-level entry points used by the parity tests (device pointers, n points):
+ *   arah_eval_sdf  : sdf_network forward + gradient + feature (hyperlayers.py:412-415; diff_operators.py:39-50)
+ *   arah_eval_skin : query_weights + skinning (utils/root_finding_utils.py:54-113, 13-33) */
+int arah_eval_sdf(ArahHandle* h, const float* xn, int32_t n, float* sdf, float* grad, float* feat, void* stream);
+int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, float* weights, float* x_bar, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,167 @@
+"""GPU parity: the CUDA path, called through the drop-in modules -> C ABI, against
+  (a) fixtures produced by the unmodified reference (tests/golden, oracle/gen_golden.py) and
+  (b) the CPU oracle (oracle/arah_oracle.c) on the same seeded inputs.
+Tolerances: tests/helpers.py::TOL (fp32 path; north_star budget PSNR delta <= 0.05 dB)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_CASES, TOL, check_render, load_golden, psnr
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _build(fr):
+    from arah_release_b200 import ref_layout as rl
+    from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
+    dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
+    tracer = BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples, far_surface_vol_samples=fr.far_samples)
+    net = IDHRNetwork(dev, rend, skin, tracer, cano_view_dirs=fr.cano_view_dirs).eval()
+    inputs = rl.inputs_from_frame(fr, sdf, DEV)
+    return net, inputs
+
+
+def _render_dict(net, inputs, stages=True):
+    out = net(inputs)
+    torch.cuda.synchronize()
+    d = {'rgb_values': out['rgb_values'][0].cpu().numpy(), 'network_body_mask': out['network_body_mask'][0].cpu().numpy(),
+         'points_cam': out['points_cam'][0].cpu().numpy()}
+    tr = net.tracer_outputs()
+    names = ['points_hat_norm', 'network_body_mask', 'dists', 'sampled_pts', 'sampled_dists', 'sampled_transforms', 'sampler_converge_mask']
+    for n, v in zip(names, tr):
+        d['trace.' + n] = v[0].cpu().numpy()
+    return d
+
+
+def test_unit_sdf_and_skin_match_oracle():
+    from oracle import oracle as orc
+    fr, _, _ = load_golden('zju377_24x24_s0')
+    net, inputs = _build(fr)
+    r = net._prepare(inputs)
+    rng = np.random.default_rng(0)
+    xn = rng.uniform(-0.9, 0.9, size=(1000, 3)).astype(np.float32)
+    s, g, f = r.eval_sdf(torch.from_numpy(xn).to(DEV), grad=True, feat=True)
+    torch.cuda.synchronize()
+    so, go, fo = orc.sdf(fr, xn, grad=True, feat=True)
+    np.testing.assert_allclose(s.cpu().numpy(), so, atol=2e-5, rtol=0)
+    np.testing.assert_allclose(f.cpu().numpy(), fo, atol=2e-4, rtol=0)
+    np.testing.assert_allclose(g.cpu().numpy(), go, atol=2e-3, rtol=1e-3)
+    xh = rng.uniform(-0.8, 0.8, size=(777, 3)).astype(np.float32)
+    w, xb = r.eval_skin(torch.from_numpy(xh).to(DEV))
+    torch.cuda.synchronize()
+    wo, xbo, _ = orc.skin(fr, xh, jac=False)
+    np.testing.assert_allclose(w.cpu().numpy(), wo, atol=2e-5, rtol=0)
+    np.testing.assert_allclose(xb.cpu().numpy(), xbo, atol=2e-5, rtol=0)
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_render_matches_reference_golden(name):
+    fr, ref, meta = load_golden(name)
+    net, inputs = _build(fr)
+    out = _render_dict(net, inputs)
+    st = check_render(out, ref, label=name)
+    stats = net.stats()
+    assert stats['rays'] == fr.P and stats['kernel_launches'] > 0
+    assert stats['vol_rays'] == int(out['network_body_mask'].sum())
+    print(name, st, stats)
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES[:1])
+def test_render_matches_oracle(name):
+    from oracle import oracle as orc
+    fr, _, _ = load_golden(name)
+    net, inputs = _build(fr)
+    out = _render_dict(net, inputs)
+    o = orc.render(fr)
+    st = check_render(out, o, label=name + ':oracle')
+    stats = net.stats()
+    # algorithmic work counters agree with the oracle's up to borderline iterations
+    assert abs(stats['trace_sdf_evals'] - int(o['n_trace_evals'].sum())) <= 0.01 * o['n_trace_evals'].sum() + 4
+    assert abs(stats['shaded_samples'] - int(o['n_shaded'].sum())) <= 0.002 * o['n_shaded'].sum() + 4
+    assert abs(stats['corr_skin_evals'] - int(o['n_corr_evals'].sum())) <= 0.02 * o['n_corr_evals'].sum()
+    print(st, stats)
+
+
+def test_host_buffer_entry_point_equals_device_path():
+    fr, _, _ = load_golden('n32_16x16_s2')
+    net, inputs = _build(fr)
+    out = net(inputs)
+    r, P = net._last
+    rd = torch.from_numpy(fr.ray_dirs).pin_memory()
+    nf = torch.from_numpy(fr.near_far).pin_memory()
+    rgb, mask, pc = r.render_host(rd, nf)
+    np.testing.assert_array_equal(rgb.numpy(), out['rgb_values'][0].cpu().numpy())
+    np.testing.assert_array_equal(mask.numpy().astype(bool), out['network_body_mask'][0].cpu().numpy())
+    np.testing.assert_array_equal(pc.numpy(), out['points_cam'][0].cpu().numpy())
+
+
+def test_edge_cases_empty_single_and_degenerate():
+    fr, _, meta = load_golden('n32_16x16_s2')
+    net, inputs = _build(fr)
+    r = net._prepare(inputs)
+    rd = torch.from_numpy(fr.ray_dirs).to(DEV)
+    nf = torch.from_numpy(fr.near_far).to(DEV)
+    rgb, mask, pc = r.render(rd[:0], nf[:0])          # empty
+    assert rgb.shape == (0, 3) and mask.shape == (0,)
+    full = r.render(rd, nf)
+    one = r.render(rd[5:6], nf[5:6])                  # single ray == same ray inside the batch (rays are independent)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(one[0].cpu().numpy(), full[0][5:6].cpu().numpy())
+    nd = meta['n_degenerate']                         # near == far: never traced, keeps dists = near
+    tr = r.trace_outputs(rd.shape[0]) if False else None
+    r.render(rd, nf)
+    tr = r.trace_outputs(rd.shape[0])
+    assert not tr[1][0, -nd:].any()
+    np.testing.assert_allclose(tr[2][0, -nd:].cpu().numpy(), fr.near_far[-nd:, 0])
+
+
+def test_api_rejects_bad_config_and_order():
+    from arah_release_b200 import _lib
+    from arah_release_b200.renderer import ArahRenderer
+    with pytest.raises(_lib.ArahError):
+        ArahRenderer(DEV, n_steps=32, near_samples=20, far_samples=20)       # near+1+far > n_steps (ray_tracing.py:336)
+    r = ArahRenderer(DEV)
+    with pytest.raises(_lib.ArahError):
+        r.render(torch.zeros(4, 3, device=DEV), torch.zeros(4, 2, device=DEV))   # render before set_frame
+    with pytest.raises(_lib.ArahError):
+        ArahRenderer('cpu')
+
+
+def test_full_size_properties_512():
+    """BASELINE config 2 size (512x512): size-independent properties instead of an oracle run."""
+    from arah_release_b200 import synthetic as syn
+    fr = syn.make_frame(512, 512, seed=0)
+    net, inputs = _build(fr)
+    out1 = net(inputs)
+    rgb1 = out1['rgb_values'][0].clone(); m1 = out1['network_body_mask'][0].clone()
+    tr = net.tracer_outputs()
+    stats = net.stats()
+    out2 = net(inputs)
+    torch.cuda.synchronize()
+    assert torch.equal(rgb1, out2['rgb_values'][0]) and torch.equal(m1, out2['network_body_mask'][0])      # deterministic
+    rgb = rgb1.cpu().numpy()
+    assert np.isfinite(rgb).all() and rgb.min() >= 0 and rgb.max() <= 1.0 + 1e-5
+    hit = tr[1][0].cpu().numpy(); dists = tr[2][0].cpu().numpy()
+    nf = fr.near_far
+    assert ((dists >= nf[:, 0] - 1e-6) & (dists <= nf[:, 1] + 1e-6)).all()                                  # ray_tracing.py:266
+    np.testing.assert_array_equal(dists[~hit], nf[~hit, 0])
+    z = tr[4][0].cpu().numpy()
+    n_on = fr.near_samples + 1 + fr.far_samples
+    assert (np.diff(z[hit][:, :n_on], axis=1) >= 0).all()                                                   # sorted samples (:348)
+    conv = tr[6][0].cpu().numpy()
+    assert not conv[hit][:, n_on:].any()                                                                    # masked-off slots
+    # rays are independent: a random subset rendered alone reproduces the same pixels bit-for-bit
+    r, P = net._last
+    idx = torch.from_numpy(np.random.default_rng(0).choice(P, size=4096, replace=False)).to(DEV)
+    sub = r.render(inputs['ray_dirs'][0][idx], inputs['body_bounds_intersections'][0][idx])
+    torch.cuda.synchronize()
+    assert torch.equal(sub[0], rgb1[idx])
+    # subset cross-check against the CPU oracle (bounded: 256 rays)
+    from oracle import oracle as orc
+    sel = np.random.default_rng(1).choice(P, size=256, replace=False)
+    o = orc.render(fr, ray_dirs=fr.ray_dirs[sel], near_far=fr.near_far[sel], stages=False)
+    assert psnr(rgb[sel], o['rgb_values']) >= TOL['rgb_psnr_min']
+    assert (hit[sel] != o['trace.network_body_mask']).mean() <= 0.01
+    assert stats['rays'] == P and stats['shaded_samples'] > 0
+    print('512x512', P, stats)
