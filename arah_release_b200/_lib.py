@@ -23,13 +23,15 @@ class ArahFrame(C.Structure):
 
 class ArahStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ('rays', 'trace_sdf_evals', 'iso_rays', 'iso_g_evals', 'on_samples',
-                                         'corr_skin_evals', 'shaded_samples', 'hit_rays', 'vol_rays', 'kernel_launches')]
+                                         'corr_skin_evals', 'shaded_samples', 'hit_rays', 'vol_rays', 'kernel_launches',
+                                         'pack_launches')] + \
+               [(n, C.c_double) for n in ('ms_trace', 'ms_iso', 'ms_sample_corr', 'ms_shade', 'ms_composite', 'ms_total')]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+        return {n: (int(getattr(self, n)) if t is C.c_int64 else float(getattr(self, n))) for n, t in self._fields_}
 
 
-EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'arah_set_frame', 'arah_render',
+EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'arah_set_frame', 'arah_set_profiling', 'arah_render',
            'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin']
 
 _lib = None
@@ -52,6 +54,7 @@ def lib():
     L.arah_create.argtypes = [C.POINTER(ArahConfig), C.POINTER(C.c_void_p)]
     L.arah_destroy.argtypes = [C.c_void_p]
     L.arah_set_frame.argtypes = [C.c_void_p, C.POINTER(ArahFrame), C.c_void_p]
+    L.arah_set_profiling.argtypes = [C.c_void_p, C.c_int32]
     L.arah_render.argtypes = [C.c_void_p, FP, FP, C.c_int32, FP, FP, FP, FP, C.c_void_p]
     L.arah_render_host.argtypes = [C.c_void_p, FP, FP, C.c_int32, FP, FP, FP, C.c_void_p]
     L.arah_get_trace.argtypes = [C.c_void_p, FP, FP, FP, FP, FP, FP, FP, C.c_void_p]

@@ -155,7 +155,9 @@ struct ArahHandle {
     int cap_rays = 0;
     int64_t launches = 0;
     int last_P = 0;
-    float* pinned_b6 = nullptr;
+    int64_t pack_launches = 0;
+    bool profile = false, profiled = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -246,8 +248,16 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     return ARAH_OK;
 }
 
+extern "C" int arah_set_profiling(ArahHandle* h, int32_t enable) {
+    if (!h) return fail(ARAH_EINVAL, "null handle");
+    if (enable && !h->ev[0]) for (int i = 0; i < 6; ++i) CU(cudaEventCreate(&h->ev[i]));
+    h->profile = enable != 0;
+    return ARAH_OK;
+}
+
 extern "C" int arah_destroy(ArahHandle* h) {
     if (!h) return ARAH_OK;
+    for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     h->arena.release(); h->ws.release(); h->scratch.release(); h->io_in.release(); h->io_out.release();
     delete h;
     return ARAH_OK;
@@ -268,8 +278,10 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     if (!f->smpl_weights && !h->have_smpl_w) return fail(ARAH_EINVAL, "smpl_weights required on the first frame");
     const int L = h->cfg.latent_dim;
     const int din = 3 + 27 + 3 + 256 + L;     // colour-net input width in the reference's order [x|PE|n|feat|latent]
+    int64_t npack = 0;
     auto tp = [&](const float* src, int ld, float* dst, int K, int N, int Kp, int Np, int split, int lo, int hi) {
         k_pack_transpose<<<cdiv((size_t)Kp * Np, 256), 256, 0, st>>>(src, ld, dst, K, N, Kp, Np, split, lo, hi);
+        ++npack;
     };
     // SDF
     tp(f->sdf_W[0], 3, h->sdf_Wt[0], 3, 256, 3, 256, 3, 0, 0);
@@ -290,7 +302,7 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     for (int l = 1; l < 4; ++l) tp(f->skin_W[l], 128, h->skin_Wt[l], 128, 128, 128, 128, 128, 0, 0);
     tp(f->skin_W[4], 128, h->skin_Wt[4], 128, 25, 128, 32, 128, 0, 0);
     for (int l = 0; l < 4; ++l) CU(cudaMemcpyAsync(h->skin_b[l], f->skin_b[l], 128 * 4, cudaMemcpyDeviceToDevice, st));
-    k_copy_pad<<<1, 32, 0, st>>>(f->skin_b[4], h->skin_b[4], 25, 32);
+    k_copy_pad<<<1, 32, 0, st>>>(f->skin_b[4], h->skin_b[4], 25, 32); ++npack;
     // colour: reference input order [x 3 | PE 27 | n 3 | feat 256 | latent L]; ours [feat | x | PE | n]
     tp(f->col_W[0], din, h->col_Wt0, COL_IN, 256, COL_IN_PAD, 256, 256, 33, 0);
     tp(f->col_W[1], 256, h->col_Wt1, 256, 256, 256, 256, 256, 0, 0);
@@ -302,6 +314,7 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     if (L > 0) {
         k_fold_latent<<<1, 256, 0, st>>>(f->col_W[0], din, 289, f->latent, L, f->col_b[0], h->col_b[0], 256);
         k_fold_latent<<<1, 256, 0, st>>>(f->col_W[3], din + 128, 289, f->latent, L, f->col_b[3], h->col_b[3], 256);
+        npack += 2;
     } else {
         CU(cudaMemcpyAsync(h->col_b[0], f->col_b[0], 256 * 4, cudaMemcpyDeviceToDevice, st));
         CU(cudaMemcpyAsync(h->col_b[3], f->col_b[3], 256 * 4, cudaMemcpyDeviceToDevice, st));
@@ -314,7 +327,8 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     const cudaMemcpyKind kind = f->pose_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     CU(cudaMemcpyAsync(h->bone_T, f->bone_transforms, 24 * 16 * 4, kind, st));
     CU(cudaMemcpyAsync(h->verts3, f->smpl_verts, (size_t)h->cfg.n_verts * 12, kind, st));
-    k_verts4<<<cdiv(h->cfg.n_verts, 256), 256, 0, st>>>(h->verts3, h->verts4, h->cfg.n_verts);
+    k_verts4<<<cdiv(h->cfg.n_verts, 256), 256, 0, st>>>(h->verts3, h->verts4, h->cfg.n_verts); ++npack;
+    h->pack_launches = npack;
     if (f->smpl_weights) {
         CU(cudaMemcpyAsync(h->smpl_w, f->smpl_weights, (size_t)h->cfg.n_verts * 24 * 4, kind, st));
         h->have_smpl_w = true;
@@ -360,7 +374,10 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     const int nsm = h->n_sms;
     const size_t sm_sdf = tile_smem_bytes(LDA_SDF), sm_skin = tile_smem_bytes(LDA_SKIN), sm_knn = (size_t)fp.n_verts * 16;
     auto L = [&]() { h->launches++; };
+    const bool prof = h->profile;
+    h->profiled = prof;
     CU(cudaMemsetAsync(w.counters, 0, C_COUNT * 4, st));
+    if (prof) CU(cudaEventRecord(h->ev[0], st));
     k_trace_begin<<<cdiv(P, 256), 256, 0, st>>>(w); L();
     const unsigned g_ray_tiles = grid_min(cdiv(P, TM), (size_t)nsm);
     const unsigned g_knn_rays = grid_min(cdiv(P, 256), (size_t)2 * nsm);
@@ -368,16 +385,21 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
         k_knn_rays<<<g_knn_rays, 256, sm_knn, st>>>(fp, w, it); L();
         k_trace_iter<<<g_ray_tiles, 256, sm_sdf, st>>>(fp, w, it); L();
     }
+    if (prof) CU(cudaEventRecord(h->ev[1], st));
     k_iso_prepare<<<cdiv(P, 256), 256, 0, st>>>(w); L();
     k_iso_init<<<grid_min(cdiv(P, TM / 4), (size_t)nsm), 256, sm_sdf, st>>>(fp, w); L();
     for (int it = 0; it < BROYDEN_ITERS; ++it) { k_iso_iter<<<g_ray_tiles, 256, sm_sdf, st>>>(fp, w, it); L(); }
+    if (prof) CU(cudaEventRecord(h->ev[2], st));
     k_trace_finish<<<cdiv(P, 128), 128, 0, st>>>(fp, w); L();
     const unsigned g_knn_s = grid_min(cdiv(PS, 256), (size_t)2 * nsm);
     k_knn_samples<<<g_knn_s, 256, sm_knn, st>>>(fp, w); L();
     const unsigned g_smp_tiles = grid_min(cdiv(PS, TM), (size_t)2 * nsm);
     for (int it = -1; it < BROYDEN_ITERS; ++it) { k_corr_step<<<g_smp_tiles, 256, sm_skin, st>>>(fp, w, it); L(); }
+    if (prof) CU(cudaEventRecord(h->ev[3], st));
     k_shade<<<grid_min(cdiv(PS, TM), (size_t)nsm), 256, shade_smem_bytes(), st>>>(fp, w); L();
+    if (prof) CU(cudaEventRecord(h->ev[4], st));
     k_composite<<<cdiv(P, COMP_WARPS), 32 * COMP_WARPS, 0, st>>>(fp, w); L();
+    if (prof) CU(cudaEventRecord(h->ev[5], st));
     CU(cudaGetLastError());
     return ARAH_OK;
 }
@@ -439,6 +461,7 @@ extern "C" int arah_get_stats(ArahHandle* h, ArahStats* s, void* stream) {
     memset(s, 0, sizeof(*s));
     s->rays = h->last_P;
     s->kernel_launches = h->launches;
+    s->pack_launches = h->pack_launches;
     if (!h->rendered || h->last_P == 0) return ARAH_OK;
     int c[C_COUNT];
     CU(cudaStreamSynchronize((cudaStream_t)stream));
@@ -451,6 +474,12 @@ extern "C" int arah_get_stats(ArahHandle* h, ArahStats* s, void* stream) {
     s->shaded_samples = c[C_SHADE];
     s->hit_rays = c[C_STAT_HIT_RAYS];
     s->vol_rays = c[C_STAT_VOL_RAYS];
+    if (h->profiled) {
+        float ms[5] = {0, 0, 0, 0, 0}, tot = 0;
+        for (int i = 0; i < 5; ++i) CU(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+        CU(cudaEventElapsedTime(&tot, h->ev[0], h->ev[5]));
+        s->ms_trace = ms[0]; s->ms_iso = ms[1]; s->ms_sample_corr = ms[2]; s->ms_shade = ms[3]; s->ms_composite = ms[4]; s->ms_total = tot;
+    }
     return ARAH_OK;
 }
 

@@ -14,6 +14,7 @@ CUDA library is missing or the tensors are not on a CUDA device, the call raises
 Training (`self.training == True`) raises NotImplementedError: backward through root finding is SURVEY.md §8(f) row f2.
 """
 import ctypes as C
+import weakref
 
 import torch
 import torch.nn as nn
@@ -204,6 +205,9 @@ class ArahRenderer:
         return (pts_hat.unsqueeze(0), m.bool().unsqueeze(0), dists.unsqueeze(0), sp.unsqueeze(0), sd.unsqueeze(0),
                 sT.unsqueeze(0) if sT is not None else None, sc.bool().unsqueeze(0))
 
+    def set_profiling(self, enable=True):
+        check(_lib.lib().arah_set_profiling(self._h, int(bool(enable))))
+
     def stats(self):
         s = ArahStats()
         check(_lib.lib().arah_get_stats(self._h, C.byref(s), self.stream))
@@ -249,16 +253,17 @@ class BodyRayTracing(nn.Module):
         self.far_surface_vol_samples = far_surface_vol_samples
         self.sample_bg_pts = sample_bg_pts
         self.low_vram = low_vram          # accepted and ignored: the kernels never materialise P x 64 x 16 intermediates
-        self._owner = None                # set by IDHRNetwork
+        object.__setattr__(self, '_owner', None)   # weakref to the owning IDHRNetwork (not a registered submodule)
 
     def forward(self, sdf_network, skinning_model, cam_loc, ray_directions, body_bounds_intersections, loc, sc_factor,
                 smpl_verts, smpl_verts_cano, skinning_weights, vol_feat, bone_transforms, trans, coord_min, coord_max, center,
                 eval_mode=False):
         if not eval_mode:
             raise NotImplementedError('training-mode ray tracing (stochastic z perturbation) is SURVEY.md §8 row f2')
-        if self._owner is None:
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
             raise _lib.ArahError('BodyRayTracing must be owned by an IDHRNetwork (it shares its renderer handle)')
-        return self._owner._trace_only(sdf_network, cam_loc, ray_directions, body_bounds_intersections, smpl_verts,
+        return owner._trace_only(sdf_network, cam_loc, ray_directions, body_bounds_intersections, smpl_verts,
                                        skinning_weights, bone_transforms, trans, coord_min, coord_max, center)
 
 
@@ -280,7 +285,7 @@ class IDHRNetwork(nn.Module):
         if render_last_pt:
             raise _lib.ArahError('render_last_pt=True is not implemented (no shipped config sets it, configs/default.yaml:52)')
         if isinstance(ray_tracer, BodyRayTracing):
-            ray_tracer._owner = self
+            object.__setattr__(ray_tracer, '_owner', weakref.ref(self))
         self._renderers = {}
         self.last_stats = None
 

@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — rays/sec of the ARAH hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+A *step* is one frame: one pass of the hot path (set_frame weight packing + sphere tracing + joint root finding +
+sample correspondences + SDF/colour shading + compositing) over all bbox rays of a synthetic 512x512 ZJU-377-like
+frame (BASELINE.json configs[1]; synthetic data, fitted synthetic SDF/skinning nets, random-init colour net — no dataset
+or checkpoint is reachable offline).  N > 1: frames of a sequence shard across ranks (weak scaling: one frame per rank
+per step, no data-path collective; a single NCCL broadcast of the frame-invariant weights at start).
+
+JSON keys follow the driver contract; `value` = device-resident inputs (CUDA events), `e2e` = the same frame through the
+host-buffer C-ABI entry point (arah_set_frame with host pose buffers + arah_render_host: H2D of rays/pose and D2H of
+rgb/mask/points inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAC_SDF, MAC_SKIN, MAC_COL = 328704, 52736, 345344     # per-evaluation MACs (colour: latent folded)
+H = W = 512
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--size', type=int, default=512, help='image side (default = BASELINE configs[1]); smaller is for debugging only')
+    ap.add_argument('--cpu-sample-seconds', type=float, default=15.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'tf_burst': d['bf16_tflops'], 'tf_sustained': d['bf16_tflops_sustained'], 'src': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'src': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(max(mx)) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_frames(size, n_frames, first):
+    from arah_release_b200 import synthetic as syn
+    return [syn.make_frame(size, size, seed=0, frame_idx=first + i) for i in range(n_frames)]
+
+
+def algorithmic_flops(st):
+    """MACs defined through the iteration counters; FLOPs = 2 x MACs."""
+    mac = (st['trace_sdf_evals'] * MAC_SDF + st['iso_rays'] * (4 * MAC_SKIN + 2 * MAC_SDF) + st['iso_g_evals'] * (MAC_SKIN + MAC_SDF)
+           + st['corr_skin_evals'] * MAC_SKIN + st['shaded_samples'] * (2 * MAC_SDF + MAC_COL))
+    return 2.0 * mac
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_rate(frame, seconds, threads=0):
+    """rays/s of the oracle port (oracle/arah_oracle.c, all host threads) on a bounded random ray sample of the frame."""
+    from oracle import oracle as orc
+    nthr = orc.num_threads() if threads <= 0 else threads
+    rng = np.random.default_rng(0)
+    n0 = min(frame.P, 64 * nthr)
+    sel = rng.choice(frame.P, size=n0, replace=False)
+    t = time.perf_counter()
+    orc.render(frame, ray_dirs=frame.ray_dirs[sel], near_far=frame.near_far[sel], stages=False, threads=nthr)
+    r0 = n0 / (time.perf_counter() - t)
+    n = int(min(frame.P, max(n0, r0 * seconds)))
+    sel = rng.choice(frame.P, size=n, replace=False)
+    t = time.perf_counter()
+    orc.render(frame, ray_dirs=frame.ray_dirs[sel], near_far=frame.near_far[sel], stages=False, threads=nthr)
+    dt = time.perf_counter() - t
+    return n / dt, nthr, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    frame = make_frames(args.size, 1, 0)[0]
+    nthr = orc.num_threads()
+    rng = np.random.default_rng(0)
+    # bounded sample per step, sized so that the whole run stays within a few minutes
+    t = time.perf_counter()
+    n0 = min(frame.P, 32 * nthr)
+    sel = rng.choice(frame.P, size=n0, replace=False)
+    orc.render(frame, ray_dirs=frame.ray_dirs[sel], near_far=frame.near_far[sel], stages=False, threads=nthr)
+    r0 = n0 / (time.perf_counter() - t)
+    budget = 120.0 / max(args.steps + args.warmup, 1)
+    n = int(min(frame.P, max(n0, r0 * min(budget, 20.0))))
+    times = []
+    for i in range(args.warmup + args.steps):
+        sel = rng.choice(frame.P, size=n, replace=False)
+        t = time.perf_counter()
+        orc.render(frame, ray_dirs=frame.ray_dirs[sel], near_far=frame.near_far[sel], stages=False, threads=nthr)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t)
+    tot = float(sum(times))
+    val = n * args.steps / tot
+    line = {'impl': 'reference', 'metric': 'rays/sec at 512x512 ZJU-377 render', 'value': val, 'unit': 'rays/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'ZJU-377-like {args.size}x{args.size} novel-view render, fp32 (BASELINE configs[1])', 'rays_per_frame': frame.P,
+                       'n_steps': frame.n_steps, 'near_far_samples': [frame.near_samples, frame.far_samples]},
+            'cpu_baseline': {'value': val, 'unit': 'rays/s', 'cores': nthr, 'kind': 'port',
+                             'sample': f'{n} random bbox rays of the frame per step; oracle/arah_oracle.c (C restatement of the reference '
+                                       f'algorithm, OpenMP over rays); the Python reference cannot travel to this box'},
+            'e2e': {'value': val, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from arah_release_b200 import ref_layout as rl
+    from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device(f'cuda:{local}')
+    n_total = args.warmup + args.steps
+    # frames of one sequence, round-robin over ranks: rank r renders frames r, r+N, ...
+    frames = [make_frames(args.size, 1, rank + i * world)[0] for i in range(min(n_total, 4))]
+    f0 = frames[0]
+    dvn, rend, skin, _ = rl.modules_from_frame(f0, dev)
+    if world > 1:      # the single collective of the path: frame-invariant weights from rank 0
+        for m in (dvn, rend, skin):
+            for p_ in m.parameters():
+                dist.broadcast(p_.data, src=0)
+    net = IDHRNetwork(dvn, rend, skin, BodyRayTracing(n_steps=f0.n_steps, near_surface_vol_samples=f0.near_samples,
+                                                      far_surface_vol_samples=f0.far_samples), cano_view_dirs=f0.cano_view_dirs).eval()
+    sdfs = [rl.sdf_network_from_frame(f, dev) for f in frames]
+    inputs = [rl.inputs_from_frame(f, s, dev) for f, s in zip(frames, sdfs)]
+    host = [{k: (v.cpu().pin_memory() if torch.is_tensor(v) and k in ('ray_dirs', 'body_bounds_intersections', 'bone_transforms', 'smpl_verts', 'skinning_weights') else v)
+             for k, v in inp.items()} for inp in inputs]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        inp = inputs[i % len(inputs)]
+        net(inp)
+
+    def step_host(i):
+        hi = host[i % len(host)]
+        r = net._renderer(dev, 128, hi['smpl_verts'].shape[1])
+        r.set_frame_from_modules(hi['sdf_network'], net.skinning_model, net.rendering_network, net.deviation_network, hi, pose_on_host=True)
+        return r.render_host(hi['ray_dirs'][0], hi['body_bounds_intersections'][0])
+
+    rays_step = [inputs[i % len(inputs)]['ray_dirs'].shape[1] for i in range(n_total)]
+
+    # ---------------- device-resident timing (value)
+    for i in range(args.warmup):
+        step_device(i)
+    r = net._last[0]
+    r.set_profiling(True)
+    barrier()
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    shade_ms, shade_flops, step_flops, stats_last = [], [], [], None
+    for k in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (outside the event pair)
+        ev[k][0].record()
+        step_device(args.warmup + k)
+        ev[k][1].record()
+        st = r.stats()                                  # syncs; counters + stage events of this step
+        shade_ms.append(st['ms_shade'])
+        shade_flops.append(2.0 * st['shaded_samples'] * (2 * MAC_SDF + MAC_COL))
+        step_flops.append(algorithmic_flops(st))
+        stats_last = st
+    barrier()
+    clocks = clk.stop() if rank == 0 else None
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    rays_timed = sum(rays_step[args.warmup:])
+
+    # ---------------- end-to-end timing through the host-buffer entry point
+    r.set_profiling(False)
+    for i in range(min(args.warmup, 2)):
+        step_host(i)
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall = 0.0
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev2[k][0].record()
+        out = step_host(args.warmup + k)
+        ev2[k][1].record()
+        torch.cuda.synchronize()
+        wall += time.perf_counter() - t0
+    barrier()
+    t_e2e = max(sum(a.elapsed_time(b) for a, b in ev2) / 1e3, wall)     # host-visible completion dominates
+    P0 = rays_step[args.warmup]
+    h2d = P0 * 20 + 24 * 16 * 4 + f0.smpl_verts.size * 4 + f0.smpl_weights.size * 4
+    d2h = P0 * (12 + 1 + 12)
+
+    # ---------------- reduce over ranks: MAX time, SUM rays
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n = torch.tensor([float(rays_timed)], device=dev, dtype=torch.float64)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        t_dev, t_e2e, rays_all = float(t[0]), float(t[1]), float(n[0])
+    else:
+        rays_all = float(rays_timed)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ach = (sum(shade_flops) / max(sum(shade_ms), 1e-9)) / 1e9          # FLOP/ms -> TFLOP/s
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'k_shade_traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+        except Exception:
+            traffic = None
+    line = {
+        'metric': 'rays/sec at 512x512 ZJU-377 render', 'value': rays_all / t_dev, 'unit': 'rays/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'ZJU-377-like {args.size}x{args.size} novel-view render, fp32 (BASELINE configs[1])',
+                   'rays_per_frame': P0, 'n_steps': f0.n_steps, 'near_far_samples': [f0.near_samples, f0.far_samples],
+                   'parallelism': f'frames sharded over {args.gpus} GPU(s), 1 frame/rank/step', 'l2': '256 MB memset between timed steps',
+                   'timing': 'CUDA events on the launching stream, per step, summed; max over ranks'},
+        'e2e': {'value': rays_all / t_e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'api': 'arah_set_frame(pose_on_host) + arah_render_host via IDHRNetwork host wrapper'},
+        'gpu_launches': int((stats_last['kernel_launches'] + stats_last['pack_launches']) * args.steps),
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'k_shade (SDF fwd + reverse-mode grad + colour MLP, fp32 FFMA tiles)',
+                     'achieved': ach, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf_sustained'],
+                     'peak_source': pk['src'] + ' bf16 cuBLAS sustained (MEASURED_PEAKS.json)', 'traffic': traffic,
+                     'algorithmic_flops_per_launch': float(np.mean(shade_flops)), 'ms_per_launch': float(np.mean(shade_ms)),
+                     'kernel_share_of_step': float(sum(shade_ms) / (1e3 * t_dev)),
+                     'whole_step_tflops': float(sum(step_flops) / t_dev / 1e12)},
+        'stages_ms_last_step': {k: stats_last[k] for k in ('ms_trace', 'ms_iso', 'ms_sample_corr', 'ms_shade', 'ms_composite', 'ms_total')},
+        'counters_last_step': {k: stats_last[k] for k in ('rays', 'trace_sdf_evals', 'iso_rays', 'iso_g_evals', 'on_samples', 'corr_skin_evals',
+                                                           'shaded_samples', 'hit_rays', 'vol_rays')},
+    }
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        v, cores, n, dt = cpu_rate(f0, args.cpu_sample_seconds)
+        line['cpu_baseline'] = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+                                'sample': f'{n} random bbox rays of the same frame in {dt:.1f} s (oracle/arah_oracle.c, OpenMP)'}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -83,6 +83,10 @@ typedef struct ArahStats {
     int64_t hit_rays;             /* rays with a converged surface point */
     int64_t vol_rays;             /* rays with >= 1 converged sample (rendered) */
     int64_t kernel_launches;      /* CUDA kernels launched by the last render call */
+    int64_t pack_launches;        /* CUDA kernels launched by the last arah_set_frame call */
+    /* device time of each stage of the last render (ms, CUDA events on the launching stream);
+     * only filled when profiling was enabled with arah_set_profiling(h, 1), else 0 */
+    double ms_trace, ms_iso, ms_sample_corr, ms_shade, ms_composite, ms_total;
 } ArahStats;
 
 const char* arah_last_error(void);
@@ -113,6 +117,9 @@ int arah_render_host(ArahHandle* h, const float* ray_dirs, const float* near_far
 int arah_get_trace(ArahHandle* h, float* points_hat_norm, uint8_t* network_body_mask, float* dists,
                    float* sampled_pts, float* sampled_dists, float* sampled_transforms,
                    uint8_t* sampler_converge_mask, void* stream);
+
+/* Record CUDA events at the stage boundaries of every following arah_render (cheap; no synchronisation). */
+int arah_set_profiling(ArahHandle* h, int32_t enable);
 
 /* Synchronises `stream` and reads the device counters of the last render. */
 int arah_get_stats(ArahHandle* h, ArahStats* stats, void* stream);
