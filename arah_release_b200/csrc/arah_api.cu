@@ -7,6 +7,8 @@
 
 #include "../../include/arah_b200.h"
 #include "arah_kernels.cuh"
+#include "arah_umma.cuh"
+#include "arah_shade_tc.cuh"
 
 using namespace arah;
 
@@ -18,6 +20,9 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess)                                                                             \
             return fail(ARAH_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
     } while (0)
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+static inline unsigned grid_min(size_t a, size_t b) { return (unsigned)(a < b ? a : b); }
 
 extern "C" const char* arah_last_error(void) { return g_err.c_str(); }
 extern "C" int arah_version(void) { return 100; }
@@ -52,6 +57,12 @@ __global__ void k_copy_pad(const float* __restrict__ src, float* __restrict__ ds
 __global__ void k_verts4(const float* __restrict__ v3, float4* __restrict__ v4, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v4[i] = make_float4(v3[3 * i], v3[3 * i + 1], v3[3 * i + 2], 0.f);
+}
+// F = 30 f, G = 30 (f b + phi): the FiLM-sine argument becomes fma(acc, F, G) in the tensor-core epilogue
+__global__ void k_pack_film(const float* __restrict__ b, const float* __restrict__ f, const float* __restrict__ ph, float* __restrict__ F, float* __restrict__ G) {
+    const int c = threadIdx.x;
+    F[c] = 30.0f * f[c];
+    G[c] = 30.0f * (f[c] * b[c] + ph[c]);
 }
 __global__ void k_read_b6(const float* __restrict__ b6, float* __restrict__ dst) { dst[0] = b6[0]; }
 
@@ -123,6 +134,85 @@ __global__ void __launch_bounds__(256, 2) k_eval_skin(FrameParams fp, const floa
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ tcgen05 packing + probe
+// dst chunk c (k in [32c, 32c+32)) = shared-memory image of a K-major SWIZZLE_128B tile of B[N][K]:
+//   float index  c*N*32 + (n/8)*256 + (n%8)*32 + ((j ^ (n%8))*4) + e   <-   src[n][col(32c + 4j + e)]   (0 beyond K)
+// col(k) = (k < split) ? k + off_lo : k - split + off_hi   (same column permutation as k_pack_transpose)
+__global__ void k_pack_umma(const float* __restrict__ src, int src_ld, float* __restrict__ dst, int N, int K, int nchunks,
+                            int split, int off_lo, int off_hi, int transpose_src) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nchunks * N * 32) return;
+    const int c = idx / (N * 32), rem = idx % (N * 32);
+    const int n = rem / 32, q = rem % 32, j = q / 4, e = q % 4;
+    const int k = 32 * c + 4 * j + e;
+    float v = 0.f;
+    if (k < K) {
+        const int col = (k < split) ? (k + off_lo) : (k - split + off_hi);
+        v = transpose_src ? src[(size_t)col * src_ld + n] : src[(size_t)n * src_ld + col];
+        v = tf32_rn(v);                  // round once here so the tensor core's operand truncation is exact
+    }
+    dst[(size_t)c * N * 32 + (n >> 3) * 256 + (n & 7) * 32 + ((j ^ (n & 7)) << 2) + e] = v;
+}
+
+// D[128][N] = A[128][K] . W[N][K]^T on the tensor cores (TF32 operands, fp32 accumulate); validates descriptors/swizzle
+__global__ void __launch_bounds__(256, 1) k_umma_probe(const float* __restrict__ A, const float* __restrict__ Wsw, int K, int N, float* __restrict__ D) {
+    extern __shared__ uint8_t raw_smem[];
+    const uint32_t base = (smem_u32(raw_smem) + 1023u) & ~1023u;
+    float* sm = reinterpret_cast<float*>(raw_smem + (base - smem_u32(raw_smem)));
+    float* Abuf = sm;                                   // 8 chunks x 16 KB
+    float* ring = sm + 8 * A_CHUNK_FLOATS;              // 2 x 32 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * RING_SLOT_FLOATS);   // full[2], empty[2], done
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(tslot, 256);
+    if (tid < UM) {
+        for (int c = 0; c < K / UK; ++c) {
+            float v[32];
+            for (int i = 0; i < 32; ++i) v[i] = A[(size_t)tid * K + c * UK + i];
+            a_store_chunk(Abuf, tid, c, v);
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot;
+    if (tid == 0) {
+        URing rg; rg.buf = ring; rg.full = bars; rg.empty = bars + 2; rg.fill_cnt = 0; rg.mma_cnt = 0;
+        umma_layer_issue(rg, Abuf, Wsw, K / UK, N, tbase, 0u, &bars[4]);
+    }
+    mbar_wait(&bars[4], 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    for (int b = 0; b < (N / 2) / 32; ++b) {
+        const int col0 = half * (N / 2) + 32 * b;
+        float v[32];
+        tmem_ld32(tbase + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, v);
+        for (int i = 0; i < 32; ++i) D[(size_t)(32 * q + lane) * N + col0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
+extern "C" int arah_debug_umma_gemm(const float* A, const float* W, int32_t K, int32_t N, float* D, void* stream) {
+    if (!A || !W || !D) return fail(ARAH_EINVAL, "null buffer");
+    if (K <= 0 || K > 256 || (K % 32) != 0 || (N != 256 && N != 128)) return fail(ARAH_EINVAL, "K must be a multiple of 32 <= 256, N in {128,256}");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* Wsw = nullptr;
+    CU(cudaMalloc(&Wsw, (size_t)K * N * 4));
+    k_pack_umma<<<cdiv((size_t)K * N, 256), 256, 0, st>>>(W, K, Wsw, N, K, K / 32, K, 0, 0, 0);
+    const int smem = (8 * A_CHUNK_FLOATS + 2 * RING_SLOT_FLOATS) * 4 + 128 + 1024;
+    CU(cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_umma_probe<<<1, 256, smem, st>>>(A, Wsw, K, N, D);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    CU(cudaFree(Wsw));
+    return ARAH_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ handle
 struct DevBuf {
     void* p = nullptr;
@@ -149,6 +239,10 @@ struct ArahHandle {
     float* skin_Wt[5]; float* skin_b[5];
     float* col_Wt0; float* col_Wt1; float* col_Wt2; float* col_Wt3a; float* col_Wt3b; float* col_Wt4; float* col_W5; float* col_b[6];
     float* bone_T; float4* verts4; float* verts3; float* smpl_w;
+    // tensor-core shading: pre-swizzled chunk images (arah_umma.cuh)
+    float* tc_sdf_fwd[5]; float* tc_sdf_bwd[5]; float* tc_F; float* tc_G;
+    float* tc_col0; float* tc_col1; float* tc_col2; float* tc_col3b; float* tc_col3a; float* tc_col4;
+    ShadeTC tc;
     // workspace
     DevBuf ws, scratch, io_in, io_out;
     Work w;
@@ -177,7 +271,11 @@ static int alloc_arena(ArahHandle* h) {
     reg(&h->skin_Wt[4], 128 * 32); reg(&h->skin_b[4], 32);
     reg(&h->col_Wt0, COL_IN_PAD * 256); reg(&h->col_Wt1, 256 * 256); reg(&h->col_Wt2, 256 * 128);
     reg(&h->col_Wt3a, COL_IN_PAD * 256); reg(&h->col_Wt3b, 128 * 256); reg(&h->col_Wt4, 256 * 256); reg(&h->col_W5, 3 * 256);
-    reg(&h->col_b[0], 256); reg(&h->col_b[1], 256); reg(&h->col_b[2], 128); reg(&h->col_b[3], 256); reg(&h->col_b[4], 256); reg(&h->col_b[5], 64);
+    for (int l = 0; l < 5; ++l) { reg(&h->tc_sdf_fwd[l], 256 * 256); reg(&h->tc_sdf_bwd[l], 256 * 256); }
+    reg(&h->tc_F, 6 * 256); reg(&h->tc_G, 6 * 256);
+    reg(&h->tc_col0, 10 * 256 * 32); reg(&h->tc_col1, 256 * 256); reg(&h->tc_col2, 8 * 128 * 32); reg(&h->tc_col3b, 4 * 256 * 32);
+    reg(&h->tc_col3a, 10 * 256 * 32); reg(&h->tc_col4, 256 * 256);
+    reg(&h->col_b[0], 256); reg(&h->col_b[1], 256); reg(&h->col_b[2], 256); reg(&h->col_b[3], 256); reg(&h->col_b[4], 256); reg(&h->col_b[5], 64);
     reg(&h->bone_T, 24 * 16);
     float* v4 = nullptr;
     reg(&v4, (size_t)h->cfg.n_verts * 4);
@@ -221,6 +319,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
         return fail(ARAH_EINVAL, "near_samples + 1 + far_samples must be <= n_steps (ray_tracing.py:336,346)");
     if (cfg->near_samples < 0 || cfg->far_samples < 0 || (cfg->near_samples == 0 && cfg->far_samples == 0))
         return fail(ARAH_EINVAL, "need near_samples > 0 or far_samples > 0 (ray_tracing.py:107)");
+    if (cfg->shade_mode != ARAH_SHADE_TF32 && cfg->shade_mode != ARAH_SHADE_FP32) return fail(ARAH_EINVAL, "shade_mode must be ARAH_SHADE_TF32 or ARAH_SHADE_FP32");
     if (cfg->latent_dim < 0 || cfg->latent_dim > 512) return fail(ARAH_EINVAL, "latent_dim must be in [0,512]");
     if (cfg->n_verts <= 0 || (size_t)cfg->n_verts * 16 > 200 * 1024) return fail(ARAH_EINVAL, "n_verts must fit 200 KB of shared memory (<= 12800)");
     CU(cudaSetDevice(cfg->device));
@@ -233,7 +332,8 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     memset(&h->w, 0, sizeof(h->w));
     if (alloc_arena(h) != 0) { delete h; return fail(ARAH_ENOMEM, "weight arena allocation failed"); }
     if (ensure_workspace(h, cfg->max_rays > 0 ? cfg->max_rays : 4096) != 0) { h->arena.release(); delete h; return fail(ARAH_ENOMEM, "workspace allocation failed"); }
-    if (h->scratch.ensure((size_t)h->n_sms * 7 * TM * SDF_H * 4) != 0) { delete h; return fail(ARAH_ENOMEM, "scratch allocation failed"); }
+    const size_t scr_fp32 = (size_t)7 * TM * SDF_H * 4, scr_tc = (size_t)TC_SCRATCH_FLOATS * 4;
+    if (h->scratch.ensure((size_t)h->n_sms * (scr_fp32 > scr_tc ? scr_fp32 : scr_tc)) != 0) { delete h; return fail(ARAH_ENOMEM, "scratch allocation failed"); }
     h->w.scratch = (float*)h->scratch.p;
     CU(cudaFuncSetAttribute(k_trace_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SDF)));
     CU(cudaFuncSetAttribute(k_iso_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SDF)));
@@ -242,6 +342,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_corr_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SKIN)));
     CU(cudaFuncSetAttribute(k_eval_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SKIN)));
     CU(cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc_smem_bytes()));
     CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->n_verts * 16));
     CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->n_verts * 16));
     *out = h;
@@ -263,8 +364,6 @@ extern "C" int arah_destroy(ArahHandle* h) {
     return ARAH_OK;
 }
 
-static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
-static inline unsigned grid_min(size_t a, size_t b) { return (unsigned)(a < b ? a : b); }
 
 extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) {
     if (!h || !f) return fail(ARAH_EINVAL, "null argument");
@@ -323,6 +422,23 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     CU(cudaMemcpyAsync(h->col_b[2], f->col_b[2], 128 * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(h->col_b[4], f->col_b[4], 256 * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(h->col_b[5], f->col_b[5], 3 * 4, cudaMemcpyDeviceToDevice, st));
+    if (h->cfg.shade_mode == ARAH_SHADE_TF32) {
+        auto up = [&](const float* src, int ld, float* dst, int N, int K, int nchunks, int split, int lo, int hi, int transpose) {
+            k_pack_umma<<<cdiv((size_t)nchunks * N * 32, 256), 256, 0, st>>>(src, ld, dst, N, K, nchunks, split, lo, hi, transpose);
+            ++npack;
+        };
+        for (int l = 1; l < 6; ++l) {
+            up(f->sdf_W[l], 256, h->tc_sdf_fwd[l - 1], 256, 256, 8, 256, 0, 0, 0);
+            up(f->sdf_W[l], 256, h->tc_sdf_bwd[l - 1], 256, 256, 8, 256, 0, 0, 1);
+        }
+        for (int l = 0; l < 6; ++l) { k_pack_film<<<1, 256, 0, st>>>(f->sdf_b[l], f->sdf_freq + l * 256, f->sdf_phase + l * 256, h->tc_F + l * 256, h->tc_G + l * 256); ++npack; }
+        up(f->col_W[0], din, h->tc_col0, 256, COL_IN, 10, 256, 33, 0, 0);
+        up(f->col_W[1], 256, h->tc_col1, 256, 256, 8, 256, 0, 0, 0);
+        up(f->col_W[2], 256, h->tc_col2, 128, 256, 8, 256, 0, 0, 0);
+        up(f->col_W[3], din + 128, h->tc_col3b, 256, 128, 4, 128, din, 0, 0);
+        up(f->col_W[3], din + 128, h->tc_col3a, 256, COL_IN, 10, 256, 33, 0, 0);
+        up(f->col_W[4], 256, h->tc_col4, 256, 256, 8, 256, 0, 0, 0);
+    }
     // pose buffers
     const cudaMemcpyKind kind = f->pose_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     CU(cudaMemcpyAsync(h->bone_T, f->bone_transforms, 24 * 16 * 4, kind, st));
@@ -349,6 +465,13 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     fp.beta = f->beta;
     fp.n_steps = h->cfg.n_steps; fp.near_samples = h->cfg.near_samples; fp.far_samples = h->cfg.far_samples;
     fp.cano_view_dirs = h->cfg.cano_view_dirs;
+    ShadeTC& tc = h->tc;
+    tc.sdf_Wt0 = h->sdf_Wt[0]; tc.sdf_W0 = h->sdf_W[0]; tc.sdf_F = h->tc_F; tc.sdf_G = h->tc_G;
+    for (int l = 0; l < 5; ++l) { tc.sdf_fwd[l] = h->tc_sdf_fwd[l]; tc.sdf_bwd[l] = h->tc_sdf_bwd[l]; }
+    tc.sdf_w6 = h->sdf_w6; tc.sdf_b6 = b6;
+    tc.col0 = h->tc_col0; tc.col1 = h->tc_col1; tc.col2 = h->tc_col2; tc.col3b = h->tc_col3b; tc.col3a = h->tc_col3a; tc.col4 = h->tc_col4;
+    tc.col_W5 = h->col_W5;
+    for (int l = 0; l < 6; ++l) tc.col_b[l] = h->col_b[l];
     if (!(fp.cmax > fp.cmin)) return fail(ARAH_EINVAL, "coord_max must exceed coord_min");
     h->frame_set = true;
     return ARAH_OK;
@@ -396,7 +519,8 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     const unsigned g_smp_tiles = grid_min(cdiv(PS, TM), (size_t)2 * nsm);
     for (int it = -1; it < BROYDEN_ITERS; ++it) { k_corr_step<<<g_smp_tiles, 256, sm_skin, st>>>(fp, w, it); L(); }
     if (prof) CU(cudaEventRecord(h->ev[3], st));
-    k_shade<<<grid_min(cdiv(PS, TM), (size_t)nsm), 256, shade_smem_bytes(), st>>>(fp, w); L();
+    if (h->cfg.shade_mode == ARAH_SHADE_TF32) { k_shade_tc<<<grid_min(cdiv(PS, UM), (size_t)nsm), 256, shade_tc_smem_bytes(), st>>>(fp, h->tc, w); L(); }
+    else { k_shade<<<grid_min(cdiv(PS, TM), (size_t)nsm), 256, shade_smem_bytes(), st>>>(fp, w); L(); }
     if (prof) CU(cudaEventRecord(h->ev[4], st));
     k_composite<<<cdiv(P, COMP_WARPS), 32 * COMP_WARPS, 0, st>>>(fp, w); L();
     if (prof) CU(cudaEventRecord(h->ev[5], st));

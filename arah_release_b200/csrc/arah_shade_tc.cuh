@@ -1,0 +1,339 @@
+// arah_shade_tc.cuh — k_shade_tc: the shading stage on the 5th-gen tensor cores (tcgen05, TF32 operands, fp32 accumulate).
+//
+// Replaces k_shade (fp32 FFMA tiles) for /root/reference/im2mesh/metaavatar_render/renderer/
+// implicit_differentiable_renderer.py:311-361: SDF forward (6 FiLM-sine layers), reverse-mode d sdf / d x, colour MLP.
+// tools/precision_study.py bounds the effect of TF32 operand rounding in THIS stage at PSNR >= 80 dB against fp32 and
+// |dPSNR| <= 0.001 dB (budget 0.05 dB); root finding stays fp32 (its residuals must resolve 1e-5 m).
+//
+// One CTA (256 threads) per SM, tile = 128 samples:
+//   A (activations)  shared memory, 8 K-chunks x 16 KB, SWIZZLE_128B K-major, rewritten in place by every epilogue
+//   B (weights)      pre-swizzled chunk images in L2, staged by 1-D TMA bulk copies into a 2 x 32 KB ring
+//   D (accumulators) TMEM, 128 lanes x 256 fp32 columns
+//   one elected thread issues copies + tcgen05.mma and commits to mbarriers; all 8 warps run the epilogues:
+//   warp w reads TMEM lanes 32*(w%4).. (its sub-partition), columns [128*(w/4), +128) -> thread = one row x 128 columns.
+// cos factors for the reverse pass (bf16) and the 256-d feature (fp32) live in a per-CTA scratch that stays L2-resident.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "arah_kernels.cuh"
+#include "arah_umma.cuh"
+
+namespace arah {
+
+struct ShadeTC {
+    const float* sdf_Wt0;      // [3][256]
+    const float* sdf_W0;       // [256][3]
+    const float* sdf_F;        // [6][256]  30 f
+    const float* sdf_G;        // [6][256]  30 (f b + phi)
+    const float* sdf_fwd[5];   // layers 1..5, swizzled chunks of B[n=out][k=in]
+    const float* sdf_bwd[5];   // layers 1..5, swizzled chunks of B[n=in][k=out]
+    const float* sdf_w6;       // [256]
+    float sdf_b6;
+    const float* col0;         // 10 chunks, N=256: k = [feat 256 | x,PE,n 33 | pad]
+    const float* col1;         // 8 chunks
+    const float* col2;         // 8 chunks, N=128
+    const float* col3b;        // 4 chunks (lin2 output part of the skip layer)
+    const float* col3a;        // 10 chunks (network-input part)
+    const float* col4;         // 8 chunks
+    const float* col_W5;       // [3][256]
+    const float* col_b[6];
+};
+
+constexpr int TC_SCRATCH_FLOATS = 6 * UM * 256 / 2 + UM * 256;     // bf16 cos factors + fp32 feature, in float units
+__host__ __device__ constexpr size_t shade_tc_smem_bytes() {
+    return (size_t)(8 * A_CHUNK_FLOATS + 2 * RING_SLOT_FLOATS + UM * 36 + 2 * 256 + UM * 4 + 2 * UM * 4) * 4 + 256 + 1024;
+}
+
+__device__ __forceinline__ void cf_store32(__nv_bfloat16* dst, const float (&v)[32]) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), b = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+        __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), e = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+        u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&e);
+        d[i] = u;
+    }
+}
+__device__ __forceinline__ void cf_load32(const __nv_bfloat16* src, float (&v)[32]) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 u = s[i];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+            const float2 f = __bfloat1622float2(p);
+            v[8 * i + 2 * j] = f.x; v[8 * i + 2 * j + 1] = f.y;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc, Work w) {
+    extern __shared__ uint8_t raw_smem[];
+    const int n = w.counters[C_SHADE];
+    if ((int)blockIdx.x * UM >= n) return;
+    const uint32_t base = (smem_u32(raw_smem) + 1023u) & ~1023u;
+    float* sm = reinterpret_cast<float*>(raw_smem + (base - smem_u32(raw_smem)));
+    float* A = sm;
+    float* ring = A + 8 * A_CHUNK_FLOATS;
+    float (*cin)[36] = reinterpret_cast<float (*)[36]>(ring + 2 * RING_SLOT_FLOATS);
+    float* lp0 = reinterpret_cast<float*>(cin) + UM * 36;     // per-layer column parameters
+    float* lp1 = lp0 + 256;
+    float (*xs)[4] = reinterpret_cast<float (*)[4]>(lp1 + 256);
+    float (*part)[UM][4] = reinterpret_cast<float (*)[UM][4]>(reinterpret_cast<float*>(xs) + UM * 4);   // [2][UM][4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(part) + 2 * UM * 4);         // full[2] empty[2] done
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, half = warp >> 2;
+    const int r = 32 * q + lane;                 // this thread's row (TMEM lane)
+    if (tid == 0) { for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(tslot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot;
+    const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
+    URing rg; rg.buf = ring; rg.full = bars; rg.empty = bars + 2; rg.fill_cnt = 0; rg.mma_cnt = 0;
+    uint32_t done_par = 0;
+
+    float* scratch = w.scratch + (size_t)blockIdx.x * TC_SCRATCH_FLOATS;
+    __nv_bfloat16* cf = reinterpret_cast<__nv_bfloat16*>(scratch);            // [6][UM][256]
+    float* feat = scratch + 6 * UM * 256 / 2;                                  // [UM][256]
+
+    // A is complete (generic-proxy writes) and TMEM reads are done -> hand over to the MMA issuer
+    auto handoff = [&]() { fence_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
+    auto gemm = [&](const float* Wsw, int nchunks, int N, uint32_t accumulate) {
+        if (tid == 0) umma_layer_issue(rg, A, Wsw, nchunks, N, tbase, accumulate, &bars[4]);
+        mbar_wait(&bars[4], done_par);
+        done_par ^= 1u;
+        tc_fence_after();
+    };
+    auto load_params = [&](const float* p0, const float* p1) {
+        lp0[tid] = p0 ? __ldg(p0 + tid) : 0.f;
+        lp1[tid] = p1 ? __ldg(p1 + tid) : 0.f;
+        __syncthreads();
+    };
+
+    for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
+        int sl = -1;
+        if (tid < UM) {
+            const int i = tile * UM + tid;
+            float xn[3] = {0.f, 0.f, 0.f};
+            if (i < n) { sl = w.shade_list[i]; xn[0] = w.smp_xn[3 * (size_t)sl]; xn[1] = w.smp_xn[3 * (size_t)sl + 1]; xn[2] = w.smp_xn[3 * (size_t)sl + 2]; }
+            xs[tid][0] = xn[0]; xs[tid][1] = xn[1]; xs[tid][2] = xn[2]; xs[tid][3] = 0.f;
+        }
+        // ================= SDF forward =================
+        load_params(tc.sdf_F, tc.sdf_G);                       // also orders xs
+        {   // layer 0 (K = 3) directly on the FP32 pipe
+            const float x = xs[r][0], y = xs[r][1], z = xs[r][2];
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                const int col0 = 128 * half + 32 * b;
+                float h[32], c[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int cc = col0 + i;
+                    const float a = fmaf(__ldg(tc.sdf_Wt0 + 512 + cc), z, fmaf(__ldg(tc.sdf_Wt0 + 256 + cc), y, __ldg(tc.sdf_Wt0 + cc) * x));
+                    float s_, c_;
+                    __sincosf(fmaf(a, lp0[cc], lp1[cc]), &s_, &c_);
+                    h[i] = s_; c[i] = c_ * lp0[cc];
+                }
+                a_store_chunk(A, r, col0 / 32, h);
+                cf_store32(cf + ((size_t)0 * UM + r) * 256 + col0, c);
+            }
+        }
+        handoff();
+        for (int l = 1; l < 6; ++l) {
+            load_params(tc.sdf_F + l * 256, tc.sdf_G + l * 256);
+            gemm(tc.sdf_fwd[l - 1], 8, 256, 0u);
+            float dot = 0.f;
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                const int col0 = 128 * half + 32 * b;
+                float v[32], c[32];
+                tmem_ld32(trow + (uint32_t)col0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float s_, c_;
+                    __sincosf(fmaf(v[i], lp0[col0 + i], lp1[col0 + i]), &s_, &c_);
+                    v[i] = s_; c[i] = c_ * lp0[col0 + i];
+                }
+                cf_store32(cf + ((size_t)l * UM + r) * 256 + col0, c);
+                if (l < 5) a_store_chunk(A, r, col0 / 32, v);
+                else {
+                    float4* fo = reinterpret_cast<float4*>(feat + (size_t)r * 256 + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) fo[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) dot = fmaf(v[i], __ldg(tc.sdf_w6 + col0 + i), dot);
+                }
+            }
+            if (l == 5) part[half][r][0] = dot;
+            handoff();
+        }
+        if (tid < UM && sl >= 0) w.smp_sdf[sl] = sdf_to_metres(part[0][tid][0] + part[1][tid][0] + tc.sdf_b6, fp.cmin, fp.cmax);
+        // ================= reverse pass: d sdf / d xn =================
+        load_params(tc.sdf_w6, nullptr);
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {                            // g_a5 = w6 * cf5
+            const int col0 = 128 * half + 32 * b;
+            float c[32];
+            cf_load32(cf + ((size_t)5 * UM + r) * 256 + col0, c);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) c[i] *= lp0[col0 + i];
+            a_store_chunk(A, r, col0 / 32, c);
+        }
+        handoff();
+        float g3[3] = {0.f, 0.f, 0.f};
+        for (int l = 5; l >= 1; --l) {
+            gemm(tc.sdf_bwd[l - 1], 8, 256, 0u);                 // g_h(l-1) = g_a(l) @ W_l
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                const int col0 = 128 * half + 32 * b;
+                float v[32], c[32];
+                tmem_ld32(trow + (uint32_t)col0, v);
+                cf_load32(cf + ((size_t)(l - 1) * UM + r) * 256 + col0, c);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= c[i];
+                if (l > 1) a_store_chunk(A, r, col0 / 32, v);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float* w0 = tc.sdf_W0 + (col0 + i) * 3;
+                        g3[0] = fmaf(v[i], __ldg(w0), g3[0]); g3[1] = fmaf(v[i], __ldg(w0 + 1), g3[1]); g3[2] = fmaf(v[i], __ldg(w0 + 2), g3[2]);
+                    }
+                }
+            }
+            if (l == 1) { part[half][r][0] = g3[0]; part[half][r][1] = g3[1]; part[half][r][2] = g3[2]; }
+            handoff();
+        }
+        // ================= colour inputs =================
+        if (tid < UM) {
+            float v[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
+            if (sl >= 0) {
+                const int ray = sl / w.S;
+                const float* T = w.smp_T + 12 * (size_t)sl;
+                const float d[3] = {w.ray_dirs[3 * ray], w.ray_dirs[3 * ray + 1], w.ray_dirs[3 * ray + 2]};
+                const float g[3] = {part[0][tid][0] + part[1][tid][0], part[0][tid][1] + part[1][tid][1], part[0][tid][2] + part[1][tid][2]};
+                if (fp.cano_view_dirs) {
+                    float A3[9], Ai[9];
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) A3[rr * 3 + c] = T[rr * 4 + c];
+                    invert3(A3, Ai);
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr) { v[rr] = Ai[rr * 3] * -d[0] + Ai[rr * 3 + 1] * -d[1] + Ai[rr * 3 + 2] * -d[2]; nrm[rr] = g[rr]; }
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr) { v[rr] = -d[rr]; nrm[rr] = T[rr * 4] * g[0] + T[rr * 4 + 1] * g[1] + T[rr * 4 + 2] * g[2]; }
+                }
+            }
+            float* c = cin[tid];
+            c[0] = xs[tid][0]; c[1] = xs[tid][1]; c[2] = xs[tid][2];
+            c[3] = v[0]; c[4] = v[1]; c[5] = v[2];
+            int k = 6;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const float fr = (float)(1 << l);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) c[k++] = sinf(v[j] * fr);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) c[k++] = cosf(v[j] * fr);
+            }
+            c[30] = nrm[0]; c[31] = nrm[1]; c[32] = nrm[2]; c[33] = 0.f; c[34] = 0.f; c[35] = 0.f;
+        }
+        auto fill_feat = [&]() {                                  // A chunks 0..7 <- feature (this thread wrote these addresses)
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                const int col0 = 128 * half + 32 * b;
+                float v[32];
+                const float4* fi = reinterpret_cast<const float4*>(feat + (size_t)r * 256 + col0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float4 t = fi[j]; v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w; }
+                a_store_chunk(A, r, col0 / 32, v);
+            }
+        };
+        auto fill_cin = [&]() {                                   // A chunks 0..1 <- [x, PE(view), n | 0 ...] (64 wide)
+            if (half == 0) {
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { const int k = 32 * c + i; v[i] = (k < 33) ? cin[r][k] : 0.f; }
+                    a_store_chunk(A, r, c, v);
+                }
+            }
+        };
+        auto relu_epilogue = [&](int N, const float* bias, bool store) {
+            const int per = N / 2;                                // columns per thread
+            float acc3[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int b = 0; b < per / 32; ++b) {
+                const int col0 = per * half + 32 * b;
+                float v[32];
+                tmem_ld32(trow + (uint32_t)col0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + lp0[col0 + i], 0.f);
+                if (store) a_store_chunk(A, r, col0 / 32, v);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        acc3[0] = fmaf(v[i], __ldg(tc.col_W5 + col0 + i), acc3[0]);
+                        acc3[1] = fmaf(v[i], __ldg(tc.col_W5 + 256 + col0 + i), acc3[1]);
+                        acc3[2] = fmaf(v[i], __ldg(tc.col_W5 + 512 + col0 + i), acc3[2]);
+                    }
+                }
+            }
+            if (!store) { part[half][r][0] = acc3[0]; part[half][r][1] = acc3[1]; part[half][r][2] = acc3[2]; }
+            (void)bias;
+        };
+        // ================= colour MLP (decoder.py:69-124) =================
+        fill_feat();
+        handoff();                                                // (also publishes cin)
+        load_params(tc.col_b[0], nullptr);
+        gemm(tc.col0, 8, 256, 0u);                                // feature part
+        fill_cin();
+        handoff();
+        gemm(tc.col0 + (size_t)8 * 256 * UK, 2, 256, 1u);         // + [x | PE | n] part
+        relu_epilogue(256, tc.col_b[0], true);
+        handoff();
+        load_params(tc.col_b[1], nullptr);
+        gemm(tc.col1, 8, 256, 0u);
+        relu_epilogue(256, tc.col_b[1], true);
+        handoff();
+        load_params(tc.col_b[2], nullptr);
+        gemm(tc.col2, 8, 128, 0u);
+        relu_epilogue(128, tc.col_b[2], true);                    // 128 outputs -> A chunks 0..3
+        handoff();
+        load_params(tc.col_b[3], nullptr);
+        gemm(tc.col3b, 4, 256, 0u);                               // skip layer: lin2 part ...
+        fill_feat();
+        handoff();
+        gemm(tc.col3a, 8, 256, 1u);                               // ... + feature part ...
+        fill_cin();
+        handoff();
+        gemm(tc.col3a + (size_t)8 * 256 * UK, 2, 256, 1u);        // ... + [x | PE | n] part (:113-115)
+        relu_epilogue(256, tc.col_b[3], true);
+        handoff();
+        load_params(tc.col_b[4], nullptr);
+        gemm(tc.col4, 8, 256, 0u);
+        relu_epilogue(256, tc.col_b[4], false);                   // lin5 (256 -> 3) folded into the epilogue
+        handoff();
+        if (tid < UM && sl >= 0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                w.smp_rgb[3 * (size_t)sl + j] = sigmoid_(part[0][tid][j] + part[1][tid][j] + __ldg(tc.col_b[5] + j));
+        }
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
+}  // namespace arah

@@ -14,6 +14,7 @@ CUDA library is missing or the tensors are not on a CUDA device, the call raises
 Training (`self.training == True`) raises NotImplementedError: backward through root finding is SURVEY.md §8(f) row f2.
 """
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -51,13 +52,17 @@ class ArahRenderer:
     """Thin RAII wrapper around an ArahHandle (one per device/stream; not thread-safe)."""
 
     def __init__(self, device, n_steps=64, near_samples=16, far_samples=16, cano_view_dirs=True, latent_dim=128,
-                 n_verts=N_VERTS_DEFAULT, max_rays=65536):
+                 n_verts=N_VERTS_DEFAULT, max_rays=65536, shade_mode=None):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.ArahError('the ARAH hot path only exists as CUDA kernels; got device %s' % device)
+        if shade_mode is None:
+            shade_mode = os.environ.get('ARAH_SHADE_MODE', 'tf32')
+        mode = {'tf32': 0, 'fp32': 1}[shade_mode] if isinstance(shade_mode, str) else int(shade_mode)
+        self.shade_mode = 'fp32' if mode == 1 else 'tf32'
         self.cfg = ArahConfig(device=self.device.index or 0, n_steps=n_steps, near_samples=near_samples,
                               far_samples=far_samples, cano_view_dirs=int(bool(cano_view_dirs)), latent_dim=latent_dim,
-                              n_verts=n_verts, max_rays=max_rays)
+                              n_verts=n_verts, max_rays=max_rays, shade_mode=mode)
         self._h = C.c_void_p()
         check(_lib.lib().arah_create(C.byref(self.cfg), C.byref(self._h)))
         self._keep = []
@@ -272,8 +277,9 @@ class IDHRNetwork(nn.Module):
     (implicit_differentiable_renderer.py:18-40); eval forward runs entirely in libarah_b200.so."""
 
     def __init__(self, deviation_network, rendering_network, skinning_model, ray_tracer, cano_view_dirs=True,
-                 train_skinning_net=False, render_last_pt=False, low_vram=False):
+                 train_skinning_net=False, render_last_pt=False, low_vram=False, shade_mode=None):
         super().__init__()
+        self.shade_mode = shade_mode      # extra, optional: 'tf32' (tensor cores, default) | 'fp32' (FFMA tiles)
         self.deviation_network = deviation_network
         self.rendering_network = rendering_network
         self.skinning_model = skinning_model
@@ -296,7 +302,7 @@ class IDHRNetwork(nn.Module):
             rt = self.ray_tracer
             r = ArahRenderer(device, n_steps=rt.n_steps, near_samples=rt.near_surface_vol_samples,
                              far_samples=rt.far_surface_vol_samples, cano_view_dirs=self.cano_view_dirs,
-                             latent_dim=latent_dim, n_verts=n_verts)
+                             latent_dim=latent_dim, n_verts=n_verts, shade_mode=self.shade_mode)
             self._renderers[key] = r
         return r
 

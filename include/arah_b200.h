@@ -38,7 +38,12 @@ typedef struct ArahConfig {
     int32_t latent_dim;           /* colour-net per-frame latent (128; 0 = none) */
     int32_t n_verts;              /* SMPL vertices (6890) */
     int32_t max_rays;             /* initial workspace size in rays (grown on demand) */
+    int32_t shade_mode;           /* ARAH_SHADE_TF32 (default 0): shading MLPs on tcgen05 tensor cores, TF32 operands,
+                                   * fp32 accumulate; ARAH_SHADE_FP32 (1): fp32 FFMA tiles (bit-for-bit the oracle's
+                                   * arithmetic order).  Root finding is fp32 in both modes. */
 } ArahConfig;
+#define ARAH_SHADE_TF32 0
+#define ARAH_SHADE_FP32 1
 
 /* Per-frame inputs == what IDHRNetwork.forward reads from its `input` dict
  * (renderer/implicit_differentiable_renderer.py:52-71) plus the weights of the modules it owns.
@@ -129,6 +134,10 @@ int arah_get_stats(ArahHandle* h, ArahStats* stats, void* stream);
  *   arah_eval_skin : query_weights + skinning (utils/root_finding_utils.py:54-113, 13-33) */
 int arah_eval_sdf(ArahHandle* h, const float* xn, int32_t n, float* sdf, float* grad, float* feat, void* stream);
 int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, float* weights, float* x_bar, void* stream);
+
+/* Debug/bring-up: D[128][N] = A[128][K] . W[N][K]^T through the tcgen05 TF32 tile used by the shading kernel
+ * (device pointers, K multiple of 32 <= 256, N in {128, 256}); synchronises the stream. */
+int arah_debug_umma_gemm(const float* A, const float* W, int32_t K, int32_t N, float* D, void* stream);
 
 #ifdef __cplusplus
 }

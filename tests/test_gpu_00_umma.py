@@ -1,0 +1,23 @@
+"""GPU bring-up: the tcgen05 TF32 tile (arah_umma.cuh) on its own, before anything depends on it."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.mark.parametrize('K,N', [(32, 256), (256, 256), (128, 128), (96, 256)])
+def test_umma_tf32_tile_matches_matmul(K, N):
+    """tcgen05 TF32 tile (descriptors, 128B swizzle, TMEM read-back) against torch fp32 matmul; tolerance = TF32 operand rounding."""
+    import ctypes as C
+    from arah_release_b200 import _lib
+    g = torch.Generator(device='cpu').manual_seed(K * 1000 + N)
+    A = torch.randn(128, K, generator=g).to(DEV)
+    Wt = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    D = torch.zeros(128, N, device=DEV)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.lib().arah_debug_umma_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(Wt.data_ptr()), K, N, C.c_void_p(D.data_ptr()), st))
+    ref = A.double() @ Wt.double().t()
+    err = (D.double() - ref).abs().max().item()
+    assert err < 6e-3, err          # |a||w| K 2^-11 scale
+    assert err > 0 or K == 0

@@ -12,12 +12,12 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-def _build(fr):
+def _build(fr, shade_mode='fp32'):
     from arah_release_b200 import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
     tracer = BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples, far_surface_vol_samples=fr.far_samples)
-    net = IDHRNetwork(dev, rend, skin, tracer, cano_view_dirs=fr.cano_view_dirs).eval()
+    net = IDHRNetwork(dev, rend, skin, tracer, cano_view_dirs=fr.cano_view_dirs, shade_mode=shade_mode).eval()
     inputs = rl.inputs_from_frame(fr, sdf, DEV)
     return net, inputs
 
@@ -55,16 +55,19 @@ def test_unit_sdf_and_skin_match_oracle():
     np.testing.assert_allclose(xb.cpu().numpy(), xbo, atol=2e-5, rtol=0)
 
 
+@pytest.mark.parametrize('mode', ['fp32', 'tf32'])
 @pytest.mark.parametrize('name', GOLDEN_CASES)
-def test_render_matches_reference_golden(name):
+def test_render_matches_reference_golden(name, mode):
     fr, ref, meta = load_golden(name)
-    net, inputs = _build(fr)
+    net, inputs = _build(fr, mode)
     out = _render_dict(net, inputs)
-    st = check_render(out, ref, label=name)
+    # tf32 = shading MLPs on the tensor cores: same root finding (fp32), colours within TF32 operand rounding
+    tol = dict(TOL, rgb_psnr_min=55.0) if mode == 'tf32' else TOL
+    st = check_render(out, ref, label=name + ':' + mode, tol=tol)
     stats = net.stats()
     assert stats['rays'] == fr.P and stats['kernel_launches'] > 0
     assert stats['vol_rays'] == int(out['network_body_mask'].sum())
-    print(name, st, stats)
+    print(name, mode, st, stats)
 
 
 @pytest.mark.parametrize('name', GOLDEN_CASES[:1])
@@ -85,7 +88,7 @@ def test_render_matches_oracle(name):
 
 def test_host_buffer_entry_point_equals_device_path():
     fr, _, _ = load_golden('n32_16x16_s2')
-    net, inputs = _build(fr)
+    net, inputs = _build(fr, 'tf32')
     out = net(inputs)
     r, P = net._last
     rd = torch.from_numpy(fr.ray_dirs).pin_memory()
@@ -132,7 +135,7 @@ def test_full_size_properties_512():
     """BASELINE config 2 size (512x512): size-independent properties instead of an oracle run."""
     from arah_release_b200 import synthetic as syn
     fr = syn.make_frame(512, 512, seed=0)
-    net, inputs = _build(fr)
+    net, inputs = _build(fr, 'tf32')
     out1 = net(inputs)
     rgb1 = out1['rgb_values'][0].clone(); m1 = out1['network_body_mask'][0].clone()
     tr = net.tracer_outputs()
@@ -161,7 +164,8 @@ def test_full_size_properties_512():
     from oracle import oracle as orc
     sel = np.random.default_rng(1).choice(P, size=256, replace=False)
     o = orc.render(fr, ray_dirs=fr.ray_dirs[sel], near_far=fr.near_far[sel], stages=False)
-    assert psnr(rgb[sel], o['rgb_values']) >= TOL['rgb_psnr_min']
+    assert psnr(rgb[sel], o['rgb_values']) >= 55.0
     assert (hit[sel] != o['trace.network_body_mask']).mean() <= 0.01
     assert stats['rays'] == P and stats['shaded_samples'] > 0
     print('512x512', P, stats)
+

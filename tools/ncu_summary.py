@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs brought back in gpurun_out/ into profiles/ (tracked).
+
+  python tools/ncu_summary.py launches gpurun_out/r01_launches.csv profiles/r01_launches_summary.md
+  python tools/ncu_summary.py rep gpurun_out/r01_k_shade.ncu-rep profiles/r01_k_shade_ncu.md [profiles/k_shade_traffic.json]
+"""
+import csv
+import io
+import json
+import re
+import subprocess
+import sys
+from collections import defaultdict
+
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'launch__shared_mem_per_block_dynamic', 'smsp__cycles_active.avg', 'sm__cycles_elapsed.max', 'l1tex__data_bank_conflicts_pipe_lsu.sum',
+        'lts__t_bytes.sum', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_uniform.sum', 'sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active']
+
+
+def launches(src, dst):
+    rows = []
+    with open(src) as f:
+        txt = f.read()
+    start = txt.find('"ID"')
+    rd = csv.DictReader(io.StringIO(txt[start:]))
+    for r in rd:
+        if r.get('Metric Name') == 'gpu__time_duration.sum':
+            v = float(r['Metric Value'].replace(',', ''))
+            unit = r.get('Metric Unit', 'ns')
+            scale = {'ns': 1e-6, 'us': 1e-3, 'usecond': 1e-3, 'nsecond': 1e-6, 'ms': 1.0, 'msecond': 1.0, 's': 1e3, 'second': 1e3}.get(unit, 1e-6)
+            rows.append((re.sub(r'\(.*', '', r['Kernel Name']).strip(), v * scale))
+    agg = defaultdict(lambda: [0, 0.0])
+    for k, ms in rows:
+        agg[k][0] += 1
+        agg[k][1] += ms
+    tot = sum(v[1] for v in agg.values())
+    with open(dst, 'w') as f:
+        f.write(f'# ncu launch list summary ({src})\n\nAll launches of the command, device time per kernel (cold-cache, serialised: compare SHARES).\n\n')
+        f.write(f'total launches {len(rows)}, total device time {tot:.2f} ms\n\n| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n')
+        for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f'| `{k}` | {n} | {ms:.3f} | {100 * ms / tot:.1f} % |\n')
+    print(open(dst).read())
+
+
+def rep(src, dst, traffic_json=None):
+    out = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rd[0], rd[1], rd[2:]
+    with open(dst, 'w') as f:
+        f.write(f'# ncu --set full summary ({src})\n\n')
+        for row in data:
+            d = dict(zip(hdr, row))
+            u = dict(zip(hdr, units))
+            f.write(f"## {d.get('Kernel Name', '?')}  (ID {d.get('ID')})\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for k in hdr:
+                if any(k == x or k.startswith(x) for x in KEYS) or 'stall' in k.lower() and 'pct' in k.lower():
+                    f.write(f'| {k} | {d[k]} | {u[k]} |\n')
+            f.write('\n')
+            if traffic_json:
+                try:
+                    rd_b = float(d['dram__bytes_read.sum'].replace(',', ''))
+                    wr_b = float(d['dram__bytes_write.sum'].replace(',', ''))
+                    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+                    tot = rd_b * scale.get(u['dram__bytes_read.sum'], 1) + wr_b * scale.get(u['dram__bytes_write.sum'], 1)
+                    json.dump({'dram_bytes_per_launch': tot, 'kernel': d.get('Kernel Name'), 'source': src}, open(traffic_json, 'w'))
+                    traffic_json = None
+                except Exception as e:
+                    print('traffic parse failed', e)
+    print(open(dst).read()[:6000])
+
+
+if __name__ == '__main__':
+    if sys.argv[1] == 'launches':
+        launches(sys.argv[2], sys.argv[3])
+    else:
+        rep(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
