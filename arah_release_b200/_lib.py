@@ -10,7 +10,7 @@ FP = C.c_void_p
 class ArahConfig(C.Structure):
     _fields_ = [('device', C.c_int32), ('n_steps', C.c_int32), ('near_samples', C.c_int32), ('far_samples', C.c_int32),
                 ('cano_view_dirs', C.c_int32), ('latent_dim', C.c_int32), ('n_verts', C.c_int32), ('max_rays', C.c_int32),
-                ('shade_mode', C.c_int32)]
+                ('shade_mode', C.c_int32), ('root_mode', C.c_int32)]
 
 
 class ArahFrame(C.Structure):
@@ -62,7 +62,7 @@ def lib():
     L.arah_get_stats.argtypes = [C.c_void_p, C.POINTER(ArahStats), C.c_void_p]
     L.arah_eval_sdf.argtypes = [C.c_void_p, FP, C.c_int32, FP, FP, FP, C.c_void_p]
     L.arah_eval_skin.argtypes = [C.c_void_p, FP, C.c_int32, FP, FP, C.c_void_p]
-    L.arah_debug_umma_gemm.argtypes = [FP, FP, C.c_int32, C.c_int32, FP, C.c_void_p]
+    L.arah_debug_umma_gemm.argtypes = [FP, FP, C.c_int32, C.c_int32, FP, C.c_int32, C.c_void_p]
     _lib = L
     return L
 

@@ -9,6 +9,10 @@
 #include "arah_kernels.cuh"
 #include "arah_umma.cuh"
 #include "arah_shade_tc.cuh"
+#include "arah_corr_tc.cuh"
+#include "arah_shade_tc2.cuh"
+#include "arah_corr_tc2.cuh"
+#include <stdlib.h>
 
 using namespace arah;
 
@@ -155,8 +159,23 @@ __global__ void k_pack_umma(const float* __restrict__ src, int src_ld, float* __
     dst[(size_t)c * N * 32 + (n >> 3) * 256 + (n & 7) * 32 + ((j ^ (n & 7)) << 2) + e] = v;
 }
 
+// split-precision variant: per K-chunk [hi image | lo image], Npad rows (rows >= N are zero)
+__global__ void k_pack_umma_x3(const float* __restrict__ src, int src_ld, float* __restrict__ dst, int N, int Npad, int K, int nchunks) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nchunks * Npad * 32) return;
+    const int c = idx / (Npad * 32), rem = idx % (Npad * 32);
+    const int n = rem / 32, q = rem % 32, j = q / 4, e = q % 4;
+    const int k = 32 * c + 4 * j + e;
+    float v = 0.f;
+    if (k < K && n < N) v = src[(size_t)n * src_ld + k];
+    const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
+    const size_t o = (size_t)c * Npad * 32 * 2 + (n >> 3) * 256 + (n & 7) * 32 + ((j ^ (n & 7)) << 2) + e;
+    dst[o] = hi;
+    dst[o + (size_t)Npad * 32] = lo;
+}
+
 // D[128][N] = A[128][K] . W[N][K]^T on the tensor cores (TF32 operands, fp32 accumulate); validates descriptors/swizzle
-__global__ void __launch_bounds__(256, 1) k_umma_probe(const float* __restrict__ A, const float* __restrict__ Wsw, int K, int N, float* __restrict__ D) {
+__global__ void __launch_bounds__(256, 1) k_umma_probe(const float* __restrict__ A, const float* __restrict__ Wsw, int K, int N, float* __restrict__ D, int a_in_tmem) {
     extern __shared__ uint8_t raw_smem[];
     const uint32_t base = (smem_u32(raw_smem) + 1023u) & ~1023u;
     float* sm = reinterpret_cast<float*>(raw_smem + (base - smem_u32(raw_smem)));
@@ -166,8 +185,8 @@ __global__ void __launch_bounds__(256, 1) k_umma_probe(const float* __restrict__
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) { for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc(tslot, 256);
-    if (tid < UM) {
+    if (warp == 0) tmem_alloc(tslot, 512);
+    if (tid < UM && !a_in_tmem) {
         for (int c = 0; c < K / UK; ++c) {
             float v[32];
             for (int i = 0; i < 32; ++i) v[i] = A[(size_t)tid * K + c * UK + i];
@@ -179,13 +198,40 @@ __global__ void __launch_bounds__(256, 1) k_umma_probe(const float* __restrict__
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tslot;
+    const int q = warp & 3, half = warp >> 2;
+    if (a_in_tmem) {          // A via tcgen05.st into TMEM columns [256, 256+K); D in columns [0, N)
+        if (half == 0) {
+            for (int c = 0; c < K / UK; ++c) {
+                float v[32];
+                for (int i = 0; i < 32; ++i) v[i] = A[(size_t)(32 * q + lane) * K + c * UK + i];
+                a_tmem_store(tbase + ((uint32_t)(32 * q) << 16) + 256u + (uint32_t)(c * UK), v);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
     if (tid == 0) {
         URing rg; rg.buf = ring; rg.full = bars; rg.empty = bars + 2; rg.fill_cnt = 0; rg.mma_cnt = 0;
-        umma_layer_issue(rg, Abuf, Wsw, K / UK, N, tbase, 0u, &bars[4]);
+        if (!a_in_tmem) umma_layer_issue(rg, Abuf, Wsw, K / UK, N, tbase, 0u, &bars[4]);
+        else {
+            const uint32_t idesc = umma_idesc_tf32(UM, N);
+            for (int c = 0; c < K / UK; ++c) {
+                mbar_expect_tx(&bars[0], (uint32_t)N * UK * 4);
+                bulk_g2s(ring, Wsw + (size_t)c * N * UK, (uint32_t)N * UK * 4, &bars[0]);
+                mbar_wait(&bars[0], c & 1);
+                tc_fence_after();
+                for (int k = 0; k < 4; ++k)
+                    umma_tf32_ts(tbase, tbase + 256u + (uint32_t)(c * UK + k * 8), umma_smem_desc_sw128(smem_u32(ring) + k * 32), idesc, (c > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&bars[2]);
+                mbar_wait(&bars[2], c & 1);          // serialise: the probe reuses one slot
+            }
+            umma_commit(&bars[4]);
+        }
     }
     mbar_wait(&bars[4], 0);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
     for (int b = 0; b < (N / 2) / 32; ++b) {
         const int col0 = half * (N / 2) + 32 * b;
         float v[32];
@@ -194,10 +240,10 @@ __global__ void __launch_bounds__(256, 1) k_umma_probe(const float* __restrict__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 256);
+    if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
-extern "C" int arah_debug_umma_gemm(const float* A, const float* W, int32_t K, int32_t N, float* D, void* stream) {
+extern "C" int arah_debug_umma_gemm(const float* A, const float* W, int32_t K, int32_t N, float* D, int32_t a_in_tmem, void* stream) {
     if (!A || !W || !D) return fail(ARAH_EINVAL, "null buffer");
     if (K <= 0 || K > 256 || (K % 32) != 0 || (N != 256 && N != 128)) return fail(ARAH_EINVAL, "K must be a multiple of 32 <= 256, N in {128,256}");
     cudaStream_t st = (cudaStream_t)stream;
@@ -206,7 +252,7 @@ extern "C" int arah_debug_umma_gemm(const float* A, const float* W, int32_t K, i
     k_pack_umma<<<cdiv((size_t)K * N, 256), 256, 0, st>>>(W, K, Wsw, N, K, K / 32, K, 0, 0, 0);
     const int smem = (8 * A_CHUNK_FLOATS + 2 * RING_SLOT_FLOATS) * 4 + 128 + 1024;
     CU(cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_umma_probe<<<1, 256, smem, st>>>(A, Wsw, K, N, D);
+    k_umma_probe<<<1, 256, smem, st>>>(A, Wsw, K, N, D, a_in_tmem);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
     CU(cudaFree(Wsw));
@@ -243,6 +289,8 @@ struct ArahHandle {
     float* tc_sdf_fwd[5]; float* tc_sdf_bwd[5]; float* tc_F; float* tc_G;
     float* tc_col0; float* tc_col1; float* tc_col2; float* tc_col3b; float* tc_col3a; float* tc_col4;
     ShadeTC tc;
+    float* tc_skin_hid[3]; float* tc_skin_out;
+    SkinTC sk;
     // workspace
     DevBuf ws, scratch, io_in, io_out;
     Work w;
@@ -251,6 +299,7 @@ struct ArahHandle {
     int last_P = 0;
     int64_t pack_launches = 0;
     bool profile = false, profiled = false;
+    int tc_engine = 2;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -275,6 +324,8 @@ static int alloc_arena(ArahHandle* h) {
     reg(&h->tc_F, 6 * 256); reg(&h->tc_G, 6 * 256);
     reg(&h->tc_col0, 10 * 256 * 32); reg(&h->tc_col1, 256 * 256); reg(&h->tc_col2, 8 * 128 * 32); reg(&h->tc_col3b, 4 * 256 * 32);
     reg(&h->tc_col3a, 10 * 256 * 32); reg(&h->tc_col4, 256 * 256);
+    for (int l = 0; l < 3; ++l) reg(&h->tc_skin_hid[l], 4 * 128 * 32 * 2);
+    reg(&h->tc_skin_out, 4 * 32 * 32 * 2);
     reg(&h->col_b[0], 256); reg(&h->col_b[1], 256); reg(&h->col_b[2], 256); reg(&h->col_b[3], 256); reg(&h->col_b[4], 256); reg(&h->col_b[5], 64);
     reg(&h->bone_T, 24 * 16);
     float* v4 = nullptr;
@@ -320,6 +371,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     if (cfg->near_samples < 0 || cfg->far_samples < 0 || (cfg->near_samples == 0 && cfg->far_samples == 0))
         return fail(ARAH_EINVAL, "need near_samples > 0 or far_samples > 0 (ray_tracing.py:107)");
     if (cfg->shade_mode != ARAH_SHADE_TF32 && cfg->shade_mode != ARAH_SHADE_FP32) return fail(ARAH_EINVAL, "shade_mode must be ARAH_SHADE_TF32 or ARAH_SHADE_FP32");
+    if (cfg->root_mode != ARAH_ROOT_3XTF32 && cfg->root_mode != ARAH_ROOT_FP32) return fail(ARAH_EINVAL, "root_mode must be ARAH_ROOT_3XTF32 or ARAH_ROOT_FP32");
     if (cfg->latent_dim < 0 || cfg->latent_dim > 512) return fail(ARAH_EINVAL, "latent_dim must be in [0,512]");
     if (cfg->n_verts <= 0 || (size_t)cfg->n_verts * 16 > 200 * 1024) return fail(ARAH_EINVAL, "n_verts must fit 200 KB of shared memory (<= 12800)");
     CU(cudaSetDevice(cfg->device));
@@ -329,6 +381,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     ArahHandle* h = new ArahHandle();
     h->cfg = *cfg;
     h->n_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("ARAH_TC_ENGINE")) h->tc_engine = atoi(e) == 1 ? 1 : 2;
     memset(&h->w, 0, sizeof(h->w));
     if (alloc_arena(h) != 0) { delete h; return fail(ARAH_ENOMEM, "weight arena allocation failed"); }
     if (ensure_workspace(h, cfg->max_rays > 0 ? cfg->max_rays : 4096) != 0) { h->arena.release(); delete h; return fail(ARAH_ENOMEM, "workspace allocation failed"); }
@@ -343,6 +396,9 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_eval_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SKIN)));
     CU(cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes()));
     CU(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_shade_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc2_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_corr_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc2_smem_bytes()));
     CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->n_verts * 16));
     CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->n_verts * 16));
     *out = h;
@@ -439,6 +495,10 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
         up(f->col_W[3], din + 128, h->tc_col3a, 256, COL_IN, 10, 256, 33, 0, 0);
         up(f->col_W[4], 256, h->tc_col4, 256, 256, 8, 256, 0, 0, 0);
     }
+    if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
+        for (int l = 1; l < 4; ++l) { k_pack_umma_x3<<<cdiv((size_t)4 * 128 * 32, 256), 256, 0, st>>>(f->skin_W[l], 128, h->tc_skin_hid[l - 1], 128, 128, 128, 4); ++npack; }
+        k_pack_umma_x3<<<cdiv((size_t)4 * 32 * 32, 256), 256, 0, st>>>(f->skin_W[4], 128, h->tc_skin_out, 25, 32, 128, 4); ++npack;
+    }
     // pose buffers
     const cudaMemcpyKind kind = f->pose_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     CU(cudaMemcpyAsync(h->bone_T, f->bone_transforms, 24 * 16 * 4, kind, st));
@@ -472,6 +532,11 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     tc.col0 = h->tc_col0; tc.col1 = h->tc_col1; tc.col2 = h->tc_col2; tc.col3b = h->tc_col3b; tc.col3a = h->tc_col3a; tc.col4 = h->tc_col4;
     tc.col_W5 = h->col_W5;
     for (int l = 0; l < 6; ++l) tc.col_b[l] = h->col_b[l];
+    SkinTC& sk = h->sk;
+    sk.Wt0 = h->skin_Wt[0];
+    for (int l = 0; l < 5; ++l) sk.b[l] = h->skin_b[l];
+    for (int l = 0; l < 3; ++l) sk.hid[l] = h->tc_skin_hid[l];
+    sk.out = h->tc_skin_out;
     if (!(fp.cmax > fp.cmin)) return fail(ARAH_EINVAL, "coord_max must exceed coord_min");
     h->frame_set = true;
     return ARAH_OK;
@@ -517,9 +582,22 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     const unsigned g_knn_s = grid_min(cdiv(PS, 256), (size_t)2 * nsm);
     k_knn_samples<<<g_knn_s, 256, sm_knn, st>>>(fp, w); L();
     const unsigned g_smp_tiles = grid_min(cdiv(PS, TM), (size_t)2 * nsm);
-    for (int it = -1; it < BROYDEN_ITERS; ++it) { k_corr_step<<<g_smp_tiles, 256, sm_skin, st>>>(fp, w, it); L(); }
+    if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
+        const unsigned g_tc = grid_min(cdiv(PS, UM), (size_t)nsm);
+        for (int it = -1; it < BROYDEN_ITERS; ++it) {
+            if (h->tc_engine == 2) k_corr_tc2<<<g_tc, TC_THREADS, corr_tc2_smem_bytes(), st>>>(fp, h->sk, w, it);
+            else k_corr_tc<<<g_tc, 256, corr_tc_smem_bytes(), st>>>(fp, h->sk, w, it);
+            L();
+        }
+    } else {
+        for (int it = -1; it < BROYDEN_ITERS; ++it) { k_corr_step<<<g_smp_tiles, 256, sm_skin, st>>>(fp, w, it); L(); }
+    }
     if (prof) CU(cudaEventRecord(h->ev[3], st));
-    if (h->cfg.shade_mode == ARAH_SHADE_TF32) { k_shade_tc<<<grid_min(cdiv(PS, UM), (size_t)nsm), 256, shade_tc_smem_bytes(), st>>>(fp, h->tc, w); L(); }
+    if (h->cfg.shade_mode == ARAH_SHADE_TF32) {
+        if (h->tc_engine == 2) k_shade_tc2<<<grid_min(cdiv(PS, UM), (size_t)nsm), TC_THREADS, shade_tc2_smem_bytes(), st>>>(fp, h->tc, w);
+        else k_shade_tc<<<grid_min(cdiv(PS, UM), (size_t)nsm), 256, shade_tc_smem_bytes(), st>>>(fp, h->tc, w);
+        L();
+    }
     else { k_shade<<<grid_min(cdiv(PS, TM), (size_t)nsm), 256, shade_smem_bytes(), st>>>(fp, w); L(); }
     if (prof) CU(cudaEventRecord(h->ev[4], st));
     k_composite<<<cdiv(P, COMP_WARPS), 32 * COMP_WARPS, 0, st>>>(fp, w); L();

@@ -1,103 +1,61 @@
-// arah_shade_tc.cuh — k_shade_tc: the shading stage on the 5th-gen tensor cores (tcgen05, TF32 operands, fp32 accumulate).
-//
-// Replaces k_shade (fp32 FFMA tiles) for /root/reference/im2mesh/metaavatar_render/renderer/
-// implicit_differentiable_renderer.py:311-361: SDF forward (6 FiLM-sine layers), reverse-mode d sdf / d x, colour MLP.
-// tools/precision_study.py bounds the effect of TF32 operand rounding in THIS stage at PSNR >= 80 dB against fp32 and
-// |dPSNR| <= 0.001 dB (budget 0.05 dB); root finding stays fp32 (its residuals must resolve 1e-5 m).
-//
-// One CTA (256 threads) per SM, tile = 128 samples:
-//   A (activations)  shared memory, 8 K-chunks x 16 KB, SWIZZLE_128B K-major, rewritten in place by every epilogue
-//   B (weights)      pre-swizzled chunk images in L2, staged by 1-D TMA bulk copies into a 2 x 32 KB ring
-//   D (accumulators) TMEM, 128 lanes x 256 fp32 columns
-//   one elected thread issues copies + tcgen05.mma and commits to mbarriers; all 8 warps run the epilogues:
-//   warp w reads TMEM lanes 32*(w%4).. (its sub-partition), columns [128*(w/4), +128) -> thread = one row x 128 columns.
-// cos factors for the reverse pass (bf16) and the 256-d feature (fp32) live in a per-CTA scratch that stays L2-resident.
+// arah_shade_tc2.cuh — k_shade_tc2: shading on tcgen05 with engine v2 (arah_tc2.cuh): activations in TMEM (.ts MMA),
+// 6 x 32 KB weight ring filled by a TMA producer warp that runs ahead across layers, 288 threads.
+// Algorithm, scratch layout and epilogues are those of k_shade_tc (arah_shade_tc.cuh).
 #pragma once
-#include <cuda_bf16.h>
-
-#include "arah_kernels.cuh"
-#include "arah_umma.cuh"
+#include "arah_shade_tc.cuh"
+#include "arah_tc2.cuh"
 
 namespace arah {
 
-struct ShadeTC {
-    const float* sdf_Wt0;      // [3][256]
-    const float* sdf_W0;       // [256][3]
-    const float* sdf_F;        // [6][256]  30 f
-    const float* sdf_G;        // [6][256]  30 (f b + phi)
-    const float* sdf_fwd[5];   // layers 1..5, swizzled chunks of B[n=out][k=in]
-    const float* sdf_bwd[5];   // layers 1..5, swizzled chunks of B[n=in][k=out]
-    const float* sdf_w6;       // [256]
-    float sdf_b6;
-    const float* col0;         // 10 chunks, N=256: k = [feat 256 | x,PE,n 33 | pad]
-    const float* col1;         // 8 chunks
-    const float* col2;         // 8 chunks, N=128
-    const float* col3b;        // 4 chunks (lin2 output part of the skip layer)
-    const float* col3a;        // 10 chunks (network-input part)
-    const float* col4;         // 8 chunks
-    const float* col_W5;       // [3][256]
-    const float* col_b[6];
-};
-
-constexpr int TC_SCRATCH_FLOATS = 6 * UM * 256 / 2 + UM * 256;     // bf16 cos factors + fp32 feature, in float units
-__host__ __device__ constexpr size_t shade_tc_smem_bytes() {
-    return (size_t)(8 * A_CHUNK_FLOATS + 2 * RING_SLOT_FLOATS + UM * 36 + 2 * 256 + UM * 4 + 2 * UM * 4) * 4 + 256 + 1024;
+__host__ __device__ constexpr size_t shade_tc2_smem_bytes() {
+    return (size_t)(TC_NSLOTS * RING_SLOT_FLOATS + UM * 36 + 2 * 256 + UM * 4 + 2 * UM * 4) * 4 + 256 + 1024;
 }
 
-__device__ __forceinline__ void cf_store32(__nv_bfloat16* dst, const float (&v)[32]) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), b = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-        __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), e = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-        u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&e);
-        d[i] = u;
-    }
-}
-__device__ __forceinline__ void cf_load32(const __nv_bfloat16* src, float (&v)[32]) {
-    const uint4* s = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint4 u = s[i];
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-            const float2 f = __bfloat1622float2(p);
-            v[8 * i + 2 * j] = f.x; v[8 * i + 2 * j + 1] = f.y;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc, Work w) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_shade_tc2(FrameParams fp, ShadeTC tc, Work w) {
     extern __shared__ uint8_t raw_smem[];
     const int n = w.counters[C_SHADE];
     if ((int)blockIdx.x * UM >= n) return;
     const uint32_t base = (smem_u32(raw_smem) + 1023u) & ~1023u;
     float* sm = reinterpret_cast<float*>(raw_smem + (base - smem_u32(raw_smem)));
-    float* A = sm;
-    float* ring = A + 8 * A_CHUNK_FLOATS;
-    float (*cin)[36] = reinterpret_cast<float (*)[36]>(ring + 2 * RING_SLOT_FLOATS);
+    float* ring = sm;
+    float (*cin)[36] = reinterpret_cast<float (*)[36]>(ring + TC_NSLOTS * RING_SLOT_FLOATS);
     float* lp0 = reinterpret_cast<float*>(cin) + UM * 36;     // per-layer column parameters
     float* lp1 = lp0 + 256;
     float (*xs)[4] = reinterpret_cast<float (*)[4]>(lp1 + 256);
     float (*part)[UM][4] = reinterpret_cast<float (*)[UM][4]>(reinterpret_cast<float*>(xs) + UM * 4);   // [2][UM][4]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(part) + 2 * UM * 4);         // full[2] empty[2] done
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(part) + 2 * UM * 4);         // full[6] empty[6] done
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NSLOTS + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2;
     const int r = 32 * q + lane;                 // this thread's row (TMEM lane)
-    if (tid == 0) { for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc(tslot, 256);
+    TCRing rg; rg.buf = ring; rg.full = bars; rg.empty = bars + TC_NSLOTS;
+    uint64_t* done_bar = bars + 2 * TC_NSLOTS;
+    if (tid == 0) { tcring_init(rg); mbar_init(done_bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(tslot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tslot;
-    const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
-    URing rg; rg.buf = ring; rg.full = bars; rg.empty = bars + 2; rg.fill_cnt = 0; rg.mma_cnt = 0;
+    if (warp == 8) {                 // ===== TMA producer warp: runs ahead through the static chunk schedule =====
+        if (lane == 0) {
+            RingPos pp; pp.slot = 0; pp.use = 0;
+            for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
+                for (int l = 0; l < 5; ++l) tcring_produce(rg, pp, tc.sdf_fwd[l], 8, 32768u);
+                for (int l = 4; l >= 0; --l) tcring_produce(rg, pp, tc.sdf_bwd[l], 8, 32768u);
+                tcring_produce(rg, pp, tc.col0, 10, 32768u);
+                tcring_produce(rg, pp, tc.col1, 8, 32768u);
+                tcring_produce(rg, pp, tc.col2, 8, 16384u);
+                tcring_produce(rg, pp, tc.col3b, 4, 32768u);
+                tcring_produce(rg, pp, tc.col3a, 10, 32768u);
+                tcring_produce(rg, pp, tc.col4, 8, 32768u);
+            }
+        }
+        return;
+    }
+    const uint32_t trowA = tbase + ((uint32_t)(32 * q) << 16);          // activations: TMEM columns [0, 256)
+    const uint32_t trow = trowA + 256u;                                    // accumulators: TMEM columns [256, 512)
+    RingPos cp; cp.slot = 0; cp.use = 0;
     uint32_t done_par = 0;
 
     float* scratch = w.scratch + (size_t)blockIdx.x * TC_SCRATCH_FLOATS;
@@ -105,10 +63,11 @@ __global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc,
     float* feat = scratch + 6 * UM * 256 / 2;                                  // [UM][256]
 
     // A is complete (generic-proxy writes) and TMEM reads are done -> hand over to the MMA issuer
-    auto handoff = [&]() { fence_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
+    auto handoff = [&]() { tmem_st_wait(); tc_fence_before(); cta_sync_compute(); tc_fence_after(); };
     auto gemm = [&](const float* Wsw, int nchunks, int N, uint32_t accumulate) {
-        if (tid == 0) umma_layer_issue(rg, A, Wsw, nchunks, N, tbase, accumulate, &bars[4]);
-        mbar_wait(&bars[4], done_par);
+        (void)Wsw;
+        if (tid == 0) tcring_mma_layer(rg, cp, tbase, nchunks, N, tbase + 256u, accumulate, done_bar);
+        mbar_wait(done_bar, done_par);
         done_par ^= 1u;
         __syncwarp();
         tc_fence_after();
@@ -116,7 +75,7 @@ __global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc,
     auto load_params = [&](const float* p0, const float* p1) {
         lp0[tid] = p0 ? __ldg(p0 + tid) : 0.f;
         lp1[tid] = p1 ? __ldg(p1 + tid) : 0.f;
-        __syncthreads();
+        cta_sync_compute();
     };
 
     for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
@@ -143,7 +102,7 @@ __global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc,
                     __sincosf(fmaf(a, lp0[cc], lp1[cc]), &s_, &c_);
                     h[i] = s_; c[i] = c_ * lp0[cc];
                 }
-                a_store_chunk(A, r, col0 / 32, h);
+                a_tmem_store(trowA + (uint32_t)col0, h);
                 cf_store32(cf + ((size_t)0 * UM + r) * 256 + col0, c);
             }
         }
@@ -164,7 +123,7 @@ __global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc,
                     v[i] = s_; c[i] = c_ * lp0[col0 + i];
                 }
                 cf_store32(cf + ((size_t)l * UM + r) * 256 + col0, c);
-                if (l < 5) a_store_chunk(A, r, col0 / 32, v);
+                if (l < 5) a_tmem_store(trowA + (uint32_t)col0, v);
                 else {
                     float4* fo = reinterpret_cast<float4*>(feat + (size_t)r * 256 + col0);
 #pragma unroll
@@ -186,7 +145,7 @@ __global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc,
             cf_load32(cf + ((size_t)5 * UM + r) * 256 + col0, c);
 #pragma unroll
             for (int i = 0; i < 32; ++i) c[i] *= lp0[col0 + i];
-            a_store_chunk(A, r, col0 / 32, c);
+            a_tmem_store(trowA + (uint32_t)col0, c);
         }
         handoff();
         float g3[3] = {0.f, 0.f, 0.f};
@@ -200,7 +159,7 @@ __global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc,
                 cf_load32(cf + ((size_t)(l - 1) * UM + r) * 256 + col0, c);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] *= c[i];
-                if (l > 1) a_store_chunk(A, r, col0 / 32, v);
+                if (l > 1) a_tmem_store(trowA + (uint32_t)col0, v);
                 else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -256,7 +215,7 @@ __global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc,
                 const float4* fi = reinterpret_cast<const float4*>(feat + (size_t)r * 256 + col0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { const float4 t = fi[j]; v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w; }
-                a_store_chunk(A, r, col0 / 32, v);
+                a_tmem_store(trowA + (uint32_t)col0, v);
             }
         };
         auto fill_cin = [&]() {                                   // A chunks 0..1 <- [x, PE(view), n | 0 ...] (64 wide)
@@ -266,7 +225,7 @@ __global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc,
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { const int k = 32 * c + i; v[i] = (k < 33) ? cin[r][k] : 0.f; }
-                    a_store_chunk(A, r, c, v);
+                    a_tmem_store(trowA + (uint32_t)(32 * c), v);
                 }
             }
         };
@@ -280,7 +239,7 @@ __global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc,
                 tmem_ld32(trow + (uint32_t)col0, v);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + lp0[col0 + i], 0.f);
-                if (store) a_store_chunk(A, r, col0 / 32, v);
+                if (store) a_tmem_store(trowA + (uint32_t)col0, v);
                 else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -330,11 +289,11 @@ __global__ void __launch_bounds__(256, 1) k_shade_tc(FrameParams fp, ShadeTC tc,
             for (int j = 0; j < 3; ++j)
                 w.smp_rgb[3 * (size_t)sl + j] = sigmoid_(part[0][tid][j] + part[1][tid][j] + __ldg(tc.col_b[5] + j));
         }
-        __syncthreads();
+        cta_sync_compute();
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 256);
+    cta_sync_compute();
+    if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
 }  // namespace arah

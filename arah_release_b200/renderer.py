@@ -52,7 +52,7 @@ class ArahRenderer:
     """Thin RAII wrapper around an ArahHandle (one per device/stream; not thread-safe)."""
 
     def __init__(self, device, n_steps=64, near_samples=16, far_samples=16, cano_view_dirs=True, latent_dim=128,
-                 n_verts=N_VERTS_DEFAULT, max_rays=65536, shade_mode=None):
+                 n_verts=N_VERTS_DEFAULT, max_rays=65536, shade_mode=None, root_mode=None):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.ArahError('the ARAH hot path only exists as CUDA kernels; got device %s' % device)
@@ -60,9 +60,13 @@ class ArahRenderer:
             shade_mode = os.environ.get('ARAH_SHADE_MODE', 'tf32')
         mode = {'tf32': 0, 'fp32': 1}[shade_mode] if isinstance(shade_mode, str) else int(shade_mode)
         self.shade_mode = 'fp32' if mode == 1 else 'tf32'
+        if root_mode is None:
+            root_mode = os.environ.get('ARAH_ROOT_MODE', '3xtf32')
+        rmode = {'3xtf32': 0, 'fp32': 1}[root_mode] if isinstance(root_mode, str) else int(root_mode)
+        self.root_mode = 'fp32' if rmode == 1 else '3xtf32'
         self.cfg = ArahConfig(device=self.device.index or 0, n_steps=n_steps, near_samples=near_samples,
                               far_samples=far_samples, cano_view_dirs=int(bool(cano_view_dirs)), latent_dim=latent_dim,
-                              n_verts=n_verts, max_rays=max_rays, shade_mode=mode)
+                              n_verts=n_verts, max_rays=max_rays, shade_mode=mode, root_mode=rmode)
         self._h = C.c_void_p()
         check(_lib.lib().arah_create(C.byref(self.cfg), C.byref(self._h)))
         self._keep = []
@@ -277,8 +281,9 @@ class IDHRNetwork(nn.Module):
     (implicit_differentiable_renderer.py:18-40); eval forward runs entirely in libarah_b200.so."""
 
     def __init__(self, deviation_network, rendering_network, skinning_model, ray_tracer, cano_view_dirs=True,
-                 train_skinning_net=False, render_last_pt=False, low_vram=False, shade_mode=None):
+                 train_skinning_net=False, render_last_pt=False, low_vram=False, shade_mode=None, root_mode=None):
         super().__init__()
+        self.root_mode = root_mode        # extra, optional: '3xtf32' (tensor cores, default) | 'fp32'
         self.shade_mode = shade_mode      # extra, optional: 'tf32' (tensor cores, default) | 'fp32' (FFMA tiles)
         self.deviation_network = deviation_network
         self.rendering_network = rendering_network
@@ -302,7 +307,7 @@ class IDHRNetwork(nn.Module):
             rt = self.ray_tracer
             r = ArahRenderer(device, n_steps=rt.n_steps, near_samples=rt.near_surface_vol_samples,
                              far_samples=rt.far_surface_vol_samples, cano_view_dirs=self.cano_view_dirs,
-                             latent_dim=latent_dim, n_verts=n_verts, shade_mode=self.shade_mode)
+                             latent_dim=latent_dim, n_verts=n_verts, shade_mode=self.shade_mode, root_mode=self.root_mode)
             self._renderers[key] = r
         return r
 

@@ -41,9 +41,14 @@ typedef struct ArahConfig {
     int32_t shade_mode;           /* ARAH_SHADE_TF32 (default 0): shading MLPs on tcgen05 tensor cores, TF32 operands,
                                    * fp32 accumulate; ARAH_SHADE_FP32 (1): fp32 FFMA tiles (bit-for-bit the oracle's
                                    * arithmetic order).  Root finding is fp32 in both modes. */
+    int32_t root_mode;            /* ARAH_ROOT_3XTF32 (default 0): the skinning MLP of the per-sample correspondence search on
+                                   * tcgen05 in split precision (hi/lo TF32, 3 products ~ fp32); ARAH_ROOT_FP32 (1): fp32
+                                   * FFMA tiles.  Residual bookkeeping, Jacobians and Broyden updates are fp32 in both. */
 } ArahConfig;
 #define ARAH_SHADE_TF32 0
 #define ARAH_SHADE_FP32 1
+#define ARAH_ROOT_3XTF32 0
+#define ARAH_ROOT_FP32 1
 
 /* Per-frame inputs == what IDHRNetwork.forward reads from its `input` dict
  * (renderer/implicit_differentiable_renderer.py:52-71) plus the weights of the modules it owns.
@@ -136,8 +141,9 @@ int arah_eval_sdf(ArahHandle* h, const float* xn, int32_t n, float* sdf, float* 
 int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, float* weights, float* x_bar, void* stream);
 
 /* Debug/bring-up: D[128][N] = A[128][K] . W[N][K]^T through the tcgen05 TF32 tile used by the shading kernel
- * (device pointers, K multiple of 32 <= 256, N in {128, 256}); synchronises the stream. */
-int arah_debug_umma_gemm(const float* A, const float* W, int32_t K, int32_t N, float* D, void* stream);
+ * (device pointers, K multiple of 32 <= 256, N in {128, 256}; a_in_tmem != 0 stages A in tensor memory and uses the
+ * `.ts` MMA form); synchronises the stream. */
+int arah_debug_umma_gemm(const float* A, const float* W, int32_t K, int32_t N, float* D, int32_t a_in_tmem, void* stream);
 
 #ifdef __cplusplus
 }

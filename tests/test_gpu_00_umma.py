@@ -6,8 +6,9 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
+@pytest.mark.parametrize('a_in_tmem', [0, 1])
 @pytest.mark.parametrize('K,N', [(32, 256), (256, 256), (128, 128), (96, 256)])
-def test_umma_tf32_tile_matches_matmul(K, N):
+def test_umma_tf32_tile_matches_matmul(K, N, a_in_tmem):
     """tcgen05 TF32 tile (descriptors, 128B swizzle, TMEM read-back) against torch fp32 matmul; tolerance = TF32 operand rounding."""
     import ctypes as C
     from arah_release_b200 import _lib
@@ -16,7 +17,7 @@ def test_umma_tf32_tile_matches_matmul(K, N):
     Wt = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
     D = torch.zeros(128, N, device=DEV)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(_lib.lib().arah_debug_umma_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(Wt.data_ptr()), K, N, C.c_void_p(D.data_ptr()), st))
+    _lib.check(_lib.lib().arah_debug_umma_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(Wt.data_ptr()), K, N, C.c_void_p(D.data_ptr()), a_in_tmem, st))
     ref = A.double() @ Wt.double().t()
     err = (D.double() - ref).abs().max().item()
     assert err < 6e-3, err          # |a||w| K 2^-11 scale
