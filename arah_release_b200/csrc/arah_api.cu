@@ -285,6 +285,7 @@ struct ArahHandle {
     float* skin_Wt[5]; float* skin_b[5];
     float* col_Wt0; float* col_Wt1; float* col_Wt2; float* col_Wt3a; float* col_Wt3b; float* col_Wt4; float* col_W5; float* col_b[6];
     float* bone_T; float4* verts4; float* verts3; float* smpl_w;
+    float* knn_sv; float* knn_cmin; float* knn_cmax; KnnIndex knn;
     // tensor-core shading: pre-swizzled chunk images (arah_umma.cuh)
     float* tc_sdf_fwd[5]; float* tc_sdf_bwd[5]; float* tc_F; float* tc_G;
     float* tc_col0; float* tc_col1; float* tc_col2; float* tc_col3b; float* tc_col3a; float* tc_col4;
@@ -327,6 +328,8 @@ static int alloc_arena(ArahHandle* h) {
     for (int l = 0; l < 3; ++l) reg(&h->tc_skin_hid[l], 4 * 128 * 32 * 2);
     reg(&h->tc_skin_out, 4 * 32 * 32 * 2);
     reg(&h->col_b[0], 256); reg(&h->col_b[1], 256); reg(&h->col_b[2], 256); reg(&h->col_b[3], 256); reg(&h->col_b[4], 256); reg(&h->col_b[5], 64);
+    reg(&h->knn_sv, (size_t)((h->cfg.n_verts + 31) / 32) * 32 * 4); reg(&h->knn_cmin, (size_t)((h->cfg.n_verts + 31) / 32) * 4);
+    reg(&h->knn_cmax, (size_t)((h->cfg.n_verts + 31) / 32) * 4);
     reg(&h->bone_T, 24 * 16);
     float* v4 = nullptr;
     reg(&v4, (size_t)h->cfg.n_verts * 4);
@@ -373,7 +376,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     if (cfg->shade_mode != ARAH_SHADE_TF32 && cfg->shade_mode != ARAH_SHADE_FP32) return fail(ARAH_EINVAL, "shade_mode must be ARAH_SHADE_TF32 or ARAH_SHADE_FP32");
     if (cfg->root_mode != ARAH_ROOT_3XTF32 && cfg->root_mode != ARAH_ROOT_FP32) return fail(ARAH_EINVAL, "root_mode must be ARAH_ROOT_3XTF32 or ARAH_ROOT_FP32");
     if (cfg->latent_dim < 0 || cfg->latent_dim > 512) return fail(ARAH_EINVAL, "latent_dim must be in [0,512]");
-    if (cfg->n_verts <= 0 || (size_t)cfg->n_verts * 16 > 200 * 1024) return fail(ARAH_EINVAL, "n_verts must fit 200 KB of shared memory (<= 12800)");
+    if (cfg->n_verts <= 0 || cfg->n_verts > 8192) return fail(ARAH_EINVAL, "n_verts must be in [1, 8192] (kNN index: one-block Morton sort + shared-memory clusters)");
     CU(cudaSetDevice(cfg->device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, cfg->device));
@@ -399,8 +402,9 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc_smem_bytes()));
     CU(cudaFuncSetAttribute(k_shade_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc2_smem_bytes()));
     CU(cudaFuncSetAttribute(k_corr_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc2_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->n_verts * 16));
-    CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->n_verts * 16));
+    CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
+    CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
+    CU(cudaFuncSetAttribute(k_knn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
     *out = h;
     return ARAH_OK;
 }
@@ -504,6 +508,9 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     CU(cudaMemcpyAsync(h->bone_T, f->bone_transforms, 24 * 16 * 4, kind, st));
     CU(cudaMemcpyAsync(h->verts3, f->smpl_verts, (size_t)h->cfg.n_verts * 12, kind, st));
     k_verts4<<<cdiv(h->cfg.n_verts, 256), 256, 0, st>>>(h->verts3, h->verts4, h->cfg.n_verts); ++npack;
+    k_knn_build<<<1, 1024, 8192 * 8, st>>>(h->verts3, h->cfg.n_verts, (float4*)h->knn_sv, (float4*)h->knn_cmin, (float4*)h->knn_cmax); ++npack;
+    h->knn.sv = (const float4*)h->knn_sv; h->knn.cmin = (const float4*)h->knn_cmin; h->knn.cmax = (const float4*)h->knn_cmax;
+    h->knn.nc = (h->cfg.n_verts + 31) / 32;
     h->pack_launches = npack;
     if (f->smpl_weights) {
         CU(cudaMemcpyAsync(h->smpl_w, f->smpl_weights, (size_t)h->cfg.n_verts * 24 * 4, kind, st));
@@ -560,7 +567,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     const int S = w.S;
     const size_t PS = (size_t)P * S;
     const int nsm = h->n_sms;
-    const size_t sm_sdf = tile_smem_bytes(LDA_SDF), sm_skin = tile_smem_bytes(LDA_SKIN), sm_knn = (size_t)fp.n_verts * 16;
+    const size_t sm_sdf = tile_smem_bytes(LDA_SDF), sm_skin = tile_smem_bytes(LDA_SKIN), sm_knn = knn_smem_bytes(fp.n_verts);
     auto L = [&]() { h->launches++; };
     const bool prof = h->profile;
     h->profiled = prof;
@@ -568,10 +575,10 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     if (prof) CU(cudaEventRecord(h->ev[0], st));
     k_trace_begin<<<cdiv(P, 256), 256, 0, st>>>(w); L();
     const unsigned g_ray_tiles = grid_min(cdiv(P, TM), (size_t)nsm);
-    const unsigned g_knn_rays = grid_min(cdiv(P, 256), (size_t)2 * nsm);
+    const unsigned g_knn_rays = grid_min(cdiv(P, 512), (size_t)nsm);
     for (int it = 0; it < TRACE_ITERS; ++it) {
-        k_knn_rays<<<g_knn_rays, 256, sm_knn, st>>>(fp, w, it); L();
-        k_trace_iter<<<g_ray_tiles, 256, sm_sdf, st>>>(fp, w, it); L();
+        k_knn_rays<<<g_knn_rays, 512, sm_knn, st>>>(fp, h->knn, w, it); L();
+        k_trace_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it); L();
     }
     if (prof) CU(cudaEventRecord(h->ev[1], st));
     k_iso_prepare<<<cdiv(P, 256), 256, 0, st>>>(w); L();
@@ -579,8 +586,8 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     for (int it = 0; it < BROYDEN_ITERS; ++it) { k_iso_iter<<<g_ray_tiles, 256, sm_sdf, st>>>(fp, w, it); L(); }
     if (prof) CU(cudaEventRecord(h->ev[2], st));
     k_trace_finish<<<cdiv(P, 128), 128, 0, st>>>(fp, w); L();
-    const unsigned g_knn_s = grid_min(cdiv(PS, 256), (size_t)2 * nsm);
-    k_knn_samples<<<g_knn_s, 256, sm_knn, st>>>(fp, w); L();
+    const unsigned g_knn_s = grid_min(cdiv(PS, 512), (size_t)nsm);
+    k_knn_samples<<<g_knn_s, 512, sm_knn, st>>>(fp, h->knn, w); L();
     const unsigned g_smp_tiles = grid_min(cdiv(PS, TM), (size_t)2 * nsm);
     if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
         const unsigned g_tc = grid_min(cdiv(PS, UM), (size_t)nsm);

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_corr_tc2(FrameParams fp, Skin
             float xn[3] = {0.f, 0.f, 0.f};
             if (i < n) {
                 id = list ? list[i] : i;
-                st = w.corr_state[id];
+                state_load(st, &w.corr_state[id]);
                 if (iter >= 0) broyden_advance<3>(st, dx);
                 normalize3(fp, st.x, xn);
             }
@@ -134,11 +134,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_corr_tc2(FrameParams fp, Skin
                     broyden_begin<3>(st, x0, g, Ai, Tinit);
                     st.owner = owner; st.tgt[0] = tg[0]; st.tgt[1] = tg[1]; st.tgt[2] = tg[2];
                     st.g_evals = 2;
-                    w.corr_state[id] = st;
+                    state_store(&w.corr_state[id], st);
                 } else {
                     active = broyden_update<3>(st, dx, g, T12);
                     if (iter + 1 >= BROYDEN_ITERS) active = false;
-                    if (active) w.corr_state[id] = st;
+                    if (active) state_store(&w.corr_state[id], st);
                     else corr_finalize(fp, w, st);
                 }
             }

@@ -63,6 +63,21 @@ struct Work {
     float* out_wsum;          // [P]
 };
 
+// 128-bit copies of a state record (the struct is alignas(16) and a multiple of 16 bytes)
+template <class T> __device__ __forceinline__ void state_load(T& dst, const T* src) {
+    static_assert(sizeof(T) % 16 == 0, "state records are 16-byte multiples");
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(&dst);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = s[i];
+}
+template <class T> __device__ __forceinline__ void state_store(T* dst, const T& src) {
+    const uint4* s = reinterpret_cast<const uint4*>(&src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = s[i];
+}
+
 // warp-aggregated append of `value` to list (returns nothing); all 32 lanes must call
 __device__ __forceinline__ void warp_append(bool pred, int value, int* list, int* counter) {
     const unsigned m = __ballot_sync(0xffffffffu, pred);
@@ -97,22 +112,135 @@ __global__ void k_trace_begin(Work w) {
     warp_append(unfinished, r, w.listA, &w.counters[C_TRACE]);
 }
 
-// nearest posed SMPL vertex by exhaustive search; verts broadcast from shared memory (1 LDS.128 per vertex per warp)
-__device__ __forceinline__ int knn_scan(const float4* sv, int n_verts, float x, float y, float z) {
-    float bd = INFINITY;
-    int bi = 0;
-#pragma unroll 4
-    for (int v = 0; v < n_verts; ++v) {
+// ---- exact 1-NN over the posed SMPL vertices ---------------------------------------------------------------------
+// k_knn_build (once per frame) sorts the vertices along a 30-bit Morton curve and groups them into clusters of 32 with an
+// AABB each.  A query first finds the cluster with the smallest box distance, scans it, then scans only clusters whose box
+// could still hold a closer vertex: typically 2-6 of 216 clusters instead of all 6890 vertices.  The result is the exact
+// argmin of (x-v).(x-v) with the lowest original index on ties == the brute-force answer
+// (pytorch3d.ops.knn_points K=1, ray_tracing.py:386,407).
+constexpr int KNN_CLUSTER = 32;
+struct KnnIndex {
+    const float4* sv;      // [nc*32] sorted vertices (x, y, z, original index as int bits); padding = +1e30
+    const float4* cmin;    // [nc]
+    const float4* cmax;    // [nc]
+    int nc;
+};
+__host__ __device__ constexpr size_t knn_smem_bytes(int n_verts) {
+    return (size_t)((n_verts + KNN_CLUSTER - 1) / KNN_CLUSTER) * (KNN_CLUSTER * 16 + 32);
+}
+__device__ __forceinline__ uint32_t morton_spread10(uint32_t v) {
+    v &= 0x3FFu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+// single block, 1024 threads, dynamic smem = 8192 * 8 bytes; n <= 8192
+__global__ void __launch_bounds__(1024) k_knn_build(const float* __restrict__ v3, int n, float4* __restrict__ sv, float4* __restrict__ cmin, float4* __restrict__ cmax) {
+    extern __shared__ uint32_t sk[];
+    uint32_t* keys = sk;
+    uint32_t* idx = sk + 8192;
+    __shared__ float red[6][32];
+    __shared__ float bb[6];
+    const int tid = threadIdx.x;
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = tid; i < n; i += blockDim.x)
+        for (int k = 0; k < 3; ++k) { const float c = v3[3 * i + k]; lo[k] = fminf(lo[k], c); hi[k] = fmaxf(hi[k], c); }
+    for (int k = 0; k < 3; ++k) {
+        for (int o = 16; o > 0; o >>= 1) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
+        if ((tid & 31) == 0) { red[k][tid >> 5] = lo[k]; red[3 + k][tid >> 5] = hi[k]; }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float a = red[tid][0];
+        for (int i = 1; i < 32; ++i) a = (tid < 3) ? fminf(a, red[tid][i]) : fmaxf(a, red[tid][i]);
+        bb[tid] = a;
+    }
+    __syncthreads();
+    for (int i = tid; i < 8192; i += blockDim.x) {
+        uint32_t key = 0xFFFFFFFFu;
+        if (i < n) {
+            uint32_t q[3];
+            for (int k = 0; k < 3; ++k) {
+                const float t = (v3[3 * i + k] - bb[k]) / fmaxf(bb[3 + k] - bb[k], 1e-12f);
+                q[k] = (uint32_t)fminf(fmaxf(t * 1023.0f, 0.0f), 1023.0f);
+            }
+            key = morton_spread10(q[0]) | (morton_spread10(q[1]) << 1) | (morton_spread10(q[2]) << 2);
+        }
+        keys[i] = key; idx[i] = (uint32_t)i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= 8192; k <<= 1) {                       // bitonic sort of (key, idx), ties broken by idx
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < 8192; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const bool up = (i & k) == 0;
+                    const uint32_t ka = keys[i], kb = keys[p], ia = idx[i], ib = idx[p];
+                    const bool gt = (ka > kb) || (ka == kb && ia > ib);
+                    if (gt == up) { keys[i] = kb; keys[p] = ka; idx[i] = ib; idx[p] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int nc = (n + KNN_CLUSTER - 1) / KNN_CLUSTER;
+    for (int i = tid; i < nc * KNN_CLUSTER; i += blockDim.x) {
+        float4 o = make_float4(1e30f, 1e30f, 1e30f, __int_as_float(0x7fffffff));
+        if (i < n) { const int s_ = (int)idx[i]; o = make_float4(v3[3 * s_], v3[3 * s_ + 1], v3[3 * s_ + 2], __int_as_float(s_)); }
+        sv[i] = o;
+    }
+    __syncthreads();
+    for (int c = tid; c < nc; c += blockDim.x) {
+        float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+        for (int i = c * KNN_CLUSTER; i < min(n, (c + 1) * KNN_CLUSTER); ++i) {
+            const int s_ = (int)idx[i];
+            for (int k = 0; k < 3; ++k) { const float v = v3[3 * s_ + k]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
+        }
+        cmin[c] = make_float4(mn[0], mn[1], mn[2], 0.f);
+        cmax[c] = make_float4(mx[0], mx[1], mx[2], 0.f);
+    }
+}
+struct KnnSmem { const float4* sv; const float4* cmin; const float4* cmax; int nc; };
+__device__ __forceinline__ KnnSmem load_knn(float4* smem, const KnnIndex& ix) {
+    const int nv = ix.nc * KNN_CLUSTER;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) smem[v] = __ldg(ix.sv + v);
+    for (int c = threadIdx.x; c < ix.nc; c += blockDim.x) { smem[nv + c] = __ldg(ix.cmin + c); smem[nv + ix.nc + c] = __ldg(ix.cmax + c); }
+    __syncthreads();
+    KnnSmem k; k.sv = smem; k.cmin = smem + nv; k.cmax = smem + nv + ix.nc; k.nc = ix.nc;
+    return k;
+}
+__device__ __forceinline__ float box_dist2(const float4 mn, const float4 mx, float x, float y, float z) {
+    const float dx = fmaxf(fmaxf(mn.x - x, x - mx.x), 0.f), dy = fmaxf(fmaxf(mn.y - y, y - mx.y), 0.f), dz = fmaxf(fmaxf(mn.z - z, z - mx.z), 0.f);
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+__device__ __forceinline__ void knn_scan_cluster(const float4* sv, int c, float x, float y, float z, float& bd, int& bi) {
+#pragma unroll 8
+    for (int v = c * KNN_CLUSTER; v < (c + 1) * KNN_CLUSTER; ++v) {
         const float4 p = sv[v];
         const float dx = x - p.x, dy = y - p.y, dz = z - p.z;
         const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d < bd) { bd = d; bi = v; }
+        const int id = __float_as_int(p.w);
+        if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
+    }
+}
+__device__ __forceinline__ int knn_scan(const KnnSmem& k, float x, float y, float z) {
+    float lb0 = INFINITY;
+    int c0 = 0;
+    for (int c = 0; c < k.nc; ++c) {
+        const float lb = box_dist2(k.cmin[c], k.cmax[c], x, y, z);
+        if (lb < lb0) { lb0 = lb; c0 = c; }
+    }
+    float bd = INFINITY;
+    int bi = 0x7fffffff;
+    knn_scan_cluster(k.sv, c0, x, y, z, bd, bi);
+    for (int c = 0; c < k.nc; ++c) {
+        if (c == c0) continue;
+        // the box distance is a lower bound computed in the same fp32 form; keep a 1-ulp-safe margin
+        if (box_dist2(k.cmin[c], k.cmax[c], x, y, z) <= bd * 1.000001f) knn_scan_cluster(k.sv, c, x, y, z, bd, bi);
     }
     return bi;
-}
-__device__ __forceinline__ void load_verts(float4* sv, const FrameParams& fp) {
-    for (int v = threadIdx.x; v < fp.n_verts; v += blockDim.x) sv[v] = __ldg(fp.verts4 + v);
-    __syncthreads();
 }
 // NN-skinning inverse of one posed point x (incl. trans): T = sum_j W[idx][j] B_j, x_hat = T^-1 (x - trans)
 __device__ __forceinline__ void nn_inverse_skinning(const FrameParams& fp, int idx, const float* x, float* T12, float* s, float* x_hat) {
@@ -125,11 +253,11 @@ __device__ __forceinline__ void nn_inverse_skinning(const FrameParams& fp, int i
     affine_inverse_apply(T12, *s, xl, x_hat);
 }
 
-__global__ void __launch_bounds__(256) k_knn_rays(FrameParams fp, Work w, int iter) {
+__global__ void __launch_bounds__(512) k_knn_rays(FrameParams fp, KnnIndex ix, Work w, int iter) {
     extern __shared__ float4 sv[];
     const int n = w.counters[C_TRACE + iter];
     if ((int)(blockIdx.x * blockDim.x) >= n) return;
-    load_verts(sv, fp);
+    const KnnSmem kk = load_knn(sv, ix);
     const int* list = (iter & 1) ? w.listB : w.listA;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int r = list[i];
@@ -137,7 +265,7 @@ __global__ void __launch_bounds__(256) k_knn_rays(FrameParams fp, Work w, int it
         float x[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) x[k] = w.ray_dirs[3 * r + k] * t + fp.cam_loc[k];
-        const int idx = knn_scan(sv, fp.n_verts, x[0], x[1], x[2]);
+        const int idx = knn_scan(kk, x[0], x[1], x[2]);
         RayCur c;
         float xh[3];
         nn_inverse_skinning(fp, idx, x, c.T, &c.s, xh);
@@ -167,7 +295,7 @@ __device__ __forceinline__ TileSmem carve(float* base, int lda) {
     return s;
 }
 
-__global__ void __launch_bounds__(256, 1) k_trace_iter(FrameParams fp, Work w, int iter) {
+__global__ void __launch_bounds__(256, 2) k_trace_iter(FrameParams fp, Work w, int iter) {
     extern __shared__ __align__(128) float smem[];
     const int n = w.counters[C_TRACE + iter];
     if ((int)blockIdx.x * TM >= n) return;
@@ -303,7 +431,7 @@ __global__ void __launch_bounds__(256, 1) k_iso_init(FrameParams fp, Work w) {
             broyden_begin<4>(st, u0, g0, Ji, w.ray_cur[r].T);
             st.owner = r;
             st.tgt[0] = st.tgt[1] = st.tgt[2] = 0.f;
-            w.iso_state[r] = st;
+            state_store(&w.iso_state[r], st);
         }
         __syncthreads();
     }
@@ -328,7 +456,7 @@ __global__ void __launch_bounds__(256, 1) k_iso_iter(FrameParams fp, Work w, int
             float xn[3] = {0.f, 0.f, 0.f};
             if (i < n) {
                 r = list[i];
-                st = w.iso_state[r];
+                state_load(st, &w.iso_state[r]);
                 broyden_advance<4>(st, dx);
                 normalize3(fp, st.x, xn);
             }
@@ -346,7 +474,7 @@ __global__ void __launch_bounds__(256, 1) k_iso_iter(FrameParams fp, Work w, int
                 iso_residual(fp, w, r, st.x, s.logits[tid], s.sdfo[tid], g, T12);
                 active = broyden_update<4>(st, dx, g, T12);
                 if (iter + 1 >= BROYDEN_ITERS) active = false;
-                w.iso_state[r] = st;
+                state_store(&w.iso_state[r], st);
             }
             if (iter + 1 < BROYDEN_ITERS) warp_append(active, r, next, &w.counters[C_ISO + iter + 1]);
             warp_stat_add(r >= 0 ? 1 : 0, &w.counters[C_STAT_ISO_EVALS]);
@@ -433,11 +561,12 @@ __global__ void k_trace_finish(FrameParams fp, Work w) {
 }
 
 // ================================================================================================ correspondences
-__global__ void __launch_bounds__(256) k_knn_samples(FrameParams fp, Work w) {
+__global__ void __launch_bounds__(512) k_knn_samples(FrameParams fp, KnnIndex ix, Work w) {
     extern __shared__ float4 sv[];
     const int n = w.counters[C_ON];
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.counters[C_CORR] = n;
     if ((int)(blockIdx.x * blockDim.x) >= n) return;
-    load_verts(sv, fp);
+    const KnnSmem kk = load_knn(sv, ix);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int sl = w.on_list[i];
         const int r = sl / w.S;
@@ -445,7 +574,7 @@ __global__ void __launch_bounds__(256) k_knn_samples(FrameParams fp, Work w) {
         float x[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) x[k] = w.ray_dirs[3 * r + k] * z + fp.cam_loc[k];
-        const int idx = knn_scan(sv, fp.n_verts, x[0], x[1], x[2]);
+        const int idx = knn_scan(kk, x[0], x[1], x[2]);
         BroydenState<3> st;
         float s_, xh[3];
         nn_inverse_skinning(fp, idx, x, st.best_T, &s_, xh);
@@ -454,9 +583,8 @@ __global__ void __launch_bounds__(256) k_knn_samples(FrameParams fp, Work w) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) st.Jinv[k] = 0.f;
         st.best_n = 0.f; st.owner = sl; st.g_evals = 0;
-        w.corr_state[i] = st;
+        state_store(&w.corr_state[i], st);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) w.counters[C_CORR] = n;
 }
 
 constexpr int LDA_SKIN = 132;
@@ -493,7 +621,7 @@ __global__ void __launch_bounds__(256, 2) k_corr_step(FrameParams fp, Work w, in
             float xn[3] = {0.f, 0.f, 0.f};
             if (i < n) {
                 id = list ? list[i] : i;
-                st = w.corr_state[id];
+                state_load(st, &w.corr_state[id]);
                 if (iter >= 0) broyden_advance<3>(st, dx);
                 normalize3(fp, st.x, xn);
             }
@@ -524,11 +652,11 @@ __global__ void __launch_bounds__(256, 2) k_corr_step(FrameParams fp, Work w, in
                     broyden_begin<3>(st, x0, g, Ai, Tinit);
                     st.owner = owner; st.tgt[0] = tg[0]; st.tgt[1] = tg[1]; st.tgt[2] = tg[2];
                     st.g_evals = 2;                         // J-init evaluation + g(x0) (the reference evaluates twice)
-                    w.corr_state[id] = st;
+                    state_store(&w.corr_state[id], st);
                 } else {
                     active = broyden_update<3>(st, dx, g, T12);
                     if (iter + 1 >= BROYDEN_ITERS) active = false;
-                    if (active) w.corr_state[id] = st;
+                    if (active) state_store(&w.corr_state[id], st);
                     else corr_finalize(fp, w, st);
                 }
             }

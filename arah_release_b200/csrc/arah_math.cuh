@@ -202,7 +202,7 @@ ARAH_HD bool invert_gj(const float* A, float* Ai) {
 // Broyden state of one point (D = 3: canonical correspondence, D = 4: joint iso-surface search).
 // Lives in HBM between the per-iteration launches (AoS record, 16-byte aligned), in registers inside one.
 template <int D>
-struct BroydenState {
+struct alignas(16) BroydenState {
     float x[D];
     float Jinv[D * D];
     float gx[D];

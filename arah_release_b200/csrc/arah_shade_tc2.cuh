@@ -58,9 +58,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shade_tc2(FrameParams fp, Sha
     RingPos cp; cp.slot = 0; cp.use = 0;
     uint32_t done_par = 0;
 
-    float* scratch = w.scratch + (size_t)blockIdx.x * TC_SCRATCH_FLOATS;
-    __nv_bfloat16* cf = reinterpret_cast<__nv_bfloat16*>(scratch);            // [6][UM][256]
-    float* feat = scratch + 6 * UM * 256 / 2;                                  // [UM][256]
+    // per-thread private scratch, slot-major [slot][256 threads] uint4: a warp access = 512 contiguous bytes.
+    // slots 0..95: bf16 cos factors (layer l, batch b, 4 x uint4); slots 96..127: fp32 feature (batch b, 8 x float4)
+    uint4* scr = reinterpret_cast<uint4*>(w.scratch + (size_t)blockIdx.x * TC_SCRATCH_FLOATS) + tid;
+    auto cf_put = [&](int l, int b, const float (&v)[32]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+            scr[(size_t)((l * 4 + b) * 4 + i) * 256] = u;
+        }
+    };
+    auto cf_get = [&](int l, int b, float (&v)[32]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 u = scr[(size_t)((l * 4 + b) * 4 + i) * 256];
+            const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wd[j]));
+                v[8 * i + 2 * j] = f.x; v[8 * i + 2 * j + 1] = f.y;
+            }
+        }
+    };
+    auto feat_put = [&](int b, const float (&v)[32]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) scr[(size_t)(96 + b * 8 + j) * 256] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+    };
+    auto feat_get = [&](int b, float (&v)[32]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 u = scr[(size_t)(96 + b * 8 + j) * 256];
+            v[4 * j] = __uint_as_float(u.x); v[4 * j + 1] = __uint_as_float(u.y); v[4 * j + 2] = __uint_as_float(u.z); v[4 * j + 3] = __uint_as_float(u.w);
+        }
+    };
 
     // A is complete (generic-proxy writes) and TMEM reads are done -> hand over to the MMA issuer
     auto handoff = [&]() { tmem_st_wait(); tc_fence_before(); cta_sync_compute(); tc_fence_after(); };
@@ -103,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shade_tc2(FrameParams fp, Sha
                     h[i] = s_; c[i] = c_ * lp0[cc];
                 }
                 a_tmem_store(trowA + (uint32_t)col0, h);
-                cf_store32(cf + ((size_t)0 * UM + r) * 256 + col0, c);
+                cf_put(0, b, c);
             }
         }
         handoff();
@@ -122,12 +156,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shade_tc2(FrameParams fp, Sha
                     __sincosf(fmaf(v[i], lp0[col0 + i], lp1[col0 + i]), &s_, &c_);
                     v[i] = s_; c[i] = c_ * lp0[col0 + i];
                 }
-                cf_store32(cf + ((size_t)l * UM + r) * 256 + col0, c);
+                cf_put(l, b, c);
                 if (l < 5) a_tmem_store(trowA + (uint32_t)col0, v);
                 else {
-                    float4* fo = reinterpret_cast<float4*>(feat + (size_t)r * 256 + col0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) fo[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    feat_put(b, v);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) dot = fmaf(v[i], __ldg(tc.sdf_w6 + col0 + i), dot);
                 }
@@ -142,7 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shade_tc2(FrameParams fp, Sha
         for (int b = 0; b < 4; ++b) {                            // g_a5 = w6 * cf5
             const int col0 = 128 * half + 32 * b;
             float c[32];
-            cf_load32(cf + ((size_t)5 * UM + r) * 256 + col0, c);
+            cf_get(5, b, c);
 #pragma unroll
             for (int i = 0; i < 32; ++i) c[i] *= lp0[col0 + i];
             a_tmem_store(trowA + (uint32_t)col0, c);
@@ -156,7 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shade_tc2(FrameParams fp, Sha
                 const int col0 = 128 * half + 32 * b;
                 float v[32], c[32];
                 tmem_ld32(trow + (uint32_t)col0, v);
-                cf_load32(cf + ((size_t)(l - 1) * UM + r) * 256 + col0, c);
+                cf_get(l - 1, b, c);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] *= c[i];
                 if (l > 1) a_tmem_store(trowA + (uint32_t)col0, v);
@@ -212,9 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shade_tc2(FrameParams fp, Sha
             for (int b = 0; b < 4; ++b) {
                 const int col0 = 128 * half + 32 * b;
                 float v[32];
-                const float4* fi = reinterpret_cast<const float4*>(feat + (size_t)r * 256 + col0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { const float4 t = fi[j]; v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w; }
+                feat_get(b, v);
                 a_tmem_store(trowA + (uint32_t)col0, v);
             }
         };
