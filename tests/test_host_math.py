@@ -1,0 +1,108 @@
+"""CPU: the per-point math the kernels run (csrc/arah_math.cuh compiled for the host with g++) against independent
+implementations: torch tree-softmax, numpy inverses, and — in the build container — the reference's own broyden()."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+CSRC = os.path.join(ROOT, 'arah_release_b200', 'csrc')
+SO = os.path.join(CSRC, 'libhost_math_test.so')
+FP = C.POINTER(C.c_float)
+
+
+@pytest.fixture(scope='module')
+def hm():
+    src = os.path.join(CSRC, 'host_math_test.cpp')
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, 'arah_math.cuh'))):
+        cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+        subprocess.check_call([cxx, '-O2', '-std=c++17', '-x', 'c++', '-shared', '-fPIC', '-o', SO, src])
+    return C.CDLL(SO)
+
+
+def _p(a):
+    return a.ctypes.data_as(FP)
+
+
+def test_hierarchical_softmax_matches_torch_tree(hm):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    from make_synthetic_assets import tree_softmax
+    rng = np.random.default_rng(0)
+    x = (rng.normal(size=(500, 25)) * 3).astype(np.float32)
+    out = np.zeros((500, 24), np.float32)
+    hm.hm_hsoftmax(_p(x), 500, _p(out))
+    ref = tree_softmax(torch.from_numpy(x)).numpy()
+    np.testing.assert_allclose(out, ref, atol=2e-7, rtol=1e-5)
+    np.testing.assert_allclose(out.sum(1), 1.0, atol=1e-5)
+
+
+def test_hierarchical_softmax_dual_matches_autograd(hm):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    from make_synthetic_assets import tree_softmax
+    rng = np.random.default_rng(1)
+    x = (rng.normal(size=25) * 2).astype(np.float32)
+    dx = rng.normal(size=(25, 3)).astype(np.float32)
+    w = np.zeros(24, np.float32); dw = np.zeros((24, 3), np.float32)
+    hm.hm_hsoftmax_dual(_p(x), _p(dx), _p(w), _p(dw))
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    J = torch.autograd.functional.jacobian(lambda t: tree_softmax(t[None])[0], xt).numpy()       # [24,25]
+    np.testing.assert_allclose(dw, J @ dx.astype(np.float64), atol=2e-6)
+
+
+def test_small_algebra(hm):
+    out = np.zeros(64, np.float32)
+    hm.hm_misc(_p(out))
+    np.testing.assert_allclose(out[:17], torch.linspace(0, 1, 17).numpy(), atol=0)
+    np.testing.assert_allclose(out[17:33], torch.linspace(0, 1, 16).numpy(), atol=0)
+    assert abs(out[33] - 100.0) < 1e-4 and out[34] < out[33] < out[35]
+    np.testing.assert_allclose(out[36:38], torch.nn.functional.softplus(torch.tensor([0.003, 0.5]), beta=100).numpy(), rtol=1e-6)
+    A = np.array([[2, 0.1, 0], [0.3, 1.5, 0.2], [0, 0.4, 1.1]])
+    np.testing.assert_allclose(out[38:47].reshape(3, 3), np.linalg.inv(A), atol=1e-6)
+    B = np.array([[1.2, 0.1, 0, 0.3], [0.2, 0.9, 0.1, 0], [0, 0.3, 1.1, 0.5], [0.1, 0, 0.2, 1.0]])
+    np.testing.assert_allclose(out[47:63].reshape(4, 4), np.linalg.inv(B), atol=2e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+def test_per_point_broyden_equals_reference_batched_broyden(hm):
+    """The per-point restatement (broyden_begin/advance/update) reproduces utils/broyden.py of the reference, including
+    best-iterate bookkeeping that starts from T_init and the every-point-takes-one-step rule."""
+    from oracle import ref_harness as rh
+    rh.install()
+    import im2mesh.metaavatar_render  # noqa: F401
+    from im2mesh.utils.broyden import broyden as ref_broyden
+    rng = np.random.default_rng(3)
+    N = 200
+    A = (np.eye(3)[None] + 0.3 * rng.normal(size=(N, 3, 3))).astype(np.float32)
+    c = rng.normal(size=(N, 3)).astype(np.float32) * 0.2
+    eps = np.float32(0.05)
+    x0 = rng.normal(size=(N, 3)).astype(np.float32) * 0.3
+    Jinv0 = np.linalg.inv(A.astype(np.float64)).astype(np.float32)
+    Tinit = rng.normal(size=(N, 12)).astype(np.float32)
+    At, ct = torch.from_numpy(A), torch.from_numpy(c)
+
+    def g(x, mask=None):
+        xx = x[mask]
+        gx = torch.bmm(At[mask], xx) + ct[mask].unsqueeze(-1) + eps * torch.sin(3.0 * xx)
+        T = torch.zeros(xx.shape[0], 4, 4)
+        flat = torch.stack([xx[:, e % 3, 0] * (e + 1) for e in range(12)], -1)
+        T[:, :3, :] = flat.view(-1, 3, 4)
+        T[:, 3, 3] = 1
+        return gx, T
+    T0 = torch.zeros(N, 4, 4); T0[:, :3, :] = torch.from_numpy(Tinit).view(N, 3, 4); T0[:, 3, 3] = 1
+    ref = ref_broyden(g, torch.from_numpy(x0).unsqueeze(-1), T0, torch.from_numpy(Jinv0))
+    xs = np.zeros((N, 3), np.float32); Ts = np.zeros((N, 12), np.float32); diffs = np.zeros(N, np.float32); valids = np.zeros(N, np.int32)
+    for i in range(N):
+        d = C.c_float(); v = C.c_int()
+        hm.hm_broyden3(_p(A[i]), _p(c[i]), C.c_float(float(eps)), _p(x0[i]), _p(Jinv0[i]), _p(Tinit[i]), _p(xs[i]), _p(Ts[i]),
+                       C.byref(d), C.byref(v), 50)
+        diffs[i], valids[i] = d.value, v.value
+    rv = ref['valid_ids'].numpy()
+    assert (rv == valids.astype(bool)).mean() > 0.99
+    both = rv & valids.astype(bool)
+    np.testing.assert_allclose(xs[both], ref['result'].squeeze(-1).numpy()[both], atol=2e-5)
+    np.testing.assert_allclose(Ts[both], ref['transforms'][:, :3, :].reshape(N, 12).numpy()[both], atol=5e-4)
