@@ -33,7 +33,7 @@ class ArahStats(C.Structure):
 
 
 EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'arah_set_frame', 'arah_set_profiling', 'arah_render',
-           'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin', 'arah_debug_umma_gemm']
+           'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin', 'arah_debug_umma_gemm', 'arah_debug_phase_clocks']
 
 _lib = None
 
@@ -63,6 +63,7 @@ def lib():
     L.arah_eval_sdf.argtypes = [C.c_void_p, FP, C.c_int32, FP, FP, FP, C.c_void_p]
     L.arah_eval_skin.argtypes = [C.c_void_p, FP, C.c_int32, FP, FP, C.c_void_p]
     L.arah_debug_umma_gemm.argtypes = [FP, FP, C.c_int32, C.c_int32, FP, C.c_int32, C.c_void_p]
+    L.arah_debug_phase_clocks.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
     _lib = L
     return L
 

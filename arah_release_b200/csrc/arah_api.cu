@@ -12,6 +12,7 @@
 #include "arah_corr_tc.cuh"
 #include "arah_shade_tc2.cuh"
 #include "arah_corr_tc2.cuh"
+#include "arah_shade_tc3.cuh"
 #include <stdlib.h>
 
 using namespace arah;
@@ -300,7 +301,7 @@ struct ArahHandle {
     int last_P = 0;
     int64_t pack_launches = 0;
     bool profile = false, profiled = false;
-    int tc_engine = 2;
+    int tc_engine = 3;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -351,7 +352,7 @@ static int ensure_workspace(ArahHandle* h, int P) {
     const size_t o_conv = take(cap), o_dist = take(cap * 4), o_pn = take(cap * 12);
     const size_t o_z = take(PS * 4), o_xn = take(PS * 12), o_T = take(PS * 48), o_sc = take(PS), o_sdf = take(PS * 4), o_rgb = take(PS * 12);
     const size_t o_cs = take(PS * sizeof(BroydenState<3>));
-    const size_t o_la = take(PS * 4), o_lb = take(PS * 4), o_on = take(PS * 4), o_sh = take(PS * 4), o_ctr = take(C_COUNT * 4 + 64);
+    const size_t o_la = take(PS * 4), o_lb = take(PS * 4), o_on = take(PS * 4), o_sh = take(PS * 4), o_ctr = take(C_COUNT * 4 + 64), o_clk = take(16 * 8);
     if (h->ws.ensure(off) != 0) return -1;
     char* b = static_cast<char*>(h->ws.p);
     Work& w = h->w;
@@ -362,6 +363,7 @@ static int ensure_workspace(ArahHandle* h, int P) {
     w.smp_conv = (uint8_t*)(b + o_sc); w.smp_sdf = (float*)(b + o_sdf); w.smp_rgb = (float*)(b + o_rgb);
     w.corr_state = (BroydenState<3>*)(b + o_cs); w.listA = (int*)(b + o_la); w.listB = (int*)(b + o_lb);
     w.on_list = (int*)(b + o_on); w.shade_list = (int*)(b + o_sh); w.counters = (int*)(b + o_ctr);
+    w.phase_clk = (unsigned long long*)(b + o_clk);
     h->cap_rays = cap;
     return 0;
 }
@@ -384,7 +386,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     ArahHandle* h = new ArahHandle();
     h->cfg = *cfg;
     h->n_sms = prop.multiProcessorCount;
-    if (const char* e = getenv("ARAH_TC_ENGINE")) h->tc_engine = atoi(e) == 1 ? 1 : 2;
+    if (const char* e = getenv("ARAH_TC_ENGINE")) { const int v = atoi(e); h->tc_engine = (v >= 1 && v <= 3) ? v : 3; }
     memset(&h->w, 0, sizeof(h->w));
     if (alloc_arena(h) != 0) { delete h; return fail(ARAH_ENOMEM, "weight arena allocation failed"); }
     if (ensure_workspace(h, cfg->max_rays > 0 ? cfg->max_rays : 4096) != 0) { h->arena.release(); delete h; return fail(ARAH_ENOMEM, "workspace allocation failed"); }
@@ -402,6 +404,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc_smem_bytes()));
     CU(cudaFuncSetAttribute(k_shade_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc2_smem_bytes()));
     CU(cudaFuncSetAttribute(k_corr_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc2_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
@@ -572,6 +575,8 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     const bool prof = h->profile;
     h->profiled = prof;
     CU(cudaMemsetAsync(w.counters, 0, C_COUNT * 4, st));
+    Work wk = w;                      // kernels get the phase-clock pointer only while profiling
+    if (prof) CU(cudaMemsetAsync(w.phase_clk, 0, 16 * 8, st)); else wk.phase_clk = nullptr;
     if (prof) CU(cudaEventRecord(h->ev[0], st));
     k_trace_begin<<<cdiv(P, 256), 256, 0, st>>>(w); L();
     const unsigned g_ray_tiles = grid_min(cdiv(P, TM), (size_t)nsm);
@@ -583,7 +588,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     if (prof) CU(cudaEventRecord(h->ev[1], st));
     k_iso_prepare<<<cdiv(P, 256), 256, 0, st>>>(w); L();
     k_iso_init<<<grid_min(cdiv(P, TM / 4), (size_t)nsm), 256, sm_sdf, st>>>(fp, w); L();
-    for (int it = 0; it < BROYDEN_ITERS; ++it) { k_iso_iter<<<g_ray_tiles, 256, sm_sdf, st>>>(fp, w, it); L(); }
+    for (int it = 0; it < BROYDEN_ITERS; ++it) { k_iso_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it); L(); }
     if (prof) CU(cudaEventRecord(h->ev[2], st));
     k_trace_finish<<<cdiv(P, 128), 128, 0, st>>>(fp, w); L();
     const unsigned g_knn_s = grid_min(cdiv(PS, 512), (size_t)nsm);
@@ -592,7 +597,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
         const unsigned g_tc = grid_min(cdiv(PS, UM), (size_t)nsm);
         for (int it = -1; it < BROYDEN_ITERS; ++it) {
-            if (h->tc_engine == 2) k_corr_tc2<<<g_tc, TC_THREADS, corr_tc2_smem_bytes(), st>>>(fp, h->sk, w, it);
+            if (h->tc_engine >= 2) k_corr_tc2<<<g_tc, TC_THREADS, corr_tc2_smem_bytes(), st>>>(fp, h->sk, wk, it);
             else k_corr_tc<<<g_tc, 256, corr_tc_smem_bytes(), st>>>(fp, h->sk, w, it);
             L();
         }
@@ -601,7 +606,8 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     }
     if (prof) CU(cudaEventRecord(h->ev[3], st));
     if (h->cfg.shade_mode == ARAH_SHADE_TF32) {
-        if (h->tc_engine == 2) k_shade_tc2<<<grid_min(cdiv(PS, UM), (size_t)nsm), TC_THREADS, shade_tc2_smem_bytes(), st>>>(fp, h->tc, w);
+        if (h->tc_engine == 3) k_shade_tc3<<<grid_min(cdiv(PS, UM), (size_t)nsm), TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk);
+        else if (h->tc_engine == 2) k_shade_tc2<<<grid_min(cdiv(PS, UM), (size_t)nsm), TC_THREADS, shade_tc2_smem_bytes(), st>>>(fp, h->tc, w);
         else k_shade_tc<<<grid_min(cdiv(PS, UM), (size_t)nsm), 256, shade_tc_smem_bytes(), st>>>(fp, h->tc, w);
         L();
     }
@@ -689,6 +695,15 @@ extern "C" int arah_get_stats(ArahHandle* h, ArahStats* s, void* stream) {
         CU(cudaEventElapsedTime(&tot, h->ev[0], h->ev[5]));
         s->ms_trace = ms[0]; s->ms_iso = ms[1]; s->ms_sample_corr = ms[2]; s->ms_shade = ms[3]; s->ms_composite = ms[4]; s->ms_total = tot;
     }
+    return ARAH_OK;
+}
+
+extern "C" int arah_debug_phase_clocks(ArahHandle* h, uint64_t* out16, void* stream) {
+    if (!h || !out16) return fail(ARAH_EINVAL, "null argument");
+    memset(out16, 0, 16 * 8);
+    if (!h->rendered || !h->profiled || h->last_P == 0) return ARAH_OK;
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    CU(cudaMemcpy(out16, h->w.phase_clk, 16 * 8, cudaMemcpyDeviceToHost));
     return ARAH_OK;
 }
 

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_corr_tc2(FrameParams fp, Skin
     auto handoff = [&]() { tmem_st_wait(); tc_fence_before(); cta_sync_compute(); tc_fence_after(); };
     const int* list = (iter <= 0) ? nullptr : ((iter & 1) ? w.listB : w.listA);
     int* next = (iter & 1) ? w.listA : w.listB;
+    PhaseClk pc; pc.start((tid == 32) ? w.phase_clk : nullptr);
     for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
         int id = -1;
         BroydenState<3> st;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_corr_tc2(FrameParams fp, Skin
             xs[tid][0] = xn[0]; xs[tid][1] = xn[1]; xs[tid][2] = xn[2]; xs[tid][3] = 0.f;
         }
         cta_sync_compute();
+        pc.mark(0);                                   // gather + advance
         {   // layer 0 (3 -> 128) on the FP32 pipe, 64 columns per thread
             const float x = xs[r][0], y = xs[r][1], z = xs[r][2];
 #pragma unroll 1
@@ -81,12 +83,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_corr_tc2(FrameParams fp, Skin
             }
         }
         handoff();
+        pc.mark(1);                                   // layer 0
         for (int l = 1; l < 4; ++l) {
             if (tid == 0) tcring_mma_layer_x3(rg, cp, tbase, tbase + 128u, 4, 128, tbase + 256u, done_bar);
             mbar_wait(done_bar, done_par);
             done_par ^= 1u;
             __syncwarp();
             tc_fence_after();
+            pc.mark(2);                               // waiting for the layer's MMAs
 #pragma unroll 1
             for (int b = 0; b < 2; ++b) {
                 const int col0 = 64 * half + 32 * b;
@@ -97,6 +101,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_corr_tc2(FrameParams fp, Skin
                 a_tmem_store_split(tAhi + (uint32_t)col0, tAlo + (uint32_t)col0, v);
             }
             handoff();
+            pc.mark(3);                               // hidden-layer epilogue
         }
         if (tid == 0) tcring_mma_layer_x3(rg, cp, tbase, tbase + 128u, 4, 32, tbase + 256u, done_bar);
         mbar_wait(done_bar, done_par);
@@ -112,6 +117,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_corr_tc2(FrameParams fp, Skin
         tc_fence_before();
         cta_sync_compute();
         tc_fence_after();
+        pc.mark(4);                                   // output layer (MMA wait + logits)
         if (tid < UM) {
             bool active = false;
             if (id >= 0) {
@@ -150,6 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_corr_tc2(FrameParams fp, Skin
             }
         }
         cta_sync_compute();
+        pc.mark(5);                                   // per-point phase (hsoftmax, blend, Broyden, state I/O)
     }
     tc_fence_before();
     cta_sync_compute();

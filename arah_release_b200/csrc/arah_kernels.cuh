@@ -61,6 +61,14 @@ struct Work {
     uint8_t* out_mask;        // [P]
     float* out_points_cam;    // [P][3]
     float* out_wsum;          // [P]
+    unsigned long long* phase_clk;   // [16] debug: SM-clock cycles per kernel phase, accumulated by one thread per CTA (may be null)
+};
+
+// phase timer used by one designated thread per CTA: adds the cycles since the previous mark to slot `i`
+struct PhaseClk {
+    unsigned long long* dst; long long t;
+    __device__ __forceinline__ void start(unsigned long long* d) { dst = d; t = clock64(); }
+    __device__ __forceinline__ void mark(int i) { if (dst) { const long long n = clock64(); atomicAdd(dst + i, (unsigned long long)(n - t)); t = n; } }
 };
 
 // 128-bit copies of a state record (the struct is alignas(16) and a multiple of 16 bytes)
@@ -437,7 +445,7 @@ __global__ void __launch_bounds__(256, 1) k_iso_init(FrameParams fp, Work w) {
     }
 }
 
-__global__ void __launch_bounds__(256, 1) k_iso_iter(FrameParams fp, Work w, int iter) {
+__global__ void __launch_bounds__(256, 2) k_iso_iter(FrameParams fp, Work w, int iter) {
     extern __shared__ __align__(128) float smem[];
     const int n = w.counters[C_ISO + iter];
     if ((int)blockIdx.x * TM >= n) return;

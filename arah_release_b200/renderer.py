@@ -222,6 +222,11 @@ class ArahRenderer:
         check(_lib.lib().arah_get_stats(self._h, C.byref(s), self.stream))
         return s.as_dict()
 
+    def phase_clocks(self):
+        out = (C.c_uint64 * 16)()
+        check(_lib.lib().arah_debug_phase_clocks(self._h, out, self.stream))
+        return [int(v) for v in out]
+
     def eval_sdf(self, xn, grad=True, feat=False):
         xn = _f32c(xn, self.device).view(-1, 3)
         n = xn.shape[0]

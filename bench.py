@@ -225,6 +225,7 @@ def run_ours(args):
         clk.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     shade_ms, shade_flops, step_flops, stats_last = [], [], [], None
+    corr_ms, corr_flops = [], []
     for k in range(args.steps):
         flush.zero_()                                   # L2 flush between timed iterations (outside the event pair)
         ev[k][0].record()
@@ -234,7 +235,10 @@ def run_ours(args):
         shade_ms.append(st['ms_shade'])
         shade_flops.append(2.0 * st['shaded_samples'] * (2 * MAC_SDF + MAC_COL))
         step_flops.append(algorithmic_flops(st))
+        corr_ms.append(st['ms_sample_corr'])
+        corr_flops.append(2.0 * st['corr_skin_evals'] * MAC_SKIN)
         stats_last = st
+        phase_clk = r.phase_clocks()
     barrier()
     clocks = clk.stop() if rank == 0 else None
     t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
@@ -278,7 +282,7 @@ def run_ours(args):
     pk = peaks()
     ach = (sum(shade_flops) / max(sum(shade_ms), 1e-9)) / 1e9          # FLOP/ms -> TFLOP/s
     traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'k_shade_traffic.json')
+    tp = os.path.join(ROOT, 'profiles', 'k_shade_tc2_traffic.json' if r.shade_mode == 'tf32' else 'k_shade_traffic.json')
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get('dram_bytes_per_launch')
@@ -291,18 +295,27 @@ def run_ours(args):
         'config': {'workload': f'ZJU-377-like {args.size}x{args.size} novel-view render, fp32 (BASELINE configs[1])',
                    'rays_per_frame': P0, 'n_steps': f0.n_steps, 'near_far_samples': [f0.near_samples, f0.far_samples],
                    'parallelism': f'frames sharded over {args.gpus} GPU(s), 1 frame/rank/step', 'l2': '256 MB memset between timed steps',
+                   'precision': f'fp32 storage/accumulate; shading MLP operands {r.shade_mode}; root-finding skinning MLP {r.root_mode}; SDF in tracing/joint search fp32',
                    'timing': 'CUDA events on the launching stream, per step, summed; max over ranks'},
         'e2e': {'value': rays_all / t_e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'api': 'arah_set_frame(pose_on_host) + arah_render_host via IDHRNetwork host wrapper'},
         'gpu_launches': int((stats_last['kernel_launches'] + stats_last['pack_launches']) * args.steps),
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': 'k_shade (SDF fwd + reverse-mode grad + colour MLP, fp32 FFMA tiles)',
+        'roofline': {'bound': 'tensor', 'kernel': f'k_shade_tc2 (SDF fwd + reverse-mode grad + colour MLP; tcgen05 {r.shade_mode} operands, fp32 accumulate in TMEM)'
+                     if r.shade_mode == 'tf32' else 'k_shade (fp32 FFMA tiles)',
                      'achieved': ach, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf_sustained'],
                      'peak_source': pk['src'] + ' bf16 cuBLAS sustained (MEASURED_PEAKS.json)', 'traffic': traffic,
                      'algorithmic_flops_per_launch': float(np.mean(shade_flops)), 'ms_per_launch': float(np.mean(shade_ms)),
                      'kernel_share_of_step': float(sum(shade_ms) / (1e3 * t_dev)),
                      'whole_step_tflops': float(sum(step_flops) / t_dev / 1e12)},
+        'roofline_corr': {'bound': 'tensor', 'kernel': f'k_knn_samples + 51 x k_corr_tc2 (per-sample correspondence search; skinning MLP {r.root_mode}: 3 TF32 products count as 1 useful)',
+                          'achieved': (sum(corr_flops) / max(sum(corr_ms), 1e-9)) / 1e9, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
+                          'frac': (sum(corr_flops) / max(sum(corr_ms), 1e-9)) / 1e9 / pk['tf_sustained'], 'ms_per_step': float(np.mean(corr_ms)),
+                          'share_of_step': float(sum(corr_ms) / (1e3 * t_dev))},
         'stages_ms_last_step': {k: stats_last[k] for k in ('ms_trace', 'ms_iso', 'ms_sample_corr', 'ms_shade', 'ms_composite', 'ms_total')},
+        'phase_cycles_last_step': {'corr': phase_clk[:6], 'shade': phase_clk[8:15],
+                                   'note': 'SM cycles of one thread per CTA summed over CTAs/launches: corr = [gather, layer0, mma_wait, epilogue, out_layer, per_point]; '
+                                           'shade = [setup+layer0, fwd_wait, fwd_epi, rev_wait, rev_epi, colour_inputs, colour_mlp]'},
         'counters_last_step': {k: stats_last[k] for k in ('rays', 'trace_sdf_evals', 'iso_rays', 'iso_g_evals', 'on_samples', 'corr_skin_evals',
                                                            'shaded_samples', 'hit_rays', 'vol_rays')},
     }
