@@ -13,6 +13,8 @@
 #include "arah_shade_tc2.cuh"
 #include "arah_corr_tc2.cuh"
 #include "arah_shade_tc3.cuh"
+#include "arah_corr_tc3.cuh"
+#include "arah_sdf3x.cuh"
 #include <stdlib.h>
 
 using namespace arah;
@@ -293,6 +295,9 @@ struct ArahHandle {
     ShadeTC tc;
     float* tc_skin_hid[3]; float* tc_skin_out;
     SkinTC sk;
+    float* tc_sdf3x[5];
+    SdfTC sd;
+    int trace_tc = 1;
     // workspace
     DevBuf ws, scratch, io_in, io_out;
     Work w;
@@ -326,6 +331,7 @@ static int alloc_arena(ArahHandle* h) {
     reg(&h->tc_F, 6 * 256); reg(&h->tc_G, 6 * 256);
     reg(&h->tc_col0, 10 * 256 * 32); reg(&h->tc_col1, 256 * 256); reg(&h->tc_col2, 8 * 128 * 32); reg(&h->tc_col3b, 4 * 256 * 32);
     reg(&h->tc_col3a, 10 * 256 * 32); reg(&h->tc_col4, 256 * 256);
+    for (int l = 0; l < 5; ++l) reg(&h->tc_sdf3x[l], 8 * 256 * 32 * 2);
     for (int l = 0; l < 3; ++l) reg(&h->tc_skin_hid[l], 4 * 128 * 32 * 2);
     reg(&h->tc_skin_out, 4 * 32 * 32 * 2);
     reg(&h->col_b[0], 256); reg(&h->col_b[1], 256); reg(&h->col_b[2], 256); reg(&h->col_b[3], 256); reg(&h->col_b[4], 256); reg(&h->col_b[5], 64);
@@ -405,6 +411,10 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_shade_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc2_smem_bytes()));
     CU(cudaFuncSetAttribute(k_corr_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc2_smem_bytes()));
     CU(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_corr_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_iso_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
+    if (const char* e = getenv("ARAH_TRACE_TC")) h->trace_tc = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
@@ -505,6 +515,7 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
         for (int l = 1; l < 4; ++l) { k_pack_umma_x3<<<cdiv((size_t)4 * 128 * 32, 256), 256, 0, st>>>(f->skin_W[l], 128, h->tc_skin_hid[l - 1], 128, 128, 128, 4); ++npack; }
         k_pack_umma_x3<<<cdiv((size_t)4 * 32 * 32, 256), 256, 0, st>>>(f->skin_W[4], 128, h->tc_skin_out, 25, 32, 128, 4); ++npack;
+        for (int l = 1; l < 6; ++l) { k_pack_umma_x3<<<cdiv((size_t)8 * 256 * 32, 256), 256, 0, st>>>(f->sdf_W[l], 256, h->tc_sdf3x[l - 1], 256, 256, 256, 8); ++npack; }
     }
     // pose buffers
     const cudaMemcpyKind kind = f->pose_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
@@ -542,6 +553,10 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     tc.col0 = h->tc_col0; tc.col1 = h->tc_col1; tc.col2 = h->tc_col2; tc.col3b = h->tc_col3b; tc.col3a = h->tc_col3a; tc.col4 = h->tc_col4;
     tc.col_W5 = h->col_W5;
     for (int l = 0; l < 6; ++l) tc.col_b[l] = h->col_b[l];
+    SdfTC& sd = h->sd;
+    sd.Wt0 = h->sdf_Wt[0]; sd.freq = h->sdf_freq; sd.phase = h->sdf_phase; sd.w6 = h->sdf_w6; sd.b6 = b6;
+    for (int l = 0; l < 6; ++l) sd.b[l] = h->sdf_b[l];
+    for (int l = 0; l < 5; ++l) sd.hid[l] = h->tc_sdf3x[l];
     SkinTC& sk = h->sk;
     sk.Wt0 = h->skin_Wt[0];
     for (int l = 0; l < 5; ++l) sk.b[l] = h->skin_b[l];
@@ -583,12 +598,22 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     const unsigned g_knn_rays = grid_min(cdiv(P, 512), (size_t)nsm);
     for (int it = 0; it < TRACE_ITERS; ++it) {
         k_knn_rays<<<g_knn_rays, 512, sm_knn, st>>>(fp, h->knn, w, it); L();
-        k_trace_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it); L();
+        if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc)
+            k_trace_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, w, it);
+        else
+            k_trace_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it);
+        L();
     }
     if (prof) CU(cudaEventRecord(h->ev[1], st));
     k_iso_prepare<<<cdiv(P, 256), 256, 0, st>>>(w); L();
     k_iso_init<<<grid_min(cdiv(P, TM / 4), (size_t)nsm), 256, sm_sdf, st>>>(fp, w); L();
-    for (int it = 0; it < BROYDEN_ITERS; ++it) { k_iso_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it); L(); }
+    for (int it = 0; it < BROYDEN_ITERS; ++it) {
+        if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc)
+            k_iso_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, h->sk, w, it);
+        else
+            k_iso_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it);
+        L();
+    }
     if (prof) CU(cudaEventRecord(h->ev[2], st));
     k_trace_finish<<<cdiv(P, 128), 128, 0, st>>>(fp, w); L();
     const unsigned g_knn_s = grid_min(cdiv(PS, 512), (size_t)nsm);
@@ -597,7 +622,8 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
         const unsigned g_tc = grid_min(cdiv(PS, UM), (size_t)nsm);
         for (int it = -1; it < BROYDEN_ITERS; ++it) {
-            if (h->tc_engine >= 2) k_corr_tc2<<<g_tc, TC_THREADS, corr_tc2_smem_bytes(), st>>>(fp, h->sk, wk, it);
+            if (h->tc_engine >= 3) k_corr_tc3<<<g_tc, TC3_THREADS, corr_tc3_smem_bytes(), st>>>(fp, h->sk, wk, it);
+            else if (h->tc_engine == 2) k_corr_tc2<<<g_tc, TC_THREADS, corr_tc2_smem_bytes(), st>>>(fp, h->sk, wk, it);
             else k_corr_tc<<<g_tc, 256, corr_tc_smem_bytes(), st>>>(fp, h->sk, w, it);
             L();
         }

@@ -1,0 +1,403 @@
+// arah_sdf3x.cuh — the 256-wide FiLM-SIREN SDF on tcgen05 in split precision (3xTF32 ~ fp32) for the ROOT-FINDING
+// kernels (sphere tracing k_trace_tc3, joint search k_iso_tc3), engine v3 roles (8 epilogue warps, TMA producer warp,
+// MMA-issuer warp, per-chunk ready barriers).
+//
+// A 256-wide layer needs A_hi (256 cols) + A_lo (256 cols) + D (256 cols) = 768 TMEM columns, TMEM has 512.  So:
+//   A_hi : TMEM, ping-pongs with D between the two 256-column regions (in-place D -> A_hi, as in k_shade_tc3),
+//   A_lo : shared memory, 8 K-chunks x 16 KB, SWIZZLE_128B K-major (the SS form of tcgen05.mma reads it),
+//   B    : per K-chunk two 32 KB images [B_hi], [B_lo] through a 3-slot ring,
+//   D   += A_lo(smem).B_hi + A_hi(tmem).B_hi        (when B_hi(c) has landed)
+//   D   += A_hi(tmem).B_lo                          (when B_lo(c) has landed).
+// Shared memory is exactly full (128 KB + 96 KB + 3 KB), so the dynamic segment must start 1024-byte aligned (checked).
+// The activation math is the fp32 FFMA kernels' own (sinf(30 (f (acc + b) + phi)), precise sinf): root finding keeps
+// resolving 1e-5 m.
+#pragma once
+#include "arah_shade_tc3.cuh"
+#include "arah_corr_tc3.cuh"
+
+namespace arah {
+
+struct SdfTC {
+    const float* Wt0;        // [3][256]
+    const float* b[6];
+    const float* freq;       // [6][256]
+    const float* phase;      // [6][256]
+    const float* hid[5];     // layers 1..5: 8 chunks x [hi 32 KB | lo 32 KB]
+    const float* w6;
+    float b6;
+};
+
+constexpr int S3_NSLOTS = 3;
+constexpr int S3_ALO_FLOATS = 8 * A_CHUNK_FLOATS;              // 128 KB
+constexpr int S3_RING_FLOATS = S3_NSLOTS * RING_SLOT_FLOATS;   // 96 KB
+
+struct S3Bars { uint64_t* full; uint64_t* empty; uint64_t* ready; uint64_t* done; };
+
+// ---- producer: one tile's worth of SDF weight items (5 layers x 8 chunks x {hi, lo}) ----------------------------------
+__device__ __forceinline__ void s3_produce_item(float* ring, const S3Bars& bar, uint32_t& slot, uint32_t& use, const void* src, uint32_t bytes) {
+    if (use > 0) mbar_wait(&bar.empty[slot], (use - 1) & 1u);
+    mbar_expect_tx(&bar.full[slot], bytes);
+    bulk_g2s(ring + slot * RING_SLOT_FLOATS, src, bytes, &bar.full[slot]);
+    if (++slot == S3_NSLOTS) { slot = 0; ++use; }
+}
+__device__ __forceinline__ void s3_produce_sdf(float* ring, const S3Bars& bar, uint32_t& slot, uint32_t& use, const SdfTC& sd) {
+    for (int l = 0; l < 5; ++l)
+        for (int i = 0; i < 8; ++i) {
+            const int c = seg_chunk(0, i);
+            const char* p = reinterpret_cast<const char*>(sd.hid[l]) + (size_t)c * 65536;
+            s3_produce_item(ring, bar, slot, use, p, 32768u);
+            s3_produce_item(ring, bar, slot, use, p + 32768, 32768u);
+        }
+}
+// ---- MMA issuer: one tile's SDF layers -----------------------------------------------------------------------------------
+__device__ __forceinline__ void s3_mma_sdf(float* ring, const float* A_lo, const S3Bars& bar, uint32_t& slot, uint32_t& use, uint32_t& rpar, uint32_t tbase) {
+    const uint32_t idesc = umma_idesc_tf32(UM, 256);
+    for (int L = 1; L <= 5; ++L) {
+        const uint32_t ta = tbase + 256u * ((L - 1) & 1), td = tbase + 256u * (L & 1);
+        for (int i = 0; i < 8; ++i) {
+            const int c = seg_chunk(0, i);
+            mbar_wait(&bar.ready[c], (rpar >> c) & 1u);
+            rpar ^= (1u << c);
+            mbar_wait(&bar.full[slot], use & 1u);                 // B_hi(c)
+            tc_fence_after();
+            uint32_t b_addr = smem_u32(ring + slot * RING_SLOT_FLOATS);
+            const uint32_t al = smem_u32(A_lo + c * A_CHUNK_FLOATS);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                umma_tf32(td, umma_smem_desc_sw128(al + k * 32), umma_smem_desc_sw128(b_addr + k * 32), idesc, (i > 0 || k > 0) ? 1u : 0u);   // A_lo . B_hi
+                umma_tf32_ts(td, ta + (uint32_t)(c * UK + k * 8), umma_smem_desc_sw128(b_addr + k * 32), idesc, 1u);                            // A_hi . B_hi
+            }
+            umma_commit(&bar.empty[slot]);
+            if (++slot == S3_NSLOTS) { slot = 0; ++use; }
+            mbar_wait(&bar.full[slot], use & 1u);                 // B_lo(c)
+            tc_fence_after();
+            b_addr = smem_u32(ring + slot * RING_SLOT_FLOATS);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_tf32_ts(td, ta + (uint32_t)(c * UK + k * 8), umma_smem_desc_sw128(b_addr + k * 32), idesc, 1u);                            // A_hi . B_lo
+            umma_commit(&bar.empty[slot]);
+            if (++slot == S3_NSLOTS) { slot = 0; ++use; }
+        }
+        umma_commit(bar.done);
+    }
+}
+// ---- compute warps: SDF of the 128 rows whose normalised points sit in xs[r][0..2]; returns this thread's partial of
+//      w6 . h5 over its 128 columns (caller adds the two halves and b6).  Must be called by all 8 compute warps.
+__device__ __forceinline__ float s3_compute_sdf(const SdfTC& sd, const float* xs3, float* A_lo, const S3Bars& bar, uint32_t& done_par, uint32_t tbase) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = warp >> 2, r = 32 * q + lane;
+    const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
+    auto put = [&](int reg, int chunk, const float (&v)[32]) {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { hi[i] = tf32_rn(v[i]); lo[i] = v[i] - hi[i]; }
+        tmem_st32(trow + 256u * reg + 32u * chunk, hi);
+        a_store_chunk(A_lo, r, chunk, lo);                         // rounds lo to TF32
+        fence_async_smem();
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar.ready[chunk]);
+    };
+    {
+        const float x = xs3[3 * r], y = xs3[3 * r + 1], z = xs3[3 * r + 2];
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+            const int col0 = 128 * half + 32 * b;
+            float h[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int cc = col0 + i;
+                const float a = fmaf(__ldg(sd.Wt0 + 512 + cc), z, fmaf(__ldg(sd.Wt0 + 256 + cc), y, __ldg(sd.Wt0 + cc) * x));
+                h[i] = sinf(30.0f * (__ldg(sd.freq + cc) * (a + __ldg(sd.b[0] + cc)) + __ldg(sd.phase + cc)));
+            }
+            put(0, col0 / 32, h);
+        }
+    }
+    float dot = 0.f;
+    for (int L = 1; L <= 5; ++L) {
+        mbar_wait(bar.done, done_par);
+        done_par ^= 1u;
+        __syncwarp();
+        tc_fence_after();
+        const int dreg = L & 1;
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+            const int col0 = 128 * half + 32 * b;
+            float v[32];
+            tmem_ld32(trow + 256u * dreg + (uint32_t)col0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int cc = L * 256 + col0 + i;
+                v[i] = sinf(30.0f * (__ldg(sd.freq + cc) * (v[i] + __ldg(sd.b[L] + col0 + i)) + __ldg(sd.phase + cc)));
+            }
+            if (L < 5) put(dreg, col0 / 32, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dot = fmaf(v[i], __ldg(sd.w6 + col0 + i), dot);
+            }
+        }
+    }
+    return dot;
+}
+
+// =====================================================================================================================
+// k_trace_tc3: one sphere-tracing step (ray_tracing.py:198-241) for the active rays, 128 rays per tile.
+__host__ __device__ constexpr size_t trace_tc3_smem_bytes() { return (size_t)(S3_ALO_FLOATS + S3_RING_FLOATS + UM * 3 + 2 * UM) * 4 + 160; }
+
+__global__ void __launch_bounds__(TC3_THREADS, 1) k_trace_tc3(FrameParams fp, SdfTC sd, Work w, int iter) {
+    extern __shared__ __align__(1024) uint8_t raw_smem[];
+    const int n = w.counters[C_TRACE + iter];
+    if ((int)blockIdx.x * UM >= n) return;
+    if (smem_u32(raw_smem) & 1023u) __trap();                       // SWIZZLE_128B tiles need the segment 1024-aligned
+    float* A_lo = reinterpret_cast<float*>(raw_smem);
+    float* ring = A_lo + S3_ALO_FLOATS;
+    float* xs3 = ring + S3_RING_FLOATS;                             // [128][3]
+    float (*part)[UM] = reinterpret_cast<float (*)[UM]>(xs3 + UM * 3);   // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs3 + UM * 3 + 2 * UM);
+    S3Bars bar; bar.full = bars; bar.empty = bars + S3_NSLOTS; bar.ready = bars + 2 * S3_NSLOTS; bar.done = bar.ready + 8;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar.done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < S3_NSLOTS; ++i) { mbar_init(&bar.full[i], 1); mbar_init(&bar.empty[i], 1); }
+        for (int i = 0; i < 8; ++i) mbar_init(&bar.ready[i], 4);
+        mbar_init(bar.done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tslot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot;
+    const int ntiles = (n + UM - 1) / UM;
+    if (warp == 8) {
+        if (lane == 0) { uint32_t slot = 0, use = 0; for (int t = blockIdx.x; t < ntiles; t += gridDim.x) s3_produce_sdf(ring, bar, slot, use, sd); }
+        return;
+    }
+    if (warp == 9) {
+        if (lane == 0) { uint32_t slot = 0, use = 0, rpar = 0; for (int t = blockIdx.x; t < ntiles; t += gridDim.x) s3_mma_sdf(ring, A_lo, bar, slot, use, rpar, tbase); }
+        return;
+    }
+    const int half = warp >> 2, r = 32 * (warp & 3) + lane;
+    uint32_t done_par = 0;
+    const int* list = (iter & 1) ? w.listB : w.listA;
+    int* next = (iter & 1) ? w.listA : w.listB;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int ray = -1;
+        if (tid < UM) {
+            const int i = tile * UM + tid;
+            float xn[3] = {0.f, 0.f, 0.f};
+            if (i < n) { ray = list[i]; const RayCur& c = w.ray_cur[ray]; xn[0] = c.xn[0]; xn[1] = c.xn[1]; xn[2] = c.xn[2]; }
+            xs3[3 * tid] = xn[0]; xs3[3 * tid + 1] = xn[1]; xs3[3 * tid + 2] = xn[2];
+        }
+        cta_sync_compute();
+        const float dot = s3_compute_sdf(sd, xs3, A_lo, bar, done_par, tbase);
+        part[half][r] = dot;
+        cta_sync_compute();
+        if (tid < UM) {                                             // marching logic, identical to k_trace_iter
+            bool still = false;
+            if (ray >= 0) {
+                const float sdf = sdf_to_metres(part[0][tid] + part[1][tid] + sd.b6, fp.cmin, fp.cmax);
+                float t = w.ray_t[ray];
+                const float far_ = w.near_far[2 * ray + 1];
+                const float sm = fminf(fmaxf(sdf, -0.1f), 0.1f);
+                bool diverge = false;
+                if (fabsf(sm) > CVG_THRESH && fabsf(sdf) < 1e6f) { t = t + sm; diverge = t >= far_; w.ray_t[ray] = t; }
+                still = !(fabsf(sdf) <= CVG_THRESH || diverge);
+                w.ray_flags[ray] = (still ? 1 : 0) | (diverge ? 2 : 0);
+            }
+            if (iter + 1 < TRACE_ITERS) warp_append(still, ray, next, &w.counters[C_TRACE + iter + 1]);
+            warp_stat_add(ray >= 0 ? 1 : 0, &w.counters[C_STAT_TRACE_EVALS]);
+        }
+        cta_sync_compute();
+    }
+    tc_fence_before();
+    cta_sync_compute();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace arah
+
+namespace arah {
+
+// ---- skinning MLP (3xTF32) on the same 3-slot ring / barrier set, for the joint-search kernel -----------------------------
+// TMEM: X hi [0,128) | lo [128,256), accumulators ping-pong Da = [256,384) / Db = [384,512) (as k_corr_tc3).
+__device__ __forceinline__ void s3_produce_skin(float* ring, const S3Bars& bar, uint32_t& slot, uint32_t& use, const SkinTC& sk) {
+    for (int s = 0; s < 4; ++s) {
+        const char* wsrc = reinterpret_cast<const char*>((s < 3) ? sk.hid[s] : sk.out);
+        const uint32_t bytes = (s < 3) ? 32768u : 8192u;
+        for (int i = 0; i < 4; ++i) s3_produce_item(ring, bar, slot, use, wsrc + (size_t)seg_chunk(1, i) * bytes, bytes);
+    }
+}
+__device__ __forceinline__ void s3_mma_skin(float* ring, const S3Bars& bar, uint32_t& slot, uint32_t& use, uint32_t& rpar, uint32_t tbase) {
+    for (int s = 0; s < 4; ++s) {
+        const int N = (s < 3) ? 128 : 32;
+        const uint32_t idesc = umma_idesc_tf32(UM, N);
+        const uint32_t td = tbase + ((s & 1) ? 384u : 256u);
+        for (int i = 0; i < 4; ++i) {
+            const int c = seg_chunk(1, i);
+            mbar_wait(&bar.ready[c], (rpar >> c) & 1u);
+            rpar ^= (1u << c);
+            mbar_wait(&bar.full[slot], use & 1u);
+            tc_fence_after();
+            const uint32_t bh = smem_u32(ring + slot * RING_SLOT_FLOATS), bl = bh + (uint32_t)N * UK * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t col = (uint32_t)(c * UK + k * 8), ko = k * 32;
+                umma_tf32_ts(td, tbase + 128u + col, umma_smem_desc_sw128(bh + ko), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                umma_tf32_ts(td, tbase + col, umma_smem_desc_sw128(bl + ko), idesc, 1u);
+                umma_tf32_ts(td, tbase + col, umma_smem_desc_sw128(bh + ko), idesc, 1u);
+            }
+            umma_commit(&bar.empty[slot]);
+            if (++slot == S3_NSLOTS) { slot = 0; ++use; }
+        }
+        umma_commit(bar.done);
+    }
+}
+// compute warps: logits[r][0..31] for the 128 rows in xs3
+__device__ __forceinline__ void s3_compute_skin(const SkinTC& sk, const float* xs3, const S3Bars& bar, uint32_t& done_par, uint32_t tbase, float (*logits)[32]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = warp >> 2, r = 32 * q + lane;
+    const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
+    auto put = [&](int chunk, const float (&v)[32]) {
+        a_tmem_store_split(trow + 32u * chunk, trow + 128u + 32u * chunk, v);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar.ready[chunk]);
+    };
+    auto wait_done = [&]() { mbar_wait(bar.done, done_par); done_par ^= 1u; __syncwarp(); tc_fence_after(); };
+    {
+        const float x = xs3[3 * r], y = xs3[3 * r + 1], z = xs3[3 * r + 2];
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+            const int col0 = 64 * half + 32 * b;
+            float h[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int cc = col0 + i;
+                h[i] = softplus100_fast(fmaf(__ldg(sk.Wt0 + 256 + cc), z, fmaf(__ldg(sk.Wt0 + 128 + cc), y, __ldg(sk.Wt0 + cc) * x)) + __ldg(sk.b[0] + cc));
+            }
+            put(col0 / 32, h);
+        }
+    }
+    for (int l = 1; l < 4; ++l) {
+        wait_done();
+        const uint32_t tD = trow + ((l & 1) ? 256u : 384u);
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+            const int col0 = 64 * half + 32 * b;
+            float v[32];
+            tmem_ld32(tD + (uint32_t)col0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = softplus100_fast(v[i] + __ldg(sk.b[l] + col0 + i));
+            put(col0 / 32, v);
+        }
+    }
+    wait_done();
+    if (half == 0) {
+        float v[32];
+        tmem_ld32(trow + 384u, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) logits[r][i] = v[i] + __ldg(sk.b[4] + i);
+    }
+    tc_fence_before();
+}
+
+// =====================================================================================================================
+// k_iso_tc3: one joint-search Broyden step (root_finding_utils.py:426-461 + broyden.py:47-76), 128 rays per tile:
+// skinning MLP then SDF, both 3xTF32; residual, Jacobian update and bookkeeping fp32 as in k_iso_iter.
+__global__ void __launch_bounds__(TC3_THREADS, 1) k_iso_tc3(FrameParams fp, SdfTC sd, SkinTC sk, Work w, int iter) {
+    extern __shared__ __align__(1024) uint8_t raw_smem[];
+    const int n = w.counters[C_ISO + iter];
+    if ((int)blockIdx.x * UM >= n) return;
+    if (smem_u32(raw_smem) & 1023u) __trap();
+    float* A_lo = reinterpret_cast<float*>(raw_smem);
+    float (*logits)[32] = reinterpret_cast<float (*)[32]>(A_lo);        // aliases A_lo: only alive between the two MLPs
+    float* ring = A_lo + S3_ALO_FLOATS;
+    float* xs3 = ring + S3_RING_FLOATS;
+    float (*part)[UM] = reinterpret_cast<float (*)[UM]>(xs3 + UM * 3);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs3 + UM * 3 + 2 * UM);
+    S3Bars bar; bar.full = bars; bar.empty = bars + S3_NSLOTS; bar.ready = bars + 2 * S3_NSLOTS; bar.done = bar.ready + 8;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar.done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < S3_NSLOTS; ++i) { mbar_init(&bar.full[i], 1); mbar_init(&bar.empty[i], 1); }
+        for (int i = 0; i < 8; ++i) mbar_init(&bar.ready[i], 4);
+        mbar_init(bar.done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tslot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot;
+    const int ntiles = (n + UM - 1) / UM;
+    if (warp == 8) {
+        if (lane == 0) {
+            uint32_t slot = 0, use = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) { s3_produce_skin(ring, bar, slot, use, sk); s3_produce_sdf(ring, bar, slot, use, sd); }
+        }
+        return;
+    }
+    if (warp == 9) {
+        if (lane == 0) {
+            uint32_t slot = 0, use = 0, rpar = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) { s3_mma_skin(ring, bar, slot, use, rpar, tbase); s3_mma_sdf(ring, A_lo, bar, slot, use, rpar, tbase); }
+        }
+        return;
+    }
+    const int half = warp >> 2, r = 32 * (warp & 3) + lane;
+    uint32_t done_par = 0;
+    const int* list = (iter & 1) ? w.listB : w.listA;
+    int* next = (iter & 1) ? w.listA : w.listB;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int ray = -1;
+        BroydenState<4> st;
+        float dx[4];
+        if (tid < UM) {
+            const int i = tile * UM + tid;
+            float xn[3] = {0.f, 0.f, 0.f};
+            if (i < n) {
+                ray = list[i];
+                state_load(st, &w.iso_state[ray]);
+                broyden_advance<4>(st, dx);
+                normalize3(fp, st.x, xn);
+            }
+            xs3[3 * tid] = xn[0]; xs3[3 * tid + 1] = xn[1]; xs3[3 * tid + 2] = xn[2];
+        }
+        cta_sync_compute();
+        s3_compute_skin(sk, xs3, bar, done_par, tbase, logits);
+        cta_sync_compute();
+        tc_fence_after();
+        float lg[25];
+        if (tid < UM) {
+#pragma unroll
+            for (int k = 0; k < 25; ++k) lg[k] = logits[tid][k];
+        }
+        cta_sync_compute();                                            // logits consumed: A_lo may be overwritten
+        const float dot = s3_compute_sdf(sd, xs3, A_lo, bar, done_par, tbase);
+        part[half][r] = dot;
+        cta_sync_compute();
+        if (tid < UM) {
+            bool active = false;
+            if (ray >= 0) {
+                float g[4], T12[12], lg32[32];
+#pragma unroll
+                for (int k = 0; k < 25; ++k) lg32[k] = lg[k];
+                iso_residual(fp, w, ray, st.x, lg32, part[0][tid] + part[1][tid] + sd.b6, g, T12);
+                active = broyden_update<4>(st, dx, g, T12);
+                if (iter + 1 >= BROYDEN_ITERS) active = false;
+                state_store(&w.iso_state[ray], st);
+            }
+            if (iter + 1 < BROYDEN_ITERS) warp_append(active, ray, next, &w.counters[C_ISO + iter + 1]);
+            warp_stat_add(ray >= 0 ? 1 : 0, &w.counters[C_STAT_ISO_EVALS]);
+        }
+        cta_sync_compute();
+    }
+    tc_fence_before();
+    cta_sync_compute();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace arah

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
     const float* lp0 = prm + P_B;
     const float* lp1 = prm + P_B + 256;
 
-    PhaseClk pc; pc.start((tid == 32) ? w.phase_clk + 8 : nullptr);
+    PhaseClk pc; pc.start((tid == 32 && w.phase_clk) ? w.phase_clk + 8 : nullptr);
     for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
         int sl = -1;
         if (tid < UM) {
