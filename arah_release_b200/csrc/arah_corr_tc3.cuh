@@ -9,7 +9,7 @@
 namespace arah {
 
 __host__ __device__ constexpr size_t corr_tc3_smem_bytes() {
-    return (size_t)(TC3_NSLOTS * RING_SLOT_FLOATS + UM * 32 + UM * 4 + 24 * 16 + 3 * 128 + 5 * 128) * 4 + 512 + 1024;
+    return (size_t)(TC3_NSLOTS * RING_SLOT_FLOATS + 2 * UM * 32 + 2 * UM * 4 + 24 * 16 + 3 * 128 + 5 * 128) * 4 + 512 + 1024;
 }
 
 __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc3(FrameParams fp, SkinTC sk, Work w, int iter) {
@@ -19,9 +19,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc3(FrameParams fp, Ski
     const uint32_t base = (smem_u32(raw_smem) + 1023u) & ~1023u;
     float* sm = reinterpret_cast<float*>(raw_smem + (base - smem_u32(raw_smem)));
     float* ring = sm;
-    float (*logits)[32] = reinterpret_cast<float (*)[32]>(ring + TC3_NSLOTS * RING_SLOT_FLOATS);
-    float (*xs)[4] = reinterpret_cast<float (*)[4]>(reinterpret_cast<float*>(logits) + UM * 32);
-    float* sB = reinterpret_cast<float*>(xs) + UM * 4;            // bone transforms [24][16]
+    float (*logits)[32] = reinterpret_cast<float (*)[32]>(ring + TC3_NSLOTS * RING_SLOT_FLOATS);      // [2*UM][32]: tiles A, B
+    float (*xs)[4] = reinterpret_cast<float (*)[4]>(reinterpret_cast<float*>(logits) + 2 * UM * 32);  // [2*UM][4]
+    float* sB = reinterpret_cast<float*>(xs) + 2 * UM * 4;        // bone transforms [24][16]
     float* sW0 = sB + 24 * 16;                                    // layer-0 weights [3][128]
     float* sb = sW0 + 3 * 128;                                    // biases: 4 x 128 then 32  (sb + 128*l)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 5 * 128);
@@ -118,14 +118,19 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc3(FrameParams fp, Ski
     const int* list = (iter <= 0) ? nullptr : ((iter & 1) ? w.listB : w.listA);
     int* next = (iter & 1) ? w.listA : w.listB;
     PhaseClk pc; pc.start((tid == 32) ? w.phase_clk : nullptr);
-    for (int tile = blockIdx.x; tile < ntiles_mine; tile += gridDim.x) {
+    // Two tiles (A, B) per trip: their MLPs run back to back on all 8 warps, their per-point phases (state gather, hierarchical
+    // softmax, LBS blend, Broyden update) run CONCURRENTLY: warps 0-3 own tile A's points, warps 4-7 tile B's.
+    const int sub = tid >> 7, pt = tid & (UM - 1);                 // which tile of the pair / which point this thread owns
+    for (int tileA = blockIdx.x; tileA < ntiles_mine; tileA += 2 * gridDim.x) {
+        const int tileB = tileA + gridDim.x;
+        const int my_tile = sub ? tileB : tileA;
         int id = -1;
         BroydenState<3> st;
         float dx[3];
-        if (tid < UM) {
-            const int i = tile * UM + tid;
+        {
+            const int i = my_tile * UM + pt;
             float xn[3] = {0.f, 0.f, 0.f};
-            if (i < n) {
+            if (my_tile < ntiles_mine && i < n) {
                 id = list ? list[i] : i;
                 state_load(st, &w.corr_state[id]);
                 if (iter >= 0) broyden_advance<3>(st, dx);
@@ -135,48 +140,51 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc3(FrameParams fp, Ski
         }
         cta_sync_compute();
         pc.mark(0);
-        {   // layer 0 (3 -> 128) on the FP32 pipe
-            const float x = xs[r][0], y = xs[r][1], z = xs[r][2];
+        for (int t = 0; t < 2; ++t) {
+            if ((t ? tileB : tileA) >= ntiles_mine) break;
+            {   // layer 0 (3 -> 128) on the FP32 pipe
+                const float x = xs[t * UM + r][0], y = xs[t * UM + r][1], z = xs[t * UM + r][2];
 #pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
-                const int col0 = 64 * half + 32 * b;
-                float h[32];
+                for (int b = 0; b < 2; ++b) {
+                    const int col0 = 64 * half + 32 * b;
+                    float h[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int cc = col0 + i;
-                    h[i] = softplus100_fast(fmaf(sW0[256 + cc], z, fmaf(sW0[128 + cc], y, sW0[cc] * x)) + sb[cc]);
+                    for (int i = 0; i < 32; ++i) {
+                        const int cc = col0 + i;
+                        h[i] = softplus100_fast(fmaf(sW0[256 + cc], z, fmaf(sW0[128 + cc], y, sW0[cc] * x)) + sb[cc]);
+                    }
+                    a_put(col0 / 32, h);
                 }
-                a_put(col0 / 32, h);
             }
-        }
-        pc.mark(1);
-        for (int l = 1; l < 4; ++l) {
-            wait_done();
-            pc.mark(2);
-            const uint32_t tD = trow + ((l & 1) ? 256u : 384u);          // segment l-1: D = Da for even index
+            pc.mark(1);
+            for (int l = 1; l < 4; ++l) {
+                wait_done();
+                pc.mark(2);
+                const uint32_t tD = trow + ((l & 1) ? 256u : 384u);
 #pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
-                const int col0 = 64 * half + 32 * b;
-                float v[32];
-                tmem_ld32(tD + (uint32_t)col0, v);
+                for (int b = 0; b < 2; ++b) {
+                    const int col0 = 64 * half + 32 * b;
+                    float v[32];
+                    tmem_ld32(tD + (uint32_t)col0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = softplus100_fast(v[i] + sb[128 * l + col0 + i]);
-                a_put(col0 / 32, v);
+                    for (int i = 0; i < 32; ++i) v[i] = softplus100_fast(v[i] + sb[128 * l + col0 + i]);
+                    a_put(col0 / 32, v);
+                }
+                pc.mark(3);
             }
-            pc.mark(3);
-        }
-        wait_done();                                                     // output layer (segment 3): D = Db
-        if (half == 0) {
-            float v[32];
-            tmem_ld32(trow + 384u, v);
+            wait_done();                                                 // output layer: D = Db; X is free for the next tile's layer 0
+            if (half == 0) {
+                float v[32];
+                tmem_ld32(trow + 384u, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) logits[r][i] = v[i] + sb[512 + i];
+                for (int i = 0; i < 32; ++i) logits[t * UM + r][i] = v[i] + sb[512 + i];
+            }
+            tc_fence_before();
+            cta_sync_compute();                                          // Db read before the next tile's second GEMM rewrites it
+            tc_fence_after();
+            pc.mark(4);
         }
-        tc_fence_before();
-        cta_sync_compute();
-        tc_fence_after();
-        pc.mark(4);
-        if (tid < UM) {
+        {
             bool active = false;
             if (id >= 0) {
                 float T12[12], xb[3], g[3], lg[25], wj[NJ];
