@@ -358,7 +358,7 @@ static int ensure_workspace(ArahHandle* h, int P) {
     const size_t o_conv = take(cap), o_dist = take(cap * 4), o_pn = take(cap * 12);
     const size_t o_z = take(PS * 4), o_xn = take(PS * 12), o_T = take(PS * 48), o_sc = take(PS), o_sdf = take(PS * 4), o_rgb = take(PS * 12);
     const size_t o_cs = take(PS * sizeof(BroydenState<3>));
-    const size_t o_la = take(PS * 4), o_lb = take(PS * 4), o_on = take(PS * 4), o_sh = take(PS * 4), o_ctr = take(C_COUNT * 4 + 64), o_clk = take(16 * 8);
+    const size_t o_la = take(PS * 4), o_lb = take(PS * 4), o_on = take(PS * 4), o_sh = take(PS * 4), o_ctr = take(C_COUNT * 4 + 64), o_clk = take(32 * 8);
     if (h->ws.ensure(off) != 0) return -1;
     char* b = static_cast<char*>(h->ws.p);
     Work& w = h->w;
@@ -591,7 +591,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     h->profiled = prof;
     CU(cudaMemsetAsync(w.counters, 0, C_COUNT * 4, st));
     Work wk = w;                      // kernels get the phase-clock pointer only while profiling
-    if (prof) CU(cudaMemsetAsync(w.phase_clk, 0, 16 * 8, st)); else wk.phase_clk = nullptr;
+    if (prof) CU(cudaMemsetAsync(w.phase_clk, 0, 32 * 8, st)); else wk.phase_clk = nullptr;
     if (prof) CU(cudaEventRecord(h->ev[0], st));
     k_trace_begin<<<cdiv(P, 256), 256, 0, st>>>(w); L();
     const unsigned g_ray_tiles = grid_min(cdiv(P, TM), (size_t)nsm);
@@ -599,7 +599,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     for (int it = 0; it < TRACE_ITERS; ++it) {
         k_knn_rays<<<g_knn_rays, 512, sm_knn, st>>>(fp, h->knn, w, it); L();
         if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc)
-            k_trace_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, w, it);
+            k_trace_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, wk, it);
         else
             k_trace_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it);
         L();
@@ -726,10 +726,10 @@ extern "C" int arah_get_stats(ArahHandle* h, ArahStats* s, void* stream) {
 
 extern "C" int arah_debug_phase_clocks(ArahHandle* h, uint64_t* out16, void* stream) {
     if (!h || !out16) return fail(ARAH_EINVAL, "null argument");
-    memset(out16, 0, 16 * 8);
+    memset(out16, 0, 32 * 8);
     if (!h->rendered || !h->profiled || h->last_P == 0) return ARAH_OK;
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    CU(cudaMemcpy(out16, h->w.phase_clk, 16 * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out16, h->w.phase_clk, 32 * 8, cudaMemcpyDeviceToHost));
     return ARAH_OK;
 }
 

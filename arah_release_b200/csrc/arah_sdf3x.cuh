@@ -9,8 +9,8 @@
 //   D   += A_lo(smem).B_hi + A_hi(tmem).B_hi        (when B_hi(c) has landed)
 //   D   += A_hi(tmem).B_lo                          (when B_lo(c) has landed).
 // Shared memory is exactly full (128 KB + 96 KB + 3 KB), so the dynamic segment must start 1024-byte aligned (checked).
-// The activation math is the fp32 FFMA kernels' own (sinf(30 (f (acc + b) + phi)), precise sinf): root finding keeps
-// resolving 1e-5 m.
+// The activation math is the fp32 FFMA kernels' own formula sin(30 (f (acc + b) + phi)) with a 1-2 ulp Cody-Waite sine
+// (sin_cw): root finding keeps resolving 1e-5 m.
 #pragma once
 #include "arah_shade_tc3.cuh"
 #include "arah_corr_tc3.cuh"
@@ -32,6 +32,13 @@ constexpr int S3_ALO_FLOATS = 8 * A_CHUNK_FLOATS;              // 128 KB
 constexpr int S3_RING_FLOATS = S3_NSLOTS * RING_SLOT_FLOATS;   // 96 KB
 
 struct S3Bars { uint64_t* full; uint64_t* empty; uint64_t* ready; uint64_t* done; };
+
+// 32 consecutive per-column parameters as 8 LDG.128 (the L1 is almost entirely carved out as shared memory in these kernels)
+__device__ __forceinline__ void ldg32(const float* __restrict__ p, float (&v)[32]) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float4 t = __ldg(q + j); v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w; }
+}
 
 // ---- producer: one tile's worth of SDF weight items (5 layers x 8 chunks x {hi, lo}) ----------------------------------
 __device__ __forceinline__ void s3_produce_item(float* ring, const S3Bars& bar, uint32_t& slot, uint32_t& use, const void* src, uint32_t bytes) {
@@ -83,7 +90,7 @@ __device__ __forceinline__ void s3_mma_sdf(float* ring, const float* A_lo, const
 }
 // ---- compute warps: SDF of the 128 rows whose normalised points sit in xs[r][0..2]; returns this thread's partial of
 //      w6 . h5 over its 128 columns (caller adds the two halves and b6).  Must be called by all 8 compute warps.
-__device__ __forceinline__ float s3_compute_sdf(const SdfTC& sd, const float* xs3, float* A_lo, const S3Bars& bar, uint32_t& done_par, uint32_t tbase) {
+__device__ __forceinline__ float s3_compute_sdf(const SdfTC& sd, const float* xs3, float* A_lo, const S3Bars& bar, uint32_t& done_par, uint32_t tbase, PhaseClk* pc = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, half = warp >> 2, r = 32 * q + lane;
     const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
@@ -104,39 +111,42 @@ __device__ __forceinline__ float s3_compute_sdf(const SdfTC& sd, const float* xs
 #pragma unroll 1
         for (int b = 0; b < 4; ++b) {
             const int col0 = 128 * half + 32 * b;
-            float h[32];
+            float h[32], w0[32], w1[32], w2[32], pf[32], pb[32], pp[32];
+            ldg32(sd.Wt0 + col0, w0); ldg32(sd.Wt0 + 256 + col0, w1); ldg32(sd.Wt0 + 512 + col0, w2);
+            ldg32(sd.freq + col0, pf); ldg32(sd.b[0] + col0, pb); ldg32(sd.phase + col0, pp);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const int cc = col0 + i;
-                const float a = fmaf(__ldg(sd.Wt0 + 512 + cc), z, fmaf(__ldg(sd.Wt0 + 256 + cc), y, __ldg(sd.Wt0 + cc) * x));
-                h[i] = sinf(30.0f * (__ldg(sd.freq + cc) * (a + __ldg(sd.b[0] + cc)) + __ldg(sd.phase + cc)));
+                const float a = fmaf(w2[i], z, fmaf(w1[i], y, w0[i] * x));
+                h[i] = sin_cw(30.0f * (pf[i] * (a + pb[i]) + pp[i]));
             }
             put(0, col0 / 32, h);
         }
     }
+    if (pc) pc->mark(1);
     float dot = 0.f;
     for (int L = 1; L <= 5; ++L) {
         mbar_wait(bar.done, done_par);
         done_par ^= 1u;
         __syncwarp();
         tc_fence_after();
+        if (pc) pc->mark(2);
         const int dreg = L & 1;
 #pragma unroll 1
         for (int b = 0; b < 4; ++b) {
             const int col0 = 128 * half + 32 * b;
-            float v[32];
+            float v[32], pf[32], pb[32], pp[32];
+            ldg32(sd.freq + L * 256 + col0, pf); ldg32(sd.b[L] + col0, pb); ldg32(sd.phase + L * 256 + col0, pp);
             tmem_ld32(trow + 256u * dreg + (uint32_t)col0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int cc = L * 256 + col0 + i;
-                v[i] = sinf(30.0f * (__ldg(sd.freq + cc) * (v[i] + __ldg(sd.b[L] + col0 + i)) + __ldg(sd.phase + cc)));
-            }
+            for (int i = 0; i < 32; ++i) v[i] = sin_cw(30.0f * (pf[i] * (v[i] + pb[i]) + pp[i]));
             if (L < 5) put(dreg, col0 / 32, v);
             else {
+                ldg32(sd.w6 + col0, pf);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dot = fmaf(v[i], __ldg(sd.w6 + col0 + i), dot);
+                for (int i = 0; i < 32; ++i) dot = fmaf(v[i], pf[i], dot);
             }
         }
+        if (pc) pc->mark(3);
     }
     return dot;
 }
@@ -182,6 +192,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_trace_tc3(FrameParams fp, Sd
     uint32_t done_par = 0;
     const int* list = (iter & 1) ? w.listB : w.listA;
     int* next = (iter & 1) ? w.listA : w.listB;
+    PhaseClk pc; pc.start((tid == 32 && w.phase_clk) ? w.phase_clk + 16 : nullptr);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int ray = -1;
         if (tid < UM) {
@@ -191,7 +202,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_trace_tc3(FrameParams fp, Sd
             xs3[3 * tid] = xn[0]; xs3[3 * tid + 1] = xn[1]; xs3[3 * tid + 2] = xn[2];
         }
         cta_sync_compute();
-        const float dot = s3_compute_sdf(sd, xs3, A_lo, bar, done_par, tbase);
+        pc.mark(0);
+        const float dot = s3_compute_sdf(sd, xs3, A_lo, bar, done_par, tbase, &pc);
         part[half][r] = dot;
         cta_sync_compute();
         if (tid < UM) {                                             // marching logic, identical to k_trace_iter
@@ -210,6 +222,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_trace_tc3(FrameParams fp, Sd
             warp_stat_add(ray >= 0 ? 1 : 0, &w.counters[C_STAT_TRACE_EVALS]);
         }
         cta_sync_compute();
+        pc.mark(4);
     }
     tc_fence_before();
     cta_sync_compute();
@@ -272,12 +285,10 @@ __device__ __forceinline__ void s3_compute_skin(const SkinTC& sk, const float* x
 #pragma unroll 1
         for (int b = 0; b < 2; ++b) {
             const int col0 = 64 * half + 32 * b;
-            float h[32];
+            float h[32], w0[32], w1[32], w2[32], pb[32];
+            ldg32(sk.Wt0 + col0, w0); ldg32(sk.Wt0 + 128 + col0, w1); ldg32(sk.Wt0 + 256 + col0, w2); ldg32(sk.b[0] + col0, pb);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int cc = col0 + i;
-                h[i] = softplus100_fast(fmaf(__ldg(sk.Wt0 + 256 + cc), z, fmaf(__ldg(sk.Wt0 + 128 + cc), y, __ldg(sk.Wt0 + cc) * x)) + __ldg(sk.b[0] + cc));
-            }
+            for (int i = 0; i < 32; ++i) h[i] = softplus100_fast(fmaf(w2[i], z, fmaf(w1[i], y, w0[i] * x)) + pb[i]);
             put(col0 / 32, h);
         }
     }
@@ -287,19 +298,21 @@ __device__ __forceinline__ void s3_compute_skin(const SkinTC& sk, const float* x
 #pragma unroll 1
         for (int b = 0; b < 2; ++b) {
             const int col0 = 64 * half + 32 * b;
-            float v[32];
+            float v[32], pb[32];
+            ldg32(sk.b[l] + col0, pb);
             tmem_ld32(tD + (uint32_t)col0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = softplus100_fast(v[i] + __ldg(sk.b[l] + col0 + i));
+            for (int i = 0; i < 32; ++i) v[i] = softplus100_fast(v[i] + pb[i]);
             put(col0 / 32, v);
         }
     }
     wait_done();
     if (half == 0) {
-        float v[32];
+        float v[32], pb[32];
+        ldg32(sk.b[4], pb);
         tmem_ld32(trow + 384u, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) logits[r][i] = v[i] + __ldg(sk.b[4] + i);
+        for (int i = 0; i < 32; ++i) logits[r][i] = v[i] + pb[i];
     }
     tc_fence_before();
 }

@@ -326,9 +326,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
             for (int l = 0; l < 4; ++l) {
                 const float fr = (float)(1 << l);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) c[k++] = sinf(v[j] * fr);
+                for (int j = 0; j < 3; ++j) c[k++] = sin_cw(v[j] * fr);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) c[k++] = cosf(v[j] * fr);
+                for (int j = 0; j < 3; ++j) c[k++] = sin_cw(v[j] * fr + 1.57079632679489662f);      // cos; |arg| <= 8, TF32 consumer
             }
             c[30] = nrm[0]; c[31] = nrm[1]; c[32] = nrm[2]; c[33] = 0.f; c[34] = 0.f; c[35] = 0.f;
         }

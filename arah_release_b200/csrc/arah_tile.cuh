@@ -49,7 +49,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) break;
-        if (++spins > (1 << 24)) __trap();     // never hang the GPU box: a lost copy becomes a launch failure
+        if (++spins > (1 << 22)) __trap();     // never hang the GPU box: a lost copy becomes a launch failure
     }
 }
 

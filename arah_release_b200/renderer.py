@@ -223,7 +223,7 @@ class ArahRenderer:
         return s.as_dict()
 
     def phase_clocks(self):
-        out = (C.c_uint64 * 16)()
+        out = (C.c_uint64 * 32)()
         check(_lib.lib().arah_debug_phase_clocks(self._h, out, self.stream))
         return [int(v) for v in out]
 

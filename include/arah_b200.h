@@ -141,10 +141,10 @@ int arah_eval_sdf(ArahHandle* h, const float* xn, int32_t n, float* sdf, float* 
 int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, float* weights, float* x_bar, void* stream);
 
 /* Debug: SM-clock cycles spent per kernel phase by one designated thread per CTA, summed over CTAs and launches of the last
- * profiled render (arah_set_profiling(h,1)): out16[0..5] correspondence step (gather, layer 0, MMA wait, epilogues, output
+ * profiled render (arah_set_profiling(h,1)): out32[0..5] correspondence step (gather, layer 0, MMA wait, epilogues, output
  * layer, per-point phase), out16[8..14] shading (setup+layer0, fwd wait, fwd epilogue, rev wait, rev epilogue, colour inputs,
- * colour MLP). */
-int arah_debug_phase_clocks(ArahHandle* h, uint64_t* out16, void* stream);
+ * colour MLP), out32[16..20] sphere-tracing step (gather, layer 0, MMA wait, epilogues, marching).  32 entries. */
+int arah_debug_phase_clocks(ArahHandle* h, uint64_t* out32, void* stream);
 
 /* Debug/bring-up: D[128][N] = A[128][K] . W[N][K]^T through the tcgen05 TF32 tile used by the shading kernel
  * (device pointers, K multiple of 32 <= 256, N in {128, 256}; a_in_tmem != 0 stages A in tensor memory and uses the

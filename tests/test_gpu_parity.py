@@ -12,12 +12,13 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-def _build(fr, shade_mode='fp32'):
+def _build(fr, shade_mode='fp32', root_mode=None):
     from arah_release_b200 import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
     tracer = BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples, far_surface_vol_samples=fr.far_samples)
-    net = IDHRNetwork(dev, rend, skin, tracer, cano_view_dirs=fr.cano_view_dirs, shade_mode=shade_mode).eval()
+    net = IDHRNetwork(dev, rend, skin, tracer, cano_view_dirs=fr.cano_view_dirs, shade_mode=shade_mode,
+                      root_mode=root_mode if root_mode is not None else ('fp32' if shade_mode == 'fp32' else '3xtf32')).eval()
     inputs = rl.inputs_from_frame(fr, sdf, DEV)
     return net, inputs
 
@@ -61,7 +62,9 @@ def test_render_matches_reference_golden(name, mode):
     fr, ref, meta = load_golden(name)
     net, inputs = _build(fr, mode)
     out = _render_dict(net, inputs)
-    # tf32 = shading MLPs on the tensor cores: same root finding (fp32), colours within TF32 operand rounding
+    # 'fp32' = every MLP on fp32 FFMA tiles (the oracle's arithmetic); 'tf32' = tensor cores: shading in TF32, all root
+    # finding (sphere tracing, joint search, correspondences) in 3xTF32 split precision -> same masks/depths, colours
+    # within TF32 operand rounding
     tol = dict(TOL, rgb_psnr_min=55.0) if mode == 'tf32' else TOL
     st = check_render(out, ref, label=name + ':' + mode, tol=tol)
     stats = net.stats()
