@@ -282,7 +282,7 @@ def run_ours(args):
     pk = peaks()
     ach = (sum(shade_flops) / max(sum(shade_ms), 1e-9)) / 1e9          # FLOP/ms -> TFLOP/s
     traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'k_shade_tc2_traffic.json' if r.shade_mode == 'tf32' else 'k_shade_traffic.json')
+    tp = os.path.join(ROOT, 'profiles', 'k_shade_tc3_traffic.json' if r.shade_mode == 'tf32' else 'k_shade_traffic.json')
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get('dram_bytes_per_launch')
@@ -295,20 +295,20 @@ def run_ours(args):
         'config': {'workload': f'ZJU-377-like {args.size}x{args.size} novel-view render, fp32 (BASELINE configs[1])',
                    'rays_per_frame': P0, 'n_steps': f0.n_steps, 'near_far_samples': [f0.near_samples, f0.far_samples],
                    'parallelism': f'frames sharded over {args.gpus} GPU(s), 1 frame/rank/step', 'l2': '256 MB memset between timed steps',
-                   'precision': f'fp32 storage/accumulate; shading MLP operands {r.shade_mode}; root-finding skinning MLP {r.root_mode}; SDF in tracing/joint search fp32',
+                   'precision': f'fp32 storage/accumulate; shading MLP operands {r.shade_mode}; root finding (sphere tracing, joint search, correspondences) {r.root_mode}',
                    'timing': 'CUDA events on the launching stream, per step, summed; max over ranks'},
         'e2e': {'value': rays_all / t_e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'api': 'arah_set_frame(pose_on_host) + arah_render_host via IDHRNetwork host wrapper'},
         'gpu_launches': int((stats_last['kernel_launches'] + stats_last['pack_launches']) * args.steps),
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': f'k_shade_tc2 (SDF fwd + reverse-mode grad + colour MLP; tcgen05 {r.shade_mode} operands, fp32 accumulate in TMEM)'
+        'roofline': {'bound': 'tensor', 'kernel': f'k_shade_tc3 (SDF fwd + reverse-mode grad + colour MLP; tcgen05 {r.shade_mode} operands, fp32 accumulate in TMEM)'
                      if r.shade_mode == 'tf32' else 'k_shade (fp32 FFMA tiles)',
                      'achieved': ach, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf_sustained'],
                      'peak_source': pk['src'] + ' bf16 cuBLAS sustained (MEASURED_PEAKS.json)', 'traffic': traffic,
                      'algorithmic_flops_per_launch': float(np.mean(shade_flops)), 'ms_per_launch': float(np.mean(shade_ms)),
                      'kernel_share_of_step': float(sum(shade_ms) / (1e3 * t_dev)),
                      'whole_step_tflops': float(sum(step_flops) / t_dev / 1e12)},
-        'roofline_corr': {'bound': 'tensor', 'kernel': f'k_knn_samples + 51 x k_corr_tc2 (per-sample correspondence search; skinning MLP {r.root_mode}: 3 TF32 products count as 1 useful)',
+        'roofline_corr': {'bound': 'tensor', 'kernel': f'k_knn_samples + 51 x k_corr_tc3 (per-sample correspondence search; skinning MLP {r.root_mode}: 3 TF32 products count as 1 useful)',
                           'achieved': (sum(corr_flops) / max(sum(corr_ms), 1e-9)) / 1e9, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
                           'frac': (sum(corr_flops) / max(sum(corr_ms), 1e-9)) / 1e9 / pk['tf_sustained'], 'ms_per_step': float(np.mean(corr_ms)),
                           'share_of_step': float(sum(corr_ms) / (1e3 * t_dev))},
