@@ -23,6 +23,8 @@ CASES = {
     'zju377_24x24_s0': (dict(H=24, W=24, seed=0), 0),
     'cano_20x20_s1': (dict(H=20, W=20, seed=1, cano_view_dirs=True, max_angle=0.8, beta=2e-3), 0),
     'n32_16x16_s2': (dict(H=16, W=16, seed=2, n_steps=32, near_samples=8, far_samples=4, beta=1e-2), 3),
+    # BASELINE configs[4] shape (H36M-style): 128 near-surface samples need n_steps >= 145 (ray_tracing.py:336,346), canonical view dirs
+    'h36m_n160_12x12_s4': (dict(H=12, W=12, seed=4, n_steps=160, near_samples=128, far_samples=16, cano_view_dirs=True, beta=3e-3), 0),
 }
 T_RAYS = 48
 
@@ -38,10 +40,12 @@ def build_case(kw, n_degenerate):
     return fr
 
 
-def main():
+def main(only=None):
     out_dir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
     for name, (kw, ndeg) in CASES.items():
+        if only and name not in only:
+            continue
         fr = build_case(kw, ndeg)
         c = rh.Counters()
         t = time.time()
@@ -60,4 +64,4 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    main(sys.argv[1:] or None)
