@@ -15,6 +15,8 @@
 #include "arah_shade_tc3.cuh"
 #include "arah_corr_tc3.cuh"
 #include "arah_sdf3x.cuh"
+#include "arah_shade_tc4.cuh"
+#include "arah_corr_tc4.cuh"
 #include <stdlib.h>
 
 using namespace arah;
@@ -298,6 +300,8 @@ struct ArahHandle {
     float* tc_sdf3x[5];
     SdfTC sd;
     int trace_tc = 1;
+    int corr_cluster = 1;      // 2-CTA clusters + weight multicast in the correspondence kernel (measured: -2 ms)
+    int shade_cluster = 0;     // same for shading (measured: +2 ms -- the kernel is not L2-bound; kept selectable)
     // workspace
     DevBuf ws, scratch, io_in, io_out;
     Work w;
@@ -306,7 +310,7 @@ struct ArahHandle {
     int last_P = 0;
     int64_t pack_launches = 0;
     bool profile = false, profiled = false;
-    int tc_engine = 3;
+    int tc_engine = 4;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -392,7 +396,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     ArahHandle* h = new ArahHandle();
     h->cfg = *cfg;
     h->n_sms = prop.multiProcessorCount;
-    if (const char* e = getenv("ARAH_TC_ENGINE")) { const int v = atoi(e); h->tc_engine = (v >= 1 && v <= 3) ? v : 3; }
+    if (const char* e = getenv("ARAH_TC_ENGINE")) { const int v = atoi(e); h->tc_engine = (v >= 1 && v <= 4) ? v : 4; }
     memset(&h->w, 0, sizeof(h->w));
     if (alloc_arena(h) != 0) { delete h; return fail(ARAH_ENOMEM, "weight arena allocation failed"); }
     if (ensure_workspace(h, cfg->max_rays > 0 ? cfg->max_rays : 4096) != 0) { h->arena.release(); delete h; return fail(ARAH_ENOMEM, "workspace allocation failed"); }
@@ -412,6 +416,10 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_corr_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc2_smem_bytes()));
     CU(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_corr_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_shade_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_corr_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
+    if (const char* e = getenv("ARAH_CORR_CLUSTER")) h->corr_cluster = atoi(e) != 0;
+    if (const char* e = getenv("ARAH_SHADE_CLUSTER")) h->shade_cluster = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_iso_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     if (const char* e = getenv("ARAH_TRACE_TC")) h->trace_tc = atoi(e) != 0;
@@ -622,7 +630,17 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
         const unsigned g_tc = grid_min(cdiv(PS, UM), (size_t)nsm);
         for (int it = -1; it < BROYDEN_ITERS; ++it) {
-            if (h->tc_engine >= 3) k_corr_tc3<<<g_tc, TC3_THREADS, corr_tc3_smem_bytes(), st>>>(fp, h->sk, wk, it);
+            if (h->tc_engine >= 4 && h->corr_cluster) {
+                cudaLaunchConfig_t lc{};
+                unsigned g = (g_tc + 1u) & ~1u;
+                if (g > (unsigned)(nsm & ~1)) g = (unsigned)(nsm & ~1);
+                lc.gridDim = dim3(g); lc.blockDim = dim3(TC3_THREADS); lc.dynamicSmemBytes = corr_tc3_smem_bytes(); lc.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                CU(cudaLaunchKernelEx(&lc, k_corr_tc4, fp, h->sk, wk, it));
+            }
+            else if (h->tc_engine >= 3) k_corr_tc3<<<g_tc, TC3_THREADS, corr_tc3_smem_bytes(), st>>>(fp, h->sk, wk, it);
             else if (h->tc_engine == 2) k_corr_tc2<<<g_tc, TC_THREADS, corr_tc2_smem_bytes(), st>>>(fp, h->sk, wk, it);
             else k_corr_tc<<<g_tc, 256, corr_tc_smem_bytes(), st>>>(fp, h->sk, w, it);
             L();
@@ -632,7 +650,19 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     }
     if (prof) CU(cudaEventRecord(h->ev[3], st));
     if (h->cfg.shade_mode == ARAH_SHADE_TF32) {
-        if (h->tc_engine == 3) k_shade_tc3<<<grid_min(cdiv(PS, UM), (size_t)nsm), TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk);
+        if (h->tc_engine >= 4 && h->shade_cluster) {
+            // 2-CTA clusters: the pair shares (multicasts) the weight stream
+            cudaLaunchConfig_t lc{};
+            unsigned g = grid_min(cdiv(PS, UM), (size_t)nsm);
+            g = (g + 1u) & ~1u;
+            if (g > (unsigned)(nsm & ~1)) g = (unsigned)(nsm & ~1);
+            lc.gridDim = dim3(g); lc.blockDim = dim3(TC3_THREADS); lc.dynamicSmemBytes = shade_tc3_smem_bytes(); lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&lc, k_shade_tc4, fp, h->tc, wk));
+        }
+        else if (h->tc_engine >= 3) k_shade_tc3<<<grid_min(cdiv(PS, UM), (size_t)nsm), TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk);
         else if (h->tc_engine == 2) k_shade_tc2<<<grid_min(cdiv(PS, UM), (size_t)nsm), TC_THREADS, shade_tc2_smem_bytes(), st>>>(fp, h->tc, w);
         else k_shade_tc<<<grid_min(cdiv(PS, UM), (size_t)nsm), 256, shade_tc_smem_bytes(), st>>>(fp, h->tc, w);
         L();
