@@ -576,18 +576,20 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
 }
 
 static int render_device(ArahHandle* h, const float* ray_dirs, const float* near_far, int P, float* rgb, uint8_t* mask,
-                         float* points_cam, float* wsum, cudaStream_t st) {
+                         float* points_cam, float* wsum, cudaStream_t st, const float* u_all = nullptr,
+                         const float* u_near = nullptr, const float* u_far = nullptr, bool trace_only = false) {
     if (!h->frame_set) return fail(ARAH_ESTATE, "arah_set_frame must be called before arah_render");
     if (P < 0) return fail(ARAH_EINVAL, "P < 0");
     h->launches = 0;
     h->last_P = P;
     h->rendered = true;
     if (P == 0) return ARAH_OK;
-    if (!ray_dirs || !near_far || !rgb || !mask) return fail(ARAH_EINVAL, "null buffer");
+    if (!ray_dirs || !near_far || (!trace_only && (!rgb || !mask))) return fail(ARAH_EINVAL, "null buffer");
     CU(cudaSetDevice(h->cfg.device));
     if (ensure_workspace(h, P) != 0) return fail(ARAH_ENOMEM, "workspace allocation failed");
     Work& w = h->w;
     w.P = P; w.ray_dirs = ray_dirs; w.near_far = near_far;
+    w.train = u_all ? 1 : 0; w.u_all = u_all; w.u_near = u_near; w.u_far = u_far;
     w.out_rgb = rgb; w.out_mask = mask; w.out_points_cam = points_cam; w.out_wsum = wsum;
     const FrameParams& fp = h->fp;
     const int S = w.S;
@@ -649,6 +651,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
         for (int it = -1; it < BROYDEN_ITERS; ++it) { k_corr_step<<<g_smp_tiles, 256, sm_skin, st>>>(fp, w, it); L(); }
     }
     if (prof) CU(cudaEventRecord(h->ev[3], st));
+    if (trace_only) { CU(cudaGetLastError()); return ARAH_OK; }
     if (h->cfg.shade_mode == ARAH_SHADE_TF32) {
         if (h->tc_engine >= 4 && h->shade_cluster) {
             // 2-CTA clusters: the pair shares (multicasts) the weight stream

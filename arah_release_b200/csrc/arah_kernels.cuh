@@ -62,6 +62,12 @@ struct Work {
     float* out_points_cam;    // [P][3]
     float* out_wsum;          // [P]
     unsigned long long* phase_clk;   // [16] debug: SM-clock cycles per kernel phase, accumulated by one thread per CTA (may be null)
+    // training-mode tracing (BodyRayTracing.forward(eval_mode=False), ray_tracing.py:249,298-311): all rays enter the joint
+    // search and the z samples are jittered with the caller's three torch.rand draws
+    int train;                // 0 = eval
+    const float* u_all;       // [P][S]
+    const float* u_near;      // [P][near+1]
+    const float* u_far;       // [P][far]
 };
 
 // phase timer used by one designated thread per CTA: adds the cycles since the previous mark to slot `i`
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(256, 2) k_trace_iter(FrameParams fp, Work w, i
 // ================================================================================================ joint iso search
 __global__ void k_iso_prepare(Work w) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool go = (r < w.P) && !(w.ray_flags[r] & 2);        // eval mode: non-diverged rays (ray_tracing.py:249)
+    const bool go = (r < w.P) && (w.train || !(w.ray_flags[r] & 2));   // eval: non-diverged rays; training: all (ray_tracing.py:249)
     warp_append(go, r, w.listA, &w.counters[C_ISO]);
 }
 
@@ -501,7 +507,7 @@ __global__ void k_trace_finish(FrameParams fp, Work w) {
         const uint8_t fl = w.ray_flags[r];
         float xopt[3], zopt;
         bool conv = false;
-        if (!(fl & 2)) {
+        if (w.train || !(fl & 2)) {
             const BroydenState<4>& st = w.iso_state[r];
             xopt[0] = st.best_x[0]; xopt[1] = st.best_x[1]; xopt[2] = st.best_x[2]; zopt = st.best_x[3];
             conv = st.best_n < CVG_THRESH;
@@ -528,24 +534,40 @@ __global__ void k_trace_finish(FrameParams fp, Work w) {
             }
             w.out_points_cam[3 * r] = pc[0]; w.out_points_cam[3 * r + 1] = pc[1]; w.out_points_cam[3 * r + 2] = pc[2];
         }
-        // ---- z placement (ray_sampler, ray_tracing.py:317-350)
+        // ---- z placement (ray_sampler, ray_tracing.py:317-350); training adds perturb_z_vals (:298-311)
         float* z = w.z_vals + (size_t)r * S;
         const int nn = fp.near_samples + 1, nf = fp.far_samples;
+        const bool tr = w.train != 0;
+        // stratified jitter of an analytic ascending run f(0..n-1): lower/upper = mid points to the neighbours
+        auto jitter = [&](auto f, int i, int n, const float* u, int fix) -> float {
+            const float zi = f(i);
+            if (!tr) return zi;
+            const float lo = (i == 0) ? zi : 0.5f * (zi + f(i - 1));
+            const float up = (i == n - 1) ? zi : 0.5f * (f(i + 1) + zi);
+            const float t = (i == fix) ? 0.5f : u[i];
+            return __fadd_rn(lo, __fmul_rn(up - lo, t));
+        };
+        auto f_all = [&](int i) -> float { return dist + (fr - dist) * linspace01(i, S); };
+        const float* ua = tr ? w.u_all + (size_t)r * S : nullptr;
         if (!conv) {
-            for (int i = 0; i < S; ++i) z[i] = dist + (fr - dist) * linspace01(i, S);
+            for (int i = 0; i < S; ++i) z[i] = jitter(f_all, i, S, ua, -1);
             count = S;
         } else {
             count = nn + nf;
-            for (int i = count; i < S; ++i) z[i] = dist + (fr - dist) * linspace01(i, S);
+            for (int i = count; i < S; ++i) z[i] = jitter(f_all, i, S, ua, -1);
             // merge of two ascending runs == torch.sort of their concatenation (:348)
             const float zs0 = dist - 0.05f;
             const float span = fmaxf(dist - 0.05f - nr, 1e-5f);
+            auto f_near = [&](int i) -> float { return zs0 + 0.1f * linspace01(i, nn); };
+            auto f_far = [&](int i) -> float { return nr + span * linspace01(i, nf); };
+            const float* un = tr ? w.u_near + (size_t)r * nn : nullptr;
+            const float* uf = (tr && nf > 0) ? w.u_far + (size_t)r * nf : nullptr;
             int a = 0, b = 0;
-            float va = zs0 + 0.1f * linspace01(0, nn);
-            float vb = (nf > 0) ? (nr + span * linspace01(0, nf)) : INFINITY;
+            float va = jitter(f_near, 0, nn, un, fp.near_samples / 2);
+            float vb = (nf > 0) ? jitter(f_far, 0, nf, uf, -1) : INFINITY;
             for (int k = 0; k < count; ++k) {
-                if (b >= nf || (a < nn && va <= vb)) { z[k] = va; ++a; va = (a < nn) ? (zs0 + 0.1f * linspace01(a, nn)) : INFINITY; }
-                else { z[k] = vb; ++b; vb = (b < nf) ? (nr + span * linspace01(b, nf)) : INFINITY; }
+                if (b >= nf || (a < nn && va <= vb)) { z[k] = va; ++a; va = (a < nn) ? jitter(f_near, a, nn, un, fp.near_samples / 2) : INFINITY; }
+                else { z[k] = vb; ++b; vb = (b < nf) ? jitter(f_far, b, nf, uf, -1) : INFINITY; }
             }
         }
         // slots that are off keep zeros / false (generate_point_samples_opt scatters into zeros, :549-555)

@@ -350,3 +350,22 @@ def fold_weight_norm(layer: dict) -> tuple[np.ndarray, np.ndarray]:
     v = layer['v']
     n = np.sqrt((v * v).sum(axis=1, keepdims=True, dtype=F32)).astype(F32)
     return (v * (layer['g'] / n)).astype(F32), layer['b']
+
+
+def train_aux_points(frame: Frame, seed: int = 0, n_uniform: int = 1024, n_inside: int = 256) -> dict:
+    """Seeded stand-ins for the extra training inputs the reference's dataset emits
+    (/root/reference/im2mesh/data/zju_mocap.py:464-575): ``points_uniform`` (normalised [-1,1]^3, off-surface),
+    ``points_skinning`` (24 canonical points, metres) with their target weights, ``points_inside`` (normalised, inside
+    the body), a body mask per ray and a pseudo ground-truth colour per ray."""
+    rng = np.random.default_rng(seed * 1013 + 7)
+    pu = (rng.random((n_uniform, 3)) * 2.0 - 1.0).astype(F32)
+    idx = rng.choice(frame.minimal_shape.shape[0], size=N_JOINTS, replace=False)
+    ps = frame.minimal_shape[idx].astype(F32)
+    pw = frame.smpl_weights[idx].astype(F32)
+    d = float(frame.coord_max - frame.coord_min)
+    jn = ((JOINTS_CANO - frame.center.astype(np.float64) - float(frame.coord_min) + 0.05 * d) / d / 1.1 - 0.5) * 2.0
+    pin = (jn[rng.integers(0, N_JOINTS, size=n_inside)] + rng.normal(scale=0.01, size=(n_inside, 3))).astype(F32)
+    body_mask = (rng.random(frame.P) < 0.6)
+    rgb_gt = rng.random((frame.P, 3)).astype(F32)
+    return {'points_uniform': pu, 'points_skinning': ps, 'sampled_weights': pw, 'points_inside': pin,
+            'body_mask': body_mask, 'rgb_gt': rgb_gt}

@@ -473,7 +473,21 @@ static void color_forward(const OracleFrame *f, const Packed *p, const float *xn
 }
 
 /* ---------------------------------------------------------------- one ray, end to end */
-static void render_ray(const OracleFrame *f, const Packed *p, const float *d, float near, float far, int ray, const OracleOut *out) {
+/* training-mode stochastic inputs (ray_tracing.py:298-311): the three torch.rand draws of ray_sampler, per ray */
+typedef struct { const float *u_all /*[P][S]*/, *u_near /*[P][near+1]*/, *u_far /*[P][far]*/; } TrainNoise;
+
+/* perturb_z_vals (ray_tracing.py:298-311): stratified jitter inside the mid-point intervals; slot `fix` keeps t = 0.5 */
+static void perturb_z(float *z, int n, const float *u, int fix) {
+    float lo[MAX_STEPS], up[MAX_STEPS];
+    for (int i = 0; i < n; ++i) {
+        lo[i] = (i == 0) ? z[0] : 0.5f * (z[i] + z[i - 1]);
+        up[i] = (i == n - 1) ? z[n - 1] : 0.5f * (z[i + 1] + z[i]);
+    }
+    for (int i = 0; i < n; ++i) { const float t = (i == fix) ? 0.5f : u[i]; z[i] = lo[i] + (up[i] - lo[i]) * t; }
+}
+
+static void render_ray(const OracleFrame *f, const Packed *p, const float *d, float near, float far, int ray, const OracleOut *out,
+                       const TrainNoise *tn /* NULL = eval mode */) {
     const int S = f->n_steps;
     const float thr = 1e-5f;
     /* ---- sphere tracing (ray_tracing.py:174-241) */
@@ -499,7 +513,7 @@ static void render_ray(const OracleFrame *f, const Packed *p, const float *d, fl
     memcpy(xopt, x0, sizeof(x0));
     memcpy(Topt, cur_T, sizeof(Topt));
     int conv = 0, n_iso = 0;
-    if (!diverge) {
+    if (!diverge || tn) {                                      /* training: all rays (ray_tracing.py:249) */
         float J[16], Jl[9], xn[3], args[6 * SDF_H], gs[3], Ji[16];
         forward_skinning_jac(f, p, x0, Jl);
         normalize_pts(f, x0, xn);
@@ -536,11 +550,14 @@ static void render_ray(const OracleFrame *f, const Packed *p, const float *d, fl
     uint8_t on[MAX_STEPS];
     for (int i = 0; i < S; ++i) { z[i] = dist + (far - dist) * linspace01(i, S); on[i] = 1; }
     const int nn = f->near_samples + 1, nf = f->far_samples;
+    if (tn) perturb_z(z, S, tn->u_all + (size_t)ray * S, -1);
     if (conv) {
         for (int i = nn; i < S; ++i) on[i] = 0;
         for (int i = 0; i < nn; ++i) z[i] = dist - 0.05f + (0.05f * 2) * linspace01(i, nn);
+        if (tn) perturb_z(z, nn, tn->u_near + (size_t)ray * nn, f->near_samples / 2);
         if (nf > 0) {
             for (int i = 0; i < nf; ++i) { on[nn + i] = 1; z[nn + i] = near + fmaxf(dist - 0.05f - near, 1e-5f) * linspace01(i, nf); }
+            if (tn) perturb_z(z + nn, nf, tn->u_far + (size_t)ray * nf, -1);
             qsort(z, nn + nf, sizeof(float), cmp_float);
         }
     }
@@ -635,7 +652,25 @@ int arah_oracle_render(const OracleFrame *f, const float *ray_dirs, const float 
     if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
 #pragma omp parallel for schedule(dynamic, 4)
-    for (int r = 0; r < P; ++r) render_ray(f, &p, ray_dirs + (size_t)r * 3, near_far[r * 2], near_far[r * 2 + 1], r, out);
+    for (int r = 0; r < P; ++r) render_ray(f, &p, ray_dirs + (size_t)r * 3, near_far[r * 2], near_far[r * 2 + 1], r, out, NULL);
+    unpack(&p);
+    return 0;
+}
+
+/* BodyRayTracing.forward(eval_mode=False) + the forward VALUES of the training render (the implicit-gradient correction of
+ * implicit_differentiable_renderer.py:315-334 does not change values); u_* are the reference's three torch.rand draws. */
+int arah_oracle_render_train(const OracleFrame *f, const float *ray_dirs, const float *near_far, int P, const OracleOut *out, int n_threads,
+                             const float *u_all, const float *u_near, const float *u_far) {
+    if (f->n_steps > MAX_STEPS || f->near_samples + 1 + f->far_samples > f->n_steps) return -1;
+    if (!u_all || !u_near || (f->far_samples > 0 && !u_far)) return -2;
+    Packed p;
+    pack(f, &p);
+    const TrainNoise tn = {u_all, u_near, u_far};
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int r = 0; r < P; ++r) render_ray(f, &p, ray_dirs + (size_t)r * 3, near_far[r * 2], near_far[r * 2 + 1], r, out, &tn);
     unpack(&p);
     return 0;
 }

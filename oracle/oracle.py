@@ -52,6 +52,7 @@ def lib():
             build()
         _lib = C.CDLL(_SO)
         _lib.arah_oracle_render.argtypes = [C.POINTER(OracleFrame), FP, FP, C.c_int, C.POINTER(OracleOut), C.c_int]
+        _lib.arah_oracle_render_train.argtypes = [C.POINTER(OracleFrame), FP, FP, C.c_int, C.POINTER(OracleOut), C.c_int, FP, FP, FP]
         _lib.arah_oracle_sdf.argtypes = [C.POINTER(OracleFrame), FP, C.c_int, FP, FP, FP]
         _lib.arah_oracle_skin.argtypes = [C.POINTER(OracleFrame), FP, C.c_int, FP, FP, FP]
         _lib.arah_oracle_color.argtypes = [C.POINTER(OracleFrame), FP, FP, FP, FP, C.c_int, FP]
@@ -110,8 +111,10 @@ def make_frame(frame):
     return of, keep
 
 
-def render(frame, ray_dirs=None, near_far=None, threads: int = 0, stages: bool = True):
-    """Full hot path on CPU.  Returns a dict with the same keys as oracle.ref_harness.run_reference plus counters."""
+def render(frame, ray_dirs=None, near_far=None, threads: int = 0, stages: bool = True, train_noise=None):
+    """Full hot path on CPU.  Returns a dict with the same keys as oracle.ref_harness.run_reference plus counters.
+    ``train_noise`` = (u_all [P,S], u_near [P,near+1], u_far [P,far]): training-mode tracing (eval_mode=False) with the
+    reference's three torch.rand draws supplied by the caller."""
     of, keep = make_frame(frame)
     rd = np.ascontiguousarray(frame.ray_dirs if ray_dirs is None else ray_dirs, dtype=np.float32)
     nf = np.ascontiguousarray(frame.near_far if near_far is None else near_far, dtype=np.float32)
@@ -142,13 +145,30 @@ def render(frame, ray_dirs=None, near_far=None, threads: int = 0, stages: bool =
     oo.weights_sum = _fp(o['weights_sum'])
     for k in ('n_trace_evals', 'n_iso_evals', 'n_corr_evals', 'n_shaded'):
         setattr(oo, k, o[k].ctypes.data_as(I32))
-    rc = lib().arah_oracle_render(C.byref(of), _fp(rd), _fp(nf), P, C.byref(oo), int(threads))
+    if train_noise is not None:
+        tn = [np.ascontiguousarray(a, np.float32).reshape(P, -1) for a in train_noise]
+        assert tn[0].shape[1] == S and tn[1].shape[1] == frame.near_samples + 1 and tn[2].shape[1] == frame.far_samples
+        rc = lib().arah_oracle_render_train(C.byref(of), _fp(rd), _fp(nf), P, C.byref(oo), int(threads), _fp(tn[0]), _fp(tn[1]), _fp(tn[2]))
+    else:
+        rc = lib().arah_oracle_render(C.byref(of), _fp(rd), _fp(nf), P, C.byref(oo), int(threads))
     if rc != 0:
         raise RuntimeError(f'arah_oracle_render failed ({rc})')
     for k in ('trace.network_body_mask', 'network_body_mask', 'trace.sampler_converge_mask'):
         if k in o:
             o[k] = o[k].astype(bool)
     return o
+
+
+def train_noise(frame, seed, P=None):
+    """The three torch.rand draws of ray_sampler in training mode (ray_tracing.py:305), in the reference's order and shapes,
+    from torch's CPU generator (the reference draws on the CPU even for CUDA runs: ``torch.rand(shape).to(upper)``)."""
+    import torch
+    P = frame.P if P is None else P
+    torch.manual_seed(seed)
+    u_all = torch.rand(1, P, frame.n_steps)
+    u_near = torch.rand(1, P, frame.near_samples + 1)
+    u_far = torch.rand(1, P, frame.far_samples)
+    return u_all[0].numpy(), u_near[0].numpy(), u_far[0].numpy()
 
 
 def sdf(frame, xn, grad=True, feat=False):

@@ -256,3 +256,83 @@ def run_reference(frame, *, stages=True, threads=None, counters=None):
         if undo:
             undo()
     return out
+
+
+# --------------------------------------------------------------------------------------
+# training mode (BASELINE configs[2])
+# --------------------------------------------------------------------------------------
+
+LOSS_WEIGHTS = dict(rgb_weight=1.0, perceptual_weight=0.0, eikonal_weight=0.1, mask_weight=1.0, off_surface_weight=0.01,
+                    inside_weight=0.01, params_weight=0.0, skinning_weight=10.0)
+
+
+def run_reference_train(frame, aux, *, seed=0, train_skinning_net=True, threads=None, loss_weights=None):
+    """One training forward + backward of the UNMODIFIED reference IDHRNetwork (self.training == True) on CPU.
+
+    ``aux`` = arah_release_b200.synthetic.train_aux_points(frame).  torch.manual_seed(seed) is set right before the forward,
+    so the reference's own torch.rand calls (three in ray_sampler, ray_tracing.py:305; one for the eikonal points,
+    implicit_differentiable_renderer.py:126) are reproducible: the host mirror draws the same numbers in the same order.
+    Returns numpy dict: tracer 7-tuple (train mode), model outputs, loss terms, gradients of every parameter tensor.
+    """
+    install()
+    if threads:
+        torch.set_num_threads(threads)
+    idhr, sdf_network = build_reference_modules(frame)
+    idhr.train_skinning_net = bool(train_skinning_net)
+    idhr.train()
+    from im2mesh.metaavatar_render.renderer.loss import IDHRLoss
+    # leaves: hypernetwork outputs (SDF weights), latent code
+    sdf_leaves = {}
+    for l in range(6):
+        film = sdf_network[l][0]
+        for n in ('weights', 'biases', 'freq', 'phase_shift'):
+            v = getattr(film, n).clone().requires_grad_(True)
+            setattr(film, n, v)
+            sdf_leaves[f'sdf.{l}.{n}'] = v
+    for n in ('weights', 'biases'):
+        v = getattr(sdf_network[6], n).clone().requires_grad_(True)
+        setattr(sdf_network[6], n, v)
+        sdf_leaves[f'sdf.6.{n}'] = v
+    inputs = reference_inputs(frame, sdf_network)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    latent = inputs['pose_cond']['latent_code'].clone().requires_grad_(True)
+    inputs['pose_cond']['latent_code'] = latent
+    inputs['body_mask'] = t(aux['body_mask']).view(1, -1)
+    inputs['points_uniform'] = t(aux['points_uniform']).float().view(1, -1, 3)
+    inputs['points_skinning'] = t(aux['points_skinning']).float().view(1, -1, 3)
+    inputs['points_inside'] = t(aux['points_inside']).float().view(1, -1, 3)
+    out = {}
+    torch.manual_seed(seed)
+    state = torch.get_rng_state()
+    with torch.no_grad():
+        tr = idhr.ray_tracer(sdf_network, idhr.skinning_model, cam_loc=inputs['cam_loc'], ray_directions=inputs['ray_dirs'],
+                             body_bounds_intersections=inputs['body_bounds_intersections'], loc=inputs['loc'],
+                             sc_factor=inputs['sc_factor'], smpl_verts=inputs['smpl_verts'],
+                             smpl_verts_cano=inputs['minimal_shape'], skinning_weights=inputs['skinning_weights'],
+                             vol_feat=inputs['vol_feat'], bone_transforms=inputs['bone_transforms'], trans=inputs['trans'],
+                             coord_min=inputs['coord_min'], coord_max=inputs['coord_max'], center=inputs['center'],
+                             eval_mode=False)
+    names = ['points_hat_norm', 'network_body_mask', 'dists', 'sampled_pts', 'sampled_dists', 'sampled_transforms',
+             'sampler_converge_mask']
+    for n, v in zip(names, tr):
+        out['trace.' + n] = v[0].numpy().copy()
+    torch.set_rng_state(state)           # replay: the full forward draws the same jitter, then the eikonal points
+    res = idhr(inputs)
+    for k in ('rgb_values', 'sdf_output', 'off_surface_sdf', 'grad_theta', 'pred_weights', 'inside_sdf'):
+        out['out.' + k] = res[k].detach().numpy().copy()
+    out['out.network_body_mask'] = res['network_body_mask'][0].numpy().copy()
+    lw = dict(LOSS_WEIGHTS)
+    lw.update(loss_weights or {})
+    crit = IDHRLoss(rgb_loss_type='l1', **lw)
+    gt = {'rgb': t(aux['rgb_gt']).float().view(1, -1, 3), 'sampled_weights': t(aux['sampled_weights']).float().view(1, -1, 24)}
+    res['sdf_params'] = None
+    losses = crit(res, gt)
+    for k, v in losses.items():
+        out['loss.' + k] = np.asarray(float(v.reshape(-1)[0]) if torch.is_tensor(v) else float(v), np.float64)
+    losses['loss'].backward()
+    for k, v in sdf_leaves.items():
+        out['grad.' + k] = v.grad.numpy().copy()
+    out['grad.latent'] = latent.grad.numpy().copy()
+    for k, p in idhr.named_parameters():
+        out['grad.' + k] = (p.grad.numpy().copy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32))
+    return out
