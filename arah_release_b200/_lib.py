@@ -32,8 +32,15 @@ class ArahStats(C.Structure):
         return {n: (int(getattr(self, n)) if t is C.c_int64 else float(getattr(self, n))) for n, t in self._fields_}
 
 
+class ArahTrainGrads(C.Structure):
+    _fields_ = [('sdf_W', FP * 7), ('sdf_b', FP * 7), ('sdf_freq', FP), ('sdf_phase', FP), ('skin_W', FP * 5), ('skin_b', FP * 5),
+                ('col_W', FP * 6), ('col_b', FP * 6), ('latent', FP), ('beta', FP)]
+
+
 EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'arah_set_frame', 'arah_set_profiling', 'arah_render',
-           'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin', 'arah_debug_umma_gemm', 'arah_debug_phase_clocks']
+           'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin', 'arah_debug_umma_gemm', 'arah_debug_phase_clocks',
+           'arah_set_training', 'arah_train_trace', 'arah_train_shade_forward', 'arah_train_shade_backward', 'arah_train_sdf_forward',
+           'arah_train_sdf_backward', 'arah_train_skin_forward', 'arah_train_skin_backward']
 
 _lib = None
 
@@ -64,6 +71,14 @@ def lib():
     L.arah_eval_skin.argtypes = [C.c_void_p, FP, C.c_int32, FP, FP, C.c_void_p]
     L.arah_debug_umma_gemm.argtypes = [FP, FP, C.c_int32, C.c_int32, FP, C.c_int32, C.c_void_p]
     L.arah_debug_phase_clocks.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
+    L.arah_set_training.argtypes = [C.c_void_p, C.c_int32]
+    L.arah_train_trace.argtypes = [C.c_void_p, FP, FP, C.c_int32, FP, FP, FP, C.c_void_p]
+    L.arah_train_shade_forward.argtypes = [C.c_void_p, FP, FP, C.c_int32, C.c_int32, FP, FP, C.c_void_p]
+    L.arah_train_shade_backward.argtypes = [C.c_void_p, FP, FP, C.POINTER(ArahTrainGrads), C.c_void_p]
+    L.arah_train_sdf_forward.argtypes = [C.c_void_p, C.c_int32, FP, C.c_int32, C.c_int32, FP, FP, C.c_void_p]
+    L.arah_train_sdf_backward.argtypes = [C.c_void_p, C.c_int32, FP, FP, C.POINTER(ArahTrainGrads), C.c_void_p]
+    L.arah_train_skin_forward.argtypes = [C.c_void_p, FP, C.c_int32, FP, C.c_void_p]
+    L.arah_train_skin_backward.argtypes = [C.c_void_p, FP, C.POINTER(ArahTrainGrads), C.c_void_p]
     _lib = L
     return L
 

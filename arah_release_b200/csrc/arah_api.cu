@@ -17,6 +17,7 @@
 #include "arah_sdf3x.cuh"
 #include "arah_shade_tc4.cuh"
 #include "arah_corr_tc4.cuh"
+#include "arah_train_cuda.cuh"
 #include <stdlib.h>
 
 using namespace arah;
@@ -312,6 +313,12 @@ struct ArahHandle {
     bool profile = false, profiled = false;
     int tc_engine = 4;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // training (arah_train.h): raw reference-layout weight copies + the engine's saved activations
+    bool training = false, train_traced = false;
+    DevBuf raw;
+    arah::train::AllParams tp{};
+    arah::train::Session<arah::train::CudaBK>* sess = nullptr;
+    int col_d0 = 0;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -440,7 +447,8 @@ extern "C" int arah_set_profiling(ArahHandle* h, int32_t enable) {
 extern "C" int arah_destroy(ArahHandle* h) {
     if (!h) return ARAH_OK;
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    h->arena.release(); h->ws.release(); h->scratch.release(); h->io_in.release(); h->io_out.release();
+    h->arena.release(); h->ws.release(); h->scratch.release(); h->io_in.release(); h->io_out.release(); h->raw.release();
+    if (h->sess) { h->sess->release(); delete h->sess; }
     delete h;
     return ARAH_OK;
 }
@@ -571,6 +579,37 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     for (int l = 0; l < 3; ++l) sk.hid[l] = h->tc_skin_hid[l];
     sk.out = h->tc_skin_out;
     if (!(fp.cmax > fp.cmin)) return fail(ARAH_EINVAL, "coord_max must exceed coord_min");
+    if (h->training) {
+        // raw reference-layout copies for the training engine (arah_train.h reads [out][in] weights directly)
+        const int d0 = 33 + 256 + L, d3 = d0 + 128;
+        const size_t n_sdfW[7] = {256 * 3, 65536, 65536, 65536, 65536, 65536, 256}, n_sdfb[7] = {256, 256, 256, 256, 256, 256, 1};
+        const size_t n_skW[5] = {128 * 3, 16384, 16384, 16384, 25 * 128}, n_skb[5] = {128, 128, 128, 128, 25};
+        const size_t n_cW[6] = {(size_t)256 * d0, 65536, 128 * 256, (size_t)256 * d3, 65536, 3 * 256}, n_cb[6] = {256, 256, 128, 256, 256, 3};
+        size_t tot = 0;
+        auto pad = [](size_t n) { return (n + 63) / 64 * 64; };
+        for (int i = 0; i < 7; ++i) tot += pad(n_sdfW[i]) + pad(n_sdfb[i]);
+        tot += 2 * pad(6 * 256);
+        for (int i = 0; i < 5; ++i) tot += pad(n_skW[i]) + pad(n_skb[i]);
+        for (int i = 0; i < 6; ++i) tot += pad(n_cW[i]) + pad(n_cb[i]);
+        tot += pad((size_t)(L > 0 ? L : 1));
+        if (h->raw.ensure(tot * 4) != 0) return fail(ARAH_ENOMEM, "training weight copies");
+        float* cur = (float*)h->raw.p;
+        cudaError_t ce = cudaSuccess;
+        auto cp = [&](const float* src, size_t n) { float* d = cur; cur += pad(n); if (ce == cudaSuccess) ce = cudaMemcpyAsync(d, src, n * 4, cudaMemcpyDeviceToDevice, st); return (const float*)d; };
+        arah::train::AllParams& T = h->tp;
+        for (int i = 0; i < 7; ++i) { T.sdf.W[i] = cp(f->sdf_W[i], n_sdfW[i]); T.sdf.b[i] = cp(f->sdf_b[i], n_sdfb[i]); }
+        T.sdf.freq = cp(f->sdf_freq, 6 * 256); T.sdf.phase = cp(f->sdf_phase, 6 * 256);
+        for (int i = 0; i < 5; ++i) { T.skin.W[i] = cp(f->skin_W[i], n_skW[i]); T.skin.b[i] = cp(f->skin_b[i], n_skb[i]); }
+        for (int i = 0; i < 6; ++i) { T.col.W[i] = cp(f->col_W[i], n_cW[i]); T.col.b[i] = cp(f->col_b[i], n_cb[i]); }
+        T.col.latent = L > 0 ? cp(f->latent, (size_t)L) : nullptr;
+        T.col.latent_dim = L;
+        if (ce != cudaSuccess) return fail(ARAH_ECUDA, cudaGetErrorString(ce));
+        T.bone_T = h->bone_T;
+        T.nm.cmin = fp.cmin; T.nm.cmax = fp.cmax;
+        for (int k = 0; k < 3; ++k) T.nm.center[k] = fp.center[k];
+        h->col_d0 = d0;
+    }
+    h->train_traced = false;
     h->frame_set = true;
     return ARAH_OK;
 }
@@ -783,4 +822,122 @@ extern "C" int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, floa
     k_eval_skin<<<g, 256, tile_smem_bytes(LDA_SKIN), (cudaStream_t)stream>>>(h->fp, x_hat, n, weights, x_bar);
     CU(cudaGetLastError());
     return ARAH_OK;
+}
+
+
+// ================================================================================================ training (arah_train.h)
+using arah::train::CudaBK;
+
+static arah::train::AllGrads to_grads(const ArahTrainGrads* g) {
+    arah::train::AllGrads G{};
+    if (!g) return G;
+    for (int i = 0; i < 7; ++i) { G.sdf.W[i] = g->sdf_W[i]; G.sdf.b[i] = g->sdf_b[i]; }
+    G.sdf.freq = g->sdf_freq; G.sdf.phase = g->sdf_phase;
+    for (int i = 0; i < 5; ++i) { G.skin.W[i] = g->skin_W[i]; G.skin.b[i] = g->skin_b[i]; }
+    for (int i = 0; i < 6; ++i) { G.col.W[i] = g->col_W[i]; G.col.b[i] = g->col_b[i]; }
+    G.col.latent = g->latent; G.beta = g->beta;
+    return G;
+}
+static int train_ready(ArahHandle* h) {
+    if (!h) return fail(ARAH_EINVAL, "null handle");
+    if (!h->training) return fail(ARAH_ESTATE, "call arah_set_training(h, 1) before arah_set_frame");
+    if (!h->frame_set || !h->raw.p) return fail(ARAH_ESTATE, "arah_set_frame must follow arah_set_training(h, 1)");
+    if (!h->sess) h->sess = new arah::train::Session<CudaBK>();
+    return ARAH_OK;
+}
+static int train_done(ArahHandle* h, int rc, const char* what) {
+    h->launches += CudaBK::launches(); CudaBK::launches() = 0;
+    if (rc == -1) return fail(ARAH_ENOMEM, std::string(what) + ": device allocation failed");
+    if (rc == -2) return fail(ARAH_EINVAL, std::string(what) + ": bad slot");
+    CU(cudaGetLastError());
+    return ARAH_OK;
+}
+
+extern "C" int arah_set_training(ArahHandle* h, int32_t enable) {
+    if (!h) return fail(ARAH_EINVAL, "null handle");
+    h->training = enable != 0;
+    if (!h->training && h->sess) { h->sess->release(); delete h->sess; h->sess = nullptr; h->raw.release(); }
+    return ARAH_OK;
+}
+
+extern "C" int arah_train_trace(ArahHandle* h, const float* ray_dirs, const float* near_far, int32_t P, const float* u_all,
+                                const float* u_near, const float* u_far, void* stream) {
+    if (!h) return fail(ARAH_EINVAL, "null handle");
+    if (!u_all || !u_near || (h->cfg.far_samples > 0 && !u_far)) return fail(ARAH_EINVAL, "training-mode tracing needs the three uniform draws");
+    const int rc = render_device(h, ray_dirs, near_far, P, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream, u_all, u_near, u_far, true);
+    if (rc == ARAH_OK) h->train_traced = true;
+    return rc;
+}
+
+extern "C" int arah_train_shade_forward(ArahHandle* h, const float* view_dirs, const float* view_dirs_orig, int32_t ray_augm,
+                                        int32_t train_skinning_net, float* rgb, float* weights_sum, void* stream) {
+    int rc = train_ready(h);
+    if (rc != ARAH_OK) return rc;
+    if (!h->train_traced) return fail(ARAH_ESTATE, "arah_train_shade_forward needs a preceding arah_train_trace");
+    if (!view_dirs || !rgb || !weights_sum) return fail(ARAH_EINVAL, "null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->cfg.device));
+    const Work& w = h->w;
+    int M = 0;
+    CU(cudaMemcpyAsync(&M, w.counters + C_SHADE, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    arah::train::ShadeGeom g{};
+    g.P = h->last_P; g.S = w.S; g.cano_view_dirs = h->cfg.cano_view_dirs; g.ray_augm = ray_augm ? 1 : 0;
+    g.list = w.shade_list; g.smp_xn = w.smp_xn; g.smp_T = w.smp_T; g.z_vals = w.z_vals; g.smp_conv = w.smp_conv;
+    g.view = view_dirs; g.view_orig = view_dirs_orig ? view_dirs_orig : view_dirs;
+    g.sdf_scale = h->fp.cmax - h->fp.cmin; g.beta_raw = h->fp.beta;
+    CudaBK::launches() = 0;
+    rc = h->sess->shade_forward(h->tp, g, M, train_skinning_net != 0, rgb, weights_sum, st);
+    return train_done(h, rc, "arah_train_shade_forward");
+}
+
+extern "C" int arah_train_shade_backward(ArahHandle* h, const float* g_rgb, const float* g_weights_sum, const ArahTrainGrads* grads, void* stream) {
+    int rc = train_ready(h);
+    if (rc != ARAH_OK) return rc;
+    if (!g_rgb || !grads) return fail(ARAH_EINVAL, "null buffer");
+    CU(cudaSetDevice(h->cfg.device));
+    CudaBK::launches() = 0;
+    rc = h->sess->shade_backward(h->tp, to_grads(grads), g_rgb, g_weights_sum, (cudaStream_t)stream);
+    return train_done(h, rc, "arah_train_shade_backward");
+}
+
+extern "C" int arah_train_sdf_forward(ArahHandle* h, int32_t slot, const float* points, int32_t n, int32_t with_grad, float* sdf,
+                                      float* grad, void* stream) {
+    int rc = train_ready(h);
+    if (rc != ARAH_OK) return rc;
+    if (n < 0 || (n > 0 && (!points || !sdf))) return fail(ARAH_EINVAL, "bad arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    CudaBK::launches() = 0;
+    rc = h->sess->sdf_forward(h->tp, slot, points, n, with_grad != 0, sdf, grad, (cudaStream_t)stream);
+    return train_done(h, rc, "arah_train_sdf_forward");
+}
+
+extern "C" int arah_train_sdf_backward(ArahHandle* h, int32_t slot, const float* g_sdf, const float* g_grad, const ArahTrainGrads* grads, void* stream) {
+    int rc = train_ready(h);
+    if (rc != ARAH_OK) return rc;
+    if (!grads) return fail(ARAH_EINVAL, "null gradient table");
+    CU(cudaSetDevice(h->cfg.device));
+    CudaBK::launches() = 0;
+    rc = h->sess->sdf_backward(h->tp, to_grads(grads), slot, g_sdf, g_grad, (cudaStream_t)stream);
+    return train_done(h, rc, "arah_train_sdf_backward");
+}
+
+extern "C" int arah_train_skin_forward(ArahHandle* h, const float* points, int32_t n, float* weights, void* stream) {
+    int rc = train_ready(h);
+    if (rc != ARAH_OK) return rc;
+    if (n < 0 || (n > 0 && (!points || !weights))) return fail(ARAH_EINVAL, "bad arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    CudaBK::launches() = 0;
+    rc = h->sess->skin_forward(h->tp, points, n, weights, (cudaStream_t)stream);
+    return train_done(h, rc, "arah_train_skin_forward");
+}
+
+extern "C" int arah_train_skin_backward(ArahHandle* h, const float* g_weights, const ArahTrainGrads* grads, void* stream) {
+    int rc = train_ready(h);
+    if (rc != ARAH_OK) return rc;
+    if (!g_weights || !grads) return fail(ARAH_EINVAL, "null buffer");
+    CU(cudaSetDevice(h->cfg.device));
+    CudaBK::launches() = 0;
+    rc = h->sess->skin_backward(h->tp, to_grads(grads), g_weights, (cudaStream_t)stream);
+    return train_done(h, rc, "arah_train_skin_backward");
 }

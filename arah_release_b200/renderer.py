@@ -11,7 +11,12 @@ Their eval `forward` packs the modules' weights + the per-frame buffers into an 
 (include/arah_b200.h) on torch's current CUDA stream.  There is no PyTorch / CPU implementation of the path here: if the
 CUDA library is missing or the tensors are not on a CUDA device, the call raises.
 
-Training (`self.training == True`) raises NotImplementedError: backward through root finding is SURVEY.md §8(f) row f2.
+Training (`self.training == True`, implicit_differentiable_renderer.py:73-78,117-178,235-249): the tracer runs in training
+mode inside the CUDA library (all rays enter the joint search, jittered z samples); the differentiable part is three
+`torch.autograd.Function`s whose forward AND backward are hand-written kernels behind the C ABI (arah_train_*): shading
+(implicit-gradient LBS correction, SDF, SDF input gradient as normal, colour MLP, compositing), auxiliary SDF evaluations
+(eikonal / off-surface / inside) and skinning-weight prediction.  torch only applies weight-norm and ||variance|| (tiny
+parameter-space ops) and carries the graph to the hypernetwork / optimiser.
 """
 import ctypes as C
 import os
@@ -21,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import ArahConfig, ArahFrame, ArahStats, check
+from ._lib import ArahConfig, ArahFrame, ArahStats, ArahTrainGrads, check
 
 N_VERTS_DEFAULT = 6890
 
@@ -46,6 +51,13 @@ def _effective_weight(lin):
     if hasattr(lin, 'parametrizations') and hasattr(lin.parametrizations, 'weight'):
         return lin.weight.detach()
     return lin.weight.detach()
+
+
+def _effective_weight_grad(lin):
+    """Same as _effective_weight but keeping the autograd graph to weight_g / weight_v (training)."""
+    if hasattr(lin, 'weight_g') and hasattr(lin, 'weight_v'):
+        return torch._weight_norm(lin.weight_v, lin.weight_g, 0)
+    return lin.weight
 
 
 class ArahRenderer:
@@ -202,17 +214,54 @@ class ArahRenderer:
         check(_lib.lib().arah_render_host(self._h, _ptr(rd), _ptr(nf), P, _ptr(rgb), _ptr(mask), _ptr(pc), self.stream))
         return rgb, mask, pc
 
-    def trace_outputs(self, P, transforms=True):
+    def trace_outputs(self, P, transforms=True, points=True):
         """BodyRayTracing.forward's 7-tuple for the last render (ray_tracing.py:166-172), batch dim added."""
         S, dev = self.n_steps, self.device
         pts_hat = torch.empty(P, 3, device=dev); m = torch.empty(P, device=dev, dtype=torch.uint8); dists = torch.empty(P, device=dev)
-        sp = torch.empty(P, S, 3, device=dev); sd = torch.empty(P, S, device=dev)
+        sp = torch.empty(P, S, 3, device=dev) if points else None; sd = torch.empty(P, S, device=dev) if points else None
         sT = torch.empty(P, S, 4, 4, device=dev) if transforms else None
         sc = torch.empty(P, S, device=dev, dtype=torch.uint8)
-        check(_lib.lib().arah_get_trace(self._h, _ptr(pts_hat), _ptr(m), _ptr(dists), _ptr(sp), _ptr(sd),
-                                        _ptr(sT) if sT is not None else None, _ptr(sc), self.stream))
-        return (pts_hat.unsqueeze(0), m.bool().unsqueeze(0), dists.unsqueeze(0), sp.unsqueeze(0), sd.unsqueeze(0),
-                sT.unsqueeze(0) if sT is not None else None, sc.bool().unsqueeze(0))
+        check(_lib.lib().arah_get_trace(self._h, _ptr(pts_hat), _ptr(m), _ptr(dists), _ptr(sp) if sp is not None else None,
+                                        _ptr(sd) if sd is not None else None, _ptr(sT) if sT is not None else None, _ptr(sc), self.stream))
+        return (pts_hat.unsqueeze(0), m.bool().unsqueeze(0), dists.unsqueeze(0), sp.unsqueeze(0) if sp is not None else None,
+                sd.unsqueeze(0) if sd is not None else None, sT.unsqueeze(0) if sT is not None else None, sc.bool().unsqueeze(0))
+
+    # ------------------------------------------------------------------ training (arah_train_*)
+    def set_training(self, enable=True):
+        check(_lib.lib().arah_set_training(self._h, int(bool(enable))))
+
+    def train_trace(self, ray_dirs, near_far, u_all, u_near, u_far):
+        """BodyRayTracing.forward(eval_mode=False); results via trace_outputs()."""
+        rd = _f32c(ray_dirs, self.device).view(-1, 3)
+        nf = _f32c(near_far, self.device).view(-1, 2)
+        P = rd.shape[0]
+        ua, un = _f32c(u_all, self.device).view(P, -1), _f32c(u_near, self.device).view(P, -1)
+        uf = _f32c(u_far, self.device).view(P, -1) if u_far is not None and u_far.numel() else None
+        check(_lib.lib().arah_train_trace(self._h, _ptr(rd), _ptr(nf), P, _ptr(ua), _ptr(un), _ptr(uf) if uf is not None else None, self.stream))
+        self._io_keep = (rd, nf, ua, un, uf)
+        self._train_P = P
+        return P
+
+    def _grad_table(self, shapes):
+        """Zero-filled gradient buffers + the ArahTrainGrads pointing at them.  shapes: dict name -> shape (None = skip)."""
+        g = ArahTrainGrads()
+        bufs = {}
+        def z(name):
+            shp = shapes.get(name)
+            if shp is None:
+                return None
+            t = torch.zeros(shp, device=self.device, dtype=torch.float32)
+            bufs[name] = t
+            return _ptr(t)
+        for i in range(7):
+            g.sdf_W[i] = z(f'sdf_W{i}'); g.sdf_b[i] = z(f'sdf_b{i}')
+        g.sdf_freq = z('sdf_freq'); g.sdf_phase = z('sdf_phase')
+        for i in range(5):
+            g.skin_W[i] = z(f'skin_W{i}'); g.skin_b[i] = z(f'skin_b{i}')
+        for i in range(6):
+            g.col_W[i] = z(f'col_W{i}'); g.col_b[i] = z(f'col_b{i}')
+        g.latent = z('latent'); g.beta = z('beta')
+        return g, bufs
 
     def set_profiling(self, enable=True):
         check(_lib.lib().arah_set_profiling(self._h, int(bool(enable))))
@@ -245,6 +294,104 @@ class ArahRenderer:
         return w, xb
 
 
+
+# =====================================================================================================================
+# training: torch.autograd.Function wrappers around the hand-written forward/backward pairs of the C ABI
+# =====================================================================================================================
+SDF_NAMES = [f'sdf_W{i}' for i in range(7)] + [f'sdf_b{i}' for i in range(7)] + ['sdf_freq', 'sdf_phase']
+SKIN_NAMES = [f'skin_W{i}' for i in range(5)] + [f'skin_b{i}' for i in range(5)]
+COL_NAMES = [f'col_W{i}' for i in range(6)] + [f'col_b{i}' for i in range(6)] + ['latent', 'beta']
+
+
+def _shapes(names, tensors):
+    return {n: tuple(t.shape) for n, t in zip(names, tensors)}
+
+
+class _ShadeFn(torch.autograd.Function):
+    """get_rbg_value_vol_sdf in training mode for all rays (implicit_differentiable_renderer.py:261-396)."""
+
+    @staticmethod
+    def forward(ctx, r, view, view_orig, ray_augm, train_skin, *params):
+        P = r._train_P
+        rgb = torch.empty(P, 3, device=r.device, dtype=torch.float32)
+        ws = torch.empty(P, device=r.device, dtype=torch.float32)
+        v = _f32c(view, r.device).view(-1, 3)
+        vo = _f32c(view_orig, r.device).view(-1, 3) if view_orig is not None else None
+        check(_lib.lib().arah_train_shade_forward(r._h, _ptr(v), _ptr(vo) if vo is not None else None, int(bool(ray_augm)),
+                                                  int(bool(train_skin)), _ptr(rgb), _ptr(ws), r.stream))
+        ctx.r = r
+        ctx.names = SDF_NAMES + SKIN_NAMES + COL_NAMES
+        ctx.shapes = _shapes(ctx.names, params)
+        ctx.train_skin = bool(train_skin)
+        ctx.keep = (v, vo)
+        return rgb, ws
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_ws):
+        r = ctx.r
+        shapes = dict(ctx.shapes)
+        if not ctx.train_skin:
+            for n in SKIN_NAMES:
+                shapes[n] = None
+        g, bufs = r._grad_table(shapes)
+        g_rgb = _f32c(g_rgb, r.device)
+        g_ws = _f32c(g_ws, r.device) if g_ws is not None else None
+        check(_lib.lib().arah_train_shade_backward(r._h, _ptr(g_rgb), _ptr(g_ws) if g_ws is not None else None, C.byref(g), r.stream))
+        return (None, None, None, None, None) + tuple(bufs.get(n) for n in ctx.names)
+
+
+class _SdfFn(torch.autograd.Function):
+    """sdf_network(points) [+ gradient(sdf, points)] for the regularisers (implicit_differentiable_renderer.py:117-140)."""
+
+    @staticmethod
+    def forward(ctx, r, slot, points, with_grad, *params):
+        pts = _f32c(points, r.device).view(-1, 3)
+        n = pts.shape[0]
+        sdf = torch.empty(n, 1, device=r.device, dtype=torch.float32)
+        grad = torch.empty(n, 3, device=r.device, dtype=torch.float32) if with_grad else None
+        check(_lib.lib().arah_train_sdf_forward(r._h, int(slot), _ptr(pts), n, int(bool(with_grad)), _ptr(sdf),
+                                                _ptr(grad) if grad is not None else None, r.stream))
+        ctx.r, ctx.slot, ctx.with_grad = r, int(slot), bool(with_grad)
+        ctx.shapes = _shapes(SDF_NAMES, params)
+        ctx.keep = pts
+        if with_grad:
+            return sdf, grad
+        return sdf
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_grad=None):
+        r = ctx.r
+        g, bufs = r._grad_table(ctx.shapes)
+        gs = _f32c(g_sdf, r.device) if g_sdf is not None else None
+        gg = _f32c(g_grad, r.device) if (g_grad is not None and ctx.with_grad) else None
+        check(_lib.lib().arah_train_sdf_backward(r._h, ctx.slot, _ptr(gs) if gs is not None else None, _ptr(gg) if gg is not None else None,
+                                                 C.byref(g), r.stream))
+        return (None, None, None, None) + tuple(bufs.get(n) for n in SDF_NAMES)
+
+
+class _SkinFn(torch.autograd.Function):
+    """query_weights(points_skinning) (utils/root_finding_utils.py:54-113)."""
+
+    @staticmethod
+    def forward(ctx, r, points, *params):
+        pts = _f32c(points, r.device).view(-1, 3)
+        n = pts.shape[0]
+        w = torch.empty(n, 24, device=r.device, dtype=torch.float32)
+        check(_lib.lib().arah_train_skin_forward(r._h, _ptr(pts), n, _ptr(w), r.stream))
+        ctx.r = r
+        ctx.shapes = _shapes(SKIN_NAMES, params)
+        ctx.keep = pts
+        return w
+
+    @staticmethod
+    def backward(ctx, g_w):
+        r = ctx.r
+        g, bufs = r._grad_table(ctx.shapes)
+        gw = _f32c(g_w, r.device)
+        check(_lib.lib().arah_train_skin_backward(r._h, _ptr(gw), C.byref(g), r.stream))
+        return (None, None) + tuple(bufs.get(n) for n in SKIN_NAMES)
+
+
 # =====================================================================================================================
 class BodyRayTracing(nn.Module):
     """Ray-tracer for the articulated body SDF — same constructor as the reference (ray_tracing.py:16-49).
@@ -272,13 +419,19 @@ class BodyRayTracing(nn.Module):
     def forward(self, sdf_network, skinning_model, cam_loc, ray_directions, body_bounds_intersections, loc, sc_factor,
                 smpl_verts, smpl_verts_cano, skinning_weights, vol_feat, bone_transforms, trans, coord_min, coord_max, center,
                 eval_mode=False):
-        if not eval_mode:
-            raise NotImplementedError('training-mode ray tracing (stochastic z perturbation) is SURVEY.md §8 row f2')
         owner = self._owner() if self._owner is not None else None
         if owner is None:
             raise _lib.ArahError('BodyRayTracing must be owned by an IDHRNetwork (it shares its renderer handle)')
         return owner._trace_only(sdf_network, cam_loc, ray_directions, body_bounds_intersections, smpl_verts,
-                                       skinning_weights, bone_transforms, trans, coord_min, coord_max, center)
+                                       skinning_weights, bone_transforms, trans, coord_min, coord_max, center, train=not eval_mode)
+
+    def draw_jitter(self, P):
+        """The three uniform draws of ray_sampler in training mode, in the reference's order and shapes and — like the
+        reference, which calls torch.rand(shape).to(device) (ray_tracing.py:305) — from the CPU generator."""
+        u_all = torch.rand(1, P, self.n_steps)
+        u_near = torch.rand(1, P, self.near_surface_vol_samples + 1)
+        u_far = torch.rand(1, P, self.far_surface_vol_samples) if self.far_surface_vol_samples > 0 else None
+        return u_all, u_near, u_far
 
 
 class IDHRNetwork(nn.Module):
@@ -316,7 +469,7 @@ class IDHRNetwork(nn.Module):
             self._renderers[key] = r
         return r
 
-    def _prepare(self, input):
+    def _prepare(self, input, training=False):
         ray_dirs = input['ray_dirs']
         if ray_dirs.device.type != 'cuda':
             raise _lib.ArahError('IDHRNetwork (B200) needs CUDA tensors; there is no CPU fallback')
@@ -324,13 +477,85 @@ class IDHRNetwork(nn.Module):
             raise _lib.ArahError('one frame per call (the reference assumes the same, ray_tracing.py:129-132)')
         latent_dim = _effective_weight(self.rendering_network.lin0).shape[1] - 289
         r = self._renderer(ray_dirs.device, latent_dim, input['smpl_verts'].shape[1])
+        r.set_training(training)
         r.set_frame_from_modules(input['sdf_network'], self.skinning_model, self.rendering_network, self.deviation_network, input)
         return r
 
+    # ------------------------------------------------------------------ training
+    def _param_tensors(self, input):
+        """Parameter tensors WITH their autograd graph, in the order / layout of ArahTrainGrads."""
+        net = input['sdf_network']
+        sdf = [net[l][0].weights.reshape(256, -1) for l in range(6)] + [net[6].weights.reshape(1, 256)]
+        sdf += [net[l][0].biases.reshape(-1) for l in range(6)] + [net[6].biases.reshape(-1)]
+        sdf += [torch.stack([net[l][0].freq.reshape(-1) for l in range(6)]), torch.stack([net[l][0].phase_shift.reshape(-1) for l in range(6)])]
+        dec = self.skinning_model.skinning_decoder_fwd
+        skin = [_effective_weight_grad(getattr(dec, f'lin{i}')) for i in range(5)] + [getattr(dec, f'lin{i}').bias for i in range(5)]
+        rn = self.rendering_network
+        col = [_effective_weight_grad(getattr(rn, f'lin{i}')) for i in range(6)] + [getattr(rn, f'lin{i}').bias for i in range(6)]
+        lat = input['pose_cond'].get('latent_code') if isinstance(input.get('pose_cond'), dict) else None
+        if lat is None:
+            lat = torch.zeros(0, device=sdf[0].device)
+        col += [lat.reshape(-1), torch.linalg.norm(self.deviation_network.variance).reshape(1)]
+        return sdf, skin, col
+
+    def _rand_device(self, shape, device):
+        """torch.rand on the compute device (the eikonal points, implicit_differentiable_renderer.py:126); tests override it."""
+        return torch.rand(*shape, device=device, dtype=torch.float32)
+
+    def _forward_train(self, input):
+        ray_dirs = input['ray_dirs']
+        device = ray_dirs.device
+        batch_size, P, _ = ray_dirs.shape
+        r = self._prepare(input, training=True)
+        sdf_p, skin_p, col_p = self._param_tensors(input)
+        pose_cond = input.get('pose_cond', {})
+        rt = self.ray_tracer
+        # tracer, no gradient (:84-108)
+        with torch.no_grad():
+            u_all, u_near, u_far = rt.draw_jitter(P) if isinstance(rt, BodyRayTracing) else BodyRayTracing.draw_jitter(rt, P)
+            r.train_trace(ray_dirs[0], input['body_bounds_intersections'][0], u_all, u_near, u_far)
+            _, _, _, _, _, _, conv = r.trace_outputs(P, transforms=False, points=False)
+        vol_mask = conv.any(-1)                                         # :148
+        # view augmentation (:150-162)
+        ray_augm = False
+        view_orig = ray_dirs
+        view = ray_dirs
+        if 'view_noise' in pose_cond.keys():
+            vn = pose_cond['view_noise']
+            if vn is not None:
+                if vn.size(-1) == 3 and vn.size(-2) == 3:
+                    view = torch.matmul(vn, ray_dirs.transpose(1, 2)).transpose(1, 2)
+                    ray_augm = True
+                else:
+                    view = ray_dirs + vn
+            else:
+                view = torch.zeros_like(ray_dirs)
+        rgb, ws = _ShadeFn.apply(r, view[0].detach(), view_orig[0].detach(), ray_augm, self.train_skinning_net, *(sdf_p + skin_p + col_p))
+        # regularisers (:73-78,117-140)
+        out_extra = {}
+        if 'points_skinning' in input.keys():
+            out_extra['pred_weights'] = _SkinFn.apply(r, input['points_skinning'].reshape(-1, 3), *skin_p).view(
+                input['points_skinning'].shape[0], -1, 24)
+        if 'points_inside' in input.keys():
+            out_extra['inside_sdf'] = _SdfFn.apply(r, 1, input['points_inside'].reshape(-1, 3), False, *sdf_p)
+        n_eik = 1024
+        eik = (self._rand_device((batch_size, n_eik, 3), device) - 0.5) * 2
+        points_uniform = input['points_uniform'].reshape(-1, 3)
+        points_all = torch.cat([eik.reshape(-1, 3), points_uniform], dim=0)
+        sdf_all, grad_all = _SdfFn.apply(r, 0, points_all, True, *sdf_p)
+        n_e, n_u = batch_size * n_eik, batch_size * 1024
+        uniform_sdf = sdf_all[n_e:n_e + n_u, :].reshape(batch_size, 1024, 1)
+        grad_eik = grad_all[:n_e, :]
+        self._last = (r, P)
+        output = {'rgb_values': rgb.unsqueeze(0), 'sdf_output': ws.unsqueeze(0), 'network_body_mask': vol_mask,
+                  'body_mask': input['body_mask'], 'off_surface_mask': vol_mask, 'off_surface_sdf': uniform_sdf,
+                  'grad_theta': grad_eik, 'surface_normals': None}
+        output.update(out_extra)
+        return output
+
     def forward(self, input):
         if self.training:
-            raise NotImplementedError('training forward/backward through root finding is SURVEY.md §8 row f2; '
-                                      'call .eval() for rendering')
+            return self._forward_train(input)
         r = self._prepare(input)
         P = input['ray_dirs'].shape[1]
         rgb, mask, pc = r.render(input['ray_dirs'][0], input['body_bounds_intersections'][0])
@@ -338,7 +563,7 @@ class IDHRNetwork(nn.Module):
         return {'points_cam': pc.unsqueeze(0), 'network_body_mask': mask.unsqueeze(0), 'rgb_values': rgb.unsqueeze(0)}
 
     def _trace_only(self, sdf_network, cam_loc, ray_directions, body_bounds_intersections, smpl_verts, skinning_weights,
-                    bone_transforms, trans, coord_min, coord_max, center):
+                    bone_transforms, trans, coord_min, coord_max, center, train=False):
         inp = {'ray_dirs': ray_directions, 'cam_loc': cam_loc, 'pose': torch.eye(4, device=ray_directions.device).view(1, 4, 4),
                'body_bounds_intersections': body_bounds_intersections, 'smpl_verts': smpl_verts,
                'skinning_weights': skinning_weights, 'bone_transforms': bone_transforms, 'trans': trans,
@@ -347,7 +572,11 @@ class IDHRNetwork(nn.Module):
                                                         device=ray_directions.device)}}
         r = self._prepare(inp)
         P = ray_directions.shape[1]
-        r.render(ray_directions[0], body_bounds_intersections[0])
+        if train:
+            u_all, u_near, u_far = self.ray_tracer.draw_jitter(P)
+            r.train_trace(ray_directions[0], body_bounds_intersections[0], u_all, u_near, u_far)
+        else:
+            r.render(ray_directions[0], body_bounds_intersections[0])
         return r.trace_outputs(P)
 
     def tracer_outputs(self):

@@ -151,6 +151,51 @@ int arah_debug_phase_clocks(ArahHandle* h, uint64_t* out32, void* stream);
  * `.ts` MMA form); synchronises the stream. */
 int arah_debug_umma_gemm(const float* A, const float* W, int32_t K, int32_t N, float* D, int32_t a_in_tmem, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training (BASELINE configs[2]; IDHRNetwork.forward with self.training == True,
+ * renderer/implicit_differentiable_renderer.py:73-78,117-178,235-249, get_rbg_value_vol_sdf :261-396).
+ *
+ * The tracer runs without gradient (the reference wraps it in torch.no_grad, :84); the differentiable part — implicit-
+ * gradient LBS correction, SDF forward, SDF input gradient as normal (differentiated a second time in backward), colour
+ * MLP, sigma-from-SDF compositing, plus the auxiliary SDF / skinning evaluations of the regularisers — is a hand-written
+ * forward/backward pair per entry point.  The host side (renderer.py) wraps each pair in a torch.autograd.Function.
+ * Weights are those of the last arah_set_frame issued AFTER arah_set_training(h, 1) (raw reference-layout copies are kept
+ * for the backward).  Gradient buffers are caller-zeroed fp32 device buffers in the layout of the corresponding ArahFrame
+ * member ([out][in], weight-norm applied: d L / d (g v / ||v||)); entry points ACCUMULATE into them; NULL members are skipped.
+ * One forward may be outstanding per context: shading (1), SDF evaluation slots 0..2, skinning evaluation (1).
+ * arah_train_shade_forward synchronises the stream once (it reads the number of converged samples). */
+typedef struct ArahTrainGrads {
+    float* sdf_W[7]; float* sdf_b[7]; float* sdf_freq; float* sdf_phase;
+    float* skin_W[5]; float* skin_b[5];
+    float* col_W[6]; float* col_b[6];
+    float* latent;                /* [latent_dim] */
+    float* beta;                  /* [1]  d L / d ||variance|| */
+} ArahTrainGrads;
+
+int arah_set_training(ArahHandle* h, int32_t enable);
+
+/* BodyRayTracing.forward(eval_mode=False) (renderer/ray_tracing.py:51-172): every ray enters the joint search (:249) and the
+ * z samples are jittered (:298-311) with the caller's three uniform draws u_all [P][n_steps], u_near [P][near+1],
+ * u_far [P][far] (the reference draws them with torch.rand on the CPU generator in this order).  Results: arah_get_trace. */
+int arah_train_trace(ArahHandle* h, const float* ray_dirs, const float* near_far, int32_t P, const float* u_all, const float* u_near,
+                     const float* u_far, void* stream);
+
+/* Differentiable shading of the samples of the last arah_train_trace.  view_dirs [P][3]: ray directions after view
+ * augmentation (:152-162), view_dirs_orig [P][3] (may be NULL = same); ray_augm: apply the back-facing test of :342-350.
+ * -> rgb [P][3] ('rgb_values'), weights_sum [P] ('sdf_output'); both 0 for rays without a converged sample. */
+int arah_train_shade_forward(ArahHandle* h, const float* view_dirs, const float* view_dirs_orig, int32_t ray_augm,
+                             int32_t train_skinning_net, float* rgb, float* weights_sum, void* stream);
+int arah_train_shade_backward(ArahHandle* h, const float* g_rgb, const float* g_weights_sum, const ArahTrainGrads* grads, void* stream);
+
+/* sdf_network(points) and (with_grad) gradient(sdf, points) for the eikonal / off-surface / inside terms (:117-140):
+ * points [n][3] normalised -> sdf [n] (raw network output), grad [n][3].  Backward takes d L / d sdf and d L / d grad. */
+int arah_train_sdf_forward(ArahHandle* h, int32_t slot, const float* points, int32_t n, int32_t with_grad, float* sdf, float* grad, void* stream);
+int arah_train_sdf_backward(ArahHandle* h, int32_t slot, const float* g_sdf, const float* g_grad, const ArahTrainGrads* grads, void* stream);
+
+/* query_weights(points_skinning) (:73-78; utils/root_finding_utils.py:54-113): points [n][3] in metres -> weights [n][24]. */
+int arah_train_skin_forward(ArahHandle* h, const float* points, int32_t n, float* weights, void* stream);
+int arah_train_skin_backward(ArahHandle* h, const float* g_weights, const ArahTrainGrads* grads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,186 @@
+"""GPU: the training path (BASELINE configs[2]) through the drop-in modules -> C ABI -> CUDA kernels,
+against one training step of the UNMODIFIED reference (tests/golden/train_*.npz) and against the torch oracle
+(oracle/train_oracle.py) at a larger size.  Gradients are read from the .grad of the modules' own parameters, i.e. after
+torch's weight-norm / norm backward, exactly as an optimiser would see them."""
+import numpy as np
+import pytest
+import torch
+
+from helpers_train import TRAIN_CASES, compare_grad, load_train_golden
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def build_net(fr, train_skinning_net, leaves=True):
+    from arah_release_b200 import ref_layout as rl
+    from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
+    dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
+    sdf_leaves = {}
+    if leaves:                          # hypernetwork outputs stand in as leaves so that their .grad can be read
+        for l in range(6):
+            film = sdf[l][0]
+            for n in ('weights', 'biases', 'freq', 'phase_shift'):
+                v = getattr(film, n).clone().requires_grad_(True); setattr(film, n, v); sdf_leaves[f'sdf.{l}.{n}'] = v
+        for n in ('weights', 'biases'):
+            v = getattr(sdf[6], n).clone().requires_grad_(True); setattr(sdf[6], n, v); sdf_leaves[f'sdf.6.{n}'] = v
+    net = IDHRNetwork(dev, rend, skin, BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples,
+                                                      far_surface_vol_samples=fr.far_samples),
+                      cano_view_dirs=fr.cano_view_dirs, train_skinning_net=train_skinning_net, shade_mode='fp32', root_mode='fp32')
+    net.train()
+    # the reference draws the eikonal points on the compute device; the CPU goldens drew them from the CPU generator
+    net._rand_device = lambda shape, device: torch.rand(*shape).to(device)
+    return net, sdf, sdf_leaves
+
+
+def train_inputs(fr, sdf, aux):
+    from arah_release_b200 import ref_layout as rl
+    inp = rl.inputs_from_frame(fr, sdf, DEV)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    inp['pose_cond']['latent_code'] = inp['pose_cond']['latent_code'].clone().requires_grad_(True)
+    inp['body_mask'] = t(aux['body_mask']).view(1, -1)
+    inp['points_uniform'] = t(aux['points_uniform']).float().view(1, -1, 3)
+    inp['points_skinning'] = t(aux['points_skinning']).float().view(1, -1, 3)
+    inp['points_inside'] = t(aux['points_inside']).float().view(1, -1, 3)
+    return inp
+
+
+def loss_of(out, aux, lw):
+    from oracle import train_oracle as to
+    o = {'rgb_values': out['rgb_values'][0], 'sdf_output': out['sdf_output'][0], 'vol_mask': out['network_body_mask'][0],
+         'grad_theta': out['grad_theta'], 'off_surface_sdf': out['off_surface_sdf'], 'inside_sdf': out['inside_sdf'],
+         'pred_weights': out['pred_weights'][0]}
+    return to.loss_terms(o, aux, lw, device=DEV)
+
+
+@pytest.mark.parametrize('name', TRAIN_CASES)
+def test_train_trace_matches_reference(name):
+    """BodyRayTracing.forward(eval_mode=False) through the sub-boundary (ray_tracing.py:51-172)."""
+    fr, aux, ref, grads, meta = load_train_golden(name)
+    net, sdf, _ = build_net(fr, meta['train_skinning_net'], leaves=False)
+    inp = train_inputs(fr, sdf, aux)
+    torch.manual_seed(meta['seed'])
+    with torch.no_grad():
+        tr = net.ray_tracer(sdf, net.skinning_model, cam_loc=inp['cam_loc'], ray_directions=inp['ray_dirs'],
+                            body_bounds_intersections=inp['body_bounds_intersections'], loc=inp['loc'], sc_factor=inp['sc_factor'],
+                            smpl_verts=inp['smpl_verts'], smpl_verts_cano=inp['minimal_shape'], skinning_weights=inp['skinning_weights'],
+                            vol_feat=inp['vol_feat'], bone_transforms=inp['bone_transforms'], trans=inp['trans'],
+                            coord_min=inp['coord_min'], coord_max=inp['coord_max'], center=inp['center'], eval_mode=False)
+    pn, mask, dists, sp, sd, sT, sc = [v[0].cpu().numpy() for v in tr]
+    assert (mask != ref['trace.network_body_mask']).mean() <= 0.01
+    # a ray whose joint search flips (training mode also searches diverged rays, from far-off starts) changes its whole
+    # sample layout (near+1+far vs n_steps slots): compare samples on rays whose hit flag agrees
+    agree = mask == ref['trace.network_body_mask']
+    cm = ref['trace.sampler_converge_mask'].astype(bool)
+    assert (cm != sc)[agree].mean() <= 1e-3
+    both = cm & sc & agree[:, None]
+    assert np.abs(sd - ref['trace.sampled_dists'])[agree].max() <= 1e-5
+    assert np.abs(sp - ref['trace.sampled_pts'])[both].max() <= 3e-4
+    assert np.abs(sT - ref['trace.sampled_transforms'])[both].max() <= 5e-4
+    m2 = mask & ref['trace.network_body_mask']
+    assert np.abs(dists - ref['trace.dists'])[m2].max() <= 1e-4 if m2.any() else True
+    print(name, 'train trace ok: rays', mask.size, 'hit', int(mask.sum()), 'samples', int(sc.sum()))
+
+
+@pytest.mark.parametrize('name', TRAIN_CASES)
+def test_train_step_matches_reference(name):
+    """Forward outputs, loss and the gradient of every parameter tensor after loss.backward()."""
+    from oracle import train_oracle as to
+    fr, aux, ref, grads, meta = load_train_golden(name)
+    net, sdf, sdf_leaves = build_net(fr, meta['train_skinning_net'])
+    inp = train_inputs(fr, sdf, aux)
+    torch.manual_seed(meta['seed'])
+    out = net(inp)
+    hit = net.tracer_outputs()[1][0].cpu().numpy()
+    agree = hit == ref['trace.network_body_mask']
+    assert (~agree).mean() <= 0.01
+    strict = bool(agree.all())          # a flipped ray (see test_train_trace_matches_reference) perturbs loss and gradients
+    assert np.abs(out['rgb_values'][0].detach().cpu().numpy() - ref['out.rgb_values'][0])[agree].max() <= 2e-4
+    assert np.abs(out['sdf_output'][0].detach().cpu().numpy() - ref['out.sdf_output'][0])[agree].max() <= 2e-4
+    assert (out['network_body_mask'][0].cpu().numpy() != ref['out.network_body_mask']).mean() <= 0.01
+    gt_ref = ref['out.grad_theta']
+    assert np.abs(out['grad_theta'].detach().cpu().numpy() - gt_ref).max() <= 1e-4 * max(1.0, np.abs(gt_ref).max())
+    assert np.abs(out['off_surface_sdf'].detach().cpu().numpy() - ref['out.off_surface_sdf']).max() <= 1e-5
+    assert np.abs(out['inside_sdf'].detach().cpu().numpy() - ref['out.inside_sdf']).max() <= 1e-5
+    assert np.abs(out['pred_weights'].detach().cpu().numpy() - ref['out.pred_weights']).max() <= 1e-5
+    lw = dict(to.LOSS_WEIGHTS); lw.update(meta['loss_weights'])
+    terms = loss_of(out, aux, lw)
+    lref = float(ref['loss.loss'])
+    assert abs(float(terms['loss'].detach()) - lref) <= (2e-4 if strict else 1e-2) * max(1.0, abs(lref)), (float(terms['loss'].detach()), lref)
+    terms['loss'].backward()
+    torch.cuda.synchronize()
+    ours = {'grad.' + k: v.grad for k, v in sdf_leaves.items()}
+    ours['grad.latent'] = inp['pose_cond']['latent_code'].grad
+    for k, p in net.named_parameters():
+        ours['grad.' + k] = p.grad
+    worst, worst_k = 1.0, None
+    for k, dig in grads.items():
+        g = ours[k]
+        g = np.zeros(1, np.float32) if g is None else g.detach().cpu().numpy()
+        if g.size == 1 and 'full' in dig and np.asarray(dig['full']).size > 1:
+            g = np.zeros(np.asarray(dig['full']).shape, np.float32)
+        elif g.size == 1 and 'idx' in dig:
+            g = np.zeros(int(dig['idx'].max()) + 1, np.float32)
+        # the tracer feeds slightly different samples (<= 1e-3 flipped convergence flags): looser than the host-engine test
+        st = compare_grad(k, g, dig, cos_min=0.999 if strict else 0.99, rel_fro=2e-2 if strict else 0.1)
+        if st['cos'] < worst:
+            worst, worst_k = st['cos'], k
+    print(name, 'rays agreeing', int(agree.sum()), '/', agree.size, 'loss', float(terms['loss'].detach()), 'ref', lref, 'min gradient cosine vs reference', worst, worst_k, net.stats())
+
+
+def test_train_step_1024_rays_vs_torch_oracle():
+    """BASELINE configs[2] size (about 1k rays) with view-rotation augmentation: CUDA forward/backward vs torch autograd over the
+    oracle restatement, fed with the SAME traced samples (read back through arah_get_trace)."""
+    from arah_release_b200 import synthetic as syn
+    from oracle import train_oracle as to
+    fr = syn.make_frame(H=36, W=36, seed=9)
+    aux = syn.train_aux_points(fr, seed=9)
+    net, sdf, sdf_leaves = build_net(fr, True)
+    inp = train_inputs(fr, sdf, aux)
+    c, s_ = np.cos(0.3), np.sin(0.3)
+    Rz = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]], np.float32)
+    inp['pose_cond']['view_noise'] = torch.from_numpy(Rz).to(DEV).view(1, 3, 3)
+    torch.manual_seed(21)
+    out = net(inp)
+    tr = net.tracer_outputs()
+    trace = {'sampled_pts': tr[3][0].cpu().numpy(), 'sampled_dists': tr[4][0].cpu().numpy(), 'sampled_transforms': tr[5][0].cpu().numpy(),
+             'sampler_converge_mask': tr[6][0].cpu().numpy()}
+    w = torch.from_numpy(np.random.default_rng(0).normal(size=(fr.P, 3)).astype(np.float32))
+    wv = torch.from_numpy(np.random.default_rng(1).normal(size=fr.P).astype(np.float32))
+    (out['rgb_values'][0] * w.to(DEV)).sum().add((out['sdf_output'][0] * wv.to(DEV)).sum()).backward()
+    torch.cuda.synchronize()
+    p = to.make_params(fr)
+    e = to.effective_weights(p)
+    view = (torch.from_numpy(Rz) @ torch.from_numpy(fr.ray_dirs).t()).t().numpy()
+    rgb_o, ws_o = to.shade(fr, p, e, trace, view, fr.ray_dirs, train_skinning_net=True, ray_augm=True)
+    ((rgb_o * w).sum() + (ws_o * wv).sum()).backward()
+    assert np.abs(out['rgb_values'][0].detach().cpu().numpy() - rgb_o.detach().numpy()).max() <= 2e-5
+    assert np.abs(out['sdf_output'][0].detach().cpu().numpy() - ws_o.detach().numpy()).max() <= 2e-5
+    ours = {}
+    for k, v in sdf_leaves.items():
+        ours[k] = v.grad
+    for k, q in net.named_parameters():
+        ours[k.replace('rendering_network.', 'col.').replace('skinning_model.skinning_decoder_fwd.', 'skin.').replace('deviation_network.', '')] = q.grad
+    ours['latent'] = inp['pose_cond']['latent_code'].grad
+    worst, worst_k = 1.0, None
+    for k, v in p.items():
+        if v.grad is None:
+            continue
+        a = ours[k].detach().cpu().numpy().reshape(-1).astype(np.float64)
+        b = v.grad.numpy().reshape(-1).astype(np.float64)
+        nb = np.sqrt((b * b).sum())
+        if nb < 1e-12:
+            continue
+        cos = float((a * b).sum() / max(np.sqrt((a * a).sum()) * nb, 1e-300))
+        rel = abs(np.sqrt((a * a).sum()) - nb) / nb
+        assert cos >= 0.99999 and rel <= 1e-3, (k, cos, rel)
+        if cos < worst:
+            worst, worst_k = cos, k
+    print('rays', fr.P, 'samples', int(trace['sampler_converge_mask'].sum()), 'min gradient cosine vs torch oracle', worst, worst_k, net.stats())
+
+
+def test_training_mode_requires_cuda_library():
+    """No eager fallback: the training branch goes through the C ABI only."""
+    import arah_release_b200.renderer as R
+    src = open(R.__file__).read()
+    assert 'arah_train_shade_backward' in src and 'torch.autograd.grad' not in src

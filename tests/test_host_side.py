@@ -56,10 +56,12 @@ def test_state_dict_layout_matches_reference_names():
             assert f'skinning_model.skinning_decoder_fwd.lin{l}.{p}' in keys
     assert 'deviation_network.variance' in keys
     assert net.ray_tracer.n_steps == 64 and net.ray_tracer.near_surface_vol_samples == 16
-    # training forward is explicitly out of scope for this round
+    # training mode has no CPU path either: CPU tensors are refused before anything is computed
+    from arah_release_b200 import _lib
+    sdf = rl.sdf_network_from_frame(fr, 'cpu')
     net.train()
-    with pytest.raises(NotImplementedError):
-        net({})
+    with pytest.raises(_lib.ArahError):
+        net(rl.inputs_from_frame(fr, sdf, 'cpu'))
 
 
 def test_synthetic_frame_is_deterministic_and_sane():
