@@ -315,6 +315,7 @@ struct ArahHandle {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // training (arah_train.h): raw reference-layout weight copies + the engine's saved activations
     bool training = false, train_traced = false;
+    int train_precision = ARAH_TRAIN_3XTF32;
     DevBuf raw;
     arah::train::AllParams tp{};
     arah::train::Session<arah::train::CudaBK>* sess = nullptr;
@@ -843,6 +844,7 @@ static int train_ready(ArahHandle* h) {
     if (!h->training) return fail(ARAH_ESTATE, "call arah_set_training(h, 1) before arah_set_frame");
     if (!h->frame_set || !h->raw.p) return fail(ARAH_ESTATE, "arah_set_frame must follow arah_set_training(h, 1)");
     if (!h->sess) h->sess = new arah::train::Session<CudaBK>();
+    CudaBK::precision() = (h->train_precision == ARAH_TRAIN_FP32) ? 1 : (h->train_precision == ARAH_TRAIN_TF32 ? 2 : 0);
     return ARAH_OK;
 }
 static int train_done(ArahHandle* h, int rc, const char* what) {
@@ -856,6 +858,7 @@ static int train_done(ArahHandle* h, int rc, const char* what) {
 extern "C" int arah_set_training(ArahHandle* h, int32_t enable) {
     if (!h) return fail(ARAH_EINVAL, "null handle");
     h->training = enable != 0;
+    if (enable == ARAH_TRAIN_3XTF32 || enable == ARAH_TRAIN_FP32 || enable == ARAH_TRAIN_TF32) h->train_precision = enable;
     if (!h->training && h->sess) { h->sess->release(); delete h->sess; h->sess = nullptr; h->raw.release(); }
     return ARAH_OK;
 }
@@ -940,4 +943,14 @@ extern "C" int arah_train_skin_backward(ArahHandle* h, const float* g_weights, c
     CudaBK::launches() = 0;
     rc = h->sess->skin_backward(h->tp, to_grads(grads), g_weights, (cudaStream_t)stream);
     return train_done(h, rc, "arah_train_skin_backward");
+}
+
+extern "C" int arah_debug_train_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_k,
+                                     int64_t sb_j, float* C, int32_t ldc, const float* bias, int32_t accumulate, int32_t mode, void* stream) {
+    if (!A || !B || !C || M < 0 || N < 0 || K <= 0) return fail(ARAH_EINVAL, "bad arguments");
+    CudaBK::precision() = (mode == ARAH_TRAIN_FP32) ? 1 : (mode == ARAH_TRAIN_TF32 ? 2 : 0);
+    CudaBK::gemm(M, N, K, A, (long)sa_i, (long)sa_k, B, (long)sb_k, (long)sb_j, C, ldc, bias, accumulate != 0, (cudaStream_t)stream);
+    CudaBK::launches() = 0;
+    CU(cudaGetLastError());
+    return ARAH_OK;
 }

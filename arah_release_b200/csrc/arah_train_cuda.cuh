@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "arah_train.h"
+#include "arah_train_tc.cuh"
 
 namespace arah {
 namespace train {
@@ -16,11 +17,11 @@ __global__ void __launch_bounds__(256) k_for_each(size_t n, F f) {
 
 // out[r][j] += sum_m f(m, j)[r];  f is called exactly once per (m, j) (it may also write per-element results)
 template <int NR, class F>
-__global__ void __launch_bounds__(256) k_col_reduce(int M, int N, int bx, F f, float* o0, float* o1, float* o2) {
+__global__ void __launch_bounds__(256) k_col_reduce(int M, int N, int bx, int rows, F f, float* o0, float* o1, float* o2) {
     __shared__ float sh[NR][256];
     const int by = 256 / bx;
     const int tx = threadIdx.x % bx, ty = threadIdx.x / bx;
-    const int m0 = blockIdx.x * 256, m1 = min(M, m0 + 256);
+    const int m0 = blockIdx.x * rows, m1 = min(M, m0 + rows);
     float* outs[3] = {o0, o1, o2};
     for (int jb = 0; jb < N; jb += bx) {          // every thread runs the same number of rounds (barriers inside)
         const int j = jb + tx;
@@ -139,12 +140,65 @@ struct CudaBK {
         if (M == 0 || N == 0) return;
         int bx = 32;
         while (bx < N && bx < 256) bx <<= 1;
-        k_col_reduce<NR, F><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(M, N, bx, f, outs[0], NR > 1 ? outs[1] : nullptr, NR > 2 ? outs[2] : nullptr);
+        // 32 rows per row-lane: enough blocks (M/32 for 256-wide matrices) to keep the memory system busy; the price is one atomic
+        // per column and block
+        const int rows = 32 * (256 / bx);
+        k_col_reduce<NR, F><<<(unsigned)((M + rows - 1) / rows), 256, 0, st>>>(M, N, bx, rows, f, outs[0], NR > 1 ? outs[1] : nullptr, NR > 2 ? outs[2] : nullptr);
+        ++launches();
+    }
+    // 0 = tcgen05 3xTF32 (default, fp32-class), 1 = fp32 SIMT FFMA, 2 = tcgen05 single-pass TF32
+    static int& precision() { static int p = 0; return p; }
+    static void gemm_tc(int M, int N, int K, const float* A, long sa_i, long sa_k, const float* B, long sb_k, long sb_j, float* C, int ldc,
+                        const float* bias, bool accumulate, Stream st) {
+        const bool akc = (sa_k == 1), bkc = (sb_k == 1);
+        const int BN = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+        dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + 127) / 128), 1);
+        int splits = 1;
+        const long tiles = (long)grid.x * grid.y;
+        if (accumulate && K >= 2048 && tiles < 296) {
+            splits = (int)((296 + tiles - 1) / tiles);
+            const int maxs = (K + 511) / 512;
+            if (splits > maxs) splits = maxs;
+            if (splits < 1) splits = 1;
+        }
+        int kchunk = (K + splits - 1) / splits;
+        kchunk = (kchunk + 31) / 32 * 32;
+        splits = (K + kchunk - 1) / kchunk;
+        grid.z = (unsigned)splits;
+        const int ua = splits > 1 ? 1 : 0, acc = accumulate ? 1 : 0;
+        const bool x3 = precision() == 0;
+        const int smem = gemm_tc_smem_bytes(BN, x3);
+        auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+        const bool va = akc && (sa_i % 4 == 0) && al16(A), vb = bkc && (sb_j % 4 == 0) && al16(B);
+        const int vc = (ldc % 4 == 0 && al16(C) && (!bias || al16(bias))) ? 1 : 0;
+#define ARAH_TC_CASE(BN_, AK, BK_, X3_, VA_, VB_) do { \
+            static bool attr_set = false; \
+            if (!attr_set) { cudaFuncSetAttribute(k_gemm_tc<BN_, AK, BK_, X3_, VA_, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_tc_smem_bytes(BN_, X3_)); attr_set = true; } \
+            k_gemm_tc<BN_, AK, BK_, X3_, VA_, VB_><<<grid, TC_THREADS_GEMM, smem, st>>>(M, N, K, A, sa_i, sa_k, B, sb_k, sb_j, C, ldc, bias, acc, kchunk, ua, vc); } while (0)
+        // vector loads only exist for k-contiguous operands: (AK, VA) in {(1,1), (1,0), (0,0)}
+#define ARAH_TC_B(BN_, X3_, AK, VA_) do { \
+            if (bkc && vb) ARAH_TC_CASE(BN_, AK, true, X3_, VA_, true); else if (bkc) ARAH_TC_CASE(BN_, AK, true, X3_, VA_, false); \
+            else ARAH_TC_CASE(BN_, AK, false, X3_, VA_, false); } while (0)
+#define ARAH_TC_AB(BN_, X3_) do { \
+            if (akc && va) ARAH_TC_B(BN_, X3_, true, true); else if (akc) ARAH_TC_B(BN_, X3_, true, false); else ARAH_TC_B(BN_, X3_, false, false); } while (0)
+#define ARAH_TC_BN(BN_) do { if (x3) ARAH_TC_AB(BN_, true); else ARAH_TC_AB(BN_, false); } while (0)
+        if (BN == 32) ARAH_TC_BN(32); else if (BN == 64) ARAH_TC_BN(64); else if (BN == 128) ARAH_TC_BN(128); else ARAH_TC_BN(256);
+#undef ARAH_TC_BN
+#undef ARAH_TC_AB
+#undef ARAH_TC_B
+#undef ARAH_TC_CASE
         ++launches();
     }
     static void gemm(int M, int N, int K, const float* A, long sa_i, long sa_k, const float* B, long sb_k, long sb_j, float* C, int ldc,
                      const float* bias, bool accumulate, Stream st) {
         if (M == 0 || N == 0) return;
+        if (precision() != 1) {
+            if (N > 256) {      // wider than one tile: column blocks of 256
+                for (int j = 0; j < N; j += 256)
+                    gemm_tc(M, (N - j) < 256 ? (N - j) : 256, K, A, sa_i, sa_k, B + (long)j * sb_j, sb_k, sb_j, C + j, ldc, bias ? bias + j : nullptr, accumulate, st);
+            } else gemm_tc(M, N, K, A, sa_i, sa_k, B, sb_k, sb_j, C, ldc, bias, accumulate, st);
+            return;
+        }
         const bool akc = (sa_k == 1), bjc = (sb_j == 1);
         const int BN = (N <= 32) ? 32 : 128;
         dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + 127) / 128), 1);

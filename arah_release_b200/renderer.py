@@ -227,8 +227,11 @@ class ArahRenderer:
                 sd.unsqueeze(0) if sd is not None else None, sT.unsqueeze(0) if sT is not None else None, sc.bool().unsqueeze(0))
 
     # ------------------------------------------------------------------ training (arah_train_*)
-    def set_training(self, enable=True):
-        check(_lib.lib().arah_set_training(self._h, int(bool(enable))))
+    def set_training(self, mode='3xtf32'):
+        """mode: False/None = off, '3xtf32' (tcgen05 tensor cores, split precision; default), 'fp32' (SIMT FFMA GEMMs) or
+        'tf32' (single-pass TF32 operands)."""
+        code = 0 if not mode else {'3xtf32': 1, 'fp32': 2, 'tf32': 3, True: 1}[mode]
+        check(_lib.lib().arah_set_training(self._h, code))
 
     def train_trace(self, ray_dirs, near_far, u_all, u_near, u_far):
         """BodyRayTracing.forward(eval_mode=False); results via trace_outputs()."""
@@ -439,8 +442,9 @@ class IDHRNetwork(nn.Module):
     (implicit_differentiable_renderer.py:18-40); eval forward runs entirely in libarah_b200.so."""
 
     def __init__(self, deviation_network, rendering_network, skinning_model, ray_tracer, cano_view_dirs=True,
-                 train_skinning_net=False, render_last_pt=False, low_vram=False, shade_mode=None, root_mode=None):
+                 train_skinning_net=False, render_last_pt=False, low_vram=False, shade_mode=None, root_mode=None, train_mode=None):
         super().__init__()
+        self.train_mode = train_mode      # extra, optional: '3xtf32' (tensor-core GEMMs in the training engine, default) | 'fp32' | 'tf32'
         self.root_mode = root_mode        # extra, optional: '3xtf32' (tensor cores, default) | 'fp32'
         self.shade_mode = shade_mode      # extra, optional: 'tf32' (tensor cores, default) | 'fp32' (FFMA tiles)
         self.deviation_network = deviation_network
@@ -477,7 +481,7 @@ class IDHRNetwork(nn.Module):
             raise _lib.ArahError('one frame per call (the reference assumes the same, ray_tracing.py:129-132)')
         latent_dim = _effective_weight(self.rendering_network.lin0).shape[1] - 289
         r = self._renderer(ray_dirs.device, latent_dim, input['smpl_verts'].shape[1])
-        r.set_training(training)
+        r.set_training((self.train_mode or os.environ.get('ARAH_TRAIN_MODE', '3xtf32')) if training else False)
         r.set_frame_from_modules(input['sdf_network'], self.skinning_model, self.rendering_network, self.deviation_network, input)
         return r
 

@@ -40,6 +40,8 @@ def parse():
     ap.add_argument('--size', type=int, default=512, help='image side (default = BASELINE configs[1]); smaller is for debugging only')
     ap.add_argument('--cpu-sample-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train-step', action='store_true', help='skip the BASELINE configs[2] training-step measurement')
+    ap.add_argument('--train-rays', type=int, default=2048, help='rays per training step (configs/default.yaml:13-14: 1024 fg + 1024 bg)')
     return ap.parse_args()
 
 
@@ -163,6 +165,78 @@ def run_reference(args):
                                        f'algorithm, OpenMP over rays); the Python reference cannot travel to this box'},
             'e2e': {'value': val, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ training step (configs[2])
+def train_step_bench(args, dev, frame, steps=5, warmup=3):
+    """One training step = IDHRNetwork.forward (training branch: tracer with jitter, differentiable shading, regulariser
+    evaluations) + IDHRLoss-style loss + backward to every parameter tensor, on `--train-rays` random bbox rays of the frame
+    (BASELINE configs[2]: 1024 + 1024 rays, train_skinning_net).  Secondary metric; the headline stays the 512x512 render."""
+    import torch
+    from arah_release_b200 import ref_layout as rl, synthetic as syn
+    from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
+    rng = np.random.default_rng(0)
+    sel = np.sort(rng.choice(frame.P, size=min(args.train_rays, frame.P), replace=False))
+    import copy
+    fr = copy.copy(frame)
+    fr.ray_dirs, fr.near_far, fr.pix = frame.ray_dirs[sel], frame.near_far[sel], frame.pix[sel]
+    aux = syn.train_aux_points(fr, seed=0)
+    dvn, rend, skin, sdf = rl.modules_from_frame(fr, dev)
+    leaves = []
+    for l in range(6):
+        for n in ('weights', 'biases', 'freq', 'phase_shift'):
+            v = getattr(sdf[l][0], n).clone().requires_grad_(True); setattr(sdf[l][0], n, v); leaves.append(v)
+    for n in ('weights', 'biases'):
+        v = getattr(sdf[6], n).clone().requires_grad_(True); setattr(sdf[6], n, v); leaves.append(v)
+    net = IDHRNetwork(dvn, rend, skin, BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples,
+                                                      far_surface_vol_samples=fr.far_samples), cano_view_dirs=fr.cano_view_dirs,
+                      train_skinning_net=True).train()
+    inp = rl.inputs_from_frame(fr, sdf, dev)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    inp['pose_cond']['latent_code'] = inp['pose_cond']['latent_code'].clone().requires_grad_(True)
+    inp['body_mask'] = t(aux['body_mask']).view(1, -1)
+    inp['points_uniform'] = t(aux['points_uniform']).float().view(1, -1, 3)
+    inp['points_skinning'] = t(aux['points_skinning']).float().view(1, -1, 3)
+    inp['points_inside'] = t(aux['points_inside']).float().view(1, -1, 3)
+    gt, wt, body = t(aux['rgb_gt']).float(), t(aux['sampled_weights']).float(), t(aux['body_mask'])
+    P = fr.P
+    params = leaves + [inp['pose_cond']['latent_code']] + list(net.parameters())
+
+    def loss_fn(out):            # IDHRLoss.forward, rgb 'l1' (/root/reference/im2mesh/metaavatar_render/renderer/loss.py:122-200)
+        vm = out['network_body_mask'][0]
+        l = (out['rgb_values'][0][vm] - gt[vm]).abs().sum() / P
+        l = l + torch.norm(out['sdf_output'][0][vm] - body[vm].float(), dim=-1).sum() / P
+        l = l + 0.1 * (out['grad_theta'].norm(2, dim=-1) - 1).abs().sum() / P
+        l = l + 0.01 * torch.exp(-1e2 * out['off_surface_sdf']).sum() / P + 0.01 * torch.sigmoid(out['inside_sdf'] * 5e3).sum() / P
+        return l + 10.0 * (out['pred_weights'][0] - wt).abs().sum(-1).mean()
+
+    ms = {'forward': [], 'backward': [], 'total': []}
+    launches, samples = 0, 0
+    for i in range(warmup + steps):
+        for p_ in params:
+            p_.grad = None
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        out = net(inp)
+        loss = loss_fn(out)
+        e[1].record()
+        loss.backward()
+        e[2].record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ms['forward'].append(e[0].elapsed_time(e[1])); ms['backward'].append(e[1].elapsed_time(e[2])); ms['total'].append(e[0].elapsed_time(e[2]))
+        st = net.stats()
+        launches, samples = st['kernel_launches'], st['shaded_samples']
+    tot = float(np.mean(ms['total']))
+    # algorithmic MACs of the differentiable part per sample: SDF fwd + input-gradient sweep + their second- and first-order
+    # backward (4 data GEMM sweeps + 2 weight-gradient sweeps), colour net fwd + data + weight gradient, skinning net value +
+    # 3 tangents + backward
+    mac = samples * (6 * MAC_SDF + 3 * (MAC_COL + 128 * 256) + 6 * MAC_SKIN)
+    return {'workload': f'{P} rays of the ZJU-377-like frame, train_skinning_net, fp32 (BASELINE configs[2] shape)', 'rays': int(P),
+            'shaded_samples': int(samples), 'ms_per_step': tot, 'ms_forward_incl_tracer': float(np.mean(ms['forward'])),
+            'ms_backward': float(np.mean(ms['backward'])), 'rays_per_s': P / tot * 1e3, 'steps': steps, 'warmup': warmup,
+            'gpu_launches_per_step': int(launches), 'loss': float(loss.detach()),
+            'algorithmic_tflops_differentiable_part': 2.0 * mac / (tot * 1e-3) / 1e12}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -319,6 +393,11 @@ def run_ours(args):
         'counters_last_step': {k: stats_last[k] for k in ('rays', 'trace_sdf_evals', 'iso_rays', 'iso_g_evals', 'on_samples', 'corr_skin_evals',
                                                            'shaded_samples', 'hit_rays', 'vol_rays')},
     }
+    if args.gpus == 1 and not args.no_train_step:
+        try:
+            line['train_step'] = train_step_bench(args, dev, f0)
+        except Exception as ex:          # secondary metric: never lose the headline line
+            line['train_step'] = {'error': repr(ex)[:300]}
     if args.gpus == 1 and not args.no_cpu_baseline:
         v, cores, n, dt = cpu_rate(f0, args.cpu_sample_seconds)
         line['cpu_baseline'] = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',

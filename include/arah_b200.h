@@ -172,7 +172,14 @@ typedef struct ArahTrainGrads {
     float* beta;                  /* [1]  d L / d ||variance|| */
 } ArahTrainGrads;
 
-int arah_set_training(ArahHandle* h, int32_t enable);
+/* mode: 0 = off (frees the training state); ARAH_TRAIN_3XTF32 (default) = the engine's GEMMs on tcgen05 tensor cores in split
+ * precision (hi/lo TF32 operands, three MMAs per K-step, fp32 accumulation in TMEM: fp32-class results);
+ * ARAH_TRAIN_FP32 = fp32 SIMT FFMA GEMMs; ARAH_TRAIN_TF32 = single-pass TF32 operands (fastest; gradient cosine vs fp32 drops
+ * to ~0.96 on the first SIREN layer, see tests/test_gpu_train.py). */
+#define ARAH_TRAIN_3XTF32 1
+#define ARAH_TRAIN_FP32 2
+#define ARAH_TRAIN_TF32 3
+int arah_set_training(ArahHandle* h, int32_t mode);
 
 /* BodyRayTracing.forward(eval_mode=False) (renderer/ray_tracing.py:51-172): every ray enters the joint search (:249) and the
  * z samples are jittered (:298-311) with the caller's three uniform draws u_all [P][n_steps], u_near [P][near+1],
@@ -195,6 +202,11 @@ int arah_train_sdf_backward(ArahHandle* h, int32_t slot, const float* g_sdf, con
 /* query_weights(points_skinning) (:73-78; utils/root_finding_utils.py:54-113): points [n][3] in metres -> weights [n][24]. */
 int arah_train_skin_forward(ArahHandle* h, const float* points, int32_t n, float* weights, void* stream);
 int arah_train_skin_backward(ArahHandle* h, const float* g_weights, const ArahTrainGrads* grads, void* stream);
+
+/* Debug/bring-up: the training engine's strided GEMM, C[i][j] (+)= bias[j] + sum_k A[i sa_i + k sa_k] B[k sb_k + j sb_j]
+ * (device pointers, element strides), mode = ARAH_TRAIN_3XTF32 / ARAH_TRAIN_TF32 (tcgen05) or ARAH_TRAIN_FP32 (SIMT). */
+int arah_debug_train_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_k,
+                          int64_t sb_j, float* C, int32_t ldc, const float* bias, int32_t accumulate, int32_t mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-def build_net(fr, train_skinning_net, leaves=True):
+def build_net(fr, train_skinning_net, leaves=True, train_mode='fp32'):
     from arah_release_b200 import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
@@ -26,7 +26,8 @@ def build_net(fr, train_skinning_net, leaves=True):
             v = getattr(sdf[6], n).clone().requires_grad_(True); setattr(sdf[6], n, v); sdf_leaves[f'sdf.6.{n}'] = v
     net = IDHRNetwork(dev, rend, skin, BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples,
                                                       far_surface_vol_samples=fr.far_samples),
-                      cano_view_dirs=fr.cano_view_dirs, train_skinning_net=train_skinning_net, shade_mode='fp32', root_mode='fp32')
+                      cano_view_dirs=fr.cano_view_dirs, train_skinning_net=train_skinning_net, shade_mode='fp32', root_mode='fp32',
+                      train_mode=train_mode)
     net.train()
     # the reference draws the eikonal points on the compute device; the CPU goldens drew them from the CPU generator
     net._rand_device = lambda shape, device: torch.rand(*shape).to(device)
@@ -82,12 +83,16 @@ def test_train_trace_matches_reference(name):
     print(name, 'train trace ok: rays', mask.size, 'hit', int(mask.sum()), 'samples', int(sc.sum()))
 
 
+@pytest.mark.parametrize('train_mode', ['fp32', '3xtf32'])
 @pytest.mark.parametrize('name', TRAIN_CASES)
-def test_train_step_matches_reference(name):
-    """Forward outputs, loss and the gradient of every parameter tensor after loss.backward()."""
+def test_train_step_matches_reference(name, train_mode):
+    """Forward outputs, loss and the gradient of every parameter tensor after loss.backward().
+    train_mode 'fp32': SIMT FFMA GEMMs; '3xtf32': the tcgen05 split-precision GEMMs that are the default."""
     from oracle import train_oracle as to
     fr, aux, ref, grads, meta = load_train_golden(name)
-    net, sdf, sdf_leaves = build_net(fr, meta['train_skinning_net'])
+    net, sdf, sdf_leaves = build_net(fr, meta['train_skinning_net'], train_mode=train_mode)
+    tc = False              # 3xTF32 is held to the fp32 tolerances
+    ftol = 2e-4
     inp = train_inputs(fr, sdf, aux)
     torch.manual_seed(meta['seed'])
     out = net(inp)
@@ -95,18 +100,18 @@ def test_train_step_matches_reference(name):
     agree = hit == ref['trace.network_body_mask']
     assert (~agree).mean() <= 0.01
     strict = bool(agree.all())          # a flipped ray (see test_train_trace_matches_reference) perturbs loss and gradients
-    assert np.abs(out['rgb_values'][0].detach().cpu().numpy() - ref['out.rgb_values'][0])[agree].max() <= 2e-4
-    assert np.abs(out['sdf_output'][0].detach().cpu().numpy() - ref['out.sdf_output'][0])[agree].max() <= 2e-4
+    assert np.abs(out['rgb_values'][0].detach().cpu().numpy() - ref['out.rgb_values'][0])[agree].max() <= ftol
+    assert np.abs(out['sdf_output'][0].detach().cpu().numpy() - ref['out.sdf_output'][0])[agree].max() <= ftol
     assert (out['network_body_mask'][0].cpu().numpy() != ref['out.network_body_mask']).mean() <= 0.01
     gt_ref = ref['out.grad_theta']
-    assert np.abs(out['grad_theta'].detach().cpu().numpy() - gt_ref).max() <= 1e-4 * max(1.0, np.abs(gt_ref).max())
-    assert np.abs(out['off_surface_sdf'].detach().cpu().numpy() - ref['out.off_surface_sdf']).max() <= 1e-5
-    assert np.abs(out['inside_sdf'].detach().cpu().numpy() - ref['out.inside_sdf']).max() <= 1e-5
-    assert np.abs(out['pred_weights'].detach().cpu().numpy() - ref['out.pred_weights']).max() <= 1e-5
+    assert np.abs(out['grad_theta'].detach().cpu().numpy() - gt_ref).max() <= (2e-2 if tc else 1e-4) * max(1.0, np.abs(gt_ref).max())
+    assert np.abs(out['off_surface_sdf'].detach().cpu().numpy() - ref['out.off_surface_sdf']).max() <= (5e-3 if tc else 1e-5)
+    assert np.abs(out['inside_sdf'].detach().cpu().numpy() - ref['out.inside_sdf']).max() <= (5e-3 if tc else 1e-5)
+    assert np.abs(out['pred_weights'].detach().cpu().numpy() - ref['out.pred_weights']).max() <= (5e-3 if tc else 1e-5)
     lw = dict(to.LOSS_WEIGHTS); lw.update(meta['loss_weights'])
     terms = loss_of(out, aux, lw)
     lref = float(ref['loss.loss'])
-    assert abs(float(terms['loss'].detach()) - lref) <= (2e-4 if strict else 1e-2) * max(1.0, abs(lref)), (float(terms['loss'].detach()), lref)
+    assert abs(float(terms['loss'].detach()) - lref) <= (2e-4 if (strict and not tc) else 1e-2) * max(1.0, abs(lref)), (float(terms['loss'].detach()), lref)
     terms['loss'].backward()
     torch.cuda.synchronize()
     ours = {'grad.' + k: v.grad for k, v in sdf_leaves.items()}
@@ -122,20 +127,22 @@ def test_train_step_matches_reference(name):
         elif g.size == 1 and 'idx' in dig:
             g = np.zeros(int(dig['idx'].max()) + 1, np.float32)
         # the tracer feeds slightly different samples (<= 1e-3 flipped convergence flags): looser than the host-engine test
-        st = compare_grad(k, g, dig, cos_min=0.999 if strict else 0.99, rel_fro=2e-2 if strict else 0.1)
+        st = compare_grad(k, g, dig, cos_min=(0.999 if strict else 0.99), rel_fro=(2e-2 if strict else 0.1) * (2.5 if tc else 1.0))
         if st['cos'] < worst:
             worst, worst_k = st['cos'], k
-    print(name, 'rays agreeing', int(agree.sum()), '/', agree.size, 'loss', float(terms['loss'].detach()), 'ref', lref, 'min gradient cosine vs reference', worst, worst_k, net.stats())
+    print(name, train_mode, 'rays agreeing', int(agree.sum()), '/', agree.size, 'loss', float(terms['loss'].detach()), 'ref', lref, 'min gradient cosine vs reference', worst, worst_k, net.stats())
 
 
-def test_train_step_1024_rays_vs_torch_oracle():
+@pytest.mark.parametrize('train_mode', ['fp32', '3xtf32', 'tf32'])
+def test_train_step_1024_rays_vs_torch_oracle(train_mode):
     """BASELINE configs[2] size (about 1k rays) with view-rotation augmentation: CUDA forward/backward vs torch autograd over the
     oracle restatement, fed with the SAME traced samples (read back through arah_get_trace)."""
     from arah_release_b200 import synthetic as syn
     from oracle import train_oracle as to
     fr = syn.make_frame(H=36, W=36, seed=9)
     aux = syn.train_aux_points(fr, seed=9)
-    net, sdf, sdf_leaves = build_net(fr, True)
+    net, sdf, sdf_leaves = build_net(fr, True, train_mode=train_mode)
+    tc = train_mode == 'tf32'
     inp = train_inputs(fr, sdf, aux)
     c, s_ = np.cos(0.3), np.sin(0.3)
     Rz = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]], np.float32)
@@ -154,8 +161,8 @@ def test_train_step_1024_rays_vs_torch_oracle():
     view = (torch.from_numpy(Rz) @ torch.from_numpy(fr.ray_dirs).t()).t().numpy()
     rgb_o, ws_o = to.shade(fr, p, e, trace, view, fr.ray_dirs, train_skinning_net=True, ray_augm=True)
     ((rgb_o * w).sum() + (ws_o * wv).sum()).backward()
-    assert np.abs(out['rgb_values'][0].detach().cpu().numpy() - rgb_o.detach().numpy()).max() <= 2e-5
-    assert np.abs(out['sdf_output'][0].detach().cpu().numpy() - ws_o.detach().numpy()).max() <= 2e-5
+    assert np.abs(out['rgb_values'][0].detach().cpu().numpy() - rgb_o.detach().numpy()).max() <= (2e-2 if tc else 2e-5)
+    assert np.abs(out['sdf_output'][0].detach().cpu().numpy() - ws_o.detach().numpy()).max() <= (2e-2 if tc else 2e-5)
     ours = {}
     for k, v in sdf_leaves.items():
         ours[k] = v.grad
@@ -173,10 +180,46 @@ def test_train_step_1024_rays_vs_torch_oracle():
             continue
         cos = float((a * b).sum() / max(np.sqrt((a * a).sum()) * nb, 1e-300))
         rel = abs(np.sqrt((a * a).sum()) - nb) / nb
-        assert cos >= 0.99999 and rel <= 1e-3, (k, cos, rel)
+        # single-pass TF32 is reported, not held to the bar (the x30 sine arguments amplify operand rounding)
+        assert (cos >= 0.9 and rel <= 0.2) if tc else (cos >= 0.99999 and rel <= 1e-3), (k, cos, rel)
         if cos < worst:
             worst, worst_k = cos, k
-    print('rays', fr.P, 'samples', int(trace['sampler_converge_mask'].sum()), 'min gradient cosine vs torch oracle', worst, worst_k, net.stats())
+    print(train_mode, 'rays', fr.P, 'samples', int(trace['sampler_converge_mask'].sum()), 'min gradient cosine vs torch oracle', worst, worst_k, net.stats())
+
+
+@pytest.mark.parametrize('mode', [2, 1, 3])
+def test_train_gemm_forms(mode):
+    """The engine's strided GEMM in its three call forms (forward NT, backward-data NN, weight-gradient TN with split-K) and
+    ragged sizes, SIMT fp32 (mode 2), tcgen05 3xTF32 (mode 1) and single-pass TF32 (mode 3), against torch.matmul in float64."""
+    import ctypes as C
+    from arah_release_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device='cpu').manual_seed(0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    tol = {2: 1e-5, 1: 2e-5, 3: 2e-3}[mode]           # fp32 SIMT, 3xTF32, single-pass TF32
+
+    def run(M, N, K, A, sa, Bm, sb, ldc, bias, acc, ref):
+        Cm = torch.full((M, ldc), 0.5, device=DEV)
+        c0 = Cm.clone()
+        _lib.check(L.arah_debug_train_gemm(M, N, K, ptr(A), sa[0], sa[1], ptr(Bm), sb[0], sb[1], ptr(Cm), ldc, ptr(bias) if bias is not None else None,
+                                           int(acc), mode, st))
+        torch.cuda.synchronize()
+        want = ref.double() + (bias.double() if bias is not None else 0) + (c0[:, :N].double() if acc else 0)
+        err = (Cm[:, :N].double() - want).abs().max().item() / max(want.abs().max().item(), 1e-9)
+        assert err <= tol, (M, N, K, sa, sb, acc, err)
+        assert torch.equal(Cm[:, N:], c0[:, N:])            # columns beyond N untouched
+        return err
+    worst = 0.0
+    for (M, N, K) in [(1000, 256, 256), (333, 128, 256), (515, 256, 3), (200, 3, 256), (129, 25, 128), (300, 1, 256), (77, 33, 256), (640, 256, 33)]:
+        A = torch.randn(M, K, generator=g).to(DEV); W = torch.randn(N, K, generator=g).to(DEV); b = torch.randn(N, generator=g).to(DEV)
+        worst = max(worst, run(M, N, K, A, (K, 1), W, (1, K), N + 3, b, False, A.double() @ W.double().t()))       # NT: x W^T + b
+        Wn = torch.randn(K, N, generator=g).to(DEV)
+        worst = max(worst, run(M, N, K, A, (K, 1), Wn, (N, 1), N, None, True, A.double() @ Wn.double()))          # NN, accumulate
+    for (n, O, I) in [(5000, 256, 256), (70000, 256, 256), (3000, 256, 3), (2500, 3, 256), (4100, 25, 128), (9000, 128, 33)]:
+        G = torch.randn(n, O, generator=g).to(DEV); X = torch.randn(n, I, generator=g).to(DEV)
+        worst = max(worst, run(O, I, n, G, (1, O), X, (I, 1), I + 1, None, True, G.double().t() @ X.double()) * 1.0)   # TN: G^T X (split-K)
+    print('train gemm mode', mode, 'worst relative error', worst)
 
 
 def test_training_mode_requires_cuda_library():
