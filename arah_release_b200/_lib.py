@@ -40,7 +40,8 @@ class ArahTrainGrads(C.Structure):
 EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'arah_set_frame', 'arah_set_profiling', 'arah_render',
            'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin', 'arah_debug_umma_gemm', 'arah_debug_phase_clocks',
            'arah_set_training', 'arah_train_trace', 'arah_train_shade_forward', 'arah_train_shade_backward', 'arah_train_sdf_forward',
-           'arah_train_sdf_backward', 'arah_train_skin_forward', 'arah_train_skin_backward', 'arah_debug_train_gemm']
+           'arah_train_sdf_backward', 'arah_train_skin_forward', 'arah_train_skin_backward', 'arah_debug_train_gemm',
+           'arah_sdf_grid', 'arah_marching_cubes', 'arah_mc_case_table']
 
 _lib = None
 
@@ -81,6 +82,9 @@ def lib():
     L.arah_train_skin_backward.argtypes = [C.c_void_p, FP, C.POINTER(ArahTrainGrads), C.c_void_p]
     L.arah_debug_train_gemm.argtypes = [C.c_int32, C.c_int32, C.c_int32, FP, C.c_int64, C.c_int64, FP, C.c_int64, C.c_int64, FP, C.c_int32, FP,
                                         C.c_int32, C.c_int32, C.c_void_p]
+    L.arah_sdf_grid.argtypes = [C.c_void_p, C.c_int32, FP, C.c_void_p]
+    L.arah_marching_cubes.argtypes = [FP, C.c_int32, C.c_float, C.c_float, C.POINTER(C.c_float), FP, C.c_int32, FP, C.c_int32, FP, C.c_void_p]
+    L.arah_mc_case_table.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

@@ -24,6 +24,7 @@ using namespace arah;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+extern "C" int arah_internal_fail(int code, const char* msg) { return fail(code, msg ? msg : ""); }      // arah_mesh.cu
 #define CU(call)                                                                                           \
     do {                                                                                                   \
         cudaError_t e_ = (call);                                                                           \
@@ -430,6 +431,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     if (const char* e = getenv("ARAH_SHADE_CLUSTER")) h->shade_cluster = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_iso_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_sdf_grid_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     if (const char* e = getenv("ARAH_TRACE_TC")) h->trace_tc = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
@@ -821,6 +823,44 @@ extern "C" int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, floa
     if (!x_hat || !weights || !x_bar) return fail(ARAH_EINVAL, "null buffer");
     const unsigned g = grid_min(cdiv(n, TM), (size_t)2 * h->n_sms);
     k_eval_skin<<<g, 256, tile_smem_bytes(LDA_SKIN), (cudaStream_t)stream>>>(h->fp, x_hat, n, weights, x_bar);
+    CU(cudaGetLastError());
+    return ARAH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ canonical SDF lattice (row f1)
+__global__ void k_grid_points(int N, float voxel, long long i0, int n, float* __restrict__ xn) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long i = i0 + t;
+    const int iz = (int)(i % N), iy = (int)((i / N) % N), ix = (int)(i / ((long long)N * N));
+    xn[3 * t] = __fadd_rn(__fmul_rn((float)ix, voxel), -1.0f);
+    xn[3 * t + 1] = __fadd_rn(__fmul_rn((float)iy, voxel), -1.0f);
+    xn[3 * t + 2] = __fadd_rn(__fmul_rn((float)iz, voxel), -1.0f);
+}
+
+extern "C" int arah_sdf_grid(ArahHandle* h, int32_t N, float* sdf, void* stream) {
+    if (!h || !h->frame_set) return fail(ARAH_ESTATE, "arah_set_frame first");
+    if (N < 2 || N > 1024) return fail(ARAH_EINVAL, "lattice side must be in [2, 1024]");
+    if (!sdf) return fail(ARAH_EINVAL, "null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->cfg.device));
+    const float voxel = (float)(2.0 / (double)(N - 1));
+    const long long n = (long long)N * N * N;
+    if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
+        const unsigned g = grid_min(cdiv((size_t)n, UM), (size_t)h->n_sms);
+        k_sdf_grid_tc3<<<g, TC3_THREADS, trace_tc3_smem_bytes(), st>>>(h->sd, N, voxel, n, sdf);
+    } else {
+        // fp32 FFMA tiles: lattice points are staged in chunks of 64^3 (the reference's own max_batch, sdf_meshing.py:14)
+        const int chunk = 64 * 64 * 64;
+        float* xn = nullptr;
+        CU(cudaMallocAsync((void**)&xn, (size_t)chunk * 3 * 4, st));
+        for (long long i0 = 0; i0 < n; i0 += chunk) {
+            const int m = (int)((n - i0 < chunk) ? (n - i0) : chunk);
+            k_grid_points<<<cdiv(m, 256), 256, 0, st>>>(N, voxel, i0, m, xn);
+            k_eval_sdf<<<grid_min(cdiv(m, TM), (size_t)h->n_sms), 256, tile_smem_bytes(LDA_SDF), st>>>(h->fp, xn, m, sdf + i0, nullptr, nullptr, (float*)h->scratch.p);
+        }
+        CU(cudaFreeAsync(xn, st));
+    }
     CU(cudaGetLastError());
     return ARAH_OK;
 }

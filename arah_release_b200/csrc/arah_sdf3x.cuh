@@ -229,6 +229,69 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_trace_tc3(FrameParams fp, Sd
     if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+// =====================================================================================================================
+// k_sdf_grid_tc3: the canonical SDF sampled on the N^3 lattice over [-1,1]^3 (utils/sdf_meshing.py:13-58).
+// The lattice coordinates are generated in the kernel with the reference's own arithmetic (index * voxel_size + origin, one
+// fp32 rounding per operation, sdf_meshing.py:25-38); out[(ix*N + iy)*N + iz] = raw network output (what `decoder(model_input)`
+// returns, :49-54).  n0/n1 bound the linear index range of this launch (chunked by the caller only for the fp32 fallback).
+__global__ void __launch_bounds__(TC3_THREADS, 1) k_sdf_grid_tc3(SdfTC sd, int N, float voxel, long long n_total, float* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t raw_smem[];
+    const long long ntiles = (n_total + UM - 1) / UM;
+    if ((long long)blockIdx.x >= ntiles) return;
+    if (smem_u32(raw_smem) & 1023u) __trap();
+    float* A_lo = reinterpret_cast<float*>(raw_smem);
+    float* ring = A_lo + S3_ALO_FLOATS;
+    float* xs3 = ring + S3_RING_FLOATS;
+    float (*part)[UM] = reinterpret_cast<float (*)[UM]>(xs3 + UM * 3);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs3 + UM * 3 + 2 * UM);
+    S3Bars bar; bar.full = bars; bar.empty = bars + S3_NSLOTS; bar.ready = bars + 2 * S3_NSLOTS; bar.done = bar.ready + 8;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar.done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < S3_NSLOTS; ++i) { mbar_init(&bar.full[i], 1); mbar_init(&bar.empty[i], 1); }
+        for (int i = 0; i < 8; ++i) mbar_init(&bar.ready[i], 4);
+        mbar_init(bar.done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tslot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot;
+    if (warp == 8) {
+        if (lane == 0) { uint32_t slot = 0, use = 0; for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) s3_produce_sdf(ring, bar, slot, use, sd); }
+        return;
+    }
+    if (warp == 9) {
+        if (lane == 0) { uint32_t slot = 0, use = 0, rpar = 0; for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) s3_mma_sdf(ring, A_lo, bar, slot, use, rpar, tbase); }
+        return;
+    }
+    const int half = warp >> 2, r = 32 * (warp & 3) + lane;
+    uint32_t done_par = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long i = tile * UM + tid;
+        if (tid < UM) {
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (i < n_total) {
+                const int iz = (int)(i % N), iy = (int)((i / N) % N), ix = (int)(i / ((long long)N * N));
+                x = __fadd_rn(__fmul_rn((float)ix, voxel), -1.0f);
+                y = __fadd_rn(__fmul_rn((float)iy, voxel), -1.0f);
+                z = __fadd_rn(__fmul_rn((float)iz, voxel), -1.0f);
+            }
+            xs3[3 * tid] = x; xs3[3 * tid + 1] = y; xs3[3 * tid + 2] = z;
+        }
+        cta_sync_compute();
+        const float dot = s3_compute_sdf(sd, xs3, A_lo, bar, done_par, tbase);
+        part[half][r] = dot;
+        cta_sync_compute();
+        if (tid < UM && i < n_total) out[i] = part[0][tid] + part[1][tid] + sd.b6;
+        cta_sync_compute();
+    }
+    tc_fence_before();
+    cta_sync_compute();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
 }  // namespace arah
 
 namespace arah {

@@ -296,6 +296,47 @@ class ArahRenderer:
         check(_lib.lib().arah_eval_skin(self._h, _ptr(x), n, _ptr(w), _ptr(xb), self.stream))
         return w, xb
 
+    # ------------------------------------------------------------------ canonical mesh
+    def sdf_grid(self, N=256):
+        """utils/sdf_meshing.py:13-58: the frame's SDF network on the N^3 lattice over [-1,1]^3 -> [N, N, N] (device)."""
+        out = torch.empty(N, N, N, device=self.device)
+        check(_lib.lib().arah_sdf_grid(self._h, int(N), _ptr(out), self.stream))
+        return out
+
+    def marching_cubes(self, vol, level=0.0, voxel_size=None, origin=(-1.0, -1.0, -1.0), max_verts=None, max_faces=None):
+        """utils/sdf_meshing.py:69-114 on the GPU: (verts [nv, 3] float32, faces [nf, 3] int32), both device tensors.
+        One host synchronisation (the vertex / face counts size the result)."""
+        vol = _f32c(vol, self.device)
+        N = vol.shape[0]
+        if tuple(vol.shape) != (N, N, N):
+            raise _lib.ArahError('marching_cubes needs a cubic [N, N, N] lattice')
+        voxel_size = 2.0 / (N - 1) if voxel_size is None else float(voxel_size)
+        org = (C.c_float * 3)(*[float(v) for v in origin])
+        counts = torch.zeros(2, dtype=torch.int32, device=self.device)
+        mv = int(max_verts) if max_verts else 6 * N * N
+        mf = int(max_faces) if max_faces else 12 * N * N
+        while True:
+            verts = torch.empty(mv, 3, device=self.device)
+            faces = torch.empty(mf, 3, dtype=torch.int32, device=self.device)
+            check(_lib.lib().arah_marching_cubes(_ptr(vol), N, float(level), voxel_size, org, _ptr(verts), mv, _ptr(faces), mf,
+                                                 _ptr(counts), self.stream))
+            nv, nf = (int(v) for v in counts.tolist())
+            if nv <= mv and nf <= mf:
+                return verts[:nv], faces[:nf]
+            mv, mf = max(mv, nv), max(mf, nf)
+
+
+def create_mesh_vertices_and_faces(renderer, N=256, max_batch=64 ** 3, offset=None, scale=None, **kwargs):
+    """Drop-in for im2mesh.utils.sdf_meshing.create_mesh_vertices_and_faces (utils/sdf_meshing.py:13-66) with the frame's
+    ArahRenderer in place of the `decoder` module: SDF lattice on the tensor cores, iso-surface on the GPU; returns numpy
+    (mesh_points [nv, 3], faces [nf, 3]) like the reference.  `max_batch` is accepted and ignored (no chunking needed)."""
+    vol = renderer.sdf_grid(N)
+    verts, faces = renderer.marching_cubes(vol, level=0.0, voxel_size=2.0 / (N - 1), origin=(-1.0, -1.0, -1.0))
+    if scale is not None:
+        verts = verts / scale
+    if offset is not None:
+        verts = verts - offset
+    return verts.cpu().numpy(), faces.cpu().numpy()
 
 
 # =====================================================================================================================
@@ -582,6 +623,18 @@ class IDHRNetwork(nn.Module):
         else:
             r.render(ray_directions[0], body_bounds_intersections[0])
         return r.trace_outputs(P)
+
+    def extract_canonical_mesh(self, input, N=256):
+        """MetaAvatarRender.forward(gen_cano_mesh=True), metaavatar_render/models/__init__.py:203-224: canonical mesh of the
+        frame's SDF (normalised coordinates) and its posed vertices `forward_skinning(unnormalize(verts)) + trans`.
+        Returns device tensors (verts [nv,3], faces [nf,3] int32, points_bar [nv,3])."""
+        r = self._prepare(input)
+        vol = r.sdf_grid(N)
+        verts, faces = r.marching_cubes(vol)
+        cmin, cmax = input['coord_min'].reshape(-1)[0], input['coord_max'].reshape(-1)[0]
+        pts_hat = (verts / 2.0 + 0.5) * 1.1 * (cmax - cmin) + cmin - 0.05 * (cmax - cmin) + input['center'].reshape(1, 3)
+        _, x_bar = r.eval_skin(pts_hat)
+        return verts, faces, x_bar + input['trans'].reshape(1, 3)
 
     def tracer_outputs(self):
         """7-tuple of the tracer for the frame rendered by the last forward()."""

@@ -140,6 +140,27 @@ int arah_get_stats(ArahHandle* h, ArahStats* stats, void* stream);
 int arah_eval_sdf(ArahHandle* h, const float* xn, int32_t n, float* sdf, float* grad, float* feat, void* stream);
 int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, float* weights, float* x_bar, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Canonical mesh extraction (MetaAvatarRender.forward(gen_cano_mesh=True),
+ * metaavatar_render/models/__init__.py:203-224).
+ *
+ * arah_sdf_grid: utils/sdf_meshing.py:13-58 — the frame's SDF network sampled on the N^3 lattice over [-1,1]^3
+ *   (voxel_size = 2/(N-1), lattice point (ix,iy,iz) -> index (ix*N + iy)*N + iz, coordinates ix*voxel_size - 1 with one fp32
+ *   rounding per operation as in the reference); sdf is a device buffer of N^3 floats holding the raw network output.
+ *   Runs on the tensor cores in split precision (root_mode 3xTF32) or on fp32 FFMA tiles (root_mode FP32).
+ * arah_marching_cubes: utils/sdf_meshing.py:69-114 — iso-surface `level` of a device lattice sdf[N][N][N]:
+ *   verts [max_verts][3] = origin + (lattice index + t) * voxel_size  (the reference's `voxel_grid_origin + verts`),
+ *   faces [max_faces][3] int32 vertex ids, outward (towards larger values) orientation, counts[0..1] (device) = number of
+ *   vertices / faces the surface HAS; if a count exceeds its max_* the output was truncated — call again with larger buffers.
+ *   One vertex per sign-changing lattice edge (t = v0/(v0-v1)); deterministic order (lattice order).  The reference delegates
+ *   this step to skimage 0.18.1 `marching_cubes_lewiner` (absent here: parity against it is unpinned; the checker is
+ *   oracle/mc_oracle.c, a CPU restatement of the same published scheme).  Works on the current device; no handle needed. */
+int arah_sdf_grid(ArahHandle* h, int32_t N, float* sdf, void* stream);
+int arah_marching_cubes(const float* sdf, int32_t N, float level, float voxel_size, const float* origin3 /* host [3] */,
+                        float* verts, int32_t max_verts, int32_t* faces, int32_t max_faces, int32_t* counts, void* stream);
+/* Host-only: the generated marching-cubes case table, tri[256][16] (edge ids, -1 terminated) and ntri[256]. */
+int arah_mc_case_table(int8_t* tri, uint8_t* ntri);
+
 /* Debug: SM-clock cycles spent per kernel phase by one designated thread per CTA, summed over CTAs and launches of the last
  * profiled render (arah_set_profiling(h,1)): out32[0..5] correspondence step (gather, layer 0, MMA wait, epilogues, output
  * layer, per-point phase), out16[8..14] shading (setup+layer0, fwd wait, fwd epilogue, rev wait, rev epilogue, colour inputs,

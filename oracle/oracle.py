@@ -36,8 +36,8 @@ class OracleOut(C.Structure):
 
 
 def build(force: bool = False):
-    src = os.path.join(_HERE, 'arah_oracle.c')
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ('arah_oracle.c', 'mc_oracle.c')]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(['make', '-C', _HERE, '-B', 'libarah_oracle.so'])
     return _SO
 
@@ -57,6 +57,8 @@ def lib():
         _lib.arah_oracle_skin.argtypes = [C.POINTER(OracleFrame), FP, C.c_int, FP, FP, FP]
         _lib.arah_oracle_color.argtypes = [C.POINTER(OracleFrame), FP, FP, FP, FP, C.c_int, FP]
         _lib.arah_oracle_knn.argtypes = [C.POINTER(OracleFrame), FP, C.c_int, I32, FP, FP]
+        _lib.arah_oracle_mc.argtypes = [FP, C.c_int, C.c_float, C.c_float, FP, FP, C.c_int, I32, C.c_int, I32]
+        _lib.arah_oracle_mc_table.argtypes = [C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -211,6 +213,46 @@ def knn(frame, x):
     T = np.zeros((n, 4, 4), np.float32)
     lib().arah_oracle_knn(C.byref(of), _fp(x), n, idx.ctypes.data_as(I32), _fp(xh), _fp(T))
     return idx, xh, T
+
+
+def grid_points(N):
+    """utils/sdf_meshing.py:20-38 — the N^3 lattice over [-1,1]^3 in the reference's order and fp32 arithmetic."""
+    voxel = np.float32(2.0 / (N - 1))
+    ax = (np.arange(N, dtype=np.float32) * voxel) + np.float32(-1.0)
+    g = np.stack(np.meshgrid(ax, ax, ax, indexing='ij'), -1).reshape(-1, 3)
+    return np.ascontiguousarray(g, np.float32), float(voxel)
+
+
+def sdf_grid(frame, N):
+    """sdf_meshing.py:40-58: raw SDF network output on the lattice, [N, N, N]."""
+    pts, _ = grid_points(N)
+    s, _, _ = sdf(frame, pts, grad=False)
+    return s.reshape(N, N, N)
+
+
+def marching_cubes(vol, level=0.0, voxel=None, origin=(-1.0, -1.0, -1.0)):
+    """mc_oracle.c: vertices [nv,3] (origin + lattice position * voxel) and faces [nf,3] of the iso-surface."""
+    vol = np.ascontiguousarray(vol, np.float32)
+    N = vol.shape[0]
+    assert vol.shape == (N, N, N)
+    voxel = np.float32(2.0 / (N - 1)) if voxel is None else np.float32(voxel)
+    org = np.asarray(origin, np.float32)
+    counts = np.zeros(2, np.int32)
+    dummy_v, dummy_f = np.zeros((1, 3), np.float32), np.zeros((1, 3), np.int32)
+    rc = lib().arah_oracle_mc(_fp(vol), N, float(level), float(voxel), _fp(org), _fp(dummy_v), 0, dummy_f.ctypes.data_as(I32), 0, counts.ctypes.data_as(I32))
+    assert rc == 0
+    nv, nf = int(counts[0]), int(counts[1])
+    v, f = np.zeros((max(nv, 1), 3), np.float32), np.zeros((max(nf, 1), 3), np.int32)
+    rc = lib().arah_oracle_mc(_fp(vol), N, float(level), float(voxel), _fp(org), _fp(v), nv, f.ctypes.data_as(I32), nf, counts.ctypes.data_as(I32))
+    assert rc == 0
+    return v[:nv], f[:nf]
+
+
+def mc_table():
+    tri, ntri = np.zeros((256, 16), np.int8), np.zeros(256, np.uint8)
+    rc = lib().arah_oracle_mc_table(tri.ctypes.data, ntri.ctypes.data)
+    assert rc == 0
+    return tri, ntri
 
 
 def num_threads():
