@@ -10,7 +10,7 @@ FP = C.c_void_p
 class ArahConfig(C.Structure):
     _fields_ = [('device', C.c_int32), ('n_steps', C.c_int32), ('near_samples', C.c_int32), ('far_samples', C.c_int32),
                 ('cano_view_dirs', C.c_int32), ('latent_dim', C.c_int32), ('n_verts', C.c_int32), ('max_rays', C.c_int32),
-                ('shade_mode', C.c_int32), ('root_mode', C.c_int32)]
+                ('shade_mode', C.c_int32), ('root_mode', C.c_int32), ('shade_cull', C.c_int32)]
 
 
 class ArahFrame(C.Structure):
@@ -26,7 +26,8 @@ class ArahStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ('rays', 'trace_sdf_evals', 'iso_rays', 'iso_g_evals', 'on_samples',
                                          'corr_skin_evals', 'shaded_samples', 'hit_rays', 'vol_rays', 'kernel_launches',
                                          'pack_launches')] + \
-               [(n, C.c_double) for n in ('ms_trace', 'ms_iso', 'ms_sample_corr', 'ms_shade', 'ms_composite', 'ms_total')]
+               [(n, C.c_double) for n in ('ms_trace', 'ms_iso', 'ms_sample_corr', 'ms_shade', 'ms_composite', 'ms_total')] + \
+               [('culled_samples', C.c_int64)]
 
     def as_dict(self):
         return {n: (int(getattr(self, n)) if t is C.c_int64 else float(getattr(self, n))) for n, t in self._fields_}
@@ -41,7 +42,7 @@ EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'ar
            'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin', 'arah_debug_umma_gemm', 'arah_debug_phase_clocks',
            'arah_set_training', 'arah_train_trace', 'arah_train_shade_forward', 'arah_train_shade_backward', 'arah_train_sdf_forward',
            'arah_train_sdf_backward', 'arah_train_skin_forward', 'arah_train_skin_backward', 'arah_debug_train_gemm',
-           'arah_sdf_grid', 'arah_marching_cubes', 'arah_mc_case_table']
+           'arah_sdf_grid', 'arah_marching_cubes', 'arah_mc_case_table', 'arah_debug_knn', 'arah_marching_cubes_workspace']
 
 _lib = None
 
@@ -83,8 +84,11 @@ def lib():
     L.arah_debug_train_gemm.argtypes = [C.c_int32, C.c_int32, C.c_int32, FP, C.c_int64, C.c_int64, FP, C.c_int64, C.c_int64, FP, C.c_int32, FP,
                                         C.c_int32, C.c_int32, C.c_void_p]
     L.arah_sdf_grid.argtypes = [C.c_void_p, C.c_int32, FP, C.c_void_p]
-    L.arah_marching_cubes.argtypes = [FP, C.c_int32, C.c_float, C.c_float, C.POINTER(C.c_float), FP, C.c_int32, FP, C.c_int32, FP, C.c_void_p]
+    L.arah_marching_cubes.argtypes = [FP, C.c_int32, C.c_float, C.c_float, C.POINTER(C.c_float), FP, C.c_int32, FP, C.c_int32, FP, FP, C.c_size_t, C.c_void_p]
+    L.arah_marching_cubes_workspace.argtypes = [C.c_int32]
+    L.arah_marching_cubes_workspace.restype = C.c_size_t
     L.arah_mc_case_table.argtypes = [C.c_void_p, C.c_void_p]
+    L.arah_debug_knn.argtypes = [C.c_void_p, FP, C.c_int32, FP, C.c_void_p]
     _lib = L
     return L
 

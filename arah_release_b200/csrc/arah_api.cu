@@ -303,6 +303,8 @@ struct ArahHandle {
     SdfTC sd;
     int trace_tc = 1;
     int corr_cluster = 1;      // 2-CTA clusters + weight multicast in the correspondence kernel (measured: -2 ms)
+    bool shade_cull_ran = false;
+    int shade_cull = 1;        // exact alpha cull before the gradient / colour pass (k_alpha_cull)
     int shade_cluster = 0;     // same for shading (measured: +2 ms -- the kernel is not L2-bound; kept selectable)
     // workspace
     DevBuf ws, scratch, io_in, io_out;
@@ -423,7 +425,10 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc_smem_bytes()));
     CU(cudaFuncSetAttribute(k_shade_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc2_smem_bytes()));
     CU(cudaFuncSetAttribute(k_corr_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc2_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_shade_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_shade_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
+    h->shade_cull = cfg->shade_cull == ARAH_CULL_OFF ? 0 : 1;
+    if (const char* e = getenv("ARAH_SHADE_CULL")) h->shade_cull = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_corr_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_shade_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_corr_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
@@ -435,6 +440,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     if (const char* e = getenv("ARAH_TRACE_TC")) h->trace_tc = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
+    CU(cudaFuncSetAttribute(k_knn_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
     *out = h;
     return ARAH_OK;
@@ -623,6 +629,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     if (!h->frame_set) return fail(ARAH_ESTATE, "arah_set_frame must be called before arah_render");
     if (P < 0) return fail(ARAH_EINVAL, "P < 0");
     h->launches = 0;
+    h->shade_cull_ran = false;
     h->last_P = P;
     h->rendered = true;
     if (P == 0) return ARAH_OK;
@@ -642,12 +649,13 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     const bool prof = h->profile;
     h->profiled = prof;
     CU(cudaMemsetAsync(w.counters, 0, C_COUNT * 4, st));
+    w.shade_ctr = C_SHADE;
     Work wk = w;                      // kernels get the phase-clock pointer only while profiling
     if (prof) CU(cudaMemsetAsync(w.phase_clk, 0, 32 * 8, st)); else wk.phase_clk = nullptr;
     if (prof) CU(cudaEventRecord(h->ev[0], st));
     k_trace_begin<<<cdiv(P, 256), 256, 0, st>>>(w); L();
     const unsigned g_ray_tiles = grid_min(cdiv(P, TM), (size_t)nsm);
-    const unsigned g_knn_rays = grid_min(cdiv(P, 512), (size_t)nsm);
+    const unsigned g_knn_rays = grid_min(cdiv(P, 16), (size_t)nsm);        // >= one query per warp; idle blocks exit before staging
     for (int it = 0; it < TRACE_ITERS; ++it) {
         k_knn_rays<<<g_knn_rays, 512, sm_knn, st>>>(fp, h->knn, w, it); L();
         if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc)
@@ -668,7 +676,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     }
     if (prof) CU(cudaEventRecord(h->ev[2], st));
     k_trace_finish<<<cdiv(P, 128), 128, 0, st>>>(fp, w); L();
-    const unsigned g_knn_s = grid_min(cdiv(PS, 512), (size_t)nsm);
+    const unsigned g_knn_s = grid_min(cdiv(PS, 16), (size_t)nsm);
     k_knn_samples<<<g_knn_s, 512, sm_knn, st>>>(fp, h->knn, w); L();
     const unsigned g_smp_tiles = grid_min(cdiv(PS, TM), (size_t)2 * nsm);
     if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
@@ -707,7 +715,19 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
             lc.attrs = at; lc.numAttrs = 1;
             CU(cudaLaunchKernelEx(&lc, k_shade_tc4, fp, h->tc, wk));
         }
-        else if (h->tc_engine >= 3) k_shade_tc3<<<grid_min(cdiv(PS, UM), (size_t)nsm), TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk);
+        else if (h->tc_engine >= 3) {
+            const unsigned g = grid_min(cdiv(PS, UM), (size_t)nsm);
+            h->shade_cull_ran = h->shade_cull != 0;
+            if (h->shade_cull) {
+                // exact alpha cull: SDF-only pass over all converged samples, alpha test, full shading of the survivors
+                k_shade_tc3<true><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk); L();
+                k_alpha_cull<<<cdiv(P, COMP_WARPS), 32 * COMP_WARPS, 0, st>>>(fp, w, w.listA); L();
+                Work w2 = wk;
+                w2.shade_list = w.listA; w2.shade_ctr = C_SHADE2;
+                k_shade_tc3<false><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, w2);
+            } else
+                k_shade_tc3<false><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk);
+        }
         else if (h->tc_engine == 2) k_shade_tc2<<<grid_min(cdiv(PS, UM), (size_t)nsm), TC_THREADS, shade_tc2_smem_bytes(), st>>>(fp, h->tc, w);
         else k_shade_tc<<<grid_min(cdiv(PS, UM), (size_t)nsm), 256, shade_tc_smem_bytes(), st>>>(fp, h->tc, w);
         L();
@@ -788,6 +808,7 @@ extern "C" int arah_get_stats(ArahHandle* h, ArahStats* s, void* stream) {
     s->on_samples = c[C_ON];
     s->corr_skin_evals = c[C_STAT_CORR_EVALS];
     s->shaded_samples = c[C_SHADE];
+    s->culled_samples = (h->shade_cull_ran) ? (int64_t)c[C_SHADE] - c[C_SHADE2] : 0;
     s->hit_rays = c[C_STAT_HIT_RAYS];
     s->vol_rays = c[C_STAT_VOL_RAYS];
     if (h->profiled) {
@@ -827,6 +848,15 @@ extern "C" int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, floa
     return ARAH_OK;
 }
 
+extern "C" int arah_debug_knn(ArahHandle* h, const float* pts, int32_t n, int32_t* idx, void* stream) {
+    if (!h || !h->frame_set) return fail(ARAH_ESTATE, "arah_set_frame first");
+    if (n <= 0) return ARAH_OK;
+    if (!pts || !idx) return fail(ARAH_EINVAL, "null buffer");
+    k_knn_points<<<grid_min(cdiv(n, 16), (size_t)h->n_sms), 512, knn_smem_bytes(h->fp.n_verts), (cudaStream_t)stream>>>(h->knn, pts, n, idx);
+    CU(cudaGetLastError());
+    return ARAH_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ canonical SDF lattice (row f1)
 __global__ void k_grid_points(int N, float voxel, long long i0, int n, float* __restrict__ xn) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -852,14 +882,13 @@ extern "C" int arah_sdf_grid(ArahHandle* h, int32_t N, float* sdf, void* stream)
     } else {
         // fp32 FFMA tiles: lattice points are staged in chunks of 64^3 (the reference's own max_batch, sdf_meshing.py:14)
         const int chunk = 64 * 64 * 64;
-        float* xn = nullptr;
-        CU(cudaMallocAsync((void**)&xn, (size_t)chunk * 3 * 4, st));
+        if (h->io_in.ensure((size_t)chunk * 3 * 4) != 0) return fail(ARAH_ENOMEM, "lattice staging allocation failed");
+        float* xn = (float*)h->io_in.p;
         for (long long i0 = 0; i0 < n; i0 += chunk) {
             const int m = (int)((n - i0 < chunk) ? (n - i0) : chunk);
             k_grid_points<<<cdiv(m, 256), 256, 0, st>>>(N, voxel, i0, m, xn);
             k_eval_sdf<<<grid_min(cdiv(m, TM), (size_t)h->n_sms), 256, tile_smem_bytes(LDA_SDF), st>>>(h->fp, xn, m, sdf + i0, nullptr, nullptr, (float*)h->scratch.p);
         }
-        CU(cudaFreeAsync(xn, st));
     }
     CU(cudaGetLastError());
     return ARAH_OK;

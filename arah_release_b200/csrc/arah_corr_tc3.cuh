@@ -8,8 +8,9 @@
 
 namespace arah {
 
+constexpr int LGS = 33;     // row stride of the logits staging tile: odd, so that row-per-lane accesses hit 32 different banks
 __host__ __device__ constexpr size_t corr_tc3_smem_bytes() {
-    return (size_t)(TC3_NSLOTS * RING_SLOT_FLOATS + 2 * UM * 32 + 2 * UM * 4 + 24 * 16 + 3 * 128 + 5 * 128) * 4 + 512 + 1024;
+    return (size_t)(TC3_NSLOTS * RING_SLOT_FLOATS + 2 * UM * LGS + 2 * UM * 4 + 24 * 16 + 3 * 128 + 5 * 128) * 4 + 512 + 1024;
 }
 
 __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc3(FrameParams fp, SkinTC sk, Work w, int iter) {
@@ -19,8 +20,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc3(FrameParams fp, Ski
     const uint32_t base = (smem_u32(raw_smem) + 1023u) & ~1023u;
     float* sm = reinterpret_cast<float*>(raw_smem + (base - smem_u32(raw_smem)));
     float* ring = sm;
-    float (*logits)[32] = reinterpret_cast<float (*)[32]>(ring + TC3_NSLOTS * RING_SLOT_FLOATS);      // [2*UM][32]: tiles A, B
-    float (*xs)[4] = reinterpret_cast<float (*)[4]>(reinterpret_cast<float*>(logits) + 2 * UM * 32);  // [2*UM][4]
+    float (*logits)[LGS] = reinterpret_cast<float (*)[LGS]>(ring + TC3_NSLOTS * RING_SLOT_FLOATS);   // [2*UM][33]: tiles A, B (odd stride: conflict-free)
+    float (*xs)[4] = reinterpret_cast<float (*)[4]>(reinterpret_cast<float*>(logits) + 2 * UM * LGS);  // [2*UM][4]
     float* sB = reinterpret_cast<float*>(xs) + 2 * UM * 4;        // bone transforms [24][16]
     float* sW0 = sB + 24 * 16;                                    // layer-0 weights [3][128]
     float* sb = sW0 + 3 * 128;                                    // biases: 4 x 128 then 32  (sb + 128*l)

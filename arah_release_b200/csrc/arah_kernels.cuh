@@ -28,6 +28,7 @@ enum Ctr {
     C_CORR = C_ISO + BROYDEN_ITERS + 1,  // [0..50] active samples entering correspondence step i
     C_ON = C_CORR + BROYDEN_ITERS + 1,   // number of "on" samples
     C_SHADE,                             // number of converged samples to shade
+    C_SHADE2,                            // ... of which alpha != 0 (exact cull): samples that need gradient + colour
     C_STAT_TRACE_EVALS, C_STAT_ISO_EVALS, C_STAT_CORR_EVALS, C_STAT_HIT_RAYS, C_STAT_VOL_RAYS,
     C_COUNT
 };
@@ -56,6 +57,7 @@ struct Work {
     int* on_list;             // [P*S] sample slot index of the k-th on-sample
     int* shade_list;          // [P*S]
     int* counters;            // [C_COUNT]
+    int shade_ctr;            // counter slot holding the length of shade_list for the tensor-core shading kernel (C_SHADE / C_SHADE2)
     float* scratch;           // shade kernel: per-CTA [7][TM][256]
     float* out_rgb;           // [P][3]
     uint8_t* out_mask;        // [P]
@@ -256,6 +258,94 @@ __device__ __forceinline__ int knn_scan(const KnnSmem& k, float x, float y, floa
     }
     return bi;
 }
+// Warp-cooperative form of knn_scan: all 32 lanes hold the SAME query.  Lanes split the cluster boxes (lower bounds kept in
+// registers), then every candidate cluster is scanned one vertex per lane (conflict-free LDS.128) and reduced with a
+// lexicographic (distance, original index) butterfly.  Clusters are visited in the same order as knn_scan, so the running
+// best evolves identically; the result is the same exact argmin with the lowest index on ties.
+__device__ __forceinline__ void knn_warp_argmin(float& d, int& id) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, id, o);
+        if (d2 < d || (d2 == d && i2 < id)) { d = d2; id = i2; }
+    }
+}
+__device__ __forceinline__ int knn_scan_warp(const KnnSmem& k, float x, float y, float z) {
+    const int lane = threadIdx.x & 31;
+    float lbs[8];                                          // nc <= 256 (n_verts <= 8192)
+    float lb0 = INFINITY;
+    int c0 = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        float lb = INFINITY;
+        if (c < k.nc) lb = box_dist2(k.cmin[c], k.cmax[c], x, y, z);
+        lbs[j] = lb;
+        if (lb < lb0) { lb0 = lb; c0 = c; }
+    }
+    knn_warp_argmin(lb0, c0);
+    if (c0 >= k.nc) c0 = 0;                                // all boxes at infinite distance (NaN/inf query): any cluster
+    float bd = INFINITY;
+    int bi = 0x7fffffff;
+    auto scan = [&](int c) {
+        const float4 p = k.sv[c * KNN_CLUSTER + lane];
+        const float dx = x - p.x, dy = y - p.y, dz = z - p.z;
+        float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        int id = __float_as_int(p.w);
+        knn_warp_argmin(d, id);
+        if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
+    };
+    scan(c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (32 * j >= k.nc) break;
+        unsigned done = 0u;
+        while (true) {
+            const bool want = (lane + 32 * j != c0) && (lbs[j] <= bd * 1.000001f);
+            const unsigned m = __ballot_sync(0xffffffffu, want) & ~done;
+            if (!m) break;
+            const int src = __ffs(m) - 1;
+            done = (src == 31) ? 0xffffffffu : ((2u << src) - 1u);
+            scan(32 * j + src);
+        }
+    }
+    return bi;
+}
+// Batch driver: a warp takes `B` consecutive queries (B = 1..32 so that every warp of the grid has work when few queries are
+// left); lane l loads query l, the queries are scanned cooperatively one after the other, lane l finishes query l.
+// Measured (B200, 15 M queries): with a full warp of queries the per-lane scan (knn_scan, 32 queries in SIMT) is ~3x
+// cheaper per query than the cooperative one (shuffle reductions); the cooperative form wins when a warp would otherwise hold
+// only a few queries (tail iterations of sphere tracing, training-size batches), where latency, not throughput, counts.
+constexpr int KNN_COOP_MAX_B = 12;
+template <class LoadQ, class Finish>
+__device__ __forceinline__ void knn_warp_batches(const KnnSmem& kk, int n, int B, LoadQ load, Finish fin) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5, total_warps = gridDim.x * wpb, gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const int nchunks = (n + B - 1) / B;
+    for (int c = gw; c < nchunks; c += total_warps) {
+        const int i0 = c * B, cnt = min(B, n - i0);
+        float x[3] = {0.f, 0.f, 0.f};
+        if (lane < cnt) load(i0 + lane, x);
+        int mine = 0;
+        if (B > KNN_COOP_MAX_B) {
+            if (lane < cnt) mine = knn_scan(kk, x[0], x[1], x[2]);
+        } else {
+            for (int j = 0; j < cnt; ++j) {
+                const float qx = __shfl_sync(0xffffffffu, x[0], j), qy = __shfl_sync(0xffffffffu, x[1], j), qz = __shfl_sync(0xffffffffu, x[2], j);
+                const int idx = knn_scan_warp(kk, qx, qy, qz);
+                if (lane == j) mine = idx;
+            }
+        }
+        if (lane < cnt) fin(i0 + lane, x, mine);
+    }
+}
+// queries per warp: spread over all warps of the grid while that keeps a warp at <= KNN_COOP_MAX_B queries, else full warps
+__device__ __forceinline__ int knn_batch_size(int n) {
+    const int total_warps = gridDim.x * (blockDim.x >> 5);
+    const int b = max(1, (n + total_warps - 1) / total_warps);
+    return b > KNN_COOP_MAX_B ? 32 : b;
+}
+
 // NN-skinning inverse of one posed point x (incl. trans): T = sum_j W[idx][j] B_j, x_hat = T^-1 (x - trans)
 __device__ __forceinline__ void nn_inverse_skinning(const FrameParams& fp, int idx, const float* x, float* T12, float* s, float* x_hat) {
     float wj[NJ];
@@ -270,22 +360,36 @@ __device__ __forceinline__ void nn_inverse_skinning(const FrameParams& fp, int i
 __global__ void __launch_bounds__(512) k_knn_rays(FrameParams fp, KnnIndex ix, Work w, int iter) {
     extern __shared__ float4 sv[];
     const int n = w.counters[C_TRACE + iter];
-    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    const int B = knn_batch_size(n);
+    if ((int)(blockIdx.x * (blockDim.x >> 5)) * B >= n) return;
     const KnnSmem kk = load_knn(sv, ix);
     const int* list = (iter & 1) ? w.listB : w.listA;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int r = list[i];
-        const float t = w.ray_t[r];
-        float x[3];
+    knn_warp_batches(kk, n, B,
+        [&](int i, float* x) {
+            const int r = list[i];
+            const float t = w.ray_t[r];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) x[k] = w.ray_dirs[3 * r + k] * t + fp.cam_loc[k];
-        const int idx = knn_scan(kk, x[0], x[1], x[2]);
-        RayCur c;
-        float xh[3];
-        nn_inverse_skinning(fp, idx, x, c.T, &c.s, xh);
-        normalize3(fp, xh, c.xn);
-        w.ray_cur[r] = c;
-    }
+            for (int k = 0; k < 3; ++k) x[k] = w.ray_dirs[3 * r + k] * t + fp.cam_loc[k];
+        },
+        [&](int i, const float* x, int idx) {
+            const int r = list[i];
+            RayCur c;
+            float xh[3];
+            nn_inverse_skinning(fp, idx, x, c.T, &c.s, xh);
+            normalize3(fp, xh, c.xn);
+            w.ray_cur[r] = c;
+        });
+}
+
+// unit-level entry (tests): nearest posed-vertex index of n arbitrary points
+__global__ void __launch_bounds__(512) k_knn_points(KnnIndex ix, const float* __restrict__ pts, int n, int* __restrict__ out_idx) {
+    extern __shared__ float4 sv[];
+    const int B = knn_batch_size(n);
+    if ((int)(blockIdx.x * (blockDim.x >> 5)) * B >= n) return;
+    const KnnSmem kk = load_knn(sv, ix);
+    knn_warp_batches(kk, n, B,
+        [&](int i, float* x) { x[0] = pts[3 * i]; x[1] = pts[3 * i + 1]; x[2] = pts[3 * i + 2]; },
+        [&](int i, const float*, int idx) { out_idx[i] = idx; });
 }
 
 // smem layout helpers -------------------------------------------------------------------------------------------
@@ -595,26 +699,28 @@ __global__ void __launch_bounds__(512) k_knn_samples(FrameParams fp, KnnIndex ix
     extern __shared__ float4 sv[];
     const int n = w.counters[C_ON];
     if (blockIdx.x == 0 && threadIdx.x == 0) w.counters[C_CORR] = n;
-    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    const int B = knn_batch_size(n);
+    if ((int)(blockIdx.x * (blockDim.x >> 5)) * B >= n) return;
     const KnnSmem kk = load_knn(sv, ix);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int sl = w.on_list[i];
-        const int r = sl / w.S;
-        const float z = w.z_vals[sl];
-        float x[3];
+    knn_warp_batches(kk, n, B,
+        [&](int i, float* x) {
+            const int sl = w.on_list[i];
+            const int r = sl / w.S;
+            const float z = w.z_vals[sl];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) x[k] = w.ray_dirs[3 * r + k] * z + fp.cam_loc[k];
-        const int idx = knn_scan(kk, x[0], x[1], x[2]);
-        BroydenState<3> st;
-        float s_, xh[3];
-        nn_inverse_skinning(fp, idx, x, st.best_T, &s_, xh);
+            for (int k = 0; k < 3; ++k) x[k] = w.ray_dirs[3 * r + k] * z + fp.cam_loc[k];
+        },
+        [&](int i, const float* x, int idx) {
+            BroydenState<3> st;
+            float s_, xh[3];
+            nn_inverse_skinning(fp, idx, x, st.best_T, &s_, xh);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { st.x[k] = xh[k]; st.best_x[k] = xh[k]; st.tgt[k] = x[k] - fp.trans[k]; st.gx[k] = 0.f; st.upd[k] = 0.f; }
+            for (int k = 0; k < 3; ++k) { st.x[k] = xh[k]; st.best_x[k] = xh[k]; st.tgt[k] = x[k] - fp.trans[k]; st.gx[k] = 0.f; st.upd[k] = 0.f; }
 #pragma unroll
-        for (int k = 0; k < 9; ++k) st.Jinv[k] = 0.f;
-        st.best_n = 0.f; st.owner = sl; st.g_evals = 0;
-        state_store(&w.corr_state[i], st);
-    }
+            for (int k = 0; k < 9; ++k) st.Jinv[k] = 0.f;
+            st.best_n = 0.f; st.owner = w.on_list[i]; st.g_evals = 0;
+            state_store(&w.corr_state[i], st);
+        });
 }
 
 constexpr int LDA_SKIN = 132;
@@ -861,6 +967,59 @@ __global__ void __launch_bounds__(256, 1) k_shade(FrameParams fp, Work w) {
 // (ballot/popc ranks), then alpha, the transmittance product (warp shuffle scan) and the weighted colour sum run
 // 32 samples at a time (implicit_differentiable_renderer.py:366-394).
 constexpr int COMP_WARPS = 4;
+// alpha of compacted sample e of a ray (implicit_differentiable_renderer.py:379-387); shared by k_composite and k_alpha_cull so
+// that both evaluate the identical fp32 expression
+__device__ __forceinline__ float sample_alpha(const float* cz, const float* cd, int e, int len, int S) {
+    const float dz = (e + 1 < len) ? (cz[e + 1] - cz[e]) : (1.0f / (float)S);     // :379-385
+    return 1.0f - expf(-cd[e] * dz);
+}
+
+// Exact alpha cull.  A converged sample whose alpha is EXACTLY 0.0f has compositing weight alpha * T == 0, so its colour (and
+// the SDF gradient that only feeds the colour network) cannot influence any output bit: rgb += 0 * c.  Given smp_sdf of every
+// converged sample (k_shade_tc3<true>), this kernel recomputes alpha with k_composite's own expression and builds the list of
+// samples that still need the full shading pass; culled samples get rgb = 0 (k_composite multiplies it by 0).  Far from the
+// surface sigma = exp(-sdf/beta)/(2 beta) underflows quickly: ~80 % of the samples of a bounding-box frame are culled.
+__global__ void __launch_bounds__(32 * COMP_WARPS) k_alpha_cull(FrameParams fp, Work w, int* __restrict__ out_list) {
+    __shared__ float strip[COMP_WARPS][2][MAX_STEPS];
+    __shared__ int slot_of[COMP_WARPS][MAX_STEPS];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * COMP_WARPS + wib;
+    if (r >= w.P) return;
+    const int S = w.S;
+    float beta = fabsf(fp.beta);
+    beta = fminf(fmaxf(beta, 1e-6f), 1e6f);
+    const float inv_beta = 1.0f / beta;
+    float* cz = strip[wib][0]; float* cd = strip[wib][1];
+    int* cs = slot_of[wib];
+    int len = 0;
+    for (int base = 0; base < S; base += 32) {
+        const int i = base + lane;
+        const size_t sl = (size_t)r * S + i;
+        const bool valid = (i < S) && w.smp_conv[sl];
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const int k = len + __popc(m & ((1u << lane) - 1u));
+            cz[k] = w.z_vals[sl];
+            cd[k] = laplace_density(w.smp_sdf[sl], inv_beta);
+            cs[k] = i;
+        }
+        len += __popc(m);
+    }
+    __syncwarp();
+    for (int base = 0; base < len; base += 32) {
+        const int e = base + lane;
+        const bool in = e < len;
+        bool keep = false;
+        int sl = 0;
+        if (in) {
+            sl = r * S + cs[e];
+            keep = sample_alpha(cz, cd, e, len, S) != 0.0f;
+            if (!keep) { w.smp_rgb[3 * (size_t)sl] = 0.f; w.smp_rgb[3 * (size_t)sl + 1] = 0.f; w.smp_rgb[3 * (size_t)sl + 2] = 0.f; }
+        }
+        warp_append(keep, sl, out_list, &w.counters[C_SHADE2]);
+    }
+}
+
 __global__ void __launch_bounds__(32 * COMP_WARPS) k_composite(FrameParams fp, Work w) {
     __shared__ float strip[COMP_WARPS][5][MAX_STEPS];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -892,10 +1051,7 @@ __global__ void __launch_bounds__(32 * COMP_WARPS) k_composite(FrameParams fp, W
         const int e = base + lane;
         const bool in = e < len;
         float alpha = 0.f;
-        if (in) {
-            const float dz = (e + 1 < len) ? (cz[e + 1] - cz[e]) : (1.0f / (float)S);     // :379-385
-            alpha = 1.0f - expf(-cd[e] * dz);
-        }
+        if (in) alpha = sample_alpha(cz, cd, e, len, S);
         const float fac = in ? (1.0f - alpha + 1e-7f) : 1.0f;
         float incl = fac;
 #pragma unroll

@@ -300,10 +300,22 @@ using namespace arah_mesh;
 
 #define MCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return arah_internal_fail(ARAH_ECUDA, (std::string(#x) + ": " + cudaGetErrorString(e_)).c_str()); } while (0)
 
+static inline size_t mc_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" size_t arah_marching_cubes_workspace(int32_t N) {
+    if (N < 2 || N > 1024) return 0;
+    const size_t n = (size_t)N * N * N;
+    const size_t nblocks = (n + MC_BLOCK - 1) / MC_BLOCK;
+    return mc_align(n) + 2 * mc_align(n * 4) + mc_align(nblocks * sizeof(uint2));
+}
+
 extern "C" int arah_marching_cubes(const float* sdf, int32_t N, float level, float voxel_size, const float* origin3,
-                                   float* verts, int32_t max_verts, int32_t* faces, int32_t max_faces, int32_t* counts, void* stream) {
-    if (!sdf || !origin3 || !counts || (max_verts > 0 && !verts) || (max_faces > 0 && !faces)) return arah_internal_fail(ARAH_EINVAL, "null buffer");
+                                   float* verts, int32_t max_verts, int32_t* faces, int32_t max_faces, int32_t* counts,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    if (!sdf || !origin3 || !counts || !workspace || (max_verts > 0 && !verts) || (max_faces > 0 && !faces)) return arah_internal_fail(ARAH_EINVAL, "null buffer");
     if (N < 2 || N > 1024) return arah_internal_fail(ARAH_EINVAL, "lattice side must be in [2, 1024]");
+    if (workspace_bytes < arah_marching_cubes_workspace(N)) return arah_internal_fail(ARAH_EINVAL, "workspace smaller than arah_marching_cubes_workspace(N)");
+    if ((uintptr_t)workspace & 15) return arah_internal_fail(ARAH_EINVAL, "workspace must be 16-byte aligned");
     int dev = 0;
     MCU(cudaGetDevice(&dev));
     const int rc = upload_tables(dev);
@@ -312,18 +324,17 @@ extern "C" int arah_marching_cubes(const float* sdf, int32_t N, float level, flo
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)N * N * N;
     const unsigned nblocks = (unsigned)((n + MC_BLOCK - 1) / MC_BLOCK);
-    // stream-ordered scratch: code bytes, per-point vertex / triangle offsets, block sums
-    uint8_t* code = nullptr; uint32_t* voff = nullptr; uint32_t* toff = nullptr; uint2* bs = nullptr;
-    MCU(cudaMallocAsync((void**)&code, n, st));
-    MCU(cudaMallocAsync((void**)&voff, n * 4, st));
-    MCU(cudaMallocAsync((void**)&toff, n * 4, st));
-    MCU(cudaMallocAsync((void**)&bs, (size_t)nblocks * sizeof(uint2), st));
+    // caller-owned scratch (no allocation here): code bytes | per-point vertex offsets | per-point triangle offsets | block sums
+    uint8_t* base = (uint8_t*)workspace;
+    uint8_t* code = base;
+    uint32_t* voff = (uint32_t*)(base + mc_align(n));
+    uint32_t* toff = (uint32_t*)(base + mc_align(n) + mc_align(n * 4));
+    uint2* bs = (uint2*)(base + mc_align(n) + 2 * mc_align(n * 4));
     k_mc_classify<<<nblocks, MC_BLOCK, 0, st>>>(sdf, N, level, code, bs);
     k_mc_scan<<<1, 1024, 0, st>>>(bs, (int)nblocks, counts);
     k_mc_vertices<<<nblocks, MC_BLOCK, 0, st>>>(sdf, N, level, voxel_size, origin3[0], origin3[1], origin3[2], code, bs, voff, toff, verts, max_verts);
     k_mc_faces<<<nblocks, MC_BLOCK, 0, st>>>(sdf, N, level, code, voff, toff, faces, max_faces);
     MCU(cudaGetLastError());
-    MCU(cudaFreeAsync(code, st)); MCU(cudaFreeAsync(voff, st)); MCU(cudaFreeAsync(toff, st)); MCU(cudaFreeAsync(bs, st));
     return ARAH_OK;
 }
 

@@ -331,7 +331,7 @@ __device__ __forceinline__ void s3_mma_skin(float* ring, const S3Bars& bar, uint
     }
 }
 // compute warps: logits[r][0..31] for the 128 rows in xs3
-__device__ __forceinline__ void s3_compute_skin(const SkinTC& sk, const float* xs3, const S3Bars& bar, uint32_t& done_par, uint32_t tbase, float (*logits)[32]) {
+__device__ __forceinline__ void s3_compute_skin(const SkinTC& sk, const float* xs3, const S3Bars& bar, uint32_t& done_par, uint32_t tbase, float (*logits)[LGS]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, half = warp >> 2, r = 32 * q + lane;
     const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_iso_tc3(FrameParams fp, SdfT
     if ((int)blockIdx.x * UM >= n) return;
     if (smem_u32(raw_smem) & 1023u) __trap();
     float* A_lo = reinterpret_cast<float*>(raw_smem);
-    float (*logits)[32] = reinterpret_cast<float (*)[32]>(A_lo);        // aliases A_lo: only alive between the two MLPs
+    float (*logits)[LGS] = reinterpret_cast<float (*)[LGS]>(A_lo);        // aliases A_lo: only alive between the two MLPs
     float* ring = A_lo + S3_ALO_FLOATS;
     float* xs3 = ring + S3_RING_FLOATS;
     float (*part)[UM] = reinterpret_cast<float (*)[UM]>(xs3 + UM * 3);

@@ -40,9 +40,13 @@ __host__ __device__ constexpr size_t shade_tc3_smem_bytes() {
     return (size_t)(TC3_NSLOTS * RING_SLOT_FLOATS + UM * 36 + 3584 + UM * 4 + 2 * UM * 4) * 4 + TC3_NSEG * sizeof(Seg) + 512 + 1024;
 }
 
+// SDF_ONLY = true: the forward pass alone (same GEMM program prefix, same epilogue arithmetic, hence bit-identical smp_sdf) for
+// the exact alpha cull (k_alpha_cull): no cos factors, no scratch traffic, no reverse pass, no colour MLP.
+template <bool SDF_ONLY>
 __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, ShadeTC tc, Work w) {
     extern __shared__ uint8_t raw_smem[];
-    const int n = w.counters[C_SHADE];
+    const int n = w.counters[w.shade_ctr];
+    constexpr int NSEG = SDF_ONLY ? 5 : TC3_NSEG;
     if ((int)blockIdx.x * UM >= n) return;
     const uint32_t base = (smem_u32(raw_smem) + 1023u) & ~1023u;
     float* sm = reinterpret_cast<float*>(raw_smem + (base - smem_u32(raw_smem)));
@@ -73,15 +77,17 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
             g.a_reg = (uint8_t)a; g.d_reg = (uint8_t)d; g.acc = (uint8_t)acc; g.order = (uint8_t)order;
         };
         for (int l = 1; l <= 5; ++l) add(tc.sdf_fwd[l - 1], 256, 0, 8, (l - 1) & 1, l & 1, 0, 0);          // A: R0,R1,R0,R1,R0
-        for (int l = 5; l >= 1; --l) add(tc.sdf_bwd[l - 1], 256, 0, 8, l & 1, (l - 1) & 1, 0, 0);          // A: R1,R0,R1,R0,R1
-        add(tc.col0, 256, 0, 8, 1, 0, 0, 0);
-        add(tc.col0, 256, 8, 2, 1, 0, 1, 2);
-        add(tc.col1, 256, 0, 8, 0, 1, 0, 0);
-        add(tc.col2, 128, 0, 8, 1, 0, 0, 0);
-        add(tc.col3b, 256, 0, 4, 0, 1, 0, 1);
-        add(tc.col3a, 256, 0, 8, 0, 1, 1, 0);
-        add(tc.col3a, 256, 8, 2, 0, 1, 1, 2);
-        add(tc.col4, 256, 0, 8, 1, 0, 0, 0);
+        if (!SDF_ONLY) {
+            for (int l = 5; l >= 1; --l) add(tc.sdf_bwd[l - 1], 256, 0, 8, l & 1, (l - 1) & 1, 0, 0);      // A: R1,R0,R1,R0,R1
+            add(tc.col0, 256, 0, 8, 1, 0, 0, 0);
+            add(tc.col0, 256, 8, 2, 1, 0, 1, 2);
+            add(tc.col1, 256, 0, 8, 0, 1, 0, 0);
+            add(tc.col2, 128, 0, 8, 1, 0, 0, 0);
+            add(tc.col3b, 256, 0, 4, 0, 1, 0, 1);
+            add(tc.col3a, 256, 0, 8, 0, 1, 1, 0);
+            add(tc.col3a, 256, 8, 2, 0, 1, 1, 2);
+            add(tc.col4, 256, 0, 8, 1, 0, 0, 0);
+        }
     }
     if (warp == 0) tmem_alloc(tslot, 512);
     for (int i = tid; i < 768; i += TC3_THREADS) { prm[P_W0T + i] = __ldg(tc.sdf_Wt0 + i); prm[P_W0 + i] = __ldg(tc.sdf_W0 + i); prm[P_W5 + i] = __ldg(tc.col_W5 + i); }
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
         if (lane == 0) {
             uint32_t slot = 0, use = 0;
             for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
-                for (int s = 0; s < TC3_NSEG; ++s) {
+                for (int s = 0; s < NSEG; ++s) {
                     const Seg g = prog[s];
                     const uint32_t bytes = (uint32_t)g.N * UK * 4;
                     for (int i = 0; i < g.nchunks; ++i) {
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
         if (lane == 0) {
             uint32_t slot = 0, use = 0, rpar = 0;
             for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
-                for (int s = 0; s < TC3_NSEG; ++s) {
+                for (int s = 0; s < NSEG; ++s) {
                     const Seg g = prog[s];
                     const uint32_t idesc = umma_idesc_tf32(UM, g.N);
                     const uint32_t ta = tbase + 256u * g.a_reg, td = tbase + 256u * g.d_reg;
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
                     h[i] = s_; c[i] = c_ * lp0[cc];
                 }
                 a_put(0, col0 / 32, h);
-                cf_put(0, b, c);
+                if (!SDF_ONLY) cf_put(0, b, c);
             }
         }
         pc.mark(0);                                               // tile setup + layer 0
@@ -247,16 +253,18 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
                     __sincosf(fmaf(v[i], lp0[col0 + i], lp1[col0 + i]), &s_, &c_);
                     v[i] = s_; c[i] = c_ * lp0[col0 + i];
                 }
-                cf_put(l, b, c);
+                if (!SDF_ONLY) cf_put(l, b, c);
                 if (l < 5) a_put(dreg, col0 / 32, v);             // in place: D(l) -> A(l+1)
                 else {
-                    feat_put(b, v);
+                    if (!SDF_ONLY) feat_put(b, v);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) dot = fmaf(v[i], prm[P_W6 + col0 + i], dot);
-                    float g[32];                                  // g_a5 = w6 * cf5, in place in R1 (A of the first reverse GEMM)
+                    if (!SDF_ONLY) {
+                        float g[32];                              // g_a5 = w6 * cf5, in place in R1 (A of the first reverse GEMM)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) g[i] = c[i] * prm[P_W6 + col0 + i];
-                    a_put(1, col0 / 32, g);
+                        for (int i = 0; i < 32; ++i) g[i] = c[i] * prm[P_W6 + col0 + i];
+                        a_put(1, col0 / 32, g);
+                    }
                 }
             }
             if (l == 5) part[half][r][0] = dot;
@@ -264,6 +272,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
         }
         cta_sync_compute();
         if (tid < UM && sl >= 0) w.smp_sdf[sl] = sdf_to_metres(part[0][tid][0] + part[1][tid][0] + tc.sdf_b6, fp.cmin, fp.cmax);
+        if (SDF_ONLY) { cta_sync_compute(); pc.mark(3); continue; }      // (part / xs are rewritten by the next tile)
         // ================= reverse pass =================
         float g3[3] = {0.f, 0.f, 0.f};
         for (int l = 5; l >= 1; --l) {

@@ -79,10 +79,11 @@ __device__ __forceinline__ int a_unit_off(int r, int c, int j) {
 }
 // fp32 -> TF32 with round-to-nearest (the tensor core would otherwise TRUNCATE the low 13 mantissa bits: 2x the
 // error and a systematic bias towards zero that accumulates coherently over K)
+// cvt.rna.tf32.f32 (round to nearest, ties away from zero) lowers to 4 SASS instructions on sm_100a (|x| >= inf test, add,
+// mask, select); every epilogue runs it once or twice per activation.  For finite values — all we ever feed it: bounded
+// activations and weights — the add-and-mask below yields the identical bit pattern in 2 instructions.
 __device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 // store 32 consecutive K values (one chunk) of row r
 __device__ __forceinline__ void a_store_chunk(float* A, int r, int c, const float (&v)[32]) {
@@ -187,9 +188,15 @@ __device__ __forceinline__ void a_store_chunk_split(float* A_hi, float* A_lo, in
     }
 }
 // softplus(beta=100) with MUFU exp/log: max(x,0) + log(1 + exp(-|100 x|)) / 100; abs error < 1e-8 thanks to the 1/100
+// log(1 + exp(-|100 x|)) / 100 + max(x, 0).  Same two MUFU results as __expf / __logf (identical roundings of the argument and
+// of the result), but through the .ftz forms: the non-ftz intrinsics carry denormal fix-up code (3-4 extra instructions per
+// call) that can never trigger here (exp's denormal results vanish in 1 + e, log's argument lies in [1, 2]).
 __device__ __forceinline__ float softplus100_fast(float x) {
-    const float e = __expf(-fabsf(x * 100.0f));
-    return fmaxf(x, 0.0f) + __logf(1.0f + e) * 0.01f;
+    const float t = x * 100.0f;
+    float e, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t) * 1.4426950408889634f));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+    return fmaxf(x, 0.0f) + (l * 0.6931471805599453f) * 0.01f;
 }
 
 }  // namespace arah

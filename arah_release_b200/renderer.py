@@ -64,7 +64,7 @@ class ArahRenderer:
     """Thin RAII wrapper around an ArahHandle (one per device/stream; not thread-safe)."""
 
     def __init__(self, device, n_steps=64, near_samples=16, far_samples=16, cano_view_dirs=True, latent_dim=128,
-                 n_verts=N_VERTS_DEFAULT, max_rays=65536, shade_mode=None, root_mode=None):
+                 n_verts=N_VERTS_DEFAULT, max_rays=65536, shade_mode=None, root_mode=None, shade_cull=None):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.ArahError('the ARAH hot path only exists as CUDA kernels; got device %s' % device)
@@ -78,7 +78,9 @@ class ArahRenderer:
         self.root_mode = 'fp32' if rmode == 1 else '3xtf32'
         self.cfg = ArahConfig(device=self.device.index or 0, n_steps=n_steps, near_samples=near_samples,
                               far_samples=far_samples, cano_view_dirs=int(bool(cano_view_dirs)), latent_dim=latent_dim,
-                              n_verts=n_verts, max_rays=max_rays, shade_mode=mode, root_mode=rmode)
+                              n_verts=n_verts, max_rays=max_rays, shade_mode=mode, root_mode=rmode,
+                              shade_cull=0 if (shade_cull is None or shade_cull) else 1)
+        self.shade_cull = bool(self.cfg.shade_cull == 0) and os.environ.get('ARAH_SHADE_CULL', '1') != '0'
         self._h = C.c_void_p()
         check(_lib.lib().arah_create(C.byref(self.cfg), C.byref(self._h)))
         self._keep = []
@@ -296,6 +298,13 @@ class ArahRenderer:
         check(_lib.lib().arah_eval_skin(self._h, _ptr(x), n, _ptr(w), _ptr(xb), self.stream))
         return w, xb
 
+    def knn(self, pts):
+        """pytorch3d.ops.knn_points(K=1) of ray_tracing.py:386,407: nearest posed SMPL vertex per point -> int32 [n]."""
+        x = _f32c(pts, self.device).view(-1, 3)
+        idx = torch.empty(x.shape[0], dtype=torch.int32, device=self.device)
+        check(_lib.lib().arah_debug_knn(self._h, _ptr(x), x.shape[0], _ptr(idx), self.stream))
+        return idx
+
     # ------------------------------------------------------------------ canonical mesh (SURVEY §8 row f1)
     def sdf_grid(self, N=256):
         """utils/sdf_meshing.py:13-58: the frame's SDF network on the N^3 lattice over [-1,1]^3 -> [N, N, N] (device)."""
@@ -315,11 +324,13 @@ class ArahRenderer:
         counts = torch.zeros(2, dtype=torch.int32, device=self.device)
         mv = int(max_verts) if max_verts else 6 * N * N
         mf = int(max_faces) if max_faces else 12 * N * N
+        ws_bytes = int(_lib.lib().arah_marching_cubes_workspace(N))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)       # torch's caching allocator: no cudaMalloc per call
         while True:
             verts = torch.empty(mv, 3, device=self.device)
             faces = torch.empty(mf, 3, dtype=torch.int32, device=self.device)
             check(_lib.lib().arah_marching_cubes(_ptr(vol), N, float(level), voxel_size, org, _ptr(verts), mv, _ptr(faces), mf,
-                                                 _ptr(counts), self.stream))
+                                                 _ptr(counts), _ptr(ws), ws_bytes, self.stream))
             nv, nf = (int(v) for v in counts.tolist())
             if nv <= mv and nf <= mf:
                 return verts[:nv], faces[:nf]
@@ -483,8 +494,10 @@ class IDHRNetwork(nn.Module):
     (implicit_differentiable_renderer.py:18-40); eval forward runs entirely in libarah_b200.so."""
 
     def __init__(self, deviation_network, rendering_network, skinning_model, ray_tracer, cano_view_dirs=True,
-                 train_skinning_net=False, render_last_pt=False, low_vram=False, shade_mode=None, root_mode=None, train_mode=None):
+                 train_skinning_net=False, render_last_pt=False, low_vram=False, shade_mode=None, root_mode=None, train_mode=None,
+                 shade_cull=None):
         super().__init__()
+        self.shade_cull = shade_cull      # extra, optional: False disables the exact alpha cull (bit-identical results either way)
         self.train_mode = train_mode      # extra, optional: '3xtf32' (tensor-core GEMMs in the training engine, default) | 'fp32' | 'tf32'
         self.root_mode = root_mode        # extra, optional: '3xtf32' (tensor cores, default) | 'fp32'
         self.shade_mode = shade_mode      # extra, optional: 'tf32' (tensor cores, default) | 'fp32' (FFMA tiles)
@@ -510,7 +523,8 @@ class IDHRNetwork(nn.Module):
             rt = self.ray_tracer
             r = ArahRenderer(device, n_steps=rt.n_steps, near_samples=rt.near_surface_vol_samples,
                              far_samples=rt.far_surface_vol_samples, cano_view_dirs=self.cano_view_dirs,
-                             latent_dim=latent_dim, n_verts=n_verts, shade_mode=self.shade_mode, root_mode=self.root_mode)
+                             latent_dim=latent_dim, n_verts=n_verts, shade_mode=self.shade_mode, root_mode=self.root_mode,
+                             shade_cull=self.shade_cull)
             self._renderers[key] = r
         return r
 

@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--cpu-sample-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-step', action='store_true', help='skip the BASELINE configs[2] training-step measurement')
+    ap.add_argument('--no-mesh', action='store_true', help='skip the canonical-mesh (row f1) measurement')
     ap.add_argument('--train-rays', type=int, default=2048, help='rays per training step (configs/default.yaml:13-14: 1024 fg + 1024 bg)')
     return ap.parse_args()
 
@@ -239,6 +240,42 @@ def train_step_bench(args, dev, frame, steps=5, warmup=3):
             'algorithmic_tflops_differentiable_part': 2.0 * mac / (tot * 1e-3) / 1e12}
 
 
+# ------------------------------------------------------------------------------------------------ canonical mesh (row f1)
+def mesh_extract_bench(net, frame, steps=3, warmup=2, N=256):
+    """MetaAvatarRender.forward(gen_cano_mesh=True) front half (models/__init__.py:203-206): 256^3 SDF lattice + iso-surface.
+    SDF lattice: tensor roofline (N^3 x 328 704 MAC, 3xTF32 counts as 1x useful); marching cubes: HBM roofline, algorithmic
+    bytes = one read of the lattice (4 N^3) + the vertices and faces written."""
+    import torch
+    from oracle import oracle as orc
+    r = net._last[0]
+    ms_g, ms_m = [], []
+    for i in range(warmup + steps):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        vol = r.sdf_grid(N)
+        e[1].record()
+        v, f = r.marching_cubes(vol, max_verts=1 << 20, max_faces=1 << 21)
+        e[2].record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ms_g.append(e[0].elapsed_time(e[1])); ms_m.append(e[1].elapsed_time(e[2]))
+    pk = peaks()
+    g, m = float(np.mean(ms_g)), float(np.mean(ms_m))
+    mc_bytes = 4.0 * N ** 3 + 12.0 * v.shape[0] + 12.0 * f.shape[0]
+    # CPU: the oracle's marching cubes on the same lattice (1 core) and its SDF on a bounded lattice sample (all cores)
+    volh = vol.cpu().numpy()
+    t = time.perf_counter(); orc.marching_cubes(volh); t_mc = time.perf_counter() - t
+    pts, _ = orc.grid_points(64)
+    t = time.perf_counter(); orc.sdf(frame, pts, grad=False); t_sdf = time.perf_counter() - t
+    return {'workload': f'{N}^3 canonical SDF lattice + iso-surface (utils/sdf_meshing.py:13-114)', 'ms_sdf_grid': g, 'ms_marching_cubes': m,
+            'n_verts': int(v.shape[0]), 'n_faces': int(f.shape[0]),
+            'sdf_grid_tflops_useful': 2.0 * MAC_SDF * N ** 3 / (g * 1e-3) / 1e12, 'sdf_grid_frac_of_bf16_peak': 2.0 * MAC_SDF * N ** 3 / (g * 1e-3) / 1e12 / pk['tf_sustained'],
+            'marching_cubes_gbs': mc_bytes / (m * 1e-3) / 1e9, 'marching_cubes_frac_of_hbm_peak': mc_bytes / (m * 1e-3) / 1e9 / pk['hbm_gbs'],
+            'gpu_launches': 5, 'steps': steps, 'warmup': warmup,
+            'cpu_port': {'ms_marching_cubes_1core': 1e3 * t_mc, 'ms_sdf_grid_extrapolated': 1e3 * t_sdf * (N / 64.0) ** 3, 'cores': orc.num_threads(),
+                         'sample': '64^3 lattice points timed, scaled by (N/64)^3'}}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -298,7 +335,7 @@ def run_ours(args):
     if rank == 0:
         clk.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    shade_ms, shade_flops, step_flops, stats_last = [], [], [], None
+    shade_ms, shade_flops, shade_flops_ref, step_flops, stats_last = [], [], [], [], None
     corr_ms, corr_flops = [], []
     for k in range(args.steps):
         flush.zero_()                                   # L2 flush between timed iterations (outside the event pair)
@@ -307,7 +344,12 @@ def run_ours(args):
         ev[k][1].record()
         st = r.stats()                                  # syncs; counters + stage events of this step
         shade_ms.append(st['ms_shade'])
-        shade_flops.append(2.0 * st['shaded_samples'] * (2 * MAC_SDF + MAC_COL))
+        # executed work of the shading stage: with the exact alpha cull every converged sample gets an SDF-only forward pass and
+        # only the survivors (alpha != 0) the full SDF fwd + gradient + colour pass; without it all samples get the full pass
+        culled, shaded = st.get('culled_samples', 0), st['shaded_samples']
+        cull_ran = r.shade_cull and r.shade_mode == 'tf32'
+        shade_flops.append(2.0 * ((shaded * MAC_SDF if cull_ran else 0) + (shaded - culled) * (2 * MAC_SDF + MAC_COL)))
+        shade_flops_ref.append(2.0 * shaded * (2 * MAC_SDF + MAC_COL))
         step_flops.append(algorithmic_flops(st))
         corr_ms.append(st['ms_sample_corr'])
         corr_flops.append(2.0 * st['corr_skin_evals'] * MAC_SKIN)
@@ -375,13 +417,18 @@ def run_ours(args):
                 'api': 'arah_set_frame(pose_on_host) + arah_render_host via IDHRNetwork host wrapper'},
         'gpu_launches': int((stats_last['kernel_launches'] + stats_last['pack_launches']) * args.steps),
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': f'k_shade_tc3 (SDF fwd + reverse-mode grad + colour MLP; tcgen05 {r.shade_mode} operands, fp32 accumulate in TMEM)'
+        'roofline': {'bound': 'tensor', 'kernel': f'shading stage: k_shade_tc3<sdf-only> + k_alpha_cull + k_shade_tc3 (SDF fwd + reverse-mode grad + colour MLP; tcgen05 {r.shade_mode} operands, fp32 accumulate in TMEM)'
                      if r.shade_mode == 'tf32' else 'k_shade (fp32 FFMA tiles)',
                      'achieved': ach, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf_sustained'],
                      'peak_source': pk['src'] + ' bf16 cuBLAS sustained (MEASURED_PEAKS.json)', 'traffic': traffic,
                      'algorithmic_flops_per_launch': float(np.mean(shade_flops)), 'ms_per_launch': float(np.mean(shade_ms)),
                      'kernel_share_of_step': float(sum(shade_ms) / (1e3 * t_dev)),
-                     'whole_step_tflops': float(sum(step_flops) / t_dev / 1e12)},
+                     'exact_alpha_cull': {'enabled': bool(r.shade_cull and r.shade_mode == 'tf32'), 'culled_samples': int(stats_last.get('culled_samples', 0)),
+                                          'shaded_samples': int(stats_last['shaded_samples']),
+                                          'reference_equivalent_tflops': float(sum(shade_flops_ref) / max(sum(shade_ms), 1e-9) / 1e9),
+                                          'note': 'achieved counts EXECUTED flops only (SDF-only pass over all converged samples + full pass over '
+                                                  'samples with alpha != 0); reference_equivalent counts the full pass for every sample as the reference executes it'},
+                     'whole_step_tflops_reference_equivalent': float(sum(step_flops) / t_dev / 1e12)},
         'roofline_corr': {'bound': 'tensor', 'kernel': f'k_knn_samples + 51 x k_corr_tc3 (per-sample correspondence search; skinning MLP {r.root_mode}: 3 TF32 products count as 1 useful)',
                           'achieved': (sum(corr_flops) / max(sum(corr_ms), 1e-9)) / 1e9, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
                           'frac': (sum(corr_flops) / max(sum(corr_ms), 1e-9)) / 1e9 / pk['tf_sustained'], 'ms_per_step': float(np.mean(corr_ms)),
@@ -398,6 +445,12 @@ def run_ours(args):
             line['train_step'] = train_step_bench(args, dev, f0)
         except Exception as ex:          # secondary metric: never lose the headline line
             line['train_step'] = {'error': repr(ex)[:300]}
+    if args.gpus == 1 and not args.no_mesh:
+        try:
+            step_device(0)                                   # make f0 the current frame of the handle again
+            line['mesh_extract'] = mesh_extract_bench(net, f0)
+        except Exception as ex:
+            line['mesh_extract'] = {'error': repr(ex)[:300]}
     if args.gpus == 1 and not args.no_cpu_baseline:
         v, cores, n, dt = cpu_rate(f0, args.cpu_sample_seconds)
         line['cpu_baseline'] = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',

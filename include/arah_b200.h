@@ -13,6 +13,7 @@
  */
 #ifndef ARAH_B200_H
 #define ARAH_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -44,7 +45,13 @@ typedef struct ArahConfig {
     int32_t root_mode;            /* ARAH_ROOT_3XTF32 (default 0): the skinning MLP of the per-sample correspondence search on
                                    * tcgen05 in split precision (hi/lo TF32, 3 products ~ fp32); ARAH_ROOT_FP32 (1): fp32
                                    * FFMA tiles.  Residual bookkeeping, Jacobians and Broyden updates are fp32 in both. */
+    int32_t shade_cull;           /* ARAH_CULL_EXACT (default 0): with shade_mode TF32, converged samples whose compositing alpha is
+                                   * exactly 0.0f in fp32 skip the SDF-gradient + colour pass — their weight alpha * T is 0, so no
+                                   * output bit can depend on their colour (results are bit-identical to ARAH_CULL_OFF, see
+                                   * tests/test_gpu_parity.py::test_alpha_cull_is_exact); ARAH_CULL_OFF (1): shade every sample. */
 } ArahConfig;
+#define ARAH_CULL_EXACT 0
+#define ARAH_CULL_OFF 1
 #define ARAH_SHADE_TF32 0
 #define ARAH_SHADE_FP32 1
 #define ARAH_ROOT_3XTF32 0
@@ -97,6 +104,7 @@ typedef struct ArahStats {
     /* device time of each stage of the last render (ms, CUDA events on the launching stream);
      * only filled when profiling was enabled with arah_set_profiling(h, 1), else 0 */
     double ms_trace, ms_iso, ms_sample_corr, ms_shade, ms_composite, ms_total;
+    int64_t culled_samples;       /* of shaded_samples: culled by the exact alpha test (only their SDF value was computed) */
 } ArahStats;
 
 const char* arah_last_error(void);
@@ -157,9 +165,16 @@ int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, float* weights,
  *   oracle/mc_oracle.c, a CPU restatement of the same published scheme).  Works on the current device; no handle needed. */
 int arah_sdf_grid(ArahHandle* h, int32_t N, float* sdf, void* stream);
 int arah_marching_cubes(const float* sdf, int32_t N, float level, float voxel_size, const float* origin3 /* host [3] */,
-                        float* verts, int32_t max_verts, int32_t* faces, int32_t max_faces, int32_t* counts, void* stream);
+                        float* verts, int32_t max_verts, int32_t* faces, int32_t max_faces, int32_t* counts,
+                        void* workspace /* device, 16-byte aligned */, size_t workspace_bytes, void* stream);
+/* Bytes of device scratch arah_marching_cubes needs for an N^3 lattice (~9.03 N^3); the library never allocates behind the call. */
+size_t arah_marching_cubes_workspace(int32_t N);
 /* Host-only: the generated marching-cubes case table, tri[256][16] (edge ids, -1 terminated) and ntri[256]. */
 int arah_mc_case_table(int8_t* tri, uint8_t* ntri);
+
+/* Unit-level: pytorch3d.ops.knn_points(K=1) as used at renderer/ray_tracing.py:386,407 — index of the nearest posed SMPL vertex
+ * (exact fp32 argmin of (x-v).(x-v), lowest index on ties) for n device points [n][3] -> idx [n] int32. */
+int arah_debug_knn(ArahHandle* h, const float* pts, int32_t n, int32_t* idx, void* stream);
 
 /* Debug: SM-clock cycles spent per kernel phase by one designated thread per CTA, summed over CTAs and launches of the last
  * profiled render (arah_set_profiling(h,1)): out32[0..5] correspondence step (gather, layer 0, MMA wait, epilogues, output

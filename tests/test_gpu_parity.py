@@ -172,3 +172,75 @@ def test_full_size_properties_512():
     assert stats['rays'] == P and stats['shaded_samples'] > 0
     print('512x512', P, stats)
 
+
+
+@pytest.mark.parametrize('n', [1, 31, 777, 5000, 20000, 200000])
+def test_knn_index_is_the_brute_force_argmin(n):
+    """The clustered 1-NN (warp-cooperative for small batches: n <= 28k here; per-lane scan for full warps) must return the
+    brute-force argmin index of pytorch3d knn_points(K=1): points near, on (zero distance) and far away from the body.
+    Both sides evaluate (x-v).(x-v) in fp32, in orders that may differ by one rounding, so an index may differ only where the
+    two candidate distances agree to 1e-6 relative in exact arithmetic (a numerical tie; pytorch3d leaves tie order unspecified,
+    SURVEY §8c) — and that must be rare."""
+    from oracle import oracle as orc
+    fr, _, _ = load_golden('cano_20x20_s1')
+    net, inputs = _build(fr)
+    r = net._prepare(inputs)
+    rng = np.random.default_rng(n)
+    lo, hi = fr.smpl_verts.min(0), fr.smpl_verts.max(0)
+    pts = rng.uniform(lo - 0.3, hi + 0.3, size=(n, 3)).astype(np.float32)
+    k = n // 4
+    if k:
+        pts[:k] = fr.smpl_verts[rng.integers(0, fr.smpl_verts.shape[0], size=k)] + rng.normal(scale=1e-3, size=(k, 3)).astype(np.float32)
+        pts[k:k + k // 2] = fr.smpl_verts[rng.integers(0, fr.smpl_verts.shape[0], size=k // 2)]          # zero distance
+        pts[-1] = 50.0                                                                                     # far outside every box
+    idx = r.knn(torch.from_numpy(pts).to(DEV)).cpu().numpy()
+    torch.cuda.synchronize()
+    ref, _, _ = orc.knn(fr, pts)
+    bad = np.nonzero(idx != ref)[0]
+    if bad.size:
+        v = fr.smpl_verts.astype(np.float64)
+        da = ((pts[bad].astype(np.float64) - v[idx[bad]]) ** 2).sum(1)
+        db = ((pts[bad].astype(np.float64) - v[ref[bad]]) ** 2).sum(1)
+        rel = np.abs(da - db) / np.maximum(np.maximum(da, db), 1e-30)
+        print(f'knn n={n}: {bad.size} index differences, max relative distance gap {rel.max():.3e}')
+        assert rel.max() <= 1e-6, (bad[:10], idx[bad][:10], ref[bad][:10], rel[:10])
+        assert bad.size <= max(2, n // 20000), bad.size
+
+
+@pytest.mark.parametrize('name', ['zju377_24x24_s0', 'cano_20x20_s1', 'h36m_n160_12x12_s4'])
+def test_alpha_cull_is_exact(name):
+    """The exact alpha cull (ArahConfig.shade_cull, k_alpha_cull) skips gradient + colour for samples whose compositing alpha is
+    exactly 0.0f; every output must be BIT-identical to shading all samples, and the cull must actually fire."""
+    fr, ref, _ = load_golden(name)
+    outs, stats = [], []
+    for cull in (True, False):
+        from arah_release_b200 import ref_layout as rl
+        from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
+        dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
+        tracer = BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples, far_surface_vol_samples=fr.far_samples)
+        net = IDHRNetwork(dev, rend, skin, tracer, cano_view_dirs=fr.cano_view_dirs, shade_mode='tf32', root_mode='3xtf32', shade_cull=cull).eval()
+        outs.append(_render_dict(net, rl.inputs_from_frame(fr, sdf, DEV), stages=False))
+        stats.append(net.stats())
+    for k in ('rgb_values', 'network_body_mask', 'points_cam'):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    assert stats[0]['shaded_samples'] == stats[1]['shaded_samples'] and stats[1]['culled_samples'] == 0
+    assert 0 < stats[0]['culled_samples'] < stats[0]['shaded_samples'], stats[0]
+    print(name, 'culled', stats[0]['culled_samples'], 'of', stats[0]['shaded_samples'])
+    check_render(outs[0], ref, label=name + ' cull', tol=dict(TOL, rgb_psnr_min=55.0), stages=False)
+
+
+def test_alpha_cull_is_exact_full_size_512():
+    from arah_release_b200 import ref_layout as rl, synthetic as syn
+    from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
+    fr = syn.make_frame(512, 512, seed=0)
+    res = []
+    for cull in (True, False):
+        dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
+        net = IDHRNetwork(dev, rend, skin, BodyRayTracing(n_steps=fr.n_steps), cano_view_dirs=fr.cano_view_dirs, shade_cull=cull).eval()
+        out = net(rl.inputs_from_frame(fr, sdf, DEV))
+        torch.cuda.synchronize()
+        res.append((out['rgb_values'].clone(), out['network_body_mask'].clone(), net.stats()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    st = res[0][2]
+    print('512x512: culled', st['culled_samples'], 'of', st['shaded_samples'])
+    assert st['culled_samples'] > 0.5 * st['shaded_samples']
