@@ -316,8 +316,11 @@ __device__ __forceinline__ int knn_scan_warp(const KnnSmem& k, float x, float y,
 // Measured (B200, 15 M queries): with a full warp of queries the per-lane scan (knn_scan, 32 queries in SIMT) is ~3x
 // cheaper per query than the cooperative one (shuffle reductions); the cooperative form wins when a warp would otherwise hold
 // only a few queries (tail iterations of sphere tracing, training-size batches), where latency, not throughput, counts.
-constexpr int KNN_COOP_MAX_B = 12;
-template <class LoadQ, class Finish>
+// Rays of neighbouring pixels sit at unrelated depths, so their per-lane scans diverge and the cooperative form stays ahead
+// up to full warps (k_knn_rays: 145 vs 193 us per launch); samples along one ray are coherent (k_knn_samples: per-lane wins
+// beyond ~12 queries per warp: 11 vs 33 ms).
+constexpr int KNN_COOP_SAMPLES = 12, KNN_COOP_RAYS = 32;
+template <int COOP_MAX_B, class LoadQ, class Finish>
 __device__ __forceinline__ void knn_warp_batches(const KnnSmem& kk, int n, int B, LoadQ load, Finish fin) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5, total_warps = gridDim.x * wpb, gw = blockIdx.x * wpb + (threadIdx.x >> 5);
@@ -327,7 +330,7 @@ __device__ __forceinline__ void knn_warp_batches(const KnnSmem& kk, int n, int B
         float x[3] = {0.f, 0.f, 0.f};
         if (lane < cnt) load(i0 + lane, x);
         int mine = 0;
-        if (B > KNN_COOP_MAX_B) {
+        if (B > COOP_MAX_B) {
             if (lane < cnt) mine = knn_scan(kk, x[0], x[1], x[2]);
         } else {
             for (int j = 0; j < cnt; ++j) {
@@ -339,11 +342,12 @@ __device__ __forceinline__ void knn_warp_batches(const KnnSmem& kk, int n, int B
         if (lane < cnt) fin(i0 + lane, x, mine);
     }
 }
-// queries per warp: spread over all warps of the grid while that keeps a warp at <= KNN_COOP_MAX_B queries, else full warps
+// queries per warp: spread over all warps of the grid while that keeps a warp at <= COOP_MAX_B queries, else full warps
+template <int COOP_MAX_B>
 __device__ __forceinline__ int knn_batch_size(int n) {
     const int total_warps = gridDim.x * (blockDim.x >> 5);
     const int b = max(1, (n + total_warps - 1) / total_warps);
-    return b > KNN_COOP_MAX_B ? 32 : b;
+    return b > COOP_MAX_B ? 32 : b;
 }
 
 // NN-skinning inverse of one posed point x (incl. trans): T = sum_j W[idx][j] B_j, x_hat = T^-1 (x - trans)
@@ -360,11 +364,11 @@ __device__ __forceinline__ void nn_inverse_skinning(const FrameParams& fp, int i
 __global__ void __launch_bounds__(512) k_knn_rays(FrameParams fp, KnnIndex ix, Work w, int iter) {
     extern __shared__ float4 sv[];
     const int n = w.counters[C_TRACE + iter];
-    const int B = knn_batch_size(n);
+    const int B = knn_batch_size<KNN_COOP_RAYS>(n);
     if ((int)(blockIdx.x * (blockDim.x >> 5)) * B >= n) return;
     const KnnSmem kk = load_knn(sv, ix);
     const int* list = (iter & 1) ? w.listB : w.listA;
-    knn_warp_batches(kk, n, B,
+    knn_warp_batches<KNN_COOP_RAYS>(kk, n, B,
         [&](int i, float* x) {
             const int r = list[i];
             const float t = w.ray_t[r];
@@ -384,10 +388,10 @@ __global__ void __launch_bounds__(512) k_knn_rays(FrameParams fp, KnnIndex ix, W
 // unit-level entry (tests): nearest posed-vertex index of n arbitrary points
 __global__ void __launch_bounds__(512) k_knn_points(KnnIndex ix, const float* __restrict__ pts, int n, int* __restrict__ out_idx) {
     extern __shared__ float4 sv[];
-    const int B = knn_batch_size(n);
+    const int B = knn_batch_size<KNN_COOP_SAMPLES>(n);
     if ((int)(blockIdx.x * (blockDim.x >> 5)) * B >= n) return;
     const KnnSmem kk = load_knn(sv, ix);
-    knn_warp_batches(kk, n, B,
+    knn_warp_batches<KNN_COOP_SAMPLES>(kk, n, B,
         [&](int i, float* x) { x[0] = pts[3 * i]; x[1] = pts[3 * i + 1]; x[2] = pts[3 * i + 2]; },
         [&](int i, const float*, int idx) { out_idx[i] = idx; });
 }
@@ -699,10 +703,10 @@ __global__ void __launch_bounds__(512) k_knn_samples(FrameParams fp, KnnIndex ix
     extern __shared__ float4 sv[];
     const int n = w.counters[C_ON];
     if (blockIdx.x == 0 && threadIdx.x == 0) w.counters[C_CORR] = n;
-    const int B = knn_batch_size(n);
+    const int B = knn_batch_size<KNN_COOP_SAMPLES>(n);
     if ((int)(blockIdx.x * (blockDim.x >> 5)) * B >= n) return;
     const KnnSmem kk = load_knn(sv, ix);
-    knn_warp_batches(kk, n, B,
+    knn_warp_batches<KNN_COOP_SAMPLES>(kk, n, B,
         [&](int i, float* x) {
             const int sl = w.on_list[i];
             const int r = sl / w.S;

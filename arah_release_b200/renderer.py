@@ -210,9 +210,19 @@ class ArahRenderer:
         nf = near_far.contiguous().view(-1, 2)
         assert rd.device.type == 'cpu' and rd.dtype == torch.float32 and nf.dtype == torch.float32
         P = rd.shape[0]
-        rgb = torch.empty(P, 3, dtype=torch.float32).pin_memory() if rgb is None else rgb
-        mask = torch.empty(P, dtype=torch.uint8).pin_memory() if mask is None else mask
-        pc = torch.empty(P, 3, dtype=torch.float32).pin_memory() if points_cam is None else points_cam
+        if rgb is None or mask is None or points_cam is None:
+            # pinned result buffers are owned by the renderer and reused (cudaHostAlloc per call costs milliseconds); the returned
+            # tensors are views that stay valid until the next render_host call
+            cache = getattr(self, '_host_out', None)
+            if cache is None or cache[0].shape[0] < P:
+                cache = (torch.empty(P, 3, dtype=torch.float32).pin_memory(), torch.empty(P, dtype=torch.uint8).pin_memory(),
+                         torch.empty(P, 3, dtype=torch.float32).pin_memory())
+                self._host_out = cache
+            rgb = cache[0][:P] if rgb is None else rgb
+            mask = cache[1][:P] if mask is None else mask
+            pc = cache[2][:P] if points_cam is None else points_cam
+        else:
+            pc = points_cam
         check(_lib.lib().arah_render_host(self._h, _ptr(rd), _ptr(nf), P, _ptr(rgb), _ptr(mask), _ptr(pc), self.stream))
         return rgb, mask, pc
 
