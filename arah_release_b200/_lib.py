@@ -38,11 +38,24 @@ class ArahTrainGrads(C.Structure):
                 ('col_W', FP * 6), ('col_b', FP * 6), ('latent', FP), ('beta', FP)]
 
 
+class ArahHyperWeights(C.Structure):
+    _fields_ = [('pe_l0_W', FP), ('pe_l0_b', FP), ('pe_W1', FP), ('pe_b1', FP), ('pe_W2', FP), ('pe_b2', FP),
+                ('map_W', FP * 4), ('map_b', FP * 4),
+                ('fc1_W', FP * 7), ('fc1_b', FP * 7), ('ln1_g', FP * 7), ('ln1_b', FP * 7),
+                ('fc2_W', FP * 7), ('fc2_b', FP * 7), ('ln2_g', FP * 7), ('ln2_b', FP * 7),
+                ('out_W', FP * 7), ('out_b', FP * 7), ('init', FP * 7), ('rel_joints', C.c_int32)]
+
+
+class ArahSdfParams(C.Structure):
+    _fields_ = [('sdf_W', FP * 7), ('sdf_b', FP * 7), ('sdf_freq', FP), ('sdf_phase', FP)]
+
+
 EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'arah_set_frame', 'arah_set_profiling', 'arah_render',
            'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin', 'arah_debug_umma_gemm', 'arah_debug_phase_clocks',
            'arah_set_training', 'arah_train_trace', 'arah_train_shade_forward', 'arah_train_shade_backward', 'arah_train_sdf_forward',
            'arah_train_sdf_backward', 'arah_train_skin_forward', 'arah_train_skin_backward', 'arah_debug_train_gemm',
-           'arah_sdf_grid', 'arah_marching_cubes', 'arah_mc_case_table', 'arah_debug_knn', 'arah_marching_cubes_workspace']
+           'arah_sdf_grid', 'arah_marching_cubes', 'arah_mc_case_table', 'arah_debug_knn', 'arah_marching_cubes_workspace',
+           'arah_hyper_forward', 'arah_hyper_workspace']
 
 _lib = None
 
@@ -89,6 +102,8 @@ def lib():
     L.arah_marching_cubes_workspace.restype = C.c_size_t
     L.arah_mc_case_table.argtypes = [C.c_void_p, C.c_void_p]
     L.arah_debug_knn.argtypes = [C.c_void_p, FP, C.c_int32, FP, C.c_void_p]
+    L.arah_hyper_forward.argtypes = [C.POINTER(ArahHyperWeights), FP, FP, FP, C.POINTER(ArahSdfParams), FP, C.c_void_p]
+    L.arah_hyper_workspace.restype = C.c_size_t
     _lib = L
     return L
 

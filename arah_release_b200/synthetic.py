@@ -369,3 +369,59 @@ def train_aux_points(frame: Frame, seed: int = 0, n_uniform: int = 1024, n_insid
     rgb_gt = rng.random((frame.P, 3)).astype(F32)
     return {'points_uniform': pu, 'points_skinning': ps, 'sampled_weights': pw, 'points_inside': pin,
             'body_mask': body_mask, 'rgb_gt': rgb_gt}
+
+
+# ---------------------------------------------------------------------------------------------------- hypernetwork (row f4)
+def make_hypernet_state_dict(seed=0, out_scale=0.02, init_scale=0.3):
+    """Seeded synthetic parameters of the MetaAvatar hypernetwork, keyed and shaped like
+    HyperBVPNet(in_features=3, num_hidden_layers=5, hierarchical_pose=True, hyper_in_ch=144, use_FiLM=True).state_dict()
+    (metaavatar/models/siren_modules.py:247-279; 86.6 M parameters).  No checkpoint is reachable offline, and the reference's
+    default init zeroes every output layer (hyperlayers.py:418-424) which would make the big GEMVs vanish from the result, so
+    every tensor gets small random values (numpy PCG64: identical on every machine).  Returns {key: np.float32 array}."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def lin(key, out, inp, scale=None):
+        sc = (1.0 / np.sqrt(inp)) if scale is None else scale
+        sd[key + '.weight'] = (rng.standard_normal((out, inp), dtype=np.float32) * np.float32(sc))
+        sd[key + '.bias'] = (rng.standard_normal(out, dtype=np.float32) * np.float32(0.1))
+
+    lin('pose_encoder.layer_0', 6, 288)
+    for j in range(24):
+        lin(f'pose_encoder.layers.{j}.0', 19, 19)
+        lin(f'pose_encoder.layers.{j}.2', 6, 19)
+    in_ch = [3, 256, 256, 256, 256, 256, 256]
+    out_ch = [256, 256, 256, 256, 256, 256, 1]
+    for l in range(7):
+        pre = f'net.layers.{l}.hyper_linear.' if l < 6 else f'net.layers.{l}.'
+        n_l = in_ch[l] * out_ch[l] + out_ch[l]
+        sd[pre + 'hypo_params_init'] = (rng.standard_normal((1, n_l), dtype=np.float32) * np.float32(init_scale / np.sqrt(in_ch[l])))
+        fc = pre + 'hypo_params.net.'
+        lin(fc + '0.net.0', 256, 144)
+        sd[fc + '0.net.1.weight'] = (1.0 + 0.1 * rng.standard_normal(256, dtype=np.float32)).astype(np.float32)
+        sd[fc + '0.net.1.bias'] = (0.1 * rng.standard_normal(256, dtype=np.float32)).astype(np.float32)
+        lin(fc + '1.net.0', 256, 256)
+        sd[fc + '1.net.1.weight'] = (1.0 + 0.1 * rng.standard_normal(256, dtype=np.float32)).astype(np.float32)
+        sd[fc + '1.net.1.bias'] = (0.1 * rng.standard_normal(256, dtype=np.float32)).astype(np.float32)
+        lin(fc + '2', n_l, 256, scale=out_scale / 16.0)
+    lin('net.mapping_network.network.0', 256, 128)
+    lin('net.mapping_network.network.2', 256, 256)
+    lin('net.mapping_network.network.4', 256, 256)
+    lin('net.mapping_network.network.6', 3072, 256, scale=0.01)
+    sd['net.mapping_network.network.6.bias'][:1536] += np.float32(1.0)           # pretrained-siren init: freq ~ 1, phase ~ 0
+    return sd
+
+
+def make_hypernet_inputs(seed=0):
+    """rots [1,24,9] (rotation matrices, root = identity as data/zju_mocap_odp.py:262), Jtrs [1,24,3] in [-1,1], latent [1,128]."""
+    rng = np.random.default_rng(1000 + seed)
+    rots = np.zeros((24, 3, 3), np.float32)
+    for j in range(24):
+        a = rng.standard_normal(3) * (0.0 if j == 0 else 0.5)
+        th = np.linalg.norm(a)
+        K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+        R = np.eye(3) if th < 1e-12 else np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+        rots[j] = R.astype(np.float32)
+    Jtrs = rng.uniform(-0.8, 0.8, size=(24, 3)).astype(np.float32)
+    latent = (0.1 * rng.standard_normal(128)).astype(np.float32)
+    return rots.reshape(1, 24, 9), Jtrs.reshape(1, 24, 3), latent.reshape(1, 128)

@@ -276,6 +276,37 @@ def mesh_extract_bench(net, frame, steps=3, warmup=2, N=256):
                          'sample': '64^3 lattice points timed, scaled by (N/64)^3'}}
 
 
+# ------------------------------------------------------------------------------------------------ hypernetwork (row f4)
+def hypernet_bench(dev, steps=20, warmup=5):
+    """HyperBVPNet.forward up to the assembled decoder (siren_modules.py:280-312): batch-1 GEMV over 86.9 M parameters.
+    HBM roofline: algorithmic bytes = every parameter read once (the caches are flushed between timed calls)."""
+    import torch
+    from arah_release_b200 import synthetic as syn
+    from arah_release_b200.hypernet import HyperSDFDecoder
+    from oracle import hyper_oracle as ho
+    sd = syn.make_hypernet_state_dict(0)
+    dec = HyperSDFDecoder({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    rots, Jtrs, latent = syn.make_hypernet_inputs(0)
+    inp = {'rots': torch.from_numpy(rots).to(dev), 'Jtrs': torch.from_numpy(Jtrs).to(dev), 'latent': torch.from_numpy(latent).to(dev)}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    ms = []
+    for i in range(warmup + steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); dec(inp); e1.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ms.append(e0.elapsed_time(e1))
+    t = time.perf_counter(); ho.forward(sd, rots, Jtrs, latent); t_cpu = time.perf_counter() - t
+    pk = peaks()
+    m = float(np.median(ms))
+    gbs = dec.weight_bytes / (m * 1e-3) / 1e9
+    return {'workload': 'MetaAvatar hypernetwork forward, 86.9 M parameters, batch 1 (configs/arah-zju/ZJUMOCAP-377_4gpus.yaml:34)',
+            'ms': m, 'algorithmic_bytes': int(dec.weight_bytes), 'achieved_gbs': gbs, 'peak_gbs': pk['hbm_gbs'], 'frac_of_hbm_peak': gbs / pk['hbm_gbs'],
+            'gpu_launches': 2, 'steps': steps, 'warmup': warmup, 'l2': '256 MB memset before every timed call',
+            'cpu_port': {'ms': 1e3 * t_cpu, 'kind': 'oracle/hyper_oracle.py (numpy fp32, BLAS threads)'}}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -451,6 +482,11 @@ def run_ours(args):
             line['mesh_extract'] = mesh_extract_bench(net, f0)
         except Exception as ex:
             line['mesh_extract'] = {'error': repr(ex)[:300]}
+    if args.gpus == 1 and not args.no_mesh:
+        try:
+            line['hypernet'] = hypernet_bench(dev)
+        except Exception as ex:
+            line['hypernet'] = {'error': repr(ex)[:300]}
     if args.gpus == 1 and not args.no_cpu_baseline:
         v, cores, n, dt = cpu_rate(f0, args.cpu_sample_seconds)
         line['cpu_baseline'] = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',

@@ -172,6 +172,54 @@ size_t arah_marching_cubes_workspace(int32_t N);
 /* Host-only: the generated marching-cubes case table, tri[256][16] (edge ids, -1 terminated) and ntri[256]. */
 int arah_mc_case_table(int8_t* tri, uint8_t* ntri);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Hypernetwork forward: pose -> the frame's SDF parameters, i.e. HyperBVPNet.forward up to the
+ * assembled decoder (metaavatar/models/siren_modules.py:280-312; called at metaavatar_render/models/__init__.py:181-183).
+ * All pointers are DEVICE pointers in the reference's own state_dict layout ([out][in] row-major), borrowed for the call —
+ * the 341 MB of output-layer matrices are read in place, never copied.  Shapes are those of
+ * configs/arah-zju/ZJUMOCAP-377_4gpus.yaml:34 (hyper_in_ch 144, hidden 256, 5 hidden SIREN layers, use_FiLM). */
+typedef struct ArahHyperWeights {
+    /* pose_encoder.* — HierarchicalPoseEncoder (siren_modules.py:196-244) */
+    const float* pe_l0_W;         /* layer_0.weight [6][288] */
+    const float* pe_l0_b;         /* [6] */
+    const float* pe_W1;           /* layers.j.0.weight stacked [24][19][19] */
+    const float* pe_b1;           /* [24][19] */
+    const float* pe_W2;           /* layers.j.2.weight stacked [24][6][19] */
+    const float* pe_b2;           /* [24][6] */
+    /* net.mapping_network.network.{0,2,4,6} — CustomMappingNetwork (hyperlayers.py:107-139) */
+    const float* map_W[4];        /* [256][128], [256][256], [256][256], [3072][256] */
+    const float* map_b[4];
+    /* net.layers.l.(hyper_linear.)hypo_params.net.{0,1,2} — FCBlock (pytorch_prototyping.py:50-81), l = 0..6 */
+    const float* fc1_W[7];        /* net.0.net.0.weight [256][144] */
+    const float* fc1_b[7];
+    const float* ln1_g[7];        /* net.0.net.1.weight (LayerNorm) [256] */
+    const float* ln1_b[7];
+    const float* fc2_W[7];        /* net.1.net.0.weight [256][256] */
+    const float* fc2_b[7];
+    const float* ln2_g[7];
+    const float* ln2_b[7];
+    const float* out_W[7];        /* net.2.weight [n_l][256], n_l = in_l*out_l + out_l: 1024, 5 x 65792, 257 */
+    const float* out_b[7];        /* [n_l] */
+    const float* init[7];         /* hypo_params_init [n_l] (hyperlayers.py:443,487); may be NULL (= zeros) */
+    int32_t rel_joints;           /* HierarchicalPoseEncoder(rel_joints=...) */
+} ArahHyperWeights;
+
+/* Outputs == the tensors HyperFCFiLM.forward hands to BatchLinearFiLM / BatchLinear (hyperlayers.py:270-285, 453-510) and
+ * ArahFrame consumes: device buffers owned by the caller. */
+typedef struct ArahSdfParams {
+    float* sdf_W[7];              /* [256][3], 5 x [256][256], [1][256] */
+    float* sdf_b[7];              /* [256] x 6, [1] */
+    float* sdf_freq;              /* [6][256] */
+    float* sdf_phase;             /* [6][256] */
+} ArahSdfParams;
+
+/* rots [24][9] ('rots': rotation matrices, root = identity), Jtrs [24][3] ('Jtrs': normalised joints), latent [128] (the
+ * geometry latent code; NULL = zeros).  workspace: arah_hyper_workspace() bytes of device scratch, 16-byte aligned.
+ * Two kernel launches on `stream`, no synchronisation. */
+int arah_hyper_forward(const ArahHyperWeights* w, const float* rots, const float* Jtrs, const float* latent,
+                       const ArahSdfParams* out, void* workspace, void* stream);
+size_t arah_hyper_workspace(void);
+
 /* Unit-level: pytorch3d.ops.knn_points(K=1) as used at renderer/ray_tracing.py:386,407 — index of the nearest posed SMPL vertex
  * (exact fp32 argmin of (x-v).(x-v), lowest index on ties) for n device points [n][3] -> idx [n] int32. */
 int arah_debug_knn(ArahHandle* h, const float* pts, int32_t n, int32_t* idx, void* stream);
