@@ -36,68 +36,85 @@ struct HeadArgs {
 };
 
 __device__ __constant__ int c_parent[NJ] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+// joints grouped by depth in the kinematic tree: a level only needs its parents' features, so 9 steps instead of 24
+__device__ __constant__ int c_level_start[10] = {0, 1, 4, 7, 10, 15, 18, 20, 22, 24};
+__device__ __constant__ int c_level_joint[NJ] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23};
 
-// y[r] = b[r] + sum_k W[r][k] x[k] for r < rows; warp per row (coalesced), x in shared memory
+constexpr int HEAD_THREADS = 1024;
+
+// y[r] = b[r] + sum_k W[r][k] x[k] for r < rows: a warp takes 4 rows at a time (coalesced row reads, 4 x cols/32 independent
+// loads in flight per lane), x in shared memory
 __device__ __forceinline__ void dense_rows(const float* __restrict__ W, const float* __restrict__ b, const float* x, int rows, int cols, float* y) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int r = warp; r < rows; r += nw) {
-        float s = 0.f;
-        for (int k = lane; k < cols; k += 32) s = fmaf(__ldg(W + (size_t)r * cols + k), x[k], s);
+    for (int r0 = 4 * warp; r0 < rows; r0 += 4 * nw) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = lane; k < cols; k += 32) {
+            const float xv = x[k];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) y[r] = s + __ldg(b + r);
+            for (int i = 0; i < 4; ++i) if (r0 + i < rows) s[i] = fmaf(__ldg(W + (size_t)(r0 + i) * cols + k), xv, s[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+        if (lane < 4 && r0 + lane < rows) {
+            const float v = lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3];
+            y[r0 + lane] = v + __ldg(b + r0 + lane);
+        }
     }
 }
-// nn.LayerNorm([256]) (eps 1e-5, biased variance) followed by ReLU, in place; blockDim.x == 256
+// nn.LayerNorm([256]) (eps 1e-5, biased variance) followed by ReLU, in place; the first 256 threads hold one element each
 __device__ __forceinline__ void layernorm_relu(float* v, const float* __restrict__ g, const float* __restrict__ b, float* red) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const float x = v[t];
+    const bool on = t < HID;
+    const float x = on ? v[t] : 0.f;
     float s = x;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) red[warp] = s;
+    if (on && lane == 0) red[warp] = s;
     __syncthreads();
     float mean = 0.f;
     for (int i = 0; i < 8; ++i) mean += red[i];
     mean *= (1.0f / HID);
     __syncthreads();
     const float d = x - mean;
-    float q = d * d;
+    float q = on ? d * d : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    if (lane == 0) red[warp] = q;
+    if (on && lane == 0) red[warp] = q;
     __syncthreads();
     float var = 0.f;
     for (int i = 0; i < 8; ++i) var += red[i];
     var *= (1.0f / HID);
-    const float y = d * rsqrtf(var + 1e-5f) * __ldg(g + t) + __ldg(b + t);
-    v[t] = fmaxf(y, 0.f);
+    if (on) v[t] = fmaxf(d * rsqrtf(var + 1e-5f) * __ldg(g + t) + __ldg(b + t), 0.f);
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_hyper_head(HeadArgs a) {
-    __shared__ float in[288], feat[NJ][6], gfeat[6], x19[19], h19[19], cond[COND], v0[HID], v1[HID], red[8];
-    const int t = threadIdx.x, l = blockIdx.x;
+__global__ void __launch_bounds__(HEAD_THREADS) k_hyper_head(HeadArgs a) {
+    __shared__ float in[288], feat[NJ][6], gfeat[6], cond[COND], v0[HID], v1[HID], red[8];
+    __shared__ float sW1[NJ * 19 * 19], x19[NJ][20], h19[NJ][20];
+    const int t = threadIdx.x, l = blockIdx.x, warp = t >> 5, lane = t & 31;
     const ArahHyperWeights& w = a.w;
     if (l == 7) {                                   // mapping network, hidden part (hyperlayers.py:112-121): LeakyReLU(0.2)
         if (t < 128) in[t] = a.latent ? a.latent[t] : 0.f;
         __syncthreads();
         dense_rows(w.map_W[0], w.map_b[0], in, HID, 128, v0);
         __syncthreads();
-        v0[t] = v0[t] > 0.f ? v0[t] : 0.2f * v0[t];
+        if (t < HID) v0[t] = v0[t] > 0.f ? v0[t] : 0.2f * v0[t];
         __syncthreads();
         dense_rows(w.map_W[1], w.map_b[1], v0, HID, HID, v1);
         __syncthreads();
-        v1[t] = v1[t] > 0.f ? v1[t] : 0.2f * v1[t];
+        if (t < HID) v1[t] = v1[t] > 0.f ? v1[t] : 0.2f * v1[t];
         __syncthreads();
         dense_rows(w.map_W[2], w.map_b[2], v1, HID, HID, v0);
         __syncthreads();
-        a.hidden[7 * HID + t] = v0[t] > 0.f ? v0[t] : 0.2f * v0[t];
+        if (t < HID) a.hidden[7 * HID + t] = v0[t] > 0.f ? v0[t] : 0.2f * v0[t];
         return;
     }
-    // ---- HierarchicalPoseEncoder (siren_modules.py:217-244)
-    for (int i = t; i < 216; i += 256) in[i] = a.rots[i];
-    for (int i = t; i < 72; i += 256) {
+    // ---- HierarchicalPoseEncoder (siren_modules.py:217-244): weights staged once (coalesced), joints evaluated level by level
+    for (int i = t; i < NJ * 361; i += HEAD_THREADS) sW1[i] = __ldg(w.pe_W1 + i);
+    for (int i = t; i < 216; i += HEAD_THREADS) in[i] = a.rots[i];
+    for (int i = t; i < 72; i += HEAD_THREADS) {
         const int j = i / 3, k = i % 3;
         float v = a.Jtrs[i];
         if (w.rel_joints && j > 0) v -= a.Jtrs[3 * c_parent[j] + k];          // :220-224
@@ -106,34 +123,37 @@ __global__ void __launch_bounds__(256) k_hyper_head(HeadArgs a) {
     __syncthreads();
     dense_rows(w.pe_l0_W, w.pe_l0_b, in, 6, 288, gfeat);                      // global_feat (:226-227)
     __syncthreads();
-    for (int j = 0; j < NJ; ++j) {
-        if (t < 19) {
+    for (int lev = 0; lev < 9; ++lev) {
+        const int n = c_level_start[lev + 1] - c_level_start[lev];
+        const int j = (warp < n) ? c_level_joint[c_level_start[lev] + warp] : -1;     // one warp per joint of the level
+        if (j >= 0 && lane < 19) {
             const int p = c_parent[j];
             float v;
-            if (t < 9) v = in[9 * j + t];
-            else if (t < 12) v = in[216 + 3 * j + (t - 9)];
-            else if (t == 12) {                                               // bone length (:235,239)
+            if (lane < 9) v = in[9 * j + lane];
+            else if (lane < 12) v = in[216 + 3 * j + (lane - 9)];
+            else if (lane == 12) {                                            // bone length (:235,239)
                 float d[3];
                 for (int k = 0; k < 3; ++k) {
                     d[k] = in[216 + 3 * j + k];
                     if (p >= 0 && !w.rel_joints) d[k] -= in[216 + 3 * p + k];
                 }
                 v = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-            } else v = (p < 0) ? gfeat[t - 13] : feat[p][t - 13];
-            x19[t] = v;
+            } else v = (p < 0) ? gfeat[lane - 13] : feat[p][lane - 13];
+            x19[j][lane] = v;
         }
-        __syncthreads();
-        if (t < 19) {
-            float s = __ldg(w.pe_b1 + 19 * j + t);
-            for (int k = 0; k < 19; ++k) s = fmaf(__ldg(w.pe_W1 + (size_t)(19 * j + t) * 19 + k), x19[k], s);
-            h19[t] = fmaxf(s, 0.f);
+        __syncwarp();
+        if (j >= 0 && lane < 19) {
+            float s = __ldg(w.pe_b1 + 19 * j + lane);
+            for (int k = 0; k < 19; ++k) s = fmaf(sW1[(19 * j + lane) * 19 + k], x19[j][k], s);
+            h19[j][lane] = fmaxf(s, 0.f);
         }
-        __syncthreads();
-        if (t < 6) {
-            float s = __ldg(w.pe_b2 + 6 * j + t);
-            for (int k = 0; k < 19; ++k) s = fmaf(__ldg(w.pe_W2 + (size_t)(6 * j + t) * 19 + k), h19[k], s);
-            feat[j][t] = s;
-            cond[6 * j + t] = s;
+        __syncwarp();
+        if (j >= 0 && lane < 6) {
+            float s = __ldg(w.pe_b2 + 6 * j + lane);
+#pragma unroll
+            for (int k = 0; k < 19; ++k) s = fmaf(__ldg(w.pe_W2 + (6 * j + lane) * 19 + k), h19[j][k], s);
+            feat[j][lane] = s;
+            cond[6 * j + lane] = s;
         }
         __syncthreads();
     }
@@ -144,7 +164,7 @@ __global__ void __launch_bounds__(256) k_hyper_head(HeadArgs a) {
     dense_rows(w.fc2_W[l], w.fc2_b[l], v0, HID, HID, v1);
     __syncthreads();
     layernorm_relu(v1, w.ln2_g[l], w.ln2_b[l], red);
-    a.hidden[l * HID + t] = v1[t];
+    if (t < HID) a.hidden[l * HID + t] = v1[t];
 }
 
 struct GemvGroup {
@@ -227,7 +247,7 @@ extern "C" int arah_hyper_forward(const ArahHyperWeights* w, const float* rots, 
     cudaStream_t st = (cudaStream_t)stream;
     HeadArgs ha;
     ha.w = *w; ha.rots = rots; ha.Jtrs = Jtrs; ha.latent = latent; ha.hidden = (float*)workspace;
-    k_hyper_head<<<NGROUP, 256, 0, st>>>(ha);
+    k_hyper_head<<<NGROUP, HEAD_THREADS, 0, st>>>(ha);
     GemvArgs ga;
     int chunk = 0;
     for (int l = 0; l < 7; ++l) {

@@ -76,9 +76,13 @@ class HyperSDFDecoder(nn.Module):
         if latent is not None:
             latent = latent.to(self.device, torch.float32).reshape(-1).contiguous()
         dev = self.device
-        W = [torch.empty(1, OUT_CH[l], IN_CH[l], device=dev) for l in range(7)]
-        b = [torch.empty(1, 1, OUT_CH[l], device=dev) for l in range(7)]
-        freq, phase = torch.empty(6, 256, device=dev), torch.empty(6, 256, device=dev)
+        # one allocation per call, carved into the reference's tensors (each slice starts on a 16-byte boundary)
+        sizes = [OUT_CH[l] * IN_CH[l] for l in range(7)] + [(OUT_CH[l] + 3) // 4 * 4 for l in range(7)] + [1536, 1536]
+        flat = torch.empty(sum(sizes), device=dev)
+        parts = torch.split(flat, sizes)
+        W = [parts[l].view(1, OUT_CH[l], IN_CH[l]) for l in range(7)]
+        b = [parts[7 + l][:OUT_CH[l]].view(1, 1, OUT_CH[l]) for l in range(7)]
+        freq, phase = parts[14].view(6, 256), parts[15].view(6, 256)
         out = ArahSdfParams()
         for l in range(7):
             out.sdf_W[l], out.sdf_b[l] = _ptr(W[l]), _ptr(b[l])
