@@ -17,6 +17,7 @@
 #include "arah_sdf3x.cuh"
 #include "arah_shade_tc4.cuh"
 #include "arah_corr_tc4.cuh"
+#include "arah_corr_tc5.cuh"
 #include "arah_train_cuda.cuh"
 #include <stdlib.h>
 
@@ -302,6 +303,7 @@ struct ArahHandle {
     float* tc_sdf3x[5];
     SdfTC sd;
     int trace_tc = 1;
+    int corr_interleave = 1;   // k_corr_tc5: the two tiles of a trip time-share the activation columns of TMEM (epilogue of one under the MMAs of the other)
     int corr_cluster = 1;      // 2-CTA clusters + weight multicast in the correspondence kernel (measured: -2 ms)
     bool shade_cull_ran = false;
     int shade_cull = 1;        // exact alpha cull before the gradient / colour pass (k_alpha_cull)
@@ -432,6 +434,8 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_corr_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_shade_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_corr_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_corr_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
+    if (const char* e = getenv("ARAH_CORR_INTERLEAVE")) h->corr_interleave = atoi(e) != 0;
     if (const char* e = getenv("ARAH_CORR_CLUSTER")) h->corr_cluster = atoi(e) != 0;
     if (const char* e = getenv("ARAH_SHADE_CLUSTER")) h->shade_cluster = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
@@ -690,7 +694,8 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 lc.attrs = at; lc.numAttrs = 1;
-                CU(cudaLaunchKernelEx(&lc, k_corr_tc4, fp, h->sk, wk, it));
+                if (h->corr_interleave) CU(cudaLaunchKernelEx(&lc, k_corr_tc5, fp, h->sk, wk, it));
+                else CU(cudaLaunchKernelEx(&lc, k_corr_tc4, fp, h->sk, wk, it));
             }
             else if (h->tc_engine >= 3) k_corr_tc3<<<g_tc, TC3_THREADS, corr_tc3_smem_bytes(), st>>>(fp, h->sk, wk, it);
             else if (h->tc_engine == 2) k_corr_tc2<<<g_tc, TC_THREADS, corr_tc2_smem_bytes(), st>>>(fp, h->sk, wk, it);
