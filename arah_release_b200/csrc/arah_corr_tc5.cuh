@@ -7,10 +7,10 @@
 //
 //   TMEM: X = [0,128) hi | [128,256) lo  (input of whichever job runs), D_A = [256,384), D_B = [384,512).
 //   jobs issued by the MMA warp per trip: (A,l1) (B,l1) (A,l2) (B,l2) (A,l3) (B,l3) (A,out) (B,out).
-//   compute warps: while job (A,s) runs they compute B's input of job s in REGISTERS (64 values per thread); when done[A]
-//   fires (X free, D_A complete) they store it to X chunk by chunk (ready[c] -> job (B,s) starts) and immediately turn D_A
-//   into A's input of job s+1, again in registers, while (B,s) runs; and so on.  An epilogue always overlaps the other tile's
-//   MMAs; the pipe only idles for the store hand-off.
+//   compute warps: while job J(k-1) (other tile) runs they turn the accumulators of J(k-2) (same tile, previous layer) into the
+//   input of job J(k) in REGISTERS (64 values per thread), then store it to X chunk by chunk as J(k-1) releases the chunks
+//   (xfree[c], committed by the MMA warp after the MMAs that read chunk c) and publish each chunk (ready[c]): J(k) can start
+//   the moment J(k-1) ends.  An epilogue always overlaps the other tile's MMAs and the store hand-off overlaps them too.
 // Weight ring, 2-CTA cluster multicast, bookkeeping and arithmetic are those of k_corr_tc4 (same per-row results: a row's
 // activations, MMAs and accumulation order do not depend on the schedule).  The Broyden state is not kept in registers across
 // the MLP phase (it is re-read from L2 for the per-point phase) to make room for the 64 staged activations.
@@ -39,13 +39,15 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
     uint64_t* full = bars;
     uint64_t* empty = bars + TC3_NSLOTS;
     uint64_t* ready = bars + 2 * TC3_NSLOTS;     // [4] X chunk c stored by its 4 warps
-    uint64_t* done = ready + 4;                  // [2] job of tile A / B complete (its D ready, X free)
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(done + 2);
+    uint64_t* done = ready + 4;                  // [2] job of tile A / B complete (its D ready)
+    uint64_t* xfree = done + 2;                  // [4] the running job has finished reading X chunk c
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(xfree + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < TC3_NSLOTS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
         for (int i = 0; i < 4; ++i) mbar_init(&ready[i], 4);
         mbar_init(&done[0], 1); mbar_init(&done[1], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&xfree[i], 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(tslot, 512);
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
                                 umma_tf32_ts(td, tbase + col, umma_smem_desc_sw128(bh + ko), idesc, 1u);                                  // A_hi . B_hi
                             }
                             umma_commit_mc2(&empty[slot]);
+                            umma_commit(&xfree[c]);
                             if (++slot == TC3_NSLOTS) { slot = 0; ++use; }
                         }
                         umma_commit(&done[t]);
@@ -120,30 +123,38 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
     // ===== compute warps =====
     const int q = warp & 3, half = warp >> 2, r = 32 * q + lane;
     const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
-    uint32_t done_par = 0;                                             // bit t: parity of done[t]
+    uint32_t done_par = 0, xpar = 0;                                   // parity bits of done[t] / xfree[c]
+    bool x_virgin = true;                                              // nothing has read X yet (first job of the kernel)
     float v[2][32];                                                    // the staged input of the next job: columns 64 half + 32 b + i
-    // job of tile t complete.  The compute-warp barrier that follows is what makes the NEXT store_x safe: the job it triggers
-    // overwrites a D region (first MMA has accumulate = 0 over all 128 columns) that every warp must have finished reading —
-    // all those reads precede this point in program order (store_x -> job (B,s) overwrites D_B, last read by epilogue(1, s);
-    // store_x -> job (A,s+1) overwrites D_A, last read by epilogue(0, s+1)).
     auto wait_done = [&](int t) {
         mbar_wait(&done[t], (done_par >> t) & 1u);
         done_par ^= (1u << t);
-        tc_fence_before();
-        cta_sync_compute();
+        __syncwarp();
         tc_fence_after();
     };
-    auto store_x = [&]() {                                             // v -> X (hi | lo), chunk by chunk, publishing each chunk
+    // v -> X (hi | lo), chunk by chunk: wait until the running job has read the chunk, store, publish
+    auto store_x = [&]() {
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             const int chunk = 2 * half + b;
+            if (!x_virgin) {
+                mbar_wait(&xfree[chunk], (xpar >> chunk) & 1u);
+                xpar ^= (1u << chunk);
+                __syncwarp();
+                tc_fence_after();
+            }
             a_tmem_store_split(trow + 32u * chunk, trow + 128u + 32u * chunk, v[b]);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[chunk]);
         }
+        // xfree[c] of the chunks owned by the OTHER half also completes once per job: keep their parity in step
+        if (!x_virgin) xpar ^= (3u << (2 * (1 - half)));
+        x_virgin = false;
     };
+    // all compute warps have finished reading a D region (the job triggered by the next store_x overwrites it)
+    auto sync_reads = [&]() { tc_fence_before(); cta_sync_compute(); tc_fence_after(); };
     auto layer0 = [&](int t) {                                         // 3 -> 128 on the FP32 pipe, into v
         const float x = xs[t * UM + r][0], y = xs[t * UM + r][1], z = xs[t * UM + r][2];
 #pragma unroll
@@ -200,32 +211,22 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
         }
         cta_sync_compute();
         pc.mark(0);
-        // ---- interleaved MLPs.  X is free here: the last job of the previous trip was waited for before its logits were read.
+        // ---- interleaved MLPs: jobs J(k), k = 0 .. 4 ntile - 1, tile k % ntile, layer k / ntile (+1)
+        const int ntile = haveB ? 2 : 1, njobs = 4 * ntile;
         layer0(0);
-        store_x();                                                     // -> job (A, l1)
+        store_x();                                                     // -> J(0)
         pc.mark(1);
-        if (haveB) {
-            layer0(1);                                                 // under (A, l1)
-            for (int s = 0; s < 4; ++s) {
-                wait_done(0);                                          // (A, s) complete: D_A ready, X free
-                pc.mark(2);
-                store_x();                                             // -> job (B, s)
-                if (s < 3) epilogue(0, s + 1); else take_logits(0);    // under (B, s)
-                pc.mark(3);
-                wait_done(1);                                          // (B, s) complete
-                pc.mark(2);
-                if (s < 3) { store_x(); epilogue(1, s + 1); }          // -> job (A, s+1); B's next input under it
-                else take_logits(1);
-                pc.mark(3);
-            }
-        } else {
-            for (int s = 0; s < 4; ++s) {
-                wait_done(0);
-                pc.mark(2);
-                if (s < 3) { epilogue(0, s + 1); cta_sync_compute(); tc_fence_after(); store_x(); } else take_logits(0);
-                pc.mark(3);
-            }
+        if (haveB) { layer0(1); store_x(); }                           // computed under J(0); stored as J(0) releases X -> J(1)
+        for (int k = ntile; k < njobs; ++k) {
+            const int t = k % ntile, s = k / ntile;
+            wait_done(t);                                              // J(k - ntile) complete: D_t holds the pre-activations of layer s
+            pc.mark(2);
+            epilogue(t, s);                                            // under J(k - 1) (the other tile)
+            sync_reads();                                              // J(k) overwrites D_t
+            store_x();                                                 // as J(k - 1) releases the X chunks -> J(k)
+            pc.mark(3);
         }
+        for (int t = 0; t < ntile; ++t) { wait_done(t); take_logits(t); }
         cta_sync_compute();                                            // logits of both tiles visible to their owner threads
         tc_fence_after();
         pc.mark(4);
