@@ -191,32 +191,40 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
     int* next = (iter & 1) ? w.listA : w.listB;
     PhaseClk pc; pc.start((tid == 32) ? w.phase_clk : nullptr);
     const int sub = tid >> 7, pt = tid & (UM - 1);                 // which tile of the pair / which point this thread owns
-    for (int trip = 0; trip < ntrips; trip += 2) {
+    // gather of a trip: the query point of this thread's sample (x + update, normalised) -> xs; returns the sample id (-1: none).
+    // The state itself is re-read for the per-point phase.
+    auto gather = [&](int trip) -> int {
         const int tileA = (int)blockIdx.x + trip * (int)gridDim.x;
-        const int tileB = tileA + (int)gridDim.x;
-        const bool haveB = trip + 1 < ntrips;                          // B exists as a (possibly all-padding) tile of this CTA
-        const int my_tile = sub ? (haveB ? tileB : ntiles_mine) : tileA;
-        int id = -1;
-        {   // the query point of this thread's sample: x + update, normalised (the state itself is re-read after the MLP)
-            const int i = my_tile * UM + pt;
-            float xn[3] = {0.f, 0.f, 0.f};
-            if (my_tile < ntiles_mine && i < n) {
-                id = list ? list[i] : i;
-                const BroydenState<3>* sp = &w.corr_state[id];
-                float x3[3] = {sp->x[0], sp->x[1], sp->x[2]};
-                if (iter >= 0) { x3[0] += sp->upd[0]; x3[1] += sp->upd[1]; x3[2] += sp->upd[2]; }      // broyden_advance
-                normalize3(fp, x3, xn);
-            }
-            xs[tid][0] = xn[0]; xs[tid][1] = xn[1]; xs[tid][2] = xn[2]; xs[tid][3] = 0.f;
+        const bool hb = trip + 1 < ntrips;
+        const int my_tile = sub ? (hb ? tileA + (int)gridDim.x : ntiles_mine) : tileA;
+        const int i = my_tile * UM + pt;
+        int sid = -1;
+        float xn[3] = {0.f, 0.f, 0.f};
+        if (my_tile < ntiles_mine && i < n) {
+            sid = list ? list[i] : i;
+            const BroydenState<3>* sp = &w.corr_state[sid];
+            float x3[3] = {sp->x[0], sp->x[1], sp->x[2]};
+            if (iter >= 0) { x3[0] += sp->upd[0]; x3[1] += sp->upd[1]; x3[2] += sp->upd[2]; }      // broyden_advance
+            normalize3(fp, x3, xn);
         }
-        cta_sync_compute();
-        pc.mark(0);
-        // ---- interleaved MLPs: jobs J(k), k = 0 .. 4 ntile - 1, tile k % ntile, layer k / ntile (+1)
+        xs[tid][0] = xn[0]; xs[tid][1] = xn[1]; xs[tid][2] = xn[2]; xs[tid][3] = 0.f;
+        return sid;
+    };
+    // Software pipeline across trips: the first two jobs of trip i+1 are fed (gather, layer 0, stores) BEFORE the per-point
+    // phase of trip i, so the hierarchical softmax / Broyden update / state traffic of trip i runs under J(0), J(1) of trip i+1,
+    // and the next gather + layer 0 run under the drain of trip i's last jobs.
+    int id = gather(0);
+    cta_sync_compute();
+    pc.mark(0);
+    layer0(0);
+    store_x();                                                         // -> J(0) of the first trip
+    if (ntrips > 1) { layer0(1); store_x(); }                          // -> J(1)
+    pc.mark(1);
+    for (int trip = 0; trip < ntrips; trip += 2) {
+        const bool haveB = trip + 1 < ntrips;                          // B exists as a (possibly all-padding) tile of this CTA
+        const bool more = trip + 2 < ntrips;                           // another trip follows
+        // ---- interleaved MLPs: jobs J(k), k = 0 .. 4 ntile - 1, tile k % ntile, layer k / ntile (+1); J(0), J(1) are already fed
         const int ntile = haveB ? 2 : 1, njobs = 4 * ntile;
-        layer0(0);
-        store_x();                                                     // -> J(0)
-        pc.mark(1);
-        if (haveB) { layer0(1); store_x(); }                           // computed under J(0); stored as J(0) releases X -> J(1)
         for (int k = ntile; k < njobs; ++k) {
             const int t = k % ntile, s = k / ntile;
             wait_done(t);                                              // J(k - ntile) complete: D_t holds the pre-activations of layer s
@@ -226,10 +234,21 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
             store_x();                                                 // as J(k - 1) releases the X chunks -> J(k)
             pc.mark(3);
         }
+        int id_next = -1;
+        if (more) {                                                    // under the last jobs of this trip
+            id_next = gather(trip + 2);
+            cta_sync_compute();
+            layer0(0);
+        }
+        pc.mark(0);
         for (int t = 0; t < ntile; ++t) { wait_done(t); take_logits(t); }
-        cta_sync_compute();                                            // logits of both tiles visible to their owner threads
-        tc_fence_after();
+        sync_reads();                                                  // logits visible to their owner threads; D_A / D_B read by everyone
         pc.mark(4);
+        if (more) {
+            store_x();                                                 // -> J(0) of the next trip
+            if (trip + 3 < ntrips) { layer0(1); store_x(); }           // -> J(1)
+            pc.mark(1);
+        }
         {
             bool active = false;
             BroydenState<3> st;
@@ -275,7 +294,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
                 warp_stat_add(fin ? st.g_evals : 0, &w.counters[C_STAT_CORR_EVALS]);
             }
         }
-        cta_sync_compute();
+        cta_sync_compute();                                            // logits consumed before the next trip's take_logits
+        id = id_next;
         pc.mark(5);
     }
     tc_fence_before();
