@@ -141,8 +141,10 @@ struct KnnIndex {
     const float4* cmax;    // [nc]
     int nc;
 };
+constexpr int KNN_SUPER = 8;          // cluster boxes per super box (Morton-contiguous, so spatially compact)
 __host__ __device__ constexpr size_t knn_smem_bytes(int n_verts) {
-    return (size_t)((n_verts + KNN_CLUSTER - 1) / KNN_CLUSTER) * (KNN_CLUSTER * 16 + 32);
+    return (size_t)((n_verts + KNN_CLUSTER - 1) / KNN_CLUSTER) * (KNN_CLUSTER * 16 + 32)
+         + (size_t)(((n_verts + KNN_CLUSTER - 1) / KNN_CLUSTER + KNN_SUPER - 1) / KNN_SUPER) * 32;
 }
 __device__ __forceinline__ uint32_t morton_spread10(uint32_t v) {
     v &= 0x3FFu;
@@ -218,13 +220,24 @@ __global__ void __launch_bounds__(1024) k_knn_build(const float* __restrict__ v3
         cmax[c] = make_float4(mx[0], mx[1], mx[2], 0.f);
     }
 }
-struct KnnSmem { const float4* sv; const float4* cmin; const float4* cmax; int nc; };
+struct KnnSmem { const float4* sv; const float4* cmin; const float4* cmax; const float4* smin; const float4* smax; int nc, ns; };
 __device__ __forceinline__ KnnSmem load_knn(float4* smem, const KnnIndex& ix) {
-    const int nv = ix.nc * KNN_CLUSTER;
+    const int nv = ix.nc * KNN_CLUSTER, ns = (ix.nc + KNN_SUPER - 1) / KNN_SUPER;
     for (int v = threadIdx.x; v < nv; v += blockDim.x) smem[v] = __ldg(ix.sv + v);
     for (int c = threadIdx.x; c < ix.nc; c += blockDim.x) { smem[nv + c] = __ldg(ix.cmin + c); smem[nv + ix.nc + c] = __ldg(ix.cmax + c); }
     __syncthreads();
-    KnnSmem k; k.sv = smem; k.cmin = smem + nv; k.cmax = smem + nv + ix.nc; k.nc = ix.nc;
+    // super boxes: the AABB of 8 consecutive cluster boxes (a box-distance test on it bounds all 8 from below)
+    for (int g = threadIdx.x; g < ns; g += blockDim.x) {
+        float4 mn = make_float4(1e30f, 1e30f, 1e30f, 0.f), mx = make_float4(-1e30f, -1e30f, -1e30f, 0.f);
+        for (int c = g * KNN_SUPER; c < min(ix.nc, (g + 1) * KNN_SUPER); ++c) {
+            const float4 a = smem[nv + c], b = smem[nv + ix.nc + c];
+            mn.x = fminf(mn.x, a.x); mn.y = fminf(mn.y, a.y); mn.z = fminf(mn.z, a.z);
+            mx.x = fmaxf(mx.x, b.x); mx.y = fmaxf(mx.y, b.y); mx.z = fmaxf(mx.z, b.z);
+        }
+        smem[nv + 2 * ix.nc + g] = mn; smem[nv + 2 * ix.nc + ns + g] = mx;
+    }
+    __syncthreads();
+    KnnSmem k; k.sv = smem; k.cmin = smem + nv; k.cmax = smem + nv + ix.nc; k.smin = smem + nv + 2 * ix.nc; k.smax = k.smin + ns; k.nc = ix.nc; k.ns = ns;
     return k;
 }
 __device__ __forceinline__ float box_dist2(const float4 mn, const float4 mx, float x, float y, float z) {
@@ -241,20 +254,32 @@ __device__ __forceinline__ void knn_scan_cluster(const float4* sv, int c, float 
         if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
     }
 }
+// One query per lane.  Two-level pruning: 27 super boxes are tested instead of 216 cluster boxes; clusters are visited in index
+// order exactly as a flat scan would (a cluster that passes `lb <= best` lies in a super box that passes it too: the super
+// AABB contains the cluster AABB, and the fp32 box distance is monotone under containment), so the result is unchanged.
 __device__ __forceinline__ int knn_scan(const KnnSmem& k, float x, float y, float z) {
     float lb0 = INFINITY;
-    int c0 = 0;
-    for (int c = 0; c < k.nc; ++c) {
+    int s0 = 0;
+    for (int g = 0; g < k.ns; ++g) {
+        const float lb = box_dist2(k.smin[g], k.smax[g], x, y, z);
+        if (lb < lb0) { lb0 = lb; s0 = g; }
+    }
+    lb0 = INFINITY;
+    int c0 = s0 * KNN_SUPER;
+    for (int c = s0 * KNN_SUPER; c < min(k.nc, (s0 + 1) * KNN_SUPER); ++c) {
         const float lb = box_dist2(k.cmin[c], k.cmax[c], x, y, z);
         if (lb < lb0) { lb0 = lb; c0 = c; }
     }
     float bd = INFINITY;
     int bi = 0x7fffffff;
     knn_scan_cluster(k.sv, c0, x, y, z, bd, bi);
-    for (int c = 0; c < k.nc; ++c) {
-        if (c == c0) continue;
+    for (int g = 0; g < k.ns; ++g) {
         // the box distance is a lower bound computed in the same fp32 form; keep a 1-ulp-safe margin
-        if (box_dist2(k.cmin[c], k.cmax[c], x, y, z) <= bd * 1.000001f) knn_scan_cluster(k.sv, c, x, y, z, bd, bi);
+        if (box_dist2(k.smin[g], k.smax[g], x, y, z) > bd * 1.000001f) continue;
+        for (int c = g * KNN_SUPER; c < min(k.nc, (g + 1) * KNN_SUPER); ++c) {
+            if (c == c0) continue;
+            if (box_dist2(k.cmin[c], k.cmax[c], x, y, z) <= bd * 1.000001f) knn_scan_cluster(k.sv, c, x, y, z, bd, bi);
+        }
     }
     return bi;
 }
@@ -316,10 +341,12 @@ __device__ __forceinline__ int knn_scan_warp(const KnnSmem& k, float x, float y,
 // Measured (B200, 15 M queries): with a full warp of queries the per-lane scan (knn_scan, 32 queries in SIMT) is ~3x
 // cheaper per query than the cooperative one (shuffle reductions); the cooperative form wins when a warp would otherwise hold
 // only a few queries (tail iterations of sphere tracing, training-size batches), where latency, not throughput, counts.
-// Rays of neighbouring pixels sit at unrelated depths, so their per-lane scans diverge and the cooperative form stays ahead
-// up to full warps (k_knn_rays: 145 vs 193 us per launch); samples along one ray are coherent (k_knn_samples: per-lane wins
-// beyond ~12 queries per warp: 11 vs 33 ms).
-constexpr int KNN_COOP_SAMPLES = 12, KNN_COOP_RAYS = 32;
+// Measured per launch (ncu, 512x512 frame): rays in the first sphere-tracing iterations (all 262 k active, still in pixel
+// order and far from the body) 260-340 us per-lane vs 940 us cooperative; once compaction has scrambled the list and the rays
+// sit at unrelated depths the per-lane scans diverge (up to 630 us vs 110 us cooperative).  So rays go per-lane only while
+// every warp of the grid is full (>= 32 queries per warp); samples along one ray stay coherent (per-lane beyond ~12 per warp:
+// 11 vs 33 ms).
+constexpr int KNN_COOP_SAMPLES = 12, KNN_COOP_RAYS = 31;
 template <int COOP_MAX_B, class LoadQ, class Finish>
 __device__ __forceinline__ void knn_warp_batches(const KnnSmem& kk, int n, int B, LoadQ load, Finish fin) {
     const int lane = threadIdx.x & 31;
@@ -361,7 +388,7 @@ __device__ __forceinline__ void nn_inverse_skinning(const FrameParams& fp, int i
     affine_inverse_apply(T12, *s, xl, x_hat);
 }
 
-__global__ void __launch_bounds__(512) k_knn_rays(FrameParams fp, KnnIndex ix, Work w, int iter) {
+__global__ void __launch_bounds__(512, 1) k_knn_rays(FrameParams fp, KnnIndex ix, Work w, int iter) {
     extern __shared__ float4 sv[];
     const int n = w.counters[C_TRACE + iter];
     const int B = knn_batch_size<KNN_COOP_RAYS>(n);
@@ -386,7 +413,7 @@ __global__ void __launch_bounds__(512) k_knn_rays(FrameParams fp, KnnIndex ix, W
 }
 
 // unit-level entry (tests): nearest posed-vertex index of n arbitrary points
-__global__ void __launch_bounds__(512) k_knn_points(KnnIndex ix, const float* __restrict__ pts, int n, int* __restrict__ out_idx) {
+__global__ void __launch_bounds__(512, 1) k_knn_points(KnnIndex ix, const float* __restrict__ pts, int n, int* __restrict__ out_idx) {
     extern __shared__ float4 sv[];
     const int B = knn_batch_size<KNN_COOP_SAMPLES>(n);
     if ((int)(blockIdx.x * (blockDim.x >> 5)) * B >= n) return;
@@ -699,7 +726,7 @@ __global__ void k_trace_finish(FrameParams fp, Work w) {
 }
 
 // ================================================================================================ correspondences
-__global__ void __launch_bounds__(512) k_knn_samples(FrameParams fp, KnnIndex ix, Work w) {
+__global__ void __launch_bounds__(512, 1) k_knn_samples(FrameParams fp, KnnIndex ix, Work w) {
     extern __shared__ float4 sv[];
     const int n = w.counters[C_ON];
     if (blockIdx.x == 0 && threadIdx.x == 0) w.counters[C_CORR] = n;
