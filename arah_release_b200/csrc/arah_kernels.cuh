@@ -341,12 +341,11 @@ __device__ __forceinline__ int knn_scan_warp(const KnnSmem& k, float x, float y,
 // Measured (B200, 15 M queries): with a full warp of queries the per-lane scan (knn_scan, 32 queries in SIMT) is ~3x
 // cheaper per query than the cooperative one (shuffle reductions); the cooperative form wins when a warp would otherwise hold
 // only a few queries (tail iterations of sphere tracing, training-size batches), where latency, not throughput, counts.
-// Measured per launch (ncu, 512x512 frame): rays in the first sphere-tracing iterations (all 262 k active, still in pixel
-// order and far from the body) 260-340 us per-lane vs 940 us cooperative; once compaction has scrambled the list and the rays
-// sit at unrelated depths the per-lane scans diverge (up to 630 us vs 110 us cooperative).  So rays go per-lane only while
-// every warp of the grid is full (>= 32 queries per warp); samples along one ray stay coherent (per-lane beyond ~12 per warp:
-// 11 vs 33 ms).
-constexpr int KNN_COOP_SAMPLES = 12, KNN_COOP_RAYS = 31;
+// Measured (512x512 frame, stage times of bench.py): samples along one ray are coherent, the per-lane scan wins beyond ~12
+// queries per warp (k_knn_samples 11 ms vs 33 ms cooperative; 7 ms with the super-box pruning).  Rays stay cooperative at
+// every size: sending the full-warp launches of the first sphere-tracing iterations through the per-lane scan made the
+// tracing stage slower (21.7 vs 15.4 ms) although ncu had timed those launches alone at 0.3 vs 0.9 ms.
+constexpr int KNN_COOP_SAMPLES = 12, KNN_COOP_RAYS = 32;
 template <int COOP_MAX_B, class LoadQ, class Finish>
 __device__ __forceinline__ void knn_warp_batches(const KnnSmem& kk, int n, int B, LoadQ load, Finish fin) {
     const int lane = threadIdx.x & 31;
