@@ -336,6 +336,86 @@ __device__ __forceinline__ int knn_scan_warp(const KnnSmem& k, float x, float y,
     }
     return bi;
 }
+// Octet form: the warp works on FOUR queries at once, 8 lanes each (all 8 lanes of an octet hold the same query).  Two-level
+// pruning like knn_scan: the octet's lanes split the super boxes, then the 8 cluster boxes of a passing super box (one per lane);
+// a cluster is scanned 4 vertices per lane and reduced with a 3-step butterfly inside the octet.  ~3x fewer instructions per
+// query than knn_scan_warp (shorter butterflies, no replicated box tests), same exact result.  `valid`: the octet has a query.
+__device__ __forceinline__ void knn_octet_argmin(float& d, int& id) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, id, o);
+        if (d2 < d || (d2 == d && i2 < id)) { d = d2; id = i2; }
+    }
+}
+__device__ __forceinline__ int knn_scan_octet(const KnnSmem& k, float x, float y, float z, bool valid) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, oct = lane >> 3;
+    float bd = INFINITY;
+    int bi = 0x7fffffff;
+    // executed by ALL 32 lanes (the butterfly uses full-mask shuffles); `on` is octet-uniform: does this octet scan cluster c
+    auto scan = [&](int c, bool on) {
+        float d = INFINITY;
+        int id = 0x7fffffff;
+        if (on) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 p = k.sv[c * KNN_CLUSTER + 4 * sub + i];
+                const float dx = x - p.x, dy = y - p.y, dz = z - p.z;
+                const float di = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                const int ii = __float_as_int(p.w);
+                if (di < d || (di == d && ii < id)) { d = di; id = ii; }
+            }
+        }
+        knn_octet_argmin(d, id);
+        if (on && (d < bd || (d == bd && id < bi))) { bd = d; bi = id; }
+    };
+    // ---- best super box, best cluster in it
+    float lb0 = INFINITY;
+    int s0 = 0x7fffffff;
+    for (int g = sub; g < k.ns; g += 8) {
+        const float lb = box_dist2(k.smin[g], k.smax[g], x, y, z);
+        if (lb < lb0) { lb0 = lb; s0 = g; }
+    }
+    knn_octet_argmin(lb0, s0);
+    if (s0 >= k.ns) s0 = 0;
+    int c0 = s0 * KNN_SUPER + sub;
+    float lc = (c0 < k.nc) ? box_dist2(k.cmin[c0], k.cmax[c0], x, y, z) : INFINITY;
+    knn_octet_argmin(lc, c0);
+    if (c0 >= k.nc) c0 = s0 * KNN_SUPER;
+    scan(c0, valid);
+    // ---- every other cluster that can still hold a closer vertex, super box by super box
+    const int ns8 = (k.ns + 7) & ~7;
+    for (int g0 = 0; g0 < ns8; g0 += 8) {
+        const int g = g0 + sub;
+        const float lbs = (g < k.ns) ? box_dist2(k.smin[g], k.smax[g], x, y, z) : INFINITY;
+        unsigned sdone = 0u;
+        while (true) {
+            const bool swant = valid && lbs <= bd * 1.000001f;
+            const unsigned sm_all = __ballot_sync(0xffffffffu, swant);
+            if (!sm_all) break;                                // no octet has a super box left in this group of 8
+            const unsigned sm = (sm_all >> (8 * oct)) & 0xffu & ~sdone;
+            const bool have = sm != 0u;
+            const int sb = have ? (__ffs(sm) - 1) : 0;
+            if (!__ballot_sync(0xffffffffu, have)) break;      // every octet has exhausted its bits (all covered by sdone)
+            if (have) sdone |= (2u << sb) - 1u;
+            // the 8 clusters of super box g0 + sb, one per lane
+            const int c = (g0 + sb) * KNN_SUPER + sub;
+            const float lbc = (have && c < k.nc && c != c0) ? box_dist2(k.cmin[c], k.cmax[c], x, y, z) : INFINITY;
+            unsigned cdone = 0u;
+            while (true) {
+                const bool cwant = have && lbc <= bd * 1.000001f;
+                const unsigned cm = (__ballot_sync(0xffffffffu, cwant) >> (8 * oct)) & 0xffu & ~cdone;
+                const bool chave = cm != 0u;
+                if (!__ballot_sync(0xffffffffu, chave)) break;
+                const int cb = chave ? (__ffs(cm) - 1) : 0;
+                if (chave) cdone |= (2u << cb) - 1u;
+                scan((g0 + sb) * KNN_SUPER + cb, chave);
+            }
+        }
+    }
+    return bi;
+}
+
 // Batch driver: a warp takes `B` consecutive queries (B = 1..32 so that every warp of the grid has work when few queries are
 // left); lane l loads query l, the queries are scanned cooperatively one after the other, lane l finishes query l.
 // Measured (B200, 15 M queries): with a full warp of queries the per-lane scan (knn_scan, 32 queries in SIMT) is ~3x
@@ -359,10 +439,20 @@ __device__ __forceinline__ void knn_warp_batches(const KnnSmem& kk, int n, int B
         if (B > COOP_MAX_B) {
             if (lane < cnt) mine = knn_scan(kk, x[0], x[1], x[2]);
         } else {
-            for (int j = 0; j < cnt; ++j) {
-                const float qx = __shfl_sync(0xffffffffu, x[0], j), qy = __shfl_sync(0xffffffffu, x[1], j), qz = __shfl_sync(0xffffffffu, x[2], j);
-                const int idx = knn_scan_warp(kk, qx, qy, qz);
-                if (lane == j) mine = idx;
+            if (cnt >= 3) {                                     // four queries at a time, one per octet
+                for (int r4 = 0; r4 < cnt; r4 += 4) {
+                    const int q = r4 + (lane >> 3);
+                    const float qx = __shfl_sync(0xffffffffu, x[0], q & 31), qy = __shfl_sync(0xffffffffu, x[1], q & 31), qz = __shfl_sync(0xffffffffu, x[2], q & 31);
+                    const int idx = knn_scan_octet(kk, qx, qy, qz, q < cnt);
+                    const int got = __shfl_sync(0xffffffffu, idx, (lane & 3) * 8);      // result of query r4 + (lane & 3)
+                    if ((lane >> 2) == (r4 >> 2)) mine = got;
+                }
+            } else {
+                for (int j = 0; j < cnt; ++j) {
+                    const float qx = __shfl_sync(0xffffffffu, x[0], j), qy = __shfl_sync(0xffffffffu, x[1], j), qz = __shfl_sync(0xffffffffu, x[2], j);
+                    const int idx = knn_scan_warp(kk, qx, qy, qz);
+                    if (lane == j) mine = idx;
+                }
             }
         }
         if (lane < cnt) fin(i0 + lane, x, mine);
