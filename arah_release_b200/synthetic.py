@@ -425,3 +425,26 @@ def make_hypernet_inputs(seed=0):
     Jtrs = rng.uniform(-0.8, 0.8, size=(24, 3)).astype(np.float32)
     latent = (0.1 * rng.standard_normal(128)).astype(np.float32)
     return rots.reshape(1, 24, 9), Jtrs.reshape(1, 24, 3), latent.reshape(1, 128)
+
+
+# ---------------------------------------------------------------------------------------------------- ray set-up (row f3)
+def make_smpl_pose_inputs(seed=0, n_verts=6890):
+    """Seeded stand-ins for what data/zju_mocap_odp.py:233-276 loads for a frame (no SMPL files offline): minimally clothed
+    shape, pose blend-shape basis, pose feature (rotation matrices minus identity, float64 as scipy returns them), skinning
+    weights (<= 4 non-zero, rows sum to 1), rigid bone transforms, translation."""
+    rng = np.random.default_rng(2000 + seed)
+    shape = rng.uniform(-1, 1, size=(n_verts, 3)).astype(np.float32) * np.array([0.35, 0.9, 0.18], np.float32)
+    posedirs = (rng.standard_normal((n_verts * 3, 207)) * 0.004).astype(np.float32)
+    pose_feature = rng.standard_normal(207) * 0.3
+    w = np.zeros((n_verts, 24), np.float32)
+    for i in range(n_verts):
+        j = rng.choice(24, size=4, replace=False)
+        v = rng.uniform(0.05, 1.0, 4); w[i, j] = (v / v.sum()).astype(np.float32)
+    B = np.zeros((24, 4, 4), np.float32)
+    for j in range(24):
+        a = rng.standard_normal(3) * 0.4
+        th = np.linalg.norm(a); Kx = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+        R = np.eye(3) + np.sin(th) / th * Kx + (1 - np.cos(th)) / th ** 2 * Kx @ Kx
+        B[j, :3, :3] = R; B[j, :3, 3] = rng.uniform(-0.1, 0.1, 3); B[j, 3, 3] = 1
+    return {'minimal_shape': shape, 'posedirs': posedirs, 'pose_feature': pose_feature, 'skinning_weights': w,
+            'bone_transforms': B, 'trans': rng.uniform(-0.5, 0.5, 3).astype(np.float32)}
