@@ -55,7 +55,7 @@ EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'ar
            'arah_set_training', 'arah_train_trace', 'arah_train_shade_forward', 'arah_train_shade_backward', 'arah_train_sdf_forward',
            'arah_train_sdf_backward', 'arah_train_skin_forward', 'arah_train_skin_backward', 'arah_debug_train_gemm',
            'arah_sdf_grid', 'arah_marching_cubes', 'arah_mc_case_table', 'arah_debug_knn', 'arah_marching_cubes_workspace',
-           'arah_hyper_forward', 'arah_hyper_workspace']
+           'arah_hyper_forward', 'arah_hyper_workspace', 'arah_pose_smpl', 'arah_frame_rays', 'arah_frame_rays_workspace']
 
 _lib = None
 
@@ -104,6 +104,11 @@ def lib():
     L.arah_debug_knn.argtypes = [C.c_void_p, FP, C.c_int32, FP, C.c_void_p]
     L.arah_hyper_forward.argtypes = [C.POINTER(ArahHyperWeights), FP, FP, FP, C.POINTER(ArahSdfParams), FP, C.c_void_p]
     L.arah_hyper_workspace.restype = C.c_size_t
+    L.arah_pose_smpl.argtypes = [FP, FP, FP, FP, FP, C.POINTER(C.c_float), C.c_int32, C.c_float, FP, FP, FP, C.c_void_p]
+    F9, F3 = C.POINTER(C.c_float), C.POINTER(C.c_float)
+    L.arah_frame_rays.argtypes = [F9, F9, F9, F3, F3, FP, C.c_int32, C.c_int32, FP, FP, FP, FP, FP, FP, FP, FP, C.c_size_t, C.c_void_p]
+    L.arah_frame_rays_workspace.argtypes = [C.c_int32, C.c_int32]
+    L.arah_frame_rays_workspace.restype = C.c_size_t
     _lib = L
     return L
 

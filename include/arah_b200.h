@@ -220,6 +220,29 @@ int arah_hyper_forward(const ArahHyperWeights* w, const float* rots, const float
                        const ArahSdfParams* out, void* workspace, void* stream);
 size_t arah_hyper_workspace(void);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Per-frame ray set-up: what the dataset classes compute on the CPU for every frame
+ * (data/zju_mocap_odp.py:250-315).  Device pointers unless marked host; asynchronous on `stream`; no allocation inside.
+ *
+ * arah_pose_smpl (:268-289): minimal_shape [n][3] + posedirs [3n][207] . pose_feature [207] (DOUBLE, as scipy hands it over; the
+ *   product is accumulated in fp64 like numpy does), T = skinning_weights [n][24] . bone_transforms [24][16], posed vertices
+ *   = T [v; 1] + trans -> verts [n][3] (== ArahFrame.smpl_verts), bounds [2][3] = min / max -/+ box_margin.
+ *   workspace: 32 bytes of device scratch.
+ * arah_frame_rays (:291-315, utils/utils.py:17-73): K, K_inv, R, T, cam_loc are HOST arrays (row-major 3x3 / 3; K already rescaled,
+ *   K_inv = inverse(K), cam_loc = -R^T T as the caller's numpy computes them); bounds [2][3] on the device.  mask_in (H*W
+ *   bytes) == NULL: the bounding-box mask of get_bound_2d_mask is rasterised into bound_mask (six cv2.fillPoly calls restated
+ *   in integer arithmetic; identical to OpenCV 4.13 for boxes that project inside the image, see oracle/rays_oracle.py).
+ *   Outputs, in np.where order (row-major): pix [P] = y*W + x, ray_dirs [P][3], near_far [P][2] (the rows with near < far),
+ *   image_mask [H*W] bytes, count[0] = P (device).  Caller sizes pix / ray_dirs / near_far for H*W rays. */
+int arah_pose_smpl(const float* minimal_shape, const float* posedirs, const double* pose_feature, const float* skinning_weights,
+                   const float* bone_transforms, const float* trans3 /* host */, int32_t n_verts, float box_margin, float* verts,
+                   float* bounds, void* workspace, void* stream);
+int arah_frame_rays(const float* K, const float* K_inv, const float* R, const float* T, const float* cam_loc /* 5 host arrays */,
+                    const float* bounds, int32_t H, int32_t W, const uint8_t* mask_in, uint8_t* bound_mask, int32_t* pix,
+                    float* ray_dirs, float* near_far, uint8_t* image_mask, int32_t* count, void* workspace, size_t workspace_bytes,
+                    void* stream);
+size_t arah_frame_rays_workspace(int32_t H, int32_t W);
+
 /* Unit-level: pytorch3d.ops.knn_points(K=1) as used at renderer/ray_tracing.py:386,407 — index of the nearest posed SMPL vertex
  * (exact fp32 argmin of (x-v).(x-v), lowest index on ties) for n device points [n][3] -> idx [n] int32. */
 int arah_debug_knn(ArahHandle* h, const float* pts, int32_t n, int32_t* idx, void* stream);
