@@ -64,6 +64,11 @@ class HyperSDFDecoder(nn.Module):
         self._ws = torch.empty(int(_lib.lib().arah_hyper_workspace()), dtype=torch.uint8, device=self.device)
         self.weight_bytes = sum(v.numel() * 4 for v in sd.values())
 
+    def launch_raw(self, rots, Jtrs, latent, out_struct):
+        """The bare C-ABI call with prepared device buffers (bench.py: device time without the tensor bookkeeping of forward)."""
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(_lib.lib().arah_hyper_forward(C.byref(self._w), _ptr(rots), _ptr(Jtrs), _ptr(latent), C.byref(out_struct), _ptr(self._ws), stream))
+
     def forward(self, model_input):
         rots = model_input['rots']
         if 'rots_noise' in model_input:                                   # siren_modules.py:289-290

@@ -297,14 +297,76 @@ def hypernet_bench(dev, steps=20, warmup=5):
         torch.cuda.synchronize()
         if i >= warmup:
             ms.append(e0.elapsed_time(e1))
+    # the same two launches through the bare C-ABI call with prepared buffers
+    from arah_release_b200._lib import ArahSdfParams
+    import ctypes as C
+    res = dec(inp)
+    d = res['decoder']
+    outs = ArahSdfParams()
+    for l in range(7):
+        lay = d[l][0] if l < 6 else d[l]
+        outs.sdf_W[l], outs.sdf_b[l] = C.c_void_p(lay.weights.data_ptr()), C.c_void_p(lay.biases.data_ptr())
+    fq, ph = torch.empty(6, 256, device=dev), torch.empty(6, 256, device=dev)
+    outs.sdf_freq, outs.sdf_phase = C.c_void_p(fq.data_ptr()), C.c_void_p(ph.data_ptr())
+    r_, j_, l_ = inp['rots'].reshape(-1).contiguous(), inp['Jtrs'].reshape(-1).contiguous(), inp['latent'].reshape(-1).contiguous()
+    ms_raw = []
+    for i in range(warmup + steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); dec.launch_raw(r_, j_, l_, outs); e1.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ms_raw.append(e0.elapsed_time(e1))
     t = time.perf_counter(); ho.forward(sd, rots, Jtrs, latent); t_cpu = time.perf_counter() - t
     pk = peaks()
-    m = float(np.median(ms))
+    m_mirror = float(np.median(ms))
+    m = float(np.median(ms_raw))
     gbs = dec.weight_bytes / (m * 1e-3) / 1e9
     return {'workload': 'MetaAvatar hypernetwork forward, 86.9 M parameters, batch 1 (configs/arah-zju/ZJUMOCAP-377_4gpus.yaml:34)',
-            'ms': m, 'algorithmic_bytes': int(dec.weight_bytes), 'achieved_gbs': gbs, 'peak_gbs': pk['hbm_gbs'], 'frac_of_hbm_peak': gbs / pk['hbm_gbs'],
+            'ms': m, 'ms_through_python_mirror': m_mirror, 'algorithmic_bytes': int(dec.weight_bytes), 'achieved_gbs': gbs, 'peak_gbs': pk['hbm_gbs'], 'frac_of_hbm_peak': gbs / pk['hbm_gbs'],
             'gpu_launches': 2, 'steps': steps, 'warmup': warmup, 'l2': '256 MB memset before every timed call',
             'cpu_port': {'ms': 1e3 * t_cpu, 'kind': 'oracle/hyper_oracle.py (numpy fp32, BLAS threads)'}}
+
+
+# ------------------------------------------------------------------------------------------------ ray set-up (row f3)
+def ray_setup_bench(dev, size, steps=10, warmup=3):
+    """data/zju_mocap_odp.py:250-315 per frame: SMPL posing + bounding box, box mask, rays, near/far, ordered compaction.
+    HBM roofline: algorithmic bytes = blend-shape basis + weights + shape read once, vertices written; per pixel one mask byte
+    written and read, per ray 24 B written."""
+    import torch
+    from arah_release_b200 import synthetic as syn
+    from arah_release_b200.rays import FrameRays
+    from oracle import rays_oracle as ro
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    from gen_golden_rays import camera
+    p = syn.make_smpl_pose_inputs(0)
+    K, R, T, _ = camera(3, size, size, 1.0)
+    fr = FrameRays(dev)
+    dp = {k: (torch.as_tensor(v, dtype=torch.float32).to(dev) if k not in ('pose_feature', 'trans') else v) for k, v in p.items()}
+    ms_pose, ms_rays, P = [], [], 0
+    for i in range(warmup + steps):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        verts, bounds = fr.pose_smpl(**dp)
+        e[1].record()
+        out = fr.gen_rays(K, R, T, bounds, size, size)
+        e[2].record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ms_pose.append(e[0].elapsed_time(e[1])); ms_rays.append(e[1].elapsed_time(e[2]))
+        P = out['n_rays']
+    t = time.perf_counter(); v_ref, b_ref = ro.pose_smpl(**p); t_pose = time.perf_counter() - t
+    t = time.perf_counter(); ref = ro.gen_rays(K, R, T, b_ref, size, size); t_rays = time.perf_counter() - t
+    pk = peaks()
+    mp, mr = float(np.median(ms_pose)), float(np.median(ms_rays))
+    pose_bytes = 6890 * (3 * 207 * 4 + 24 * 4 + 12 + 12) + 207 * 8 + 24 * 64
+    ray_bytes = 2.0 * size * size + P * (12 + 8 + 4) + size * size
+    return {'workload': f'per-frame ray set-up at {size}x{size} (data/zju_mocap_odp.py:250-315)', 'n_rays': int(P), 'n_rays_cpu_port': int(ref['pix'].shape[0]),
+            'ms_pose_smpl': mp, 'pose_smpl_gbs': pose_bytes / (mp * 1e-3) / 1e9, 'ms_frame_rays': mr, 'frame_rays_gbs': ray_bytes / (mr * 1e-3) / 1e9,
+            'frac_of_hbm_peak': {'pose_smpl': pose_bytes / (mp * 1e-3) / 1e9 / pk['hbm_gbs'], 'frame_rays': ray_bytes / (mr * 1e-3) / 1e9 / pk['hbm_gbs']},
+            'gpu_launches': 3 + 6, 'steps': steps, 'warmup': warmup,
+            'note': 'small launch-latency-bound kernels (9 launches, one host read of the ray count); timed through the Python mirror',
+            'cpu_port': {'ms_pose_smpl': 1e3 * t_pose, 'ms_frame_rays': 1e3 * t_rays, 'kind': 'oracle/rays_oracle.py (numpy; python loops for the mask)'}}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -487,6 +549,11 @@ def run_ours(args):
             line['hypernet'] = hypernet_bench(dev)
         except Exception as ex:
             line['hypernet'] = {'error': repr(ex)[:300]}
+    if args.gpus == 1 and not args.no_mesh:
+        try:
+            line['ray_setup'] = ray_setup_bench(dev, args.size)
+        except Exception as ex:
+            line['ray_setup'] = {'error': repr(ex)[:300]}
     if args.gpus == 1 and not args.no_cpu_baseline:
         v, cores, n, dt = cpu_rate(f0, args.cpu_sample_seconds)
         line['cpu_baseline'] = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
