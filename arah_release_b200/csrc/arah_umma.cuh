@@ -191,12 +191,13 @@ __device__ __forceinline__ void a_store_chunk_split(float* A_hi, float* A_lo, in
 // log(1 + exp(-|100 x|)) / 100 + max(x, 0).  Same two MUFU results as __expf / __logf (identical roundings of the argument and
 // of the result), but through the .ftz forms: the non-ftz intrinsics carry denormal fix-up code (3-4 extra instructions per
 // call) that can never trigger here (exp's denormal results vanish in 1 + e, log's argument lies in [1, 2]).
+// The two scale factors on either side are merged (100 log2 e; ln 2 / 100): 6 instructions instead of 8; against the two-step
+// scaling the result moves by < 1e-8 absolute (the log term is <= 0.0069), two orders below the 3xTF32 product error.
 __device__ __forceinline__ float softplus100_fast(float x) {
-    const float t = x * 100.0f;
     float e, l;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t) * 1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(x) * 144.26950408889634f));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
-    return fmaxf(x, 0.0f) + (l * 0.6931471805599453f) * 0.01f;
+    return fmaf(l, 0.006931471805599453f, fmaxf(x, 0.0f));
 }
 
 }  // namespace arah
