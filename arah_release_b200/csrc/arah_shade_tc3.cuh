@@ -35,9 +35,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// per-CTA parameter block: 3584 floats of first / last layer weights (+ 512 scratch) and, staged once instead of re-read from
+// L2 before every layer (a load + two CTA barriers per layer: 13 % of the SDF-only pass), the FiLM factors F, G of the six SDF
+// layers (2 x 1536) and the five colour biases (1280)
+constexpr int TC3_PRM_FLOATS = 3584 + 3072 + 1280;
 __host__ __device__ constexpr size_t shade_tc3_smem_bytes() {
     // ring | cin[128][36] | params[3584] | xs[128][4] | part[2][128][4] | prog | barriers
-    return (size_t)(TC3_NSLOTS * RING_SLOT_FLOATS + UM * 36 + 3584 + UM * 4 + 2 * UM * 4) * 4 + TC3_NSEG * sizeof(Seg) + 512 + 1024;
+    return (size_t)(TC3_NSLOTS * RING_SLOT_FLOATS + UM * 36 + TC3_PRM_FLOATS + UM * 4 + 2 * UM * 4) * 4 + TC3_NSEG * sizeof(Seg) + 512 + 1024;
 }
 
 // SDF_ONLY = true: the forward pass alone (same GEMM program prefix, same epilogue arithmetic, hence bit-identical smp_sdf) for
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
     float* ring = sm;
     float (*cin)[36] = reinterpret_cast<float (*)[36]>(ring + TC3_NSLOTS * RING_SLOT_FLOATS);
     float* prm = reinterpret_cast<float*>(cin) + UM * 36;      // [3584] per-tile constant columns, see P_* offsets
-    float (*xs)[4] = reinterpret_cast<float (*)[4]>(prm + 3584);
+    float (*xs)[4] = reinterpret_cast<float (*)[4]>(prm + TC3_PRM_FLOATS);
     float (*part)[UM][4] = reinterpret_cast<float (*)[UM][4]>(reinterpret_cast<float*>(xs) + UM * 4);
     Seg* prog = reinterpret_cast<Seg*>(reinterpret_cast<float*>(part) + 2 * UM * 4);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(prog) + ((TC3_NSEG * sizeof(Seg) + 15) / 16) * 16);
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
     uint64_t* done_bar = ready + 8;
     uint32_t* tslot = reinterpret_cast<uint32_t*>(done_bar + 1);
     // parameter block: everything the epilogues read per column, staged once per CTA
-    constexpr int P_W0T = 0, P_F = 768, P_G = 1024, P_W6 = 1280, P_W0 = 1536, P_W5 = 2304, P_B = 3072;   // P_B: 512 floats scratch for biases / F,G of the layer
+    constexpr int P_W0T = 0, P_W6 = 1280, P_W0 = 1536, P_W5 = 2304, P_LF = 3584, P_LG = P_LF + 1536, P_CB = P_LG + 1536;   // P_CB: col_b[0..4] at 0,256,512,640,896
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
@@ -92,6 +96,12 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
     if (warp == 0) tmem_alloc(tslot, 512);
     for (int i = tid; i < 768; i += TC3_THREADS) { prm[P_W0T + i] = __ldg(tc.sdf_Wt0 + i); prm[P_W0 + i] = __ldg(tc.sdf_W0 + i); prm[P_W5 + i] = __ldg(tc.col_W5 + i); }
     for (int i = tid; i < 256; i += TC3_THREADS) prm[P_W6 + i] = __ldg(tc.sdf_w6 + i);
+    for (int i = tid; i < 1536; i += TC3_THREADS) { prm[P_LF + i] = __ldg(tc.sdf_F + i); prm[P_LG + i] = __ldg(tc.sdf_G + i); }
+    if (!SDF_ONLY) {
+        const int cb_off[5] = {0, 256, 512, 640, 896}, cb_n[5] = {256, 256, 128, 256, 256};
+        for (int l = 0; l < 5; ++l)
+            for (int i = tid; i < cb_n[l]; i += TC3_THREADS) prm[P_CB + cb_off[l] + i] = __ldg(tc.col_b[l] + i);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -197,13 +207,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
         __syncwarp();
         tc_fence_after();
     };
-    auto load_layer = [&](const float* p0, const float* p1) {     // P_B[0..255] = p0, P_B[256..511] = p1
-        prm[P_B + tid] = p0 ? __ldg(p0 + tid) : 0.f;
-        prm[P_B + 256 + tid] = p1 ? __ldg(p1 + tid) : 0.f;
-        cta_sync_compute();
-    };
-    const float* lp0 = prm + P_B;
-    const float* lp1 = prm + P_B + 256;
+    const float* lp0 = prm + P_LF;                                // per-column parameters of the current layer (F | bias)
+    const float* lp1 = prm + P_LG;                                //                                             (G)
 
     PhaseClk pc; pc.start((tid == 32 && w.phase_clk) ? w.phase_clk + 8 : nullptr);
     for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
@@ -215,7 +220,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
             xs[tid][0] = xn[0]; xs[tid][1] = xn[1]; xs[tid][2] = xn[2]; xs[tid][3] = 0.f;
         }
         // ================= SDF forward =================
-        load_layer(tc.sdf_F, tc.sdf_G);
+        lp0 = prm + P_LF; lp1 = prm + P_LG;
+        cta_sync_compute();                                       // xs visible
         {   // layer 0 (K = 3) on the FP32 pipe -> A1 in R0
             const float x = xs[r][0], y = xs[r][1], z = xs[r][2];
 #pragma unroll 1
@@ -236,8 +242,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
         }
         pc.mark(0);                                               // tile setup + layer 0
         for (int l = 1; l < 6; ++l) {
-            cta_sync_compute();                                   // everyone finished reading the previous layer's F, G
-            load_layer(tc.sdf_F + l * 256, tc.sdf_G + l * 256);
+            lp0 = prm + P_LF + l * 256; lp1 = prm + P_LG + l * 256;
             wait_done();                                          // GEMM l complete: D in R[l&1]
             pc.mark(1);                                           // waiting for forward GEMMs
             const int dreg = l & 1;
@@ -341,7 +346,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
             }
             c[30] = nrm[0]; c[31] = nrm[1]; c[32] = nrm[2]; c[33] = 0.f; c[34] = 0.f; c[35] = 0.f;
         }
-        load_layer(tc.col_b[0], nullptr);                         // (sync publishes cin)
+        lp0 = prm + P_CB;
+        cta_sync_compute();                                       // publishes cin
         auto fill_cin = [&](int reg) {
             if (half == 0) {
 #pragma unroll 1
@@ -381,16 +387,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
         fill_cin(1);
         wait_done();                                              // lin0 complete, D in R0
         relu_epilogue(256, 0, true);
-        cta_sync_compute();
-        load_layer(tc.col_b[1], nullptr);
+        lp0 = prm + P_CB + 256;
         wait_done();                                              // lin1, D in R1
         relu_epilogue(256, 1, true);
-        cta_sync_compute();
-        load_layer(tc.col_b[2], nullptr);
+        lp0 = prm + P_CB + 512;
         wait_done();                                              // lin2 (N = 128), D in R0[0..127]
         relu_epilogue(128, 0, true);                              // -> A chunks 0..3 of R0
-        cta_sync_compute();
-        load_layer(tc.col_b[3], nullptr);
+        lp0 = prm + P_CB + 640;
         wait_done();                                              // lin3, lin2-output part done -> R0 may be overwritten
 #pragma unroll 1
         for (int b = 0; b < 4; ++b) { float v[32]; feat_get(b, v); a_put(0, (128 * half + 32 * b) / 32, v); }
@@ -398,8 +401,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
         fill_cin(0);
         wait_done();                                              // lin3 complete, D in R1
         relu_epilogue(256, 1, true);
-        cta_sync_compute();
-        load_layer(tc.col_b[4], nullptr);
+        lp0 = prm + P_CB + 896;
         wait_done();                                              // lin4, D in R0
         relu_epilogue(256, 0, false);                             // lin5 (256 -> 3) folded into the epilogue
         cta_sync_compute();
