@@ -92,7 +92,8 @@ def sdf_network_from_frame(frame, device):
 def modules_from_frame(frame, device):
     """(deviation_network, rendering_network, skinning_model, sdf_network) in the reference layout."""
     dev = SingleVarianceNetwork(float(frame.beta)).to(device)
-    rend = RenderingNetwork(frame.color).to(device)
+    mode = getattr(frame, 'color_mode', 'idr')
+    rend = RenderingNetwork(frame.color, mode=mode, multires_view=0 if mode == 'no_view_dir' else 4).to(device)
     skin = SkinningModel(Deformer(frame.skin)).to(device)
     return dev, rend, skin, sdf_network_from_frame(frame, device)
 

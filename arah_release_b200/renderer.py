@@ -60,6 +60,30 @@ def _effective_weight_grad(lin):
     return lin.weight
 
 
+# RenderingNetwork modes (metaavatar_render/models/decoder.py:101-106).  The kernels evaluate the 'idr' input layout
+# [points 3 | PE4(view) 27 | normals 3 | feature 256 | latent]; the two narrower modes are brought to it by inserting ZERO weight
+# columns for the inputs they do not have (lin0 and the skip layer lin3): the extra products are exact zeros, so the result
+# is that of the narrower network.  value = width of the non-latent part of the input.
+_COLOR_BASE = {'idr': 289, 'no_view_dir': 262, 'no_normal': 286}
+
+
+def _color_mode(rn):
+    mode = getattr(rn, 'mode', 'idr')
+    if mode not in _COLOR_BASE or list(getattr(rn, 'skips', [3])) != [3]:
+        raise _lib.ArahError("renderer modes 'idr' / 'no_view_dir' / 'no_normal' with skips=[3] are implemented")
+    has_view = getattr(rn, 'embedview_fn', 1) is not None
+    if (mode != 'no_view_dir' and not has_view) or getattr(rn, 'embed_fn', None) is not None:
+        raise _lib.ArahError('the colour net must use multires_view=4 (when it takes view directions) and multires=0')
+    return mode
+
+
+def _expand_color_weight(W, mode):
+    if mode == 'idr':
+        return W
+    at, n = (3, 27) if mode == 'no_view_dir' else (30, 3)
+    return torch.cat([W[:, :at], W.new_zeros(W.shape[0], n), W[:, at:]], dim=1)
+
+
 class ArahRenderer:
     """Thin RAII wrapper around an ArahHandle (one per device/stream; not thread-safe)."""
 
@@ -164,13 +188,12 @@ class ArahRenderer:
         if skin_W[4].shape[0] != 25:
             raise _lib.ArahError('skinning decoder must have 25 outputs (hierarchical softmax)')
         rn = rendering_network
-        if getattr(rn, 'mode', 'idr') != 'idr' or list(getattr(rn, 'skips', [3])) != [3] or getattr(rn, 'embedview_fn', 1) is None:
-            raise _lib.ArahError("only renderer mode 'idr' with multires_view=4, skips=[3] is implemented")
+        cmode = _color_mode(rn)
         pe = getattr(rn, 'pose_encoder_type', None)
         col_W = [_effective_weight(getattr(rn, f'lin{i}')) for i in range(6)]
         col_b = [getattr(rn, f'lin{i}').bias for i in range(6)]
-        d_in = col_W[0].shape[1]
-        latent_dim = d_in - 289
+        latent_dim = col_W[0].shape[1] - _COLOR_BASE[cmode]
+        col_W[0], col_W[3] = _expand_color_weight(col_W[0], cmode), _expand_color_weight(col_W[3], cmode)
         if latent_dim != self.cfg.latent_dim:
             raise _lib.ArahError(f'colour net expects a {latent_dim}-d pose feature, handle was built for {self.cfg.latent_dim}')
         latent = None
@@ -544,7 +567,7 @@ class IDHRNetwork(nn.Module):
             raise _lib.ArahError('IDHRNetwork (B200) needs CUDA tensors; there is no CPU fallback')
         if ray_dirs.shape[0] != 1:
             raise _lib.ArahError('one frame per call (the reference assumes the same, ray_tracing.py:129-132)')
-        latent_dim = _effective_weight(self.rendering_network.lin0).shape[1] - 289
+        latent_dim = _effective_weight(self.rendering_network.lin0).shape[1] - _COLOR_BASE[_color_mode(self.rendering_network)]
         r = self._renderer(ray_dirs.device, latent_dim, input['smpl_verts'].shape[1])
         r.set_training((self.train_mode or os.environ.get('ARAH_TRAIN_MODE', '3xtf32')) if training else False)
         r.set_frame_from_modules(input['sdf_network'], self.skinning_model, self.rendering_network, self.deviation_network, input)
@@ -561,6 +584,8 @@ class IDHRNetwork(nn.Module):
         skin = [_effective_weight_grad(getattr(dec, f'lin{i}')) for i in range(5)] + [getattr(dec, f'lin{i}').bias for i in range(5)]
         rn = self.rendering_network
         col = [_effective_weight_grad(getattr(rn, f'lin{i}')) for i in range(6)] + [getattr(rn, f'lin{i}').bias for i in range(6)]
+        cmode = _color_mode(rn)            # autograd routes the gradient of the zero-padded matrices back to the real columns
+        col[0], col[3] = _expand_color_weight(col[0], cmode), _expand_color_weight(col[3], cmode)
         lat = input['pose_cond'].get('latent_code') if isinstance(input.get('pose_cond'), dict) else None
         if lat is None:
             lat = torch.zeros(0, device=sdf[0].device)
@@ -637,7 +662,7 @@ class IDHRNetwork(nn.Module):
                'body_bounds_intersections': body_bounds_intersections, 'smpl_verts': smpl_verts,
                'skinning_weights': skinning_weights, 'bone_transforms': bone_transforms, 'trans': trans,
                'coord_min': coord_min, 'coord_max': coord_max, 'center': center, 'sdf_network': sdf_network,
-               'pose_cond': {'latent_code': torch.zeros(1, max(_effective_weight(self.rendering_network.lin0).shape[1] - 289, 0),
+               'pose_cond': {'latent_code': torch.zeros(1, max(_effective_weight(self.rendering_network.lin0).shape[1] - _COLOR_BASE[_color_mode(self.rendering_network)], 0),
                                                         device=ray_directions.device)}}
         r = self._prepare(inp)
         P = ray_directions.shape[1]

@@ -258,6 +258,7 @@ class Frame:
     near_samples: int = 16
     far_samples: int = 16
     cano_view_dirs: bool = False
+    color_mode: str = 'idr'       # RenderingNetwork mode: 'idr' | 'no_view_dir' (mono configs) | 'no_normal'
 
     @property
     def P(self):
@@ -266,7 +267,7 @@ class Frame:
 
 def make_frame(H: int = 64, W: int = 64, seed: int = 0, *, max_angle: float = 0.6, fill: float = 0.95,
                beta: float = 5e-3, cano_view_dirs: bool = False, n_steps: int = 64, near_samples: int = 16,
-               far_samples: int = 16, frame_idx: int = 0, all_pixels: bool = False) -> Frame:
+               far_samples: int = 16, frame_idx: int = 0, all_pixels: bool = False, color_mode: str = 'idr') -> Frame:
     """Build one synthetic frame.
 
     ``fill``: fraction of the image height the posed body's bbox spans (focal length is solved for it).
@@ -321,7 +322,7 @@ def make_frame(H: int = 64, W: int = 64, seed: int = 0, *, max_angle: float = 0.
     near_far = np.stack([np.maximum(tn[pix], 0.0), tf[pix]], -1)
 
     crng = np.random.default_rng(seed + 4242)
-    color = color_net_init(crng)
+    color = color_net_init(crng, d_in_total={'idr': 417, 'no_view_dir': 390, 'no_normal': 414}[color_mode])
     latent = (crng.normal(size=128) * 0.01).astype(F32)
 
     pose = np.eye(4)
@@ -333,7 +334,7 @@ def make_frame(H: int = 64, W: int = 64, seed: int = 0, *, max_angle: float = 0.
                  minimal_shape=verts.astype(F32), trans=trans.astype(F32), coord_min=meta['coord_min'],
                  coord_max=meta['coord_max'], center=meta['center'], sdf=sdf, skin=skin, color=color, latent=latent,
                  beta=F32(beta), n_steps=n_steps, near_samples=near_samples, far_samples=far_samples,
-                 cano_view_dirs=cano_view_dirs)
+                 cano_view_dirs=cano_view_dirs, color_mode=color_mode)
 
 
 def canonical_normalisation():
@@ -350,6 +351,17 @@ def fold_weight_norm(layer: dict) -> tuple[np.ndarray, np.ndarray]:
     v = layer['v']
     n = np.sqrt((v * v).sum(axis=1, keepdims=True, dtype=F32)).astype(F32)
     return (v * (layer['g'] / n)).astype(F32), layer['b']
+
+
+def expand_color_weight(W, mode):
+    """Bring a RenderingNetwork lin0 / lin3 weight [out, d_in(+128)] of mode 'no_view_dir' / 'no_normal'
+    (metaavatar_render/models/decoder.py:101-106) to the 'idr' column layout [points 3 | PE(view) 27 | normals 3 | ...] by
+    inserting zero columns: the missing inputs then contribute exact zeros, the result is that of the narrower network."""
+    if mode == 'idr':
+        return W
+    z = np.zeros((W.shape[0], 27 if mode == 'no_view_dir' else 3), W.dtype)
+    at = 3 if mode == 'no_view_dir' else 30
+    return np.concatenate([W[:, :at], z, W[:, at:]], axis=1)
 
 
 def train_aux_points(frame: Frame, seed: int = 0, n_uniform: int = 1024, n_inside: int = 256) -> dict:

@@ -25,6 +25,8 @@ CASES = {
     'n32_16x16_s2': (dict(H=16, W=16, seed=2, n_steps=32, near_samples=8, far_samples=4, beta=1e-2), 3),
     # BASELINE configs[4] shape (H36M-style): 128 near-surface samples need n_steps >= 145 (ray_tracing.py:336,346), canonical view dirs
     'h36m_n160_12x12_s4': (dict(H=12, W=12, seed=4, n_steps=160, near_samples=128, far_samples=16, cano_view_dirs=True, beta=3e-3), 0),
+    # monocular configs (configs/arah-zju/ZJUMOCAP-39x-mono_4gpus.yaml:36): colour net without view directions (390 inputs)
+    'mono_noview_16x16_s8': (dict(H=16, W=16, seed=8, color_mode='no_view_dir'), 0),
 }
 T_RAYS = 48
 

@@ -89,8 +89,11 @@ def make_frame(frame):
         w, b = _fold(frame.skin[i])
         of.skin_W[i] = c(w)
         of.skin_b[i] = c(b)
+    from arah_release_b200.synthetic import expand_color_weight
     for i in range(6):
         w, b = _fold(frame.color[i])
+        if i in (0, 3):                      # 'no_view_dir' / 'no_normal' nets (decoder.py:101-106): exact zero columns
+            w = expand_color_weight(w, getattr(frame, 'color_mode', 'idr'))
         of.col_W[i] = c(w)
         of.col_b[i] = c(b)
     of.latent = c(frame.latent)

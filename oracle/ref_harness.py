@@ -154,9 +154,10 @@ def build_reference_modules(frame):
     skinning_model = SkinningModel(skinning_decoder_fwd=deformer)
 
     # colour net: yaml:39 + config.py:96-133 (pose_encoder 'latent' -> d_feature 256+128)
-    rend = RenderingNetwork(d_feature=256 + 128, mode='idr', d_in=9, d_out=3, d_hidden=256, n_layers=5,
-                            weight_norm=True, multires=0, multires_view=4, skips=[3], squeeze_out=True,
-                            pose_encoder='latent')
+    cmode = getattr(frame, 'color_mode', 'idr')         # mono configs: configs/arah-zju/ZJUMOCAP-39x-mono_4gpus.yaml:36
+    rend = RenderingNetwork(d_feature=256 + 128, mode=cmode, d_in=6 if cmode != 'idr' else 9, d_out=3, d_hidden=256, n_layers=5,
+                            weight_norm=True, multires=0, multires_view=0 if cmode == 'no_view_dir' else 4, skips=[3],
+                            squeeze_out=True, pose_encoder='latent')
     with torch.no_grad():
         for i, L in enumerate(frame.color):
             lin = getattr(rend, f'lin{i}')

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-GOLDEN_CASES = ['zju377_24x24_s0', 'cano_20x20_s1', 'n32_16x16_s2', 'h36m_n160_12x12_s4']
+GOLDEN_CASES = ['zju377_24x24_s0', 'cano_20x20_s1', 'n32_16x16_s2', 'h36m_n160_12x12_s4', 'mono_noview_16x16_s8']
 
 # Tolerances (fp32 path).  The reference is batched MKL fp32, ours sequential-k FMA fp32.
 TOL = dict(
