@@ -18,6 +18,7 @@
 #include "arah_shade_tc4.cuh"
 #include "arah_corr_tc4.cuh"
 #include "arah_corr_tc5.cuh"
+#include "arah_iso_init_tc.cuh"
 #include "arah_train_cuda.cuh"
 #include <stdlib.h>
 
@@ -303,6 +304,7 @@ struct ArahHandle {
     float* tc_sdf3x[5];
     SdfTC sd;
     int trace_tc = 1;
+    int iso_init_tc = 1;       // k_iso_init_tc3: joint-search Jacobian initialisation on the tensor cores (forward mode, 4 rows per ray)
     int corr_interleave = 1;   // k_corr_tc5: the two tiles of a trip time-share the activation columns of TMEM (epilogue of one under the MMAs of the other)
     int corr_cluster = 1;      // 2-CTA clusters + weight multicast in the correspondence kernel (measured: -2 ms)
     bool shade_cull_ran = false;
@@ -440,6 +442,8 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     if (const char* e = getenv("ARAH_SHADE_CLUSTER")) h->shade_cluster = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_iso_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
+    CU(cudaFuncSetAttribute(k_iso_init_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
+    if (const char* e = getenv("ARAH_ISO_INIT_TC")) h->iso_init_tc = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_sdf_grid_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     if (const char* e = getenv("ARAH_TRACE_TC")) h->trace_tc = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
@@ -670,7 +674,11 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     }
     if (prof) CU(cudaEventRecord(h->ev[1], st));
     k_iso_prepare<<<cdiv(P, 256), 256, 0, st>>>(w); L();
-    k_iso_init<<<grid_min(cdiv(P, TM / 4), (size_t)nsm), 256, sm_sdf, st>>>(fp, w); L();
+    if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc && h->iso_init_tc)
+        k_iso_init_tc3<<<grid_min(cdiv(P, ISO_TC_PTS), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, h->sk, w);
+    else
+        k_iso_init<<<grid_min(cdiv(P, TM / 4), (size_t)nsm), 256, sm_sdf, st>>>(fp, w);
+    L();
     for (int it = 0; it < BROYDEN_ITERS; ++it) {
         if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc)
             k_iso_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, h->sk, w, it);
