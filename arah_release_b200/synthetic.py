@@ -460,3 +460,20 @@ def make_smpl_pose_inputs(seed=0, n_verts=6890):
         B[j, :3, :3] = R; B[j, :3, 3] = rng.uniform(-0.1, 0.1, 3); B[j, 3, 3] = 1
     return {'minimal_shape': shape, 'posedirs': posedirs, 'pose_feature': pose_feature, 'skinning_weights': w,
             'bone_transforms': B, 'trans': rng.uniform(-0.5, 0.5, 3).astype(np.float32)}
+
+
+def make_camera(seed, H, W, zoom=1.0):
+    """Seeded pinhole camera looking at a body-sized box: (K [3,3], R [3,3], T [3], bounds [2,3]) float32, as the dataset hands
+    them to the ray set-up (data/zju_mocap_odp.py:213-231,286-289).  zoom > 1 moves the camera in so that the box leaves the image."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-0.2, 0.2, 3)
+    ext = np.array([rng.uniform(0.5, 0.9), rng.uniform(1.4, 1.9), rng.uniform(0.3, 0.6)])
+    bounds = np.stack([c - ext / 2, c + ext / 2]).astype(np.float32)
+    ang, el, dist = rng.uniform(0, 2 * np.pi), rng.uniform(-0.3, 0.3), rng.uniform(2.6, 3.6) / zoom
+    cam = np.array([dist * np.cos(el) * np.sin(ang), dist * np.sin(el), dist * np.cos(el) * np.cos(ang)])
+    z = -cam / np.linalg.norm(cam); x = np.cross([0.0, 1.0, 0.0], z); x /= np.linalg.norm(x); y = np.cross(z, x)
+    R = np.stack([x, y, z]).astype(np.float32)
+    T = (-R.astype(np.float64) @ cam).astype(np.float32)
+    f = 1.05 * W
+    K = np.array([[f, 0, W / 2 + rng.uniform(-15, 15)], [0, f, H / 2 + rng.uniform(-15, 15)], [0, 0, 1]], np.float32)
+    return K, R, T, bounds

@@ -337,10 +337,8 @@ def ray_setup_bench(dev, size, steps=10, warmup=3):
     from arah_release_b200 import synthetic as syn
     from arah_release_b200.rays import FrameRays
     from oracle import rays_oracle as ro
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    from gen_golden_rays import camera
     p = syn.make_smpl_pose_inputs(0)
-    K, R, T, _ = camera(3, size, size, 1.0)
+    K, R, T, _ = syn.make_camera(3, size, size, 1.0)
     fr = FrameRays(dev)
     dp = {k: (torch.as_tensor(v, dtype=torch.float32).to(dev) if k not in ('pose_feature', 'trans') else v) for k, v in p.items()}
     ms_pose, ms_rays, P = [], [], 0

@@ -18,19 +18,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_harness as rh        # noqa: E402
 
 
-def camera(seed, H, W, zoom):
-    rng = np.random.default_rng(seed)
-    c = rng.uniform(-0.2, 0.2, 3)
-    ext = np.array([rng.uniform(0.5, 0.9), rng.uniform(1.4, 1.9), rng.uniform(0.3, 0.6)])
-    bounds = np.stack([c - ext / 2, c + ext / 2]).astype(np.float32)
-    ang, el, dist = rng.uniform(0, 2 * np.pi), rng.uniform(-0.3, 0.3), rng.uniform(2.6, 3.6) / zoom
-    cam = np.array([dist * np.cos(el) * np.sin(ang), dist * np.sin(el), dist * np.cos(el) * np.cos(ang)])
-    z = -cam / np.linalg.norm(cam); x = np.cross([0.0, 1.0, 0.0], z); x /= np.linalg.norm(x); y = np.cross(z, x)
-    R = np.stack([x, y, z]).astype(np.float32)
-    T = (-R.astype(np.float64) @ cam).astype(np.float32)
-    f = 1.05 * W
-    K = np.array([[f, 0, W / 2 + rng.uniform(-15, 15)], [0, f, H / 2 + rng.uniform(-15, 15)], [0, 0, 1]], np.float32)
-    return K, R, T, bounds
+from arah_release_b200.synthetic import make_camera as camera   # noqa: E402  (seeded synthetic camera + body box)
 
 
 def main():

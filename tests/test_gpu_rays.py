@@ -37,9 +37,7 @@ def test_frame_rays_random_cameras_vs_oracle():
     """200 random cameras / boxes (a third of them with corners outside the image): mask and pixel list against the oracle."""
     from arah_release_b200.rays import FrameRays
     from oracle import rays_oracle as ro
-    import sys, os
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'oracle'))
-    from gen_golden_rays import camera
+    from arah_release_b200.synthetic import make_camera as camera
     fr = FrameRays(DEV)
     bad_mask = bad_pix = 0
     for seed in range(200):
