@@ -41,15 +41,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
     uint64_t* ready = bars + 2 * TC3_NSLOTS;     // [4] X chunk c stored by its 4 warps
     uint64_t* done = ready + 4;                  // [2] job of tile A / B complete (its D ready)
     uint64_t* xfree = done + 2;                  // [4] the running job has finished reading X chunk c
-    uint64_t* dfree = xfree + 4;                 // [2] all 8 compute warps have finished reading D of tile A / B
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(dfree + 2);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(xfree + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < TC3_NSLOTS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
         for (int i = 0; i < 4; ++i) mbar_init(&ready[i], 4);
         mbar_init(&done[0], 1); mbar_init(&done[1], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&xfree[i], 1);
-        mbar_init(&dfree[0], 8); mbar_init(&dfree[1], 8);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(tslot, 512);
@@ -88,7 +86,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
     }
     if (warp == 9) {                                    // ===== MMA issuer =====
         if (lane == 0) {
-            uint32_t slot = 0, use = 0, rpar = 0, dpar = 0;
+            uint32_t slot = 0, use = 0, rpar = 0;
             for (int trip = 0; trip < ntrips; trip += 2) {
                 const int ntile = (trip + 1 < ntrips) ? 2 : 1;
                 for (int s = 0; s < 4; ++s) {
@@ -96,8 +94,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
                     const uint32_t idesc = umma_idesc_tf32(UM, N);
                     for (int t = 0; t < ntile; ++t) {
                         const uint32_t td = tbase + (t ? 384u : 256u);
-                        mbar_wait(&dfree[t], (dpar >> t) & 1u);        // the job's first MMA overwrites all of D_t: every reader is out
-                        dpar ^= (1u << t);
                         for (int i = 0; i < 4; ++i) {
                             const int c = seg_chunk(1, i);
                             mbar_wait(&ready[c], (rpar >> c) & 1u);
@@ -158,13 +154,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
         x_virgin = false;
     };
     // all compute warps have finished reading a D region (the job triggered by the next store_x overwrites it)
-    // D_t has been read by this warp: a non-blocking arrive; the MMA warp waits for all 8 warps before the job that overwrites D_t
-    // (a CTA-wide barrier here stalled every compute warp on the slowest one, eight times per trip)
-    auto release_d = [&](int t) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&dfree[t]);
-    };
     auto sync_reads = [&]() { tc_fence_before(); cta_sync_compute(); tc_fence_after(); };
     auto layer0 = [&](int t) {                                         // 3 -> 128 on the FP32 pipe, into v
         const float x = xs[t * UM + r][0], y = xs[t * UM + r][1], z = xs[t * UM + r][2];
@@ -224,7 +213,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
     // Software pipeline across trips: the first two jobs of trip i+1 are fed (gather, layer 0, stores) BEFORE the per-point
     // phase of trip i, so the hierarchical softmax / Broyden update / state traffic of trip i runs under J(0), J(1) of trip i+1,
     // and the next gather + layer 0 run under the drain of trip i's last jobs.
-    release_d(0); release_d(1);                                       // nothing has read D_A / D_B yet: the first jobs may start
     int id = gather(0);
     cta_sync_compute();
     pc.mark(0);
@@ -242,7 +230,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
             wait_done(t);                                              // J(k - ntile) complete: D_t holds the pre-activations of layer s
             pc.mark(2);
             epilogue(t, s);                                            // under J(k - 1) (the other tile)
-            release_d(t);                                              // J(k) overwrites D_t
+            sync_reads();                                              // J(k) overwrites D_t
             store_x();                                                 // as J(k - 1) releases the X chunks -> J(k)
             pc.mark(3);
         }
@@ -253,8 +241,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_corr_tc5(FrameParams fp, Ski
             layer0(0);
         }
         pc.mark(0);
-        for (int t = 0; t < ntile; ++t) { wait_done(t); take_logits(t); release_d(t); }
-        sync_reads();                                                  // logits visible to their owner threads
+        for (int t = 0; t < ntile; ++t) { wait_done(t); take_logits(t); }
+        sync_reads();                                                  // logits visible to their owner threads; D_A / D_B read by everyone
         pc.mark(4);
         if (more) {
             store_x();                                                 // -> J(0) of the next trip
