@@ -57,6 +57,7 @@ struct Work {
     int* on_list;             // [P*S] sample slot index of the k-th on-sample
     int* shade_list;          // [P*S]
     int* counters;            // [C_COUNT]
+    int knn_seed;             // k_knn_samples: seed each query of a run with the previous winner (exact; switchable for A/B)
     int shade_ctr;            // counter slot holding the length of shade_list for the tensor-core shading kernel (C_SHADE / C_SHADE2)
     float* scratch;           // shade kernel: per-CTA [7][TM][256]
     float* out_rgb;           // [P][3]
@@ -283,6 +284,49 @@ __device__ __forceinline__ int knn_scan(const KnnSmem& k, float x, float y, floa
     }
     return bi;
 }
+// Seeded per-lane scan for a RUN of neighbouring queries (consecutive samples of one ray): the winner of the previous query
+// (its slot in the sorted vertex array) gives a tight initial bound, so the "find the best box, scan it" pass is skipped and
+// pruning bites from the first box on.  Still exact: the seed is a real vertex, every cluster that could hold a closer (or
+// equally close, lower-index) vertex has box distance <= the bound and is scanned.  slot < 0: unseeded.  Returns the vertex
+// index, `slot` is updated to the winner's slot.
+__device__ __forceinline__ int knn_scan_seeded(const KnnSmem& k, float x, float y, float z, int& slot) {
+    float bd = INFINITY;
+    int bi = 0x7fffffff, bs = 0;
+    auto scan = [&](int c) {
+#pragma unroll 8
+        for (int v = c * KNN_CLUSTER; v < (c + 1) * KNN_CLUSTER; ++v) {
+            const float4 p = k.sv[v];
+            const float dx = x - p.x, dy = y - p.y, dz = z - p.z;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const int id = __float_as_int(p.w);
+            if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bs = v; }
+        }
+    };
+    if (slot >= 0) {
+        const float4 p = k.sv[slot];
+        const float dx = x - p.x, dy = y - p.y, dz = z - p.z;
+        bd = fmaf(dz, dz, fmaf(dy, dy, dx * dx)); bi = __float_as_int(p.w); bs = slot;
+    } else {
+        float lb0 = INFINITY;
+        int s0 = 0;
+        for (int g = 0; g < k.ns; ++g) { const float lb = box_dist2(k.smin[g], k.smax[g], x, y, z); if (lb < lb0) { lb0 = lb; s0 = g; } }
+        lb0 = INFINITY;
+        int c0 = s0 * KNN_SUPER;
+        for (int c = s0 * KNN_SUPER; c < min(k.nc, (s0 + 1) * KNN_SUPER); ++c) {
+            const float lb = box_dist2(k.cmin[c], k.cmax[c], x, y, z);
+            if (lb < lb0) { lb0 = lb; c0 = c; }
+        }
+        scan(c0);                                  // (scanned again below if it still qualifies: harmless)
+    }
+    for (int g = 0; g < k.ns; ++g) {
+        if (box_dist2(k.smin[g], k.smax[g], x, y, z) > bd * 1.000001f) continue;
+        for (int c = g * KNN_SUPER; c < min(k.nc, (g + 1) * KNN_SUPER); ++c)
+            if (box_dist2(k.cmin[c], k.cmax[c], x, y, z) <= bd * 1.000001f) scan(c);
+    }
+    slot = bs;
+    return bi;
+}
+
 // Warp-cooperative form of knn_scan: all 32 lanes hold the SAME query.  Lanes split the cluster boxes (lower bounds kept in
 // registers), then every candidate cluster is scanned one vertex per lane (conflict-free LDS.128) and reduced with a
 // lexicographic (distance, original index) butterfly.  Clusters are visited in the same order as knn_scan, so the running
@@ -822,6 +866,41 @@ __global__ void __launch_bounds__(512, 1) k_knn_samples(FrameParams fp, KnnIndex
     const int B = knn_batch_size<KNN_COOP_SAMPLES>(n);
     if ((int)(blockIdx.x * (blockDim.x >> 5)) * B >= n) return;
     const KnnSmem kk = load_knn(sv, ix);
+    auto finish = [&](int i, const float* x, int idx) {
+        BroydenState<3> st;
+        float s_, xh[3];
+        nn_inverse_skinning(fp, idx, x, st.best_T, &s_, xh);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { st.x[k] = xh[k]; st.best_x[k] = xh[k]; st.tgt[k] = x[k] - fp.trans[k]; st.gx[k] = 0.f; st.upd[k] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) st.Jinv[k] = 0.f;
+        st.best_n = 0.f; st.owner = w.on_list[i]; st.g_evals = 0;
+        state_store(&w.corr_state[i], st);
+    };
+    if (B == 32 && w.knn_seed) {
+        // throughput regime: a lane walks a run of KNN_RUN consecutive on-samples (neighbours on one ray), each query seeded by
+        // the previous winner while the ray stays the same
+        constexpr int KNN_RUN = 4;
+        const int total = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+        for (long long base = (long long)t0 * KNN_RUN; base < n; base += (long long)total * KNN_RUN) {
+            int slot = -1, prev_ray = -1;
+            for (int j = 0; j < KNN_RUN; ++j) {
+                const int i = (int)base + j;
+                if (i >= n) break;
+                const int sl = w.on_list[i];
+                const int r = sl / w.S;
+                const float z = w.z_vals[sl];
+                float x[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) x[k] = w.ray_dirs[3 * r + k] * z + fp.cam_loc[k];
+                if (r != prev_ray) slot = -1;
+                prev_ray = r;
+                const int idx = knn_scan_seeded(kk, x[0], x[1], x[2], slot);
+                finish(i, x, idx);
+            }
+        }
+        return;
+    }
     knn_warp_batches<KNN_COOP_SAMPLES>(kk, n, B,
         [&](int i, float* x) {
             const int sl = w.on_list[i];
@@ -830,17 +909,7 @@ __global__ void __launch_bounds__(512, 1) k_knn_samples(FrameParams fp, KnnIndex
 #pragma unroll
             for (int k = 0; k < 3; ++k) x[k] = w.ray_dirs[3 * r + k] * z + fp.cam_loc[k];
         },
-        [&](int i, const float* x, int idx) {
-            BroydenState<3> st;
-            float s_, xh[3];
-            nn_inverse_skinning(fp, idx, x, st.best_T, &s_, xh);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { st.x[k] = xh[k]; st.best_x[k] = xh[k]; st.tgt[k] = x[k] - fp.trans[k]; st.gx[k] = 0.f; st.upd[k] = 0.f; }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) st.Jinv[k] = 0.f;
-            st.best_n = 0.f; st.owner = w.on_list[i]; st.g_evals = 0;
-            state_store(&w.corr_state[i], st);
-        });
+        finish);
 }
 
 constexpr int LDA_SKIN = 132;

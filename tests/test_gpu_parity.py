@@ -286,3 +286,20 @@ def test_full_size_properties_h36m_1024():
     assert psnr(rgb[sel], o['rgb_values']) >= 55.0
     assert (m1.cpu().numpy()[sel] != o['network_body_mask']).mean() <= 0.02
     print('1024x1024 n160', P, {k: stats[k] for k in ('on_samples', 'corr_skin_evals', 'shaded_samples', 'culled_samples', 'hit_rays')})
+
+
+def test_knn_seed_is_exact(monkeypatch):
+    """k_knn_samples seeds each query of a run with the previous winner (knn_scan_seeded): the nearest-vertex choice, hence every
+    output bit, must equal the unseeded scan's."""
+    from arah_release_b200 import synthetic as syn
+    fr = syn.make_frame(96, 96, seed=5)
+    res = []
+    for seed_on in ('1', '0'):
+        monkeypatch.setenv('ARAH_KNN_SEED', seed_on)
+        net, inputs = _build(fr, 'tf32')
+        out = net(inputs)
+        tr = net.tracer_outputs()
+        torch.cuda.synchronize()
+        res.append((out['rgb_values'].clone(), tr[3].clone(), tr[5].clone(), tr[6].clone(), net.stats()['corr_skin_evals']))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert torch.equal(res[0][3], res[1][3]) and res[0][4] == res[1][4]
