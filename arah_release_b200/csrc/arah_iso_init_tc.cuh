@@ -10,28 +10,6 @@
 
 namespace arah {
 
-// sin and cos with one shared 3-term Cody-Waite reduction by pi (|x| < ~1e4), odd / even polynomials on [-pi/2, pi/2]
-__device__ __forceinline__ void sincos_cw(float x, float& sn, float& cs) {
-    const float k = rintf(x * 0.318309886183790672f);
-    float r = fmaf(-k, 3.140625f, x);
-    r = fmaf(-k, 9.67502593994140625e-4f, r);
-    r = fmaf(-k, 1.509957990978376e-7f, r);
-    const float s = r * r;
-    float p = fmaf(s, -2.5052108385441718775e-8f, 2.7557319223985890653e-6f);
-    p = fmaf(s, p, -1.9841269841269841270e-4f);
-    p = fmaf(s, p, 8.3333333333333333333e-3f);
-    p = fmaf(s, p, -1.6666666666666666667e-1f);
-    const float rs = fmaf(r * s, p, r);
-    float q = fmaf(s, 2.0876756987868098979e-9f, -2.7557319223985890653e-7f);
-    q = fmaf(s, q, 2.4801587301587301587e-5f);
-    q = fmaf(s, q, -1.3888888888888888889e-3f);
-    q = fmaf(s, q, 4.1666666666666666667e-2f);
-    q = fmaf(s, q, -0.5f);
-    const float rc = fmaf(s, q, 1.0f);
-    const bool odd = ((int)k) & 1;
-    sn = odd ? -rs : rs;
-    cs = odd ? -rc : rc;
-}
 // d softplus(beta = 100) / d a = sigmoid(100 a)
 __device__ __forceinline__ float sigmoid100(float a) {
     float e;

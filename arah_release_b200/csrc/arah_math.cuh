@@ -272,4 +272,44 @@ ARAH_HD float laplace_density(float sdf_m, float inv_beta) {
     return fmaxf(den, 0.0f);
 }
 
+// sin(x) to ~1-2 ulp for |x| < ~1e4 without libdevice's large-argument slow path: the 32-way unrolled epilogues would
+// otherwise inline 64 copies of the Payne-Hanek fallback (local-memory tables, divergent regions) and thrash the
+// instruction cache.  3-term Cody-Waite reduction by pi, odd Taylor polynomial to r^11 on [-pi/2, pi/2].
+ARAH_HD float sin_cw(float x) {
+    const float k = rintf(x * 0.318309886183790672f);
+    float r = fmaf(-k, 3.140625f, x);
+    r = fmaf(-k, 9.67502593994140625e-4f, r);
+    r = fmaf(-k, 1.509957990978376e-7f, r);
+    const float s = r * r;
+    float p = fmaf(s, -2.5052108385441718775e-8f, 2.7557319223985890653e-6f);
+    p = fmaf(s, p, -1.9841269841269841270e-4f);
+    p = fmaf(s, p, 8.3333333333333333333e-3f);
+    p = fmaf(s, p, -1.6666666666666666667e-1f);
+    const float res = fmaf(r * s, p, r);
+    return (((int)k) & 1) ? -res : res;
+}
+
+// sin and cos with one shared 3-term Cody-Waite reduction by pi (|x| < ~1e4), odd / even polynomials on [-pi/2, pi/2]
+ARAH_HD void sincos_cw(float x, float& sn, float& cs) {
+    const float k = rintf(x * 0.318309886183790672f);
+    float r = fmaf(-k, 3.140625f, x);
+    r = fmaf(-k, 9.67502593994140625e-4f, r);
+    r = fmaf(-k, 1.509957990978376e-7f, r);
+    const float s = r * r;
+    float p = fmaf(s, -2.5052108385441718775e-8f, 2.7557319223985890653e-6f);
+    p = fmaf(s, p, -1.9841269841269841270e-4f);
+    p = fmaf(s, p, 8.3333333333333333333e-3f);
+    p = fmaf(s, p, -1.6666666666666666667e-1f);
+    const float rs = fmaf(r * s, p, r);
+    float q = fmaf(s, 2.0876756987868098979e-9f, -2.7557319223985890653e-7f);
+    q = fmaf(s, q, 2.4801587301587301587e-5f);
+    q = fmaf(s, q, -1.3888888888888888889e-3f);
+    q = fmaf(s, q, 4.1666666666666666667e-2f);
+    q = fmaf(s, q, -0.5f);
+    const float rc = fmaf(s, q, 1.0f);
+    const bool odd = ((int)k) & 1;
+    sn = odd ? -rs : rs;
+    cs = odd ? -rc : rc;
+}
+
 }  // namespace arah

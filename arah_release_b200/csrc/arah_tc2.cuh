@@ -53,22 +53,8 @@ __device__ __forceinline__ void a_tmem_store_split(uint32_t taddr_hi, uint32_t t
     tmem_st32(taddr_lo, l);
 }
 
-// sin(x) to ~1-2 ulp for |x| < ~1e4 without libdevice's large-argument slow path: the 32-way unrolled epilogues would
-// otherwise inline 64 copies of the Payne-Hanek fallback (local-memory tables, divergent regions) and thrash the
-// instruction cache.  3-term Cody-Waite reduction by pi, odd Taylor polynomial to r^11 on [-pi/2, pi/2].
-__device__ __forceinline__ float sin_cw(float x) {
-    const float k = rintf(x * 0.318309886183790672f);
-    float r = fmaf(-k, 3.140625f, x);
-    r = fmaf(-k, 9.67502593994140625e-4f, r);
-    r = fmaf(-k, 1.509957990978376e-7f, r);
-    const float s = r * r;
-    float p = fmaf(s, -2.5052108385441718775e-8f, 2.7557319223985890653e-6f);
-    p = fmaf(s, p, -1.9841269841269841270e-4f);
-    p = fmaf(s, p, 8.3333333333333333333e-3f);
-    p = fmaf(s, p, -1.6666666666666666667e-1f);
-    const float res = fmaf(r * s, p, r);
-    return (((int)k) & 1) ? -res : res;
-}
+// sin_cw / sincos_cw (Cody-Waite sine / cosine used by the tensor-core epilogues) live in arah_math.cuh so that the host tests can
+// compile them (tests/test_host_math.py).
 
 struct RingPos {
     uint32_t slot, use;

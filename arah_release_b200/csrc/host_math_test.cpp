@@ -44,6 +44,10 @@ int hm_broyden3(const float* A9, const float* c3, float eps, const float* x0, co
     *valid = st.best_n < CVG_THRESH;
     return evals;
 }
+// the Cody-Waite sine / sine+cosine of the tensor-core epilogues (FiLM-SIREN arguments reach |x| ~ 100)
+void hm_sincos(const float* x, int n, float* s_only, float* s, float* c) {
+    for (int i = 0; i < n; ++i) { s_only[i] = sin_cw(x[i]); sincos_cw(x[i], s[i], c[i]); }
+}
 void hm_misc(float* out) {
     for (int i = 0; i < 17; ++i) out[i] = linspace01(i, 17);
     for (int i = 0; i < 16; ++i) out[17 + i] = linspace01(i, 16);

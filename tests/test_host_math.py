@@ -106,3 +106,17 @@ def test_per_point_broyden_equals_reference_batched_broyden(hm):
     both = rv & valids.astype(bool)
     np.testing.assert_allclose(xs[both], ref['result'].squeeze(-1).numpy()[both], atol=2e-5)
     np.testing.assert_allclose(Ts[both], ref['transforms'][:, :3, :].reshape(N, 12).numpy()[both], atol=5e-4)
+
+
+def test_cody_waite_sine_cosine(hm):
+    """sin_cw / sincos_cw (arah_math.cuh) replace libdevice's sinf / sincosf in the tensor-core epilogues: the FiLM-SIREN arguments
+    30 (f a + phi) reach a few hundred in magnitude, and root finding resolves 1e-5 m, so the error budget is ~1 ulp of 1."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-400, 400, 200000), rng.uniform(-4, 4, 50000), np.array([0.0, np.pi, -np.pi, np.pi / 2, 1e-8, 3000.0])]).astype(np.float32)
+    n = x.shape[0]
+    s0, s, c = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    hm.hm_sincos(_p(x), n, _p(s0), _p(s), _p(c))
+    xs = x.astype(np.float64)
+    assert np.array_equal(s0, s)                                    # same reduction, same polynomial
+    assert np.abs(s - np.sin(xs)).max() < 2.5e-7
+    assert np.abs(c - np.cos(xs)).max() < 2.5e-7
