@@ -50,12 +50,18 @@ class ArahSdfParams(C.Structure):
     _fields_ = [('sdf_W', FP * 7), ('sdf_b', FP * 7), ('sdf_freq', FP), ('sdf_phase', FP)]
 
 
+class ArahRasterCamera(C.Structure):
+    _fields_ = [('R', C.c_float * 9), ('T', C.c_float * 3), ('fx', C.c_float), ('fy', C.c_float), ('px', C.c_float), ('py', C.c_float)]
+
+
 EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'arah_set_frame', 'arah_set_profiling', 'arah_render',
            'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin', 'arah_debug_umma_gemm', 'arah_debug_phase_clocks',
            'arah_set_training', 'arah_train_trace', 'arah_train_shade_forward', 'arah_train_shade_backward', 'arah_train_sdf_forward',
            'arah_train_sdf_backward', 'arah_train_skin_forward', 'arah_train_skin_backward', 'arah_debug_train_gemm',
            'arah_sdf_grid', 'arah_marching_cubes', 'arah_mc_case_table', 'arah_debug_knn', 'arah_marching_cubes_workspace',
-           'arah_hyper_forward', 'arah_hyper_workspace', 'arah_pose_smpl', 'arah_frame_rays', 'arah_frame_rays_workspace']
+           'arah_hyper_forward', 'arah_hyper_workspace', 'arah_pose_smpl', 'arah_frame_rays', 'arah_frame_rays_workspace',
+           'arah_frame_images', 'arah_frame_images_workspace', 'arah_psnr', 'arah_psnr_workspace', 'arah_rasterize_mesh',
+           'arah_rasterize_mesh_workspace', 'arah_face_normal_image']
 
 _lib = None
 
@@ -109,6 +115,17 @@ def lib():
     L.arah_frame_rays.argtypes = [F9, F9, F9, F3, F3, FP, C.c_int32, C.c_int32, FP, FP, FP, FP, FP, FP, FP, FP, C.c_size_t, C.c_void_p]
     L.arah_frame_rays_workspace.argtypes = [C.c_int32, C.c_int32]
     L.arah_frame_rays_workspace.restype = C.c_size_t
+    L.arah_frame_images_workspace.argtypes = [C.c_int32, C.c_int32]
+    L.arah_frame_images_workspace.restype = C.c_size_t
+    L.arah_frame_images.argtypes = [FP, FP, FP, C.c_int32, C.c_int32, C.c_int32, FP, FP, FP, C.c_size_t, C.c_void_p]
+    L.arah_psnr_workspace.argtypes = []
+    L.arah_psnr_workspace.restype = C.c_size_t
+    L.arah_psnr.argtypes = [FP, FP, C.c_int64, FP, FP, C.c_size_t, C.c_void_p]
+    L.arah_rasterize_mesh_workspace.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.arah_rasterize_mesh_workspace.restype = C.c_size_t
+    L.arah_rasterize_mesh.argtypes = [FP, C.c_int32, FP, C.c_int32, C.POINTER(ArahRasterCamera), C.c_int32, C.c_int32, FP, FP, FP, C.c_size_t, C.c_void_p]
+    L.arah_face_normal_image.argtypes = [FP, C.c_int32, FP, C.c_int32, FP, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_float), C.c_float, FP,
+                                         C.c_void_p]
     _lib = L
     return L
 

@@ -685,6 +685,20 @@ class IDHRNetwork(nn.Module):
         _, x_bar = r.eval_skin(pts_hat)
         return verts, faces, x_bar + input['trans'].reshape(1, 3)
 
+    def render_normal_maps(self, input, N=256, image_size=(512, 512), mesh=None):
+        """The rest of the `gen_cano_mesh` branch (metaavatar_render/models/__init__.py:226-309): rasterise the posed mesh with
+        the frame's camera (`input['cam_rot'] [1,3,3]`, `input['cam_trans'] [1,3]`, `input['intrinsics'] [1,3,3]`, the keys the
+        reference reads at :246-248) and the canonical mesh from the front / back -> {'output_normal', 'normal_cano_front',
+        'normal_cano_back'}: [1, H, W, 3] device tensors in [0, 1], ready for `model_outputs.update(...)`.
+        `mesh` = a previous `extract_canonical_mesh` result to reuse."""
+        from .images import FrameImages
+        verts, faces, points_bar = mesh if mesh is not None else self.extract_canonical_mesh(input, N)
+        if getattr(self, '_frame_images', None) is None or self._frame_images.device != verts.device:
+            self._frame_images = FrameImages(verts.device)
+        H, W = image_size
+        return self._frame_images.normal_maps(verts, faces, points_bar, input['cam_rot'].reshape(3, 3), input['cam_trans'].reshape(3),
+                                              input['intrinsics'].reshape(3, 3), H, W)
+
     def tracer_outputs(self):
         """7-tuple of the tracer for the frame rendered by the last forward()."""
         r, P = self._last

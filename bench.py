@@ -367,6 +367,63 @@ def ray_setup_bench(dev, size, steps=10, warmup=3):
             'cpu_port': {'ms_pose_smpl': 1e3 * t_pose, 'ms_frame_rays': 1e3 * t_rays, 'kind': 'oracle/rays_oracle.py (numpy; python loops for the mask)'}}
 
 
+# ------------------------------------------------------------------------------------------------ image tail (rows f4 / f1)
+def image_tail_bench(net, frame, inp, steps=10, warmup=3, N=256):
+    """What follows the renderer in validation_step / gen_cano_mesh (lightning_model.py:176-221, models/__init__.py:226-309):
+    scatter rgb / points into images + finite-difference normal map, PSNR, and the three rasterised normal maps of the extracted
+    mesh.  HBM roofline; algorithmic bytes: every input read once and every output written once (z-buffer keys: one clear, one
+    resolve read)."""
+    import torch
+    from arah_release_b200.images import FrameImages
+    from oracle import images_oracle as io
+    out = net(inp)
+    dev = out['rgb_values'].device
+    fi = FrameImages(dev)
+    H, W = frame.H, frame.W
+    pix = torch.from_numpy(frame.pix.astype(np.int32)).to(dev)
+    rgb, pts = out['rgb_values'][0].contiguous(), out['points_cam'][0].contiguous()
+    gt = (rgb + 0.02 * torch.randn_like(rgb)).clamp(0, 1)
+    mesh = net.extract_canonical_mesh(inp, N=N)
+    verts, faces, posed = mesh
+    R, T, K = frame.pose[:3, :3], frame.pose[:3, 3], frame.K
+    ms = [[], [], []]
+    for i in range(warmup + steps):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record()
+        pp, pn = fi.assemble(rgb, pts, pix, H, W)
+        e[1].record()
+        res = fi.psnr_device(rgb, gt)
+        e[2].record()
+        maps = fi.normal_maps(verts, faces, posed, R, T, K, H, W)
+        e[3].record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            for k in range(3):
+                ms[k].append(e[k].elapsed_time(e[k + 1]))
+    m_img, m_psnr, m_maps = (float(np.median(x)) for x in ms)
+    P, V, Fc, n = int(pix.numel()), int(verts.shape[0]), int(faces.shape[0]), H * W
+    b_img = P * (12 + 12 + 4 + 24) + n * (12 + 12) + n * (12 + 12)          # rows in, scattered out, 2 clears, normals read + write
+    b_psnr = 2 * 12 * P
+    b_maps = 3 * (24 * V + 12 * Fc + 36 * Fc + 8 * n + 12 * n + 4 * n + 12 * n)
+    pk = peaks()
+    # CPU port (numpy; the rasteriser loops over faces in Python: a bounded face sample of one view, scaled to 3 views x all faces)
+    rgb_h, pts_h, gt_h, pix_h = rgb.cpu().numpy(), pts.cpu().numpy(), gt.cpu().numpy(), frame.pix
+    t = time.perf_counter(); io.frame_images(rgb_h, pts_h, pix_h, H, W); t_img = time.perf_counter() - t
+    t = time.perf_counter(); io.psnr_metric(rgb_h, gt_h); t_psnr = time.perf_counter() - t
+    vh, fh = posed.cpu().numpy(), faces.cpu().numpy()
+    ns = min(Fc, 4000)
+    t = time.perf_counter(); io.rasterize(io.project(vh, io.opencv_camera(R, T, K, H, W)), fh[:ns], H, W); t_r = time.perf_counter() - t
+    return {'workload': f'validation images + PSNR at {H}x{W} ({P} rays), 3 normal maps of the {N}^3 mesh ({V} verts, {Fc} faces)',
+            'ms_frame_images': m_img, 'ms_psnr': m_psnr, 'ms_normal_maps': m_maps, 'psnr_db': float(res[1].item()),
+            'frame_images_gbs': b_img / (m_img * 1e-3) / 1e9, 'psnr_gbs': b_psnr / (m_psnr * 1e-3) / 1e9, 'normal_maps_gbs': b_maps / (m_maps * 1e-3) / 1e9,
+            'frac_of_hbm_peak': {'frame_images': b_img / (m_img * 1e-3) / 1e9 / pk['hbm_gbs'], 'psnr': b_psnr / (m_psnr * 1e-3) / 1e9 / pk['hbm_gbs'],
+                                 'normal_maps': b_maps / (m_maps * 1e-3) / 1e9 / pk['hbm_gbs']},
+            'gpu_launches': 2 + 2 + 3 * 4, 'steps': steps, 'warmup': warmup,
+            'note': 'a few MB per call: launch-latency-bound small kernels, timed through the Python mirror',
+            'cpu_port': {'ms_frame_images': 1e3 * t_img, 'ms_psnr': 1e3 * t_psnr, 'ms_normal_maps_extrapolated': 1e3 * t_r * 3 * Fc / max(ns, 1),
+                         'kind': 'oracle/images_oracle.py (numpy; python loop over faces)', 'sample': f'{ns} faces of one view timed, scaled to 3 views x {Fc} faces'}}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -552,6 +609,11 @@ def run_ours(args):
             line['ray_setup'] = ray_setup_bench(dev, args.size)
         except Exception as ex:
             line['ray_setup'] = {'error': repr(ex)[:300]}
+    if args.gpus == 1 and not args.no_mesh:
+        try:
+            line['image_tail'] = image_tail_bench(net, f0, inputs[0])
+        except Exception as ex:
+            line['image_tail'] = {'error': repr(ex)[:300]}
     if args.gpus == 1 and not args.no_cpu_baseline:
         v, cores, n, dt = cpu_rate(f0, args.cpu_sample_seconds)
         line['cpu_baseline'] = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',

@@ -243,6 +243,37 @@ int arah_frame_rays(const float* K, const float* K_inv, const float* R, const fl
                     void* stream);
 size_t arah_frame_rays_workspace(int32_t H, int32_t W);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Image-space tail of the validation / test step (the parts after the renderer).  Device pointers
+ * unless noted; launches are asynchronous on `stream`; caller-owned workspaces sized by the *_workspace functions.
+ *
+ * arah_frame_images (im2mesh/metaavatar_render/lightning_model.py:176-205): rgb / points_cam [P][3] in ray order, pix [P] =
+ *   y*W + x of ray k (np.where order of image_mask — arah_frame_rays' `pix`): `masked_scatter_` into pred_pixels [H][W][3]
+ *   (background 0) and the finite-difference normal map of the scattered point image -> pred_normals [H][W][3] in [0,1]
+ *   (NaN -> -1 before the (n+1)/2 clip, as the reference).  Either output may be NULL.
+ * arah_psnr (:218-221, im2mesh/utils/eval.py:6-9): mse_psnr[0] = mean((pred - gt)^2) rounded to fp32, [1] = -10 log10(mse),
+ *   both stored as doubles on the device; n = number of floats (3 P for a ray list).  Bit-reproducible.
+ * arah_rasterize_mesh (im2mesh/metaavatar_render/models/__init__.py:238-254,265-277,291-299 — pytorch3d MeshRasterizer with
+ *   image_size (H, W), faces_per_pixel 1, blur_radius 0, perspective-correct depth): verts [n_verts][3] world space, faces
+ *   [n_faces][3] int32 -> pix_to_face [H][W] (index of the nearest face covering the pixel centre, lowest index on depth
+ *   ties, -1 = background), zbuf [H][W] (view depth, -1 = background; may be NULL).  `cam` is a HOST struct in pytorch3d's
+ *   convention: row vectors, view = X R + T, +X left / +Y up / +Z forward, ndc = (fx x + px z, fy y + py z) / z
+ *   (FoVPerspectiveCameras: fx = fy = 1/tan(fov/2), px = py = 0; cameras_from_opencv_projection: see images.py).
+ *   Faces with a vertex at or behind the camera plane are not drawn.
+ * arah_face_normal_image (:256-263, 279-286, 301-308): image [H][W][3] = clip((v + 1) / 2, 0, 1) with v = rot3x3 (HOST,
+ *   row-major, may be NULL) . (sign * unit face normal of pix_to_face) for covered pixels, v = background otherwise. */
+typedef struct ArahRasterCamera { float R[9]; float T[3]; float fx, fy, px, py; } ArahRasterCamera;
+size_t arah_frame_images_workspace(int32_t H, int32_t W);
+int arah_frame_images(const float* rgb, const float* points_cam, const int32_t* pix, int32_t P, int32_t H, int32_t W, float* pred_pixels,
+                      float* pred_normals, void* workspace, size_t workspace_bytes, void* stream);
+size_t arah_psnr_workspace(void);
+int arah_psnr(const float* pred, const float* gt, int64_t n, double* mse_psnr, void* workspace, size_t workspace_bytes, void* stream);
+size_t arah_rasterize_mesh_workspace(int32_t n_verts, int32_t H, int32_t W);
+int arah_rasterize_mesh(const float* verts, int32_t n_verts, const int32_t* faces, int32_t n_faces, const ArahRasterCamera* cam, int32_t H,
+                        int32_t W, int32_t* pix_to_face, float* zbuf, void* workspace, size_t workspace_bytes, void* stream);
+int arah_face_normal_image(const float* verts, int32_t n_verts, const int32_t* faces, int32_t n_faces, const int32_t* pix_to_face, int32_t H,
+                           int32_t W, float sign, const float* rot3x3, float background, float* image, void* stream);
+
 /* Unit-level: pytorch3d.ops.knn_points(K=1) as used at renderer/ray_tracing.py:386,407 — index of the nearest posed SMPL vertex
  * (exact fp32 argmin of (x-v).(x-v), lowest index on ties) for n device points [n][3] -> idx [n] int32. */
 int arah_debug_knn(ArahHandle* h, const float* pts, int32_t n, int32_t* idx, void* stream);

@@ -120,3 +120,41 @@ def test_to_image_u8():
     img = sh.to_image_u8(rgb, torch.tensor([1, 4]), 2, 3)
     assert img.shape == (2, 3, 3) and img[0, 1].tolist() == [0, 128, 255] and img[1, 1].tolist() == [255, 0, 64]
     assert int(img[0, 0].sum()) == 0
+
+
+def test_image_tail_has_no_cpu_path_and_validates_arguments():
+    """arah_release_b200/images.py: no CPU path; the C ABI rejects bad arguments before touching the device (no GPU needed)."""
+    import ctypes as C
+    from arah_release_b200 import _lib, images
+    with pytest.raises(_lib.ArahError):
+        images.FrameImages('cpu')
+    src = open(images.__file__).read()
+    assert 'oracle' not in src
+    L = _lib.lib()
+    assert L.arah_frame_images_workspace(512, 512) >= 512 * 512 * 12 and L.arah_frame_images_workspace(0, 5) == 0
+    assert L.arah_psnr_workspace() >= 8
+    assert L.arah_rasterize_mesh_workspace(100, 64, 64) >= 100 * 12 + 64 * 64 * 8
+    assert L.arah_frame_images(None, None, None, 4, 0, 8, None, None, None, 0, None) != 0          # bad image size
+    assert b'image size' in L.arah_last_error()
+    assert L.arah_frame_images(None, None, None, 100, 4, 4, None, None, None, 0, None) != 0        # P > H*W
+    assert L.arah_psnr(None, None, 3, None, None, 0, None) != 0
+    assert L.arah_rasterize_mesh(None, 0, None, 0, None, 8, 8, None, None, None, 0, None) != 0
+    assert L.arah_face_normal_image(None, 0, None, 0, None, 8, 8, C.c_float(1.0), None, C.c_float(0.0), None, None) != 0
+
+
+def test_image_tail_cameras_match_oracle():
+    """The host-side 3x3 camera algebra of images.py (product) against the oracle's restatement of pytorch3d's conventions."""
+    from arah_release_b200 import images
+    from oracle import images_oracle as io
+    for az in (0.0, 180.0, 37.0):
+        R, T = images.look_at_view_transform(2.0, 10.0, az)
+        Ro, To = io.look_at_view_transform(2.0, 10.0, az)
+        assert np.array_equal(R, Ro) and np.array_equal(T, To)
+        c, co = images.fov_perspective_camera(R, T), io.fov_camera(Ro, To)
+        assert np.array_equal(np.array(c.R[:], np.float32), co['R'].reshape(9)) and c.fx == float(co['fx']) and c.px == 0.0
+    rng = np.random.default_rng(0)
+    Rm, Tm = np.linalg.qr(rng.normal(size=(3, 3)))[0].astype(np.float32), rng.normal(size=3).astype(np.float32)
+    K = np.array([[500.0, 0, 250.5], [0, 510.0, 260.25], [0, 0, 1]], np.float32)
+    c, co = images.opencv_camera(Rm, Tm, K, 480, 512), io.opencv_camera(Rm, Tm, K, 480, 512)
+    assert np.array_equal(np.array(c.R[:], np.float32), co['R'].reshape(9)) and np.array_equal(np.array(c.T[:], np.float32), co['T'])
+    assert (c.fx, c.fy, c.px, c.py) == (float(co['fx']), float(co['fy']), float(co['px']), float(co['py']))
