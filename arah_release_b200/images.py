@@ -142,14 +142,15 @@ class FrameImages:
         v = self._f32(verts)
         f = torch.as_tensor(faces).to(self.device).reshape(-1, 3).to(torch.int32).contiguous()
         H, W = pix_to_face.shape
+        pix_to_face = pix_to_face.to(self.device, torch.int32).contiguous()
         img = torch.empty(H, W, 3, device=self.device)
         rp = None
         if rot is not None:
             r = np.ascontiguousarray(np.asarray(torch.as_tensor(rot).detach().cpu().numpy(), np.float32).reshape(9))
             rp = r.ctypes.data_as(C.POINTER(C.c_float))
-        check(_lib.lib().arah_face_normal_image(_ptr(v), v.shape[0], _ptr(f), f.shape[0], _ptr(pix_to_face.contiguous()), H, W, float(sign), rp,
+        check(_lib.lib().arah_face_normal_image(_ptr(v), v.shape[0], _ptr(f), f.shape[0], _ptr(pix_to_face), H, W, float(sign), rp,
                                                 float(background), _ptr(img), self._stream))
-        self._keep_n = (v, f)
+        self._keep_n = (v, f, pix_to_face)
         return img
 
     def normal_maps(self, verts_cano, faces, verts_posed, cam_rot, cam_trans, K, H=512, W=512):
