@@ -126,9 +126,21 @@ def cpu_rate(frame, seconds, threads=0):
     n = int(min(frame.P, max(n0, r0 * seconds)))
     sel = rng.choice(frame.P, size=n, replace=False)
     t = time.perf_counter()
-    orc.render(frame, ray_dirs=frame.ray_dirs[sel], near_far=frame.near_far[sel], stages=False, threads=nthr)
+    o = orc.render(frame, ray_dirs=frame.ray_dirs[sel], near_far=frame.near_far[sel], stages=False, threads=nthr)
     dt = time.perf_counter() - t
-    return n / dt, nthr, n, dt
+    return n / dt, nthr, n, dt, sel, o
+
+
+def parity_on_sample(ours_rgb, ours_mask, sel, o):
+    """BASELINE metric, second half ('PSNR delta vs reference'): the GPU frame against the CPU port on the timed ray sample.
+    delta = PSNR(ours, gt) - PSNR(port, gt) against a fixed pseudo ground truth (port + N(0, 0.03) noise, seed 123), bar 0.05 dB."""
+    ref = np.asarray(o['rgb_values'], np.float64)
+    mine = np.asarray(ours_rgb[sel], np.float64)
+    ps = lambda a, b: float(-10.0 * np.log10(max(float(np.mean((a - b) ** 2)), 1e-30)))
+    gt = np.clip(ref + np.random.default_rng(123).normal(scale=0.03, size=ref.shape), 0.0, 1.0)
+    return {'rays': int(len(sel)), 'psnr_vs_cpu_port_db': ps(mine, ref), 'delta_psnr_vs_pseudo_gt_db': ps(mine, gt) - ps(ref, gt), 'bar_db': 0.05,
+            'mask_agreement': float(np.mean(np.asarray(ours_mask[sel]).astype(bool) == np.asarray(o['network_body_mask']).astype(bool))),
+            'note': 'same frame, same rays: CUDA path (device-resident render) vs oracle/arah_oracle.c (pinned to the unmodified reference by tests/golden)'}
 
 
 def run_reference(args):
@@ -544,6 +556,14 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     pk = peaks()
+    ours0 = None
+    if not args.no_cpu_baseline and args.gpus == 1:
+        try:                                                            # the frame the CPU leg samples, rendered once more for the parity entry
+            o0 = net(inputs[0])
+            torch.cuda.synchronize()
+            ours0 = (o0['rgb_values'][0].cpu().numpy(), o0['network_body_mask'][0].cpu().numpy())
+        except Exception:
+            ours0 = None
     ach = (sum(shade_flops) / max(sum(shade_ms), 1e-9)) / 1e9          # FLOP/ms -> TFLOP/s
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'k_shade_tc3_traffic.json' if r.shade_mode == 'tf32' else 'k_shade_traffic.json')
@@ -615,9 +635,14 @@ def run_ours(args):
         except Exception as ex:
             line['image_tail'] = {'error': repr(ex)[:300]}
     if args.gpus == 1 and not args.no_cpu_baseline:
-        v, cores, n, dt = cpu_rate(f0, args.cpu_sample_seconds)
+        v, cores, n, dt, sel, o_cpu = cpu_rate(f0, args.cpu_sample_seconds)
         line['cpu_baseline'] = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
                                 'sample': f'{n} random bbox rays of the same frame in {dt:.1f} s (oracle/arah_oracle.c, OpenMP)'}
+        if ours0 is not None:
+            try:
+                line['parity'] = parity_on_sample(ours0[0], ours0[1], sel, o_cpu)
+            except Exception as ex:
+                line['parity'] = {'error': repr(ex)[:300]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -25,6 +25,8 @@ def main():
     ap.add_argument('--frames', type=int, default=258)
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--gather', action='store_true', help='gather the uint8 images on rank 0 at the end')
+    ap.add_argument('--normal-maps', type=int, default=0, metavar='N', help='also extract the canonical mesh on an N^3 lattice and rasterise '
+                    'the three normal maps per frame (test.py: gen_cano_mesh=True, models/__init__.py:203-309); 0 = off')
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -55,6 +57,10 @@ def main():
     for fi, f, inp in zip(mine, frames, inputs):
         out = net(inp)
         rays += f.P
+        if a.normal_maps:
+            inp = dict(inp, cam_rot=torch.from_numpy(f.pose[:3, :3].copy()).view(1, 3, 3), cam_trans=torch.from_numpy(f.pose[:3, 3].copy()).view(1, 3),
+                       intrinsics=torch.from_numpy(f.K).view(1, 3, 3))
+            out.update(net.render_normal_maps(inp, N=a.normal_maps, image_size=(f.H, f.W)))
         if a.gather:
             images[fi] = sh.to_image_u8(out['rgb_values'][0], torch.from_numpy(f.pix).to(dev), f.H, f.W)
     e1.record()
@@ -68,7 +74,7 @@ def main():
     if rank == 0:
         print(json.dumps({'workload': f'{a.frames}-frame synthetic novel-pose sequence at {a.size}x{a.size}, frames sharded over {world} GPU(s)',
                           'frames': a.frames, 'rays': int(rays), 'seconds': secs, 'rays_per_s': rays / secs, 'frames_per_s': a.frames / secs,
-                          'n_gpus': world, 'gathered_images': None if gathered is None else len(gathered)}))
+                          'normal_maps_lattice': a.normal_maps, 'n_gpus': world, 'gathered_images': None if gathered is None else len(gathered)}))
     if world > 1:
         dist.destroy_process_group()
 
