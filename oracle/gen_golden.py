@@ -27,8 +27,13 @@ CASES = {
     'h36m_n160_12x12_s4': (dict(H=12, W=12, seed=4, n_steps=160, near_samples=128, far_samples=16, cano_view_dirs=True, beta=3e-3), 0),
     # monocular configs (configs/arah-zju/ZJUMOCAP-39x-mono_4gpus.yaml:36): colour net without view directions (390 inputs)
     'mono_noview_16x16_s8': (dict(H=16, W=16, seed=8, color_mode='no_view_dir'), 0),
+    # BASELINE configs[0]: the reference's own CPU-runnable plumbing case, a 64x64 frame.  Final outputs + per-ray tracer outputs only
+    # (the per-sample stage tensors would be 4.5 MB): see FINAL_ONLY
+    'zju377_64x64_s0': (dict(H=64, W=64, seed=0), 0),
 }
 T_RAYS = 48
+FINAL_ONLY = {'zju377_64x64_s0'}
+FINAL_KEYS = ('rgb_values', 'network_body_mask', 'points_cam', 'trace.network_body_mask', 'trace.dists', 'trace.points_hat_norm')
 
 
 def build_case(kw, n_degenerate):
@@ -58,8 +63,11 @@ def main(only=None):
         meta = {'make_frame': kw, 'n_degenerate': ndeg, 'P': fr.P, 'reference_seconds': dt,
                 'reference_threads': os.cpu_count(), 'iso_calls': iso, 'corr_calls': corr,
                 'generator': 'oracle/gen_golden.py', 'reference_commit': '1040cf7'}
-        arrays = {k.replace('.', '__'): v for k, v in ref.items() if k != 'trace.sampled_transforms'}
-        arrays['trace__sampled_transforms_head'] = ref['trace.sampled_transforms'][:T_RAYS]
+        if name in FINAL_ONLY:
+            arrays = {k.replace('.', '__'): ref[k] for k in FINAL_KEYS}
+        else:
+            arrays = {k.replace('.', '__'): v for k, v in ref.items() if k != 'trace.sampled_transforms'}
+            arrays['trace__sampled_transforms_head'] = ref['trace.sampled_transforms'][:T_RAYS]
         path = os.path.join(out_dir, name + '.npz')
         np.savez_compressed(path, meta=json.dumps(meta), **arrays)
         print(name, 'P', fr.P, f'{dt:.1f}s', os.path.getsize(path) / 1e6, 'MB', meta['iso_calls'], meta['corr_calls'])

@@ -52,3 +52,17 @@ def test_oracle_unit_functions_selfconsistent():
         _, xp, _ = orc.skin(fr, xh + e, jac=False)
         _, xm, _ = orc.skin(fr, xh - e, jac=False)
         np.testing.assert_allclose((xp - xm) / (2 * h), J[:, :, k], atol=3e-2, rtol=5e-2)
+
+
+def test_oracle_matches_reference_config0_64x64():
+    """BASELINE configs[0] — the reference's own CPU-runnable case, a 64x64 frame (final outputs + per-ray tracer outputs; the
+    fixture keeps no per-sample stage tensors)."""
+    from oracle import oracle as orc
+    fr, ref, meta = load_golden('zju377_64x64_s0')
+    assert (fr.H, fr.W) == (64, 64) and fr.P == ref['rgb_values'].shape[0] and fr.P > 1000
+    out = orc.render(fr, threads=0, stages=False)
+    st = check_render(out, ref, label='config0', stages=False)
+    iso_ref, corr_ref, n_pts = meta['iso_calls'][0]['g_evals'], meta['corr_calls'][0]['g_evals'], meta['corr_calls'][0]['n']
+    assert abs(int(out['n_iso_evals'].sum()) - iso_ref) <= max(8, 0.05 * iso_ref)
+    assert abs(int(out['n_corr_evals'].sum()) - n_pts - corr_ref) <= 0.02 * corr_ref
+    print('config0', st)
