@@ -50,6 +50,22 @@ class ArahSdfParams(C.Structure):
     _fields_ = [('sdf_W', FP * 7), ('sdf_b', FP * 7), ('sdf_freq', FP), ('sdf_phase', FP)]
 
 
+class ArahLossConfig(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ('rgb_weight', 'perceptual_weight', 'eikonal_weight', 'mask_weight', 'off_surface_weight', 'inside_weight',
+                                         'params_weight', 'skinning_weight')] + [('rgb_loss_type', C.c_int32)]
+
+
+class ArahLossInputs(C.Structure):
+    _fields_ = [(n, FP) for n in ('rgb_values', 'rgb_gt', 'network_body_mask', 'body_mask', 'off_surface_mask', 'sdf_output', 'grad_theta',
+                                  'off_surface_sdf', 'inside_sdf', 'pred_weights', 'sampled_weights')] + \
+               [('sdf_params', FP * 8), ('sdf_params_count', C.c_int64 * 8)] + \
+               [(n, C.c_int32) for n in ('n_rays', 'n_eikonal', 'n_off', 'n_inside', 'n_skin', 'n_joints', 'n_param_tensors')]
+
+
+class ArahLossGrads(C.Structure):
+    _fields_ = [(n, FP) for n in ('rgb_values', 'sdf_output', 'grad_theta', 'off_surface_sdf', 'inside_sdf', 'pred_weights')] + [('sdf_params', FP * 8)]
+
+
 class ArahRasterCamera(C.Structure):
     _fields_ = [('R', C.c_float * 9), ('T', C.c_float * 3), ('fx', C.c_float), ('fy', C.c_float), ('px', C.c_float), ('py', C.c_float)]
 
@@ -61,7 +77,7 @@ EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'ar
            'arah_sdf_grid', 'arah_marching_cubes', 'arah_mc_case_table', 'arah_debug_knn', 'arah_marching_cubes_workspace',
            'arah_hyper_forward', 'arah_hyper_workspace', 'arah_pose_smpl', 'arah_frame_rays', 'arah_frame_rays_workspace',
            'arah_frame_images', 'arah_frame_images_workspace', 'arah_psnr', 'arah_psnr_workspace', 'arah_rasterize_mesh',
-           'arah_rasterize_mesh_workspace', 'arah_face_normal_image']
+           'arah_rasterize_mesh_workspace', 'arah_face_normal_image', 'arah_idhr_loss', 'arah_idhr_loss_workspace']
 
 _lib = None
 
@@ -126,6 +142,9 @@ def lib():
     L.arah_rasterize_mesh.argtypes = [FP, C.c_int32, FP, C.c_int32, C.POINTER(ArahRasterCamera), C.c_int32, C.c_int32, FP, FP, FP, C.c_size_t, C.c_void_p]
     L.arah_face_normal_image.argtypes = [FP, C.c_int32, FP, C.c_int32, FP, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_float), C.c_float, FP,
                                          C.c_void_p]
+    L.arah_idhr_loss_workspace.argtypes = []
+    L.arah_idhr_loss_workspace.restype = C.c_size_t
+    L.arah_idhr_loss.argtypes = [C.POINTER(ArahLossConfig), C.POINTER(ArahLossInputs), FP, C.POINTER(ArahLossGrads), FP, C.c_size_t, C.c_void_p]
     _lib = L
     return L
 

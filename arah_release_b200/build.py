@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libarah_b200.so')
-SOURCES = ['arah_api.cu', 'arah_mesh.cu', 'arah_hyper.cu', 'arah_rays.cu', 'arah_image.cu']
-HEADERS = ['arah_math.cuh', 'arah_tile.cuh', 'arah_kernels.cuh', 'arah_umma.cuh', 'arah_shade_tc.cuh', 'arah_corr_tc.cuh', 'arah_tc2.cuh', 'arah_shade_tc2.cuh', 'arah_corr_tc2.cuh', 'arah_shade_tc3.cuh', 'arah_corr_tc3.cuh', 'arah_sdf3x.cuh', 'arah_shade_tc4.cuh', 'arah_corr_tc4.cuh', 'arah_corr_tc5.cuh', 'arah_iso_init_tc.cuh', 'arah_train.h', 'arah_train_cuda.cuh', 'arah_train_tc.cuh', 'arah_image_core.h', os.path.join('..', '..', 'include', 'arah_b200.h')]
+SOURCES = ['arah_api.cu', 'arah_mesh.cu', 'arah_hyper.cu', 'arah_rays.cu', 'arah_image.cu', 'arah_loss.cu']
+HEADERS = ['arah_math.cuh', 'arah_tile.cuh', 'arah_kernels.cuh', 'arah_umma.cuh', 'arah_shade_tc.cuh', 'arah_corr_tc.cuh', 'arah_tc2.cuh', 'arah_shade_tc2.cuh', 'arah_corr_tc2.cuh', 'arah_shade_tc3.cuh', 'arah_corr_tc3.cuh', 'arah_sdf3x.cuh', 'arah_shade_tc4.cuh', 'arah_corr_tc4.cuh', 'arah_corr_tc5.cuh', 'arah_iso_init_tc.cuh', 'arah_train.h', 'arah_train_cuda.cuh', 'arah_train_tc.cuh', 'arah_image_core.h', 'arah_loss_core.h', os.path.join('..', '..', 'include', 'arah_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--shared',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--threads', '4']
 

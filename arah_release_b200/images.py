@@ -125,6 +125,27 @@ class FrameImages:
         m, p = self.psnr_device(pred, gt).tolist()                     # the one synchronisation (the reference returns a Python float)
         return m, p
 
+    def validation_tail(self, model_outputs, batch):
+        """The body of `LightningModel.validation_step` after the model call (lightning_model.py:176-229) minus SSIM / LPIPS:
+        reads `batch['inputs.img_height' / 'inputs.img_width' / 'inputs.image_mask' / 'inputs']` and `model_outputs['rgb_values' /
+        'points_cam']` (or a ready 'output_normal') -> {'psnr' (float), 'rgb_pred', 'normal_pred', 'rgb_gt'} with the images
+        channel-first [3, H, W] as the reference returns them (:225-227)."""
+        H, W = int(batch['inputs.img_height'].item()), int(batch['inputs.img_width'].item())
+        mask = torch.as_tensor(batch['inputs.image_mask']).to(self.device).reshape(-1)
+        pix = mask.nonzero().squeeze(1).to(torch.int32)                          # np.where order == masked_scatter_ order
+        n = int(pix.numel())
+        rgb = torch.as_tensor(model_outputs['rgb_values']).reshape(-1, 3)[:n]
+        gt = torch.as_tensor(batch['inputs']).reshape(-1, 3)[:n]
+        want_normals = 'output_normal' not in model_outputs
+        pred_pixels, pred_normals = self.assemble(rgb, model_outputs['points_cam'].reshape(-1, 3)[:n] if want_normals else None, pix, H, W,
+                                                  normals=want_normals)
+        if not want_normals:
+            pred_normals = model_outputs['output_normal'].squeeze(0)
+        gt_pixels, _ = self.assemble(gt, None, pix, H, W, normals=False)
+        # psnr_metric runs on the FULL ray lists, not on the [:n] slices (:218-221)
+        psnr = self.psnr(model_outputs['rgb_values'].reshape(-1, 3), torch.as_tensor(batch['inputs']).reshape(-1, 3))[1]
+        return {'psnr': psnr, 'rgb_pred': pred_pixels.permute(2, 0, 1), 'normal_pred': pred_normals.permute(2, 0, 1), 'rgb_gt': gt_pixels.permute(2, 0, 1)}
+
     def rasterize(self, verts, faces, camera, H=512, W=512, zbuf=False):
         """-> pix_to_face [H,W] int32 (and zbuf [H,W] if asked)."""
         v = self._f32(verts)

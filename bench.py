@@ -181,7 +181,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ training step (configs[2])
-def train_step_bench(args, dev, frame, steps=5, warmup=3):
+def train_step_bench(args, dev, frame, steps=5, warmup=3, variant='torch'):
     """One training step = IDHRNetwork.forward (training branch: tracer with jitter, differentiable shading, regulariser
     evaluations) + IDHRLoss-style loss + backward to every parameter tensor, on `--train-rays` random bbox rays of the frame
     (BASELINE configs[2]: 1024 + 1024 rays, train_skinning_net).  Secondary metric; the headline stays the 512x512 render."""
@@ -223,6 +223,26 @@ def train_step_bench(args, dev, frame, steps=5, warmup=3):
         l = l + 0.01 * torch.exp(-1e2 * out['off_surface_sdf']).sum() / P + 0.01 * torch.sigmoid(out['inside_sdf'] * 5e3).sum() / P
         return l + 10.0 * (out['pred_weights'][0] - wt).abs().sum(-1).mean()
 
+    if variant == 'fused':
+        # the same step with the fused criterion (arah_idhr_loss: terms + gradients in four launches, no host round trips) in place
+        # of the ~60 small torch kernels of loss_fn; run as the LAST secondary entry (first GPU run of these kernels)
+        from arah_release_b200.loss import IDHRLoss
+        crit = IDHRLoss(rgb_weight=1.0, perceptual_weight=0.0, eikonal_weight=0.1, mask_weight=1.0, off_surface_weight=0.01, inside_weight=0.01,
+                        params_weight=0.0, skinning_weight=10.0, rgb_loss_type='l1')
+        gtd = {'rgb': gt.view(1, -1, 3), 'sampled_weights': wt.view(1, -1, 24)}
+        msf = []
+        for i in range(warmup + steps):
+            for p_ in params:
+                p_.grad = None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            lf = crit(net(inp), gtd)['loss'].sum()
+            lf.backward()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                msf.append(e0.elapsed_time(e1))
+        return {'ms_per_step_fused_loss': float(np.mean(msf)), 'loss_fused': float(lf.detach())}
     ms = {'forward': [], 'backward': [], 'total': []}
     launches, samples = 0, 0
     for i in range(warmup + steps):
@@ -634,6 +654,11 @@ def run_ours(args):
             line['image_tail'] = image_tail_bench(net, f0, inputs[0])
         except Exception as ex:
             line['image_tail'] = {'error': repr(ex)[:300]}
+    if args.gpus == 1 and not args.no_train_step and isinstance(line.get('train_step'), dict) and 'error' not in line['train_step']:
+        try:
+            line['train_step'].update(train_step_bench(args, dev, f0, variant='fused'))
+        except Exception as ex:
+            line['train_step']['fused_loss_error'] = repr(ex)[:300]
     if args.gpus == 1 and not args.no_cpu_baseline:
         v, cores, n, dt, sel, o_cpu = cpu_rate(f0, args.cpu_sample_seconds)
         line['cpu_baseline'] = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',

@@ -341,6 +341,38 @@ int arah_train_sdf_backward(ArahHandle* h, int32_t slot, const float* g_sdf, con
 int arah_train_skin_forward(ArahHandle* h, const float* points, int32_t n, float* weights, void* stream);
 int arah_train_skin_backward(ArahHandle* h, const float* g_weights, const ArahTrainGrads* grads, void* stream);
 
+/* IDHRLoss.forward (im2mesh/metaavatar_render/renderer/loss.py:122-200) and its gradient in one fused pass (SURVEY.md §8 row f2,
+ * "fused loss reductions"): terms[9] (device floats) = loss, rgb_loss, perceptual_loss (always 0: LPIPS is outside this path and
+ * perceptual_weight > 0 is rejected), eikonal_loss, mask_loss, off_surface_loss, inside_loss, sdf_params_loss, skinning_loss;
+ * grads (may be NULL = forward only; NULL members are skipped) receive d loss / d input, weights included, written (not
+ * accumulated) over the full extent of each buffer.  Inputs are the step's outputs with the batch dimension dropped and cut to
+ * the first 2048 rays as the reference does (:124-127,132): rgb_values / rgb_gt [n_rays][3], network_body_mask / body_mask /
+ * off_surface_mask [n_rays] bytes (body_mask keeps its values: 0 / 1, 100 = patch border, :52-54), sdf_output [n_rays]
+ * ('sdf_output' = the rays' weight sums), grad_theta [n_eikonal][3], off_surface_sdf [n_off], inside_sdf [n_inside], pred_weights /
+ * sampled_weights [n_skin][n_joints], sdf_params = the hypernetwork's weight matrices flattened (siren_modules.py:310-314).
+ * A term whose weight is <= 0 is 0 and its inputs are not read (the reference returns torch.zeros(1) for it).  The mask term is
+ * the 2-norm of the whole off-surface difference vector over N, as torch.norm(dim=-1) of the reference's 1-D difference gives
+ * (:100-101; see csrc/arah_loss_core.h).  No host synchronisation; results are bit-reproducible (integer atomic + fixed trees).  Config / input / gradient structs are HOST structs of device pointers. */
+#define ARAH_LOSS_MAX_PARAM_TENSORS 8
+typedef struct ArahLossConfig {
+    float rgb_weight, perceptual_weight, eikonal_weight, mask_weight, off_surface_weight, inside_weight, params_weight, skinning_weight;
+    int32_t rgb_loss_type;                     /* 0 'l1', 1 'mse', 2 'smoothed_l1' (beta 0.1), loss.py:34-41 */
+} ArahLossConfig;
+typedef struct ArahLossInputs {
+    const float* rgb_values; const float* rgb_gt; const uint8_t* network_body_mask; const uint8_t* body_mask; const uint8_t* off_surface_mask;
+    const float* sdf_output; const float* grad_theta; const float* off_surface_sdf; const float* inside_sdf;
+    const float* pred_weights; const float* sampled_weights;
+    const float* sdf_params[ARAH_LOSS_MAX_PARAM_TENSORS]; int64_t sdf_params_count[ARAH_LOSS_MAX_PARAM_TENSORS];
+    int32_t n_rays, n_eikonal, n_off, n_inside, n_skin, n_joints, n_param_tensors;
+} ArahLossInputs;
+typedef struct ArahLossGrads {
+    float* rgb_values; float* sdf_output; float* grad_theta; float* off_surface_sdf; float* inside_sdf; float* pred_weights;
+    float* sdf_params[ARAH_LOSS_MAX_PARAM_TENSORS];
+} ArahLossGrads;
+size_t arah_idhr_loss_workspace(void);
+int arah_idhr_loss(const ArahLossConfig* cfg, const ArahLossInputs* in, float* terms, const ArahLossGrads* grads, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* Debug/bring-up: the training engine's strided GEMM, C[i][j] (+)= bias[j] + sum_k A[i sa_i + k sa_k] B[k sb_k + j sb_j]
  * (device pointers, element strides), mode = ARAH_TRAIN_3XTF32 / ARAH_TRAIN_TF32 (tcgen05) or ARAH_TRAIN_FP32 (SIMT). */
 int arah_debug_train_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_k,

@@ -68,7 +68,8 @@ def run_reference(c, d):
     leaves = {k: t(d[k], True) for k in ('rgb_values', 'sdf_output', 'pred_weights')}
     leaves.update({k: torch.from_numpy(d[k]).requires_grad_(True) for k in ('grad_theta', 'off_surface_sdf', 'inside_sdf')})
     params = [t(p, True) for p in d['sdf_params']]
-    mo = {'rgb_values': leaves['rgb_values'], 'sdf_output': leaves['sdf_output'].unsqueeze(-1), 'network_body_mask': t(d['network_body_mask']),
+    # 'sdf_output' is [1, P], as the renderer returns it (implicit_differentiable_renderer.py:229-237)
+    mo = {'rgb_values': leaves['rgb_values'], 'sdf_output': leaves['sdf_output'], 'network_body_mask': t(d['network_body_mask']),
           'body_mask': t(d['body_mask']), 'off_surface_mask': t(d['off_surface_mask']), 'surface_normals': None, 'grad_theta': leaves['grad_theta'],
           'off_surface_sdf': leaves['off_surface_sdf'], 'inside_sdf': leaves['inside_sdf'], 'pred_weights': leaves['pred_weights'], 'sdf_params': params}
     out = crit(mo, {'rgb': t(d['rgb_gt']), 'sampled_weights': t(d['sampled_weights'])})

@@ -41,19 +41,15 @@ def idhr_loss(cfg, inp, want_grads=True):
         t['rgb_loss'] = float((v * m[:, None]).sum() / N) if m.any() else 0.0
         g['rgb_values'] = (cfg['rgb_weight'] * dv * m[:, None] / N).astype(np.float32)
     if cfg['mask_weight'] > 0:                                                  # get_mask_loss_vol_sdf :96-105
-        # `weights_output[off] - gt` is [n,1] - [n]: torch BROADCASTS it to [n,n] (:100-101), so the reference's term for ray i is
-        # the 2-norm over ALL off-surface rays j of (w_i - gt_j) — restated literally here; the kernel gets the same numbers in
-        # O(n) from the histogram of gt values: sqrt(sum_v count_v (w_i - v)^2).  (Every shipped config sets mask_weight 0.)
+        # model_outputs['sdf_output'] is [1, P] (implicit_differentiable_renderer.py:229-237): `weights_output[off] - gt` is 1-D and
+        # torch.norm(dim=-1) is the 2-norm of the whole vector (:100-101) — one norm, not a sum over rays
         off = np.asarray(inp['off_surface_mask']).astype(bool)
         w_all = f64(inp['sdf_output']).reshape(-1)
         assert w_all.size == N, 'the reference does not cut sdf_output to 2048 rays (:143): shapes must agree'
-        D = w_all[off][:, None] - body[off].astype(np.float64)[None, :]
-        rown = np.sqrt((D * D).sum(-1))
-        t['mask_loss'] = float(rown.sum() / N)
-        gi = np.zeros(N)
-        with np.errstate(divide='ignore', invalid='ignore'):
-            gi[off] = np.where(rown > 0, D.sum(-1) / rown, 0.0)
-        g['sdf_output'] = (cfg['mask_weight'] * gi / N).astype(np.float32)
+        d = (w_all - body.astype(np.float64)) * off
+        norm = np.sqrt((d * d).sum())
+        t['mask_loss'] = float(norm / N) if off.any() else 0.0
+        g['sdf_output'] = (cfg['mask_weight'] * (d / norm if norm > 0 else 0 * d) / N).astype(np.float32)
     if cfg['eikonal_weight'] > 0:                                               # get_eikonal_loss :88-94
         gt_ = f64(inp['grad_theta']).reshape(-1, 3)
         n = np.sqrt((gt_ * gt_).sum(-1))

@@ -158,3 +158,28 @@ def test_image_tail_cameras_match_oracle():
     c, co = images.opencv_camera(Rm, Tm, K, 480, 512), io.opencv_camera(Rm, Tm, K, 480, 512)
     assert np.array_equal(np.array(c.R[:], np.float32), co['R'].reshape(9)) and np.array_equal(np.array(c.T[:], np.float32), co['T'])
     assert (c.fx, c.fy, c.px, c.py) == (float(co['fx']), float(co['fy']), float(co['px']), float(co['py']))
+
+
+def test_fused_loss_has_no_cpu_path_and_validates_arguments():
+    """arah_release_b200/loss.py: no CPU path; arah_idhr_loss rejects bad arguments before touching the device (no GPU needed)."""
+    import ctypes as C
+    from arah_release_b200 import _lib, loss
+    w = dict(rgb_weight=1.0, perceptual_weight=0.0, eikonal_weight=1.0, mask_weight=0.0, off_surface_weight=1.0, inside_weight=0.0, params_weight=0.0,
+             skinning_weight=0.0)
+    with pytest.raises(_lib.ArahError):
+        loss.IDHRLoss(**w)({'rgb_values': torch.zeros(1, 4, 3)}, {})
+    assert 'oracle' not in open(loss.__file__).read()
+    L = _lib.lib()
+    assert L.arah_idhr_loss_workspace() >= 148 * 7 * 8
+    cfg, inp = _lib.ArahLossConfig(), _lib.ArahLossInputs()
+    terms = (C.c_float * 9)()
+    ws = (C.c_char * int(L.arah_idhr_loss_workspace()))()
+    call = lambda: L.arah_idhr_loss(C.byref(cfg), C.byref(inp), C.cast(terms, C.c_void_p), None, C.cast(ws, C.c_void_p), len(ws), None)
+    assert call() != 0 and b'n_rays' in L.arah_last_error()                      # no rays
+    inp.n_rays, inp.body_mask = 4, C.cast(ws, C.c_void_p)
+    cfg.perceptual_weight = 1.0
+    assert call() != 0 and b'perceptual' in L.arah_last_error()
+    cfg.perceptual_weight, cfg.rgb_weight = 0.0, 1.0
+    assert call() != 0 and b'rgb term' in L.arah_last_error()                    # weight on, inputs missing
+    cfg.rgb_weight, cfg.rgb_loss_type = 0.0, 7
+    assert call() != 0 and b'rgb_loss_type' in L.arah_last_error()

@@ -110,6 +110,22 @@ def test_assemble_and_psnr_plumbing(fi, seed):
     assert abs(psnr - float(g['ref.psnr'])) < 1e-5 and mse > 0
 
 
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_validation_tail_equals_reference_validation_step(fi, seed):
+    """`FrameImages.validation_tail` on the very batch / model outputs the unmodified `validation_step` was run on."""
+    g = load_images_golden(seed)
+    H, W, P = int(g['H']), int(g['W']), len(g['pix'])
+    outputs = {'rgb_values': torch.from_numpy(g['rgb']).view(1, P, 3), 'points_cam': torch.from_numpy(g['points_cam']).view(1, P, 3)}
+    batch = {'inputs.img_height': torch.tensor([H]), 'inputs.img_width': torch.tensor([W]), 'inputs.image_mask': torch.from_numpy(g['mask']).view(1, -1),
+             'inputs': torch.from_numpy(g['gt']).view(1, P, 3)}
+    ev = fi.validation_tail(outputs, batch)
+    assert abs(ev['psnr'] - float(g['ref.psnr'])) <= 1e-5
+    assert ev['rgb_pred'].shape == (3, H, W)
+    assert np.array_equal(ev['rgb_pred'].permute(1, 2, 0).numpy(), g['ref.rgb_pred'])
+    assert np.array_equal(ev['rgb_gt'].permute(1, 2, 0).numpy(), g['ref.rgb_gt'])
+    assert np.abs(ev['normal_pred'].permute(1, 2, 0).numpy() - g['ref.normal_pred']).max() <= 1.2e-7
+
+
 def test_normal_maps_plumbing(fi):
     v, f = iso_mesh('torus', 20)
     H, W = 48, 64
