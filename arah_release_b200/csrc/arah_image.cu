@@ -102,24 +102,53 @@ __global__ void __launch_bounds__(BLK) k_project(const float* __restrict__ verts
     ndc[(size_t)v * 3] = o[0]; ndc[(size_t)v * 3 + 1] = o[1]; ndc[(size_t)v * 3 + 2] = o[2];
 }
 
-// one thread per face: iso-surface triangles of a 256^3 lattice cover a few pixels each at 512 x 512
+// Load + set up face f; false if it cannot be drawn (bad indices, non-finite / behind the camera / zero area) or misses the image.
+__device__ __forceinline__ bool raster_face(const float* __restrict__ ndc, const int32_t* __restrict__ faces, int f, int n_verts, int H, int W,
+                                            FaceSetup* s, int* x_lo, int* x_hi, int* y_lo, int* y_hi) {
+    const int i0 = faces[(size_t)f * 3], i1 = faces[(size_t)f * 3 + 1], i2 = faces[(size_t)f * 3 + 2];
+    if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) return false;
+    *s = face_setup(ndc + (size_t)i0 * 3, ndc + (size_t)i1 * 3, ndc + (size_t)i2 * 3);
+    if (!s->drawable) return false;
+    pixel_range(s->xmin, s->xmax, W, H, x_lo, x_hi);
+    pixel_range(s->ymin, s->ymax, H, W, y_lo, y_hi);
+    return *x_lo <= *x_hi && *y_lo <= *y_hi;
+}
+
+// One thread per face: iso-surface triangles of a 256^3 lattice cover a few pixels each at 512 x 512, so a lane sweeps its own
+// face's pixel box.  A face whose box exceeds RASTER_COOP_PIXELS is instead swept by the whole warp (lanes stride over the box;
+// every lane rebuilds the face's constants from the same global loads), so that a screen-filling triangle costs box/32 tests per
+// lane instead of serialising in one thread.  The per-pixel test and the (depth, face) key are the same in both shapes and the
+// z-buffer is an order-independent minimum: the result does not depend on which shape a face takes.
+constexpr int RASTER_COOP_PIXELS = 256;
 __global__ void __launch_bounds__(BLK) k_raster_faces(const float* __restrict__ ndc, const int32_t* __restrict__ faces, int n_faces, int n_verts,
                                                       int H, int W, unsigned long long* __restrict__ keys) {
-    const int f = blockIdx.x * BLK + threadIdx.x;
-    if (f >= n_faces) return;
-    const int i0 = faces[(size_t)f * 3], i1 = faces[(size_t)f * 3 + 1], i2 = faces[(size_t)f * 3 + 2];
-    if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) return;
-    const FaceSetup s = face_setup(ndc + (size_t)i0 * 3, ndc + (size_t)i1 * 3, ndc + (size_t)i2 * 3);
-    if (!s.drawable) return;
-    int x_lo, x_hi, y_lo, y_hi;
-    pixel_range(s.xmin, s.xmax, W, H, &x_lo, &x_hi);
-    pixel_range(s.ymin, s.ymax, H, W, &y_lo, &y_hi);
-    for (int y = y_lo; y <= y_hi; ++y) {
-        const float py = pix_to_ndc(H - 1 - y, H, W);
-        if (py < s.ymin || py > s.ymax) continue;
-        for (int x = x_lo; x <= x_hi; ++x) {
+    const int f = blockIdx.x * BLK + threadIdx.x, lane = threadIdx.x & 31;
+    FaceSetup s;
+    int x_lo = 0, x_hi = -1, y_lo = 0, y_hi = -1;
+    const bool draw = f < n_faces && raster_face(ndc, faces, f, n_verts, H, W, &s, &x_lo, &x_hi, &y_lo, &y_hi);
+    const bool big = draw && (long long)(x_hi - x_lo + 1) * (y_hi - y_lo + 1) > RASTER_COOP_PIXELS;
+    if (draw && !big)
+        for (int y = y_lo; y <= y_hi; ++y) {
+            const float py = pix_to_ndc(H - 1 - y, H, W);
+            if (py < s.ymin || py > s.ymax) continue;
+            for (int x = x_lo; x <= x_hi; ++x) {
+                float pz;
+                if (face_covers(s, pix_to_ndc(W - 1 - x, W, H), py, &pz)) atomicMin(keys + (size_t)y * W + x, raster_key(pz, f));
+            }
+        }
+    unsigned todo = __ballot_sync(0xffffffffu, big);            // every lane of the warp reaches this point
+    while (todo) {
+        const int fb = f - lane + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        FaceSetup sb;
+        int bx_lo, bx_hi, by_lo, by_hi;
+        if (!raster_face(ndc, faces, fb, n_verts, H, W, &sb, &bx_lo, &bx_hi, &by_lo, &by_hi)) continue;   // uniform across the warp
+        const int bw = bx_hi - bx_lo + 1;
+        const long long npx = (long long)bw * (by_hi - by_lo + 1);
+        for (long long i = lane; i < npx; i += 32) {
+            const int y = by_lo + (int)(i / bw), x = bx_lo + (int)(i % bw);
             float pz;
-            if (face_covers(s, pix_to_ndc(W - 1 - x, W, H), py, &pz)) atomicMin(keys + (size_t)y * W + x, raster_key(pz, f));
+            if (face_covers(sb, pix_to_ndc(W - 1 - x, W, H), pix_to_ndc(H - 1 - y, H, W), &pz)) atomicMin(keys + (size_t)y * W + x, raster_key(pz, fb));
         }
     }
 }

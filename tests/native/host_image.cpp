@@ -48,6 +48,20 @@ void host_rasterize(const float* ndc, const int32_t* faces, int n_faces, int n_v
         int x_lo, x_hi, y_lo, y_hi;
         pixel_range(s.xmin, s.xmax, W, H, &x_lo, &x_hi);
         pixel_range(s.ymin, s.ymax, H, W, &y_lo, &y_hi);
+        if (x_lo > x_hi || y_lo > y_hi) continue;
+        const int bw = x_hi - x_lo + 1;
+        const long long npx = (long long)bw * (y_hi - y_lo + 1);
+        if (npx > 256) {                                 // the kernel's warp-cooperative shape: a flat index over the pixel box
+            for (long long i = 0; i < npx; ++i) {
+                const int y = y_lo + (int)(i / bw), x = x_lo + (int)(i % bw);
+                float pz;
+                if (face_covers(s, pix_to_ndc(W - 1 - x, W, H), pix_to_ndc(H - 1 - y, H, W), &pz)) {
+                    const unsigned long long k = raster_key(pz, f);
+                    if (k < keys[(size_t)y * W + x]) keys[(size_t)y * W + x] = k;
+                }
+            }
+            continue;
+        }
         for (int y = y_lo; y <= y_hi; ++y) {
             const float py = pix_to_ndc(H - 1 - y, H, W);
             if (py < s.ymin || py > s.ymax) continue;
