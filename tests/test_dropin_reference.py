@@ -71,3 +71,31 @@ def test_reference_get_model_builds_with_our_classes(name, monkeypatch):
     fr = syn.make_frame(8, 8, seed=0)
     with pytest.raises(_lib.ArahError):
         model.idhr_network.eval()(rl.inputs_from_frame(fr, rl.sdf_network_from_frame(fr, 'cpu'), 'cpu'))
+
+
+def test_constructor_and_forward_signatures_accept_every_reference_argument():
+    """Every parameter of the reference's constructors / forwards exists in ours under the same name, in the same position and with
+    the same default (ours may append optional extras such as shade_mode)."""
+    import inspect
+    from oracle import ref_harness as rh
+    rh.install()
+    import im2mesh.metaavatar_render  # noqa: F401
+    from im2mesh.metaavatar_render.renderer.implicit_differentiable_renderer import IDHRNetwork as RefNet
+    from im2mesh.metaavatar_render.renderer.ray_tracing import BodyRayTracing as RefTracer
+    from im2mesh.metaavatar_render.renderer.loss import IDHRLoss as RefLoss
+    from arah_release_b200.loss import IDHRLoss
+    from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
+    for ref, ours, methods in ((RefNet, IDHRNetwork, ('__init__', 'forward')), (RefTracer, BodyRayTracing, ('__init__', 'forward')),
+                               (RefLoss, IDHRLoss, ('__init__', 'forward'))):
+        for meth in methods:
+            pr = list(inspect.signature(getattr(ref, meth)).parameters.values())
+            po = list(inspect.signature(getattr(ours, meth)).parameters.values())
+            kinds = {p.kind for p in po}
+            for i, p in enumerate(pr):
+                if p.kind in (inspect.Parameter.VAR_KEYWORD, inspect.Parameter.VAR_POSITIONAL):
+                    continue
+                match = [q for q in po if q.name == p.name]
+                assert match or inspect.Parameter.VAR_KEYWORD in kinds, f'{ours.__name__}.{meth} lacks the reference argument {p.name!r}'
+                if match:
+                    assert po.index(match[0]) == i, f'{ours.__name__}.{meth}: {p.name!r} at another position'
+                    assert match[0].default == p.default, f'{ours.__name__}.{meth}: default of {p.name!r} differs ({match[0].default!r} vs {p.default!r})'
