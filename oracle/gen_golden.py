@@ -27,6 +27,8 @@ CASES = {
     'h36m_n160_12x12_s4': (dict(H=12, W=12, seed=4, n_steps=160, near_samples=128, far_samples=16, cano_view_dirs=True, beta=3e-3), 0),
     # monocular configs (configs/arah-zju/ZJUMOCAP-39x-mono_4gpus.yaml:36): colour net without view directions (390 inputs)
     'mono_noview_16x16_s8': (dict(H=16, W=16, seed=8, color_mode='no_view_dir'), 0),
+    # third RenderingNetwork mode (decoder.py:104-106; no shipped config uses it): colour net without the normal (414 inputs)
+    'nonormal_16x16_s9': (dict(H=16, W=16, seed=9, color_mode='no_normal', cano_view_dirs=True), 0),
     # BASELINE configs[0]: the reference's own CPU-runnable plumbing case, a 64x64 frame.  Final outputs + per-ray tracer outputs only
     # (the per-sample stage tensors would be 4.5 MB): see FINAL_ONLY
     'zju377_64x64_s0': (dict(H=64, W=64, seed=0), 0),

@@ -31,3 +31,13 @@ def test_config0_64x64_matches_oracle():
     o = orc.render(fr)
     st = check_render(out, o, label='config0:oracle')
     print('config0 oracle', st)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'tf32'])
+def test_no_normal_colour_mode_matches_reference(mode):
+    """RenderingNetwork mode 'no_normal' (decoder.py:104-106) against the unmodified reference (tests/golden/nonormal_16x16_s9.npz)."""
+    fr, ref, meta = load_golden('nonormal_16x16_s9')
+    net, inputs = _build(fr, mode)
+    out = _render_dict(net, inputs)
+    st = check_render(out, ref, label='no_normal:' + mode, tol=dict(TOL, rgb_psnr_min=55.0) if mode == 'tf32' else TOL)
+    print('no_normal', mode, st)

@@ -66,3 +66,19 @@ def test_oracle_matches_reference_config0_64x64():
     assert abs(int(out['n_iso_evals'].sum()) - iso_ref) <= max(8, 0.05 * iso_ref)
     assert abs(int(out['n_corr_evals'].sum()) - n_pts - corr_ref) <= 0.02 * corr_ref
     print('config0', st)
+
+
+def test_oracle_matches_reference_no_normal_colour_mode():
+    """RenderingNetwork mode 'no_normal' (metaavatar_render/models/decoder.py:104-106; 414 inputs): the oracle and the product reach it
+    by inserting three zero weight columns where the 'idr' layout has the normal — exact."""
+    import torch
+    from arah_release_b200 import renderer as R, synthetic as syn
+    from oracle import oracle as orc
+    fr, ref, meta = load_golden('nonormal_16x16_s9')
+    assert fr.color_mode == 'no_normal'
+    out = orc.render(fr, threads=0)
+    print('no_normal', check_render(out, ref, label='no_normal'))
+    # the product's expansion (torch) is the oracle's (numpy), column for column
+    for mode, width in (('no_normal', 414), ('no_view_dir', 390)):
+        W = np.random.default_rng(0).normal(size=(5, width)).astype(np.float32)
+        assert np.array_equal(R._expand_color_weight(torch.from_numpy(W), mode).numpy(), syn.expand_color_weight(W, mode))
