@@ -86,6 +86,25 @@ class ArahError(RuntimeError):
     pass
 
 
+def declare_image_and_loss(L):
+    """Signatures of the image-tail and loss entry points (also applied to the CPU-emulated build of the same sources that
+    tests/test_cuda_emu.py loads — test infrastructure)."""
+    L.arah_frame_images_workspace.argtypes = [C.c_int32, C.c_int32]
+    L.arah_frame_images_workspace.restype = C.c_size_t
+    L.arah_frame_images.argtypes = [FP, FP, FP, C.c_int32, C.c_int32, C.c_int32, FP, FP, FP, C.c_size_t, C.c_void_p]
+    L.arah_psnr_workspace.argtypes = []
+    L.arah_psnr_workspace.restype = C.c_size_t
+    L.arah_psnr.argtypes = [FP, FP, C.c_int64, FP, FP, C.c_size_t, C.c_void_p]
+    L.arah_rasterize_mesh_workspace.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.arah_rasterize_mesh_workspace.restype = C.c_size_t
+    L.arah_rasterize_mesh.argtypes = [FP, C.c_int32, FP, C.c_int32, C.POINTER(ArahRasterCamera), C.c_int32, C.c_int32, FP, FP, FP, C.c_size_t, C.c_void_p]
+    L.arah_face_normal_image.argtypes = [FP, C.c_int32, FP, C.c_int32, FP, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_float), C.c_float, FP,
+                                         C.c_void_p]
+    L.arah_idhr_loss_workspace.argtypes = []
+    L.arah_idhr_loss_workspace.restype = C.c_size_t
+    L.arah_idhr_loss.argtypes = [C.POINTER(ArahLossConfig), C.POINTER(ArahLossInputs), FP, C.POINTER(ArahLossGrads), FP, C.c_size_t, C.c_void_p]
+
+
 def lib():
     """Load the CUDA library.  Raises if it has not been built (python -m arah_release_b200.build)."""
     global _lib
@@ -131,20 +150,7 @@ def lib():
     L.arah_frame_rays.argtypes = [F9, F9, F9, F3, F3, FP, C.c_int32, C.c_int32, FP, FP, FP, FP, FP, FP, FP, FP, C.c_size_t, C.c_void_p]
     L.arah_frame_rays_workspace.argtypes = [C.c_int32, C.c_int32]
     L.arah_frame_rays_workspace.restype = C.c_size_t
-    L.arah_frame_images_workspace.argtypes = [C.c_int32, C.c_int32]
-    L.arah_frame_images_workspace.restype = C.c_size_t
-    L.arah_frame_images.argtypes = [FP, FP, FP, C.c_int32, C.c_int32, C.c_int32, FP, FP, FP, C.c_size_t, C.c_void_p]
-    L.arah_psnr_workspace.argtypes = []
-    L.arah_psnr_workspace.restype = C.c_size_t
-    L.arah_psnr.argtypes = [FP, FP, C.c_int64, FP, FP, C.c_size_t, C.c_void_p]
-    L.arah_rasterize_mesh_workspace.argtypes = [C.c_int32, C.c_int32, C.c_int32]
-    L.arah_rasterize_mesh_workspace.restype = C.c_size_t
-    L.arah_rasterize_mesh.argtypes = [FP, C.c_int32, FP, C.c_int32, C.POINTER(ArahRasterCamera), C.c_int32, C.c_int32, FP, FP, FP, C.c_size_t, C.c_void_p]
-    L.arah_face_normal_image.argtypes = [FP, C.c_int32, FP, C.c_int32, FP, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_float), C.c_float, FP,
-                                         C.c_void_p]
-    L.arah_idhr_loss_workspace.argtypes = []
-    L.arah_idhr_loss_workspace.restype = C.c_size_t
-    L.arah_idhr_loss.argtypes = [C.POINTER(ArahLossConfig), C.POINTER(ArahLossInputs), FP, C.POINTER(ArahLossGrads), FP, C.c_size_t, C.c_void_p]
+    declare_image_and_loss(L)
     _lib = L
     return L
 

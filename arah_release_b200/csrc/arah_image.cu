@@ -12,7 +12,10 @@
 // All of it is HBM-bound byte / index work on a few MB per frame: one thread per ray / pixel / vertex / face, coalesced
 // accesses, the z-buffer is a 64-bit atomicMin on (depth bits, face index) keys — deterministic, lowest face index on ties.
 // The arithmetic lives in arah_image_core.h (shared with the host test harness); the kernels here only index.
+#ifndef ARAH_CUDA_EMU                      // tests/native/cuda_emu.h runs this file's source on the CPU (test infrastructure)
 #include <cuda_runtime.h>
+#define ARAH_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
 #include <stdint.h>
 #include <string>
 
@@ -206,8 +209,8 @@ extern "C" int arah_frame_images(const float* rgb, const float* points_cam, cons
     float* img_pts = pred_normals ? (float*)workspace : nullptr;
     if (pred_pixels) ICU(cudaMemsetAsync(pred_pixels, 0, n * 3 * sizeof(float), st));
     if (img_pts) ICU(cudaMemsetAsync(img_pts, 0, n * 3 * sizeof(float), st));
-    if (P > 0) k_img_scatter<<<nblk((size_t)P), BLK, 0, st>>>(rgb, points_cam, pix, P, (int)n, pred_pixels, img_pts);
-    if (pred_normals) k_img_normals<<<nblk(n), BLK, 0, st>>>(img_pts, H, W, pred_normals);
+    if (P > 0) ARAH_LAUNCH(k_img_scatter, nblk((size_t)P), BLK, st, rgb, points_cam, pix, P, (int)n, pred_pixels, img_pts);
+    if (pred_normals) ARAH_LAUNCH(k_img_normals, nblk(n), BLK, st, img_pts, H, W, pred_normals);
     ICU(cudaGetLastError());
     return ARAH_OK;
 }
@@ -221,8 +224,8 @@ extern "C" int arah_psnr(const float* pred, const float* gt, int64_t n, double* 
     cudaStream_t st = (cudaStream_t)stream;
     const size_t want = ((size_t)n + (size_t)BLK * 8 - 1) / ((size_t)BLK * 8);
     const int nb = (int)(want < 1 ? 1 : (want > (size_t)PSNR_MAX_BLOCKS ? (size_t)PSNR_MAX_BLOCKS : want));
-    k_sqdiff_partial<<<nb, BLK, 0, st>>>(pred, gt, (long long)n, (double*)workspace);
-    k_psnr_finish<<<1, BLK, 0, st>>>((const double*)workspace, nb, (long long)n, mse_psnr);
+    ARAH_LAUNCH(k_sqdiff_partial, nb, BLK, st, pred, gt, (long long)n, (double*)workspace);
+    ARAH_LAUNCH(k_psnr_finish, 1, BLK, st, (const double*)workspace, nb, (long long)n, mse_psnr);
     ICU(cudaGetLastError());
     return ARAH_OK;
 }
@@ -249,10 +252,10 @@ extern "C" int arah_rasterize_mesh(const float* verts, int32_t n_verts, const in
     c.fx = cam->fx; c.fy = cam->fy; c.px = cam->px; c.py = cam->py;
     ICU(cudaMemsetAsync(keys, 0xff, n * sizeof(unsigned long long), st));
     if (n_verts > 0 && n_faces > 0) {
-        k_project<<<nblk((size_t)n_verts), BLK, 0, st>>>(verts, n_verts, c, ndc);
-        k_raster_faces<<<nblk((size_t)n_faces), BLK, 0, st>>>(ndc, faces, n_faces, n_verts, H, W, keys);
+        ARAH_LAUNCH(k_project, nblk((size_t)n_verts), BLK, st, verts, n_verts, c, ndc);
+        ARAH_LAUNCH(k_raster_faces, nblk((size_t)n_faces), BLK, st, ndc, faces, n_faces, n_verts, H, W, keys);
     }
-    k_raster_resolve<<<nblk(n), BLK, 0, st>>>(keys, n, pix_to_face, zbuf);
+    ARAH_LAUNCH(k_raster_resolve, nblk(n), BLK, st, keys, n, pix_to_face, zbuf);
     ICU(cudaGetLastError());
     return ARAH_OK;
 }
@@ -266,7 +269,7 @@ extern "C" int arah_face_normal_image(const float* verts, int32_t n_verts, const
     r.use = rot3x3 != nullptr;
     for (int i = 0; i < 9; ++i) r.m[i] = rot3x3 ? rot3x3[i] : 0.0f;
     const size_t n = (size_t)H * W;
-    k_normal_image<<<nblk(n), BLK, 0, (cudaStream_t)stream>>>(verts, faces, n_faces, n_verts, pix_to_face, n, sign, r, background, image);
+    ARAH_LAUNCH(k_normal_image, nblk(n), BLK, (cudaStream_t)stream, verts, faces, n_faces, n_verts, pix_to_face, n, sign, r, background, image);
     ICU(cudaGetLastError());
     return ARAH_OK;
 }

@@ -12,7 +12,10 @@
 //   k_loss_grads   : the same partition writes the weighted element-wise derivatives
 // HBM-bound: every input read twice (value pass, derivative pass), every gradient written once; bit-reproducible.
 // The arithmetic is in arah_loss_core.h (shared with the host test harness).
+#ifndef ARAH_CUDA_EMU                      // tests/native/cuda_emu.h runs this file's source on the CPU (test infrastructure)
 #include <cuda_runtime.h>
+#define ARAH_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
 #include <stddef.h>
 #include <stdint.h>
 #include <string>
@@ -216,10 +219,10 @@ extern "C" int arah_idhr_loss(const ArahLossConfig* cfg, const ArahLossInputs* i
     cudaStream_t st = (cudaStream_t)stream;
     Scratch* s = (Scratch*)workspace;
     LCU(cudaMemsetAsync(s, 0, offsetof(Scratch, partial), st));
-    k_loss_pre<<<(unsigned)((in->n_rays + BLK - 1) / BLK), BLK, 0, st>>>(a, s);
-    k_loss_partial<<<NB, BLK, 0, st>>>(a, s);
-    k_loss_finish<<<1, BLK, 0, st>>>(a, s, terms);
-    if (grads) k_loss_grads<<<NB, BLK, 0, st>>>(a, s);
+    ARAH_LAUNCH(k_loss_pre, (unsigned)((in->n_rays + BLK - 1) / BLK), BLK, st, a, s);
+    ARAH_LAUNCH(k_loss_partial, NB, BLK, st, a, s);
+    ARAH_LAUNCH(k_loss_finish, 1, BLK, st, a, s, terms);
+    if (grads) ARAH_LAUNCH(k_loss_grads, NB, BLK, st, a, s);
     LCU(cudaGetLastError());
     return ARAH_OK;
 }

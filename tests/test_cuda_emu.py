@@ -1,0 +1,105 @@
+"""CPU: the SOURCE of csrc/arah_image.cu and csrc/arah_loss.cu — kernels, launch geometry and C-ABI entry points, unchanged —
+executed on a CPU model of CUDA (tests/native/cuda_emu.h: one OS thread per CUDA thread, barriers for __syncthreads and warp
+shuffles / ballots, locked atomics) and driven by the PRODUCT's Python mirrors through the product's ctypes signatures.
+
+The build container has no GPU; this is the closest available check of what nvcc compiles for the GPU box: indexing, grid sizes,
+reduction trees, the warp-cooperative rasteriser path, argument marshalling.  It says nothing about performance or the memory model;
+the GPU tests (test_gpu_zx_loss.py, test_gpu_zz_images.py) remain the parity tests proper.  Test infrastructure only.
+Bars as on the GPU: images / pix_to_face / depth bit-exact against the oracle, goldens of the unmodified reference within their
+stated tolerances."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+NATIVE = os.path.join(HERE, 'native')
+SO = os.path.join(NATIVE, 'libarah_emu.so')
+SRCS = [os.path.join(NATIVE, f) for f in ('emu_image.cpp', 'emu_loss.cpp', 'emu_support.cpp')]
+DEPS = SRCS + [os.path.join(NATIVE, 'cuda_emu.h'), os.path.join(ROOT, 'include', 'arah_b200.h')] + \
+    [os.path.join(ROOT, 'arah_release_b200', 'csrc', f) for f in ('arah_image.cu', 'arah_image_core.h', 'arah_loss.cu', 'arah_loss_core.h')]
+
+
+@pytest.fixture(scope='module')
+def emu_lib():
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in DEPS):
+        cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+        subprocess.check_call([cxx, '-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-ffp-contract=off', '-o', SO] + SRCS)
+    from arah_release_b200 import _lib
+    L = C.CDLL(SO)
+    L.arah_last_error.restype = C.c_char_p
+    _lib.declare_image_and_loss(L)
+    return L
+
+
+@pytest.fixture()
+def on_emulator(emu_lib, monkeypatch):
+    """Point the product's mirrors at the emulated library and lift the two things that need a GPU (device check, stream)."""
+    from arah_release_b200 import _lib, images, loss
+    monkeypatch.setattr(_lib, 'lib', lambda: emu_lib)
+    monkeypatch.setattr(loss.IDHRLoss, '_require_cuda', staticmethod(lambda dev: None))
+    monkeypatch.setattr(loss.IDHRLoss, '_stream', lambda self, dev: None)
+    monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+
+    class HostFrameImages(images.FrameImages):
+        def __init__(self):
+            self.device = torch.device('cpu')
+            self._ws = {}
+
+        @property
+        def _stream(self):
+            return None
+    return HostFrameImages
+
+
+def test_emulator_runs_block_reductions_and_ballots(emu_lib):
+    """Sanity of the execution model itself on the PSNR kernels: a two-stage block reduction over 9 CTAs, against numpy."""
+    rng = np.random.default_rng(0)
+    a, b = rng.random(17001).astype(np.float32), rng.random(17001).astype(np.float32)
+    out = np.zeros(2)
+    ws = np.zeros(int(emu_lib.arah_psnr_workspace()), np.uint8)
+    rc = emu_lib.arah_psnr(a.ctypes.data, b.ctypes.data, a.size, out.ctypes.data, ws.ctypes.data, ws.size, None)
+    assert rc == 0
+    d = (a - b).astype(np.float32)
+    mse = float(np.mean((d * d).astype(np.float64)))
+    assert abs(out[0] - mse) <= 1e-7 * mse and abs(out[1] + 10 * np.log10(mse)) <= 1e-5
+
+
+@pytest.mark.parametrize('seed', [0, 1])
+def test_image_tail_kernels_on_emulator(on_emulator, seed):
+    import test_gpu_zz_images as G
+    G_fi = on_emulator()
+    G.DEV, G._fi = 'cpu', (lambda: G_fi)
+    try:
+        G.test_frame_images_match_reference_validation_step(seed)
+        if seed == 0:
+            G.test_frame_images_edge_cases()
+            G.test_rasterize_degenerate_inputs()
+    finally:
+        G.DEV = 'cuda:0'
+
+
+@pytest.mark.parametrize('mesh,H,W', [('hand', 48, 64), ('torus', 40, 40)])
+def test_rasteriser_kernels_on_emulator(on_emulator, mesh, H, W):
+    """'hand': large triangles -> the warp-cooperative sweep (ballot path); 'torus': small faces -> one lane per face."""
+    import test_gpu_zz_images as G
+    G_fi = on_emulator()
+    G.DEV, G._fi = 'cpu', (lambda: G_fi)
+    try:
+        G.test_rasterize_bit_exact_against_oracle(mesh, H, W)
+    finally:
+        G.DEV = 'cuda:0'
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2, 3])
+def test_loss_kernels_on_emulator(on_emulator, seed):
+    import test_gpu_zx_loss as G
+    G.DEV = 'cpu'
+    try:
+        G.test_fused_loss_matches_reference(seed)
+    finally:
+        G.DEV = 'cuda:0'
