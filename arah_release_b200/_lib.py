@@ -77,7 +77,7 @@ EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'ar
            'arah_sdf_grid', 'arah_marching_cubes', 'arah_mc_case_table', 'arah_debug_knn', 'arah_marching_cubes_workspace',
            'arah_hyper_forward', 'arah_hyper_workspace', 'arah_pose_smpl', 'arah_frame_rays', 'arah_frame_rays_workspace',
            'arah_frame_images', 'arah_frame_images_workspace', 'arah_psnr', 'arah_psnr_workspace', 'arah_rasterize_mesh',
-           'arah_rasterize_mesh_workspace', 'arah_face_normal_image', 'arah_idhr_loss', 'arah_idhr_loss_workspace']
+           'arah_rasterize_mesh_workspace', 'arah_face_normal_image', 'arah_idhr_loss', 'arah_idhr_loss_workspace', 'arah_ssim', 'arah_ssim_workspace']
 
 _lib = None
 
@@ -100,6 +100,9 @@ def declare_image_and_loss(L):
     L.arah_rasterize_mesh.argtypes = [FP, C.c_int32, FP, C.c_int32, C.POINTER(ArahRasterCamera), C.c_int32, C.c_int32, FP, FP, FP, C.c_size_t, C.c_void_p]
     L.arah_face_normal_image.argtypes = [FP, C.c_int32, FP, C.c_int32, FP, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_float), C.c_float, FP,
                                          C.c_void_p]
+    L.arah_ssim_workspace.argtypes = []
+    L.arah_ssim_workspace.restype = C.c_size_t
+    L.arah_ssim.argtypes = [FP, FP, FP, C.c_int32, C.c_int32, FP, FP, C.c_size_t, C.c_void_p]
     L.arah_idhr_loss_workspace.argtypes = []
     L.arah_idhr_loss_workspace.restype = C.c_size_t
     L.arah_idhr_loss.argtypes = [C.POINTER(ArahLossConfig), C.POINTER(ArahLossInputs), FP, C.POINTER(ArahLossGrads), FP, C.c_size_t, C.c_void_p]

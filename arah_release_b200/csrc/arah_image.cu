@@ -4,6 +4,7 @@
 //   arah_frame_images   : masked_scatter_ of rgb / points_cam into H x W images and the finite-difference normal map of the
 //                         depth image                                  (im2mesh/metaavatar_render/lightning_model.py:176-205)
 //   arah_psnr           : mean squared error + PSNR of two float lists  (:218-221, im2mesh/utils/eval.py:6-9)
+//   arah_ssim           : SSIM of the two images inside the mask's bounding rectangle  (:222, im2mesh/utils/eval.py:11-19)
 //   arah_rasterize_mesh : nearest face per pixel of a triangle mesh seen by a pytorch3d-convention perspective camera
 //                         (MeshRasterizer, faces_per_pixel 1, blur 0: im2mesh/metaavatar_render/models/__init__.py:238-254,
 //                         265-277, 291-299; algorithm restated from pytorch3d 0.6.1, see oracle/images_oracle.py)
@@ -93,6 +94,49 @@ __global__ void __launch_bounds__(BLK) k_psnr_finish(const double* __restrict__ 
         out[0] = (double)mse;
         out[1] = -10.0 * log((double)mse) / log(10.0);
     }
+}
+
+// ------------------------------------------------------------------------------------------------ SSIM
+constexpr int SSIM_BLOCKS = 148;                       // 1 CTA per SM; the crop is not known on the host (no synchronisation)
+struct SsimScratch { int x0, x1, y0, y1; double partial[SSIM_BLOCKS]; };
+
+__global__ void k_ssim_init(SsimScratch* s) { s->x0 = 0x7fffffff; s->x1 = -1; s->y0 = 0x7fffffff; s->y1 = -1; }
+
+// cv2.boundingRect of the mask: integer atomics, order-independent
+__global__ void __launch_bounds__(BLK) k_ssim_rect(const uint8_t* __restrict__ mask, int H, int W, SsimScratch* s) {
+    const size_t i = (size_t)blockIdx.x * BLK + threadIdx.x;
+    if (i >= (size_t)H * W || mask[i] == 0) return;
+    const int y = (int)(i / W), x = (int)(i % W);
+    atomicMin(&s->x0, x); atomicMax(&s->x1, x); atomicMin(&s->y0, y); atomicMax(&s->y1, y);
+}
+
+// one item = one interior pixel of the crop x one channel; fixed grid-stride partition, fp64, fixed trees: bit-reproducible
+__global__ void __launch_bounds__(BLK) k_ssim_partial(const float* __restrict__ X, const float* __restrict__ Y, int W, SsimScratch* s) {
+    __shared__ double sh[BLK / 32];
+    const int x0 = s->x0, y0 = s->y0, iw = s->x1 - s->x0 + 1 - 2 * SSIM_PAD, ih = s->y1 - s->y0 + 1 - 2 * SSIM_PAD;
+    double acc = 0.0;
+    if (iw > 0 && ih > 0) {
+        const long long items = 3ll * iw * ih, stride = (long long)SSIM_BLOCKS * BLK;
+        for (long long i = (long long)blockIdx.x * BLK + threadIdx.x; i < items; i += stride) {
+            const int ch = (int)(i % 3);
+            const long long p = i / 3;
+            acc += ssim_pixel(X, Y, W, y0 + SSIM_PAD + (int)(p / iw), x0 + SSIM_PAD + (int)(p % iw), ch);
+        }
+    }
+    const double t = block_sum(acc, sh);
+    if (threadIdx.x == 0) s->partial[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(BLK) k_ssim_finish(const SsimScratch* s, double* __restrict__ out) {
+    __shared__ double sh[BLK / 32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < SSIM_BLOCKS; i += BLK) acc += s->partial[i];
+    const double t = block_sum(acc, sh);
+    if (threadIdx.x != 0) return;
+    const int w = s->x1 >= s->x0 ? s->x1 - s->x0 + 1 : 0, h = s->y1 >= s->y0 ? s->y1 - s->y0 + 1 : 0;
+    const long long n = 3ll * (w - 2 * SSIM_PAD) * (h - 2 * SSIM_PAD);
+    out[0] = (w >= SSIM_WIN && h >= SSIM_WIN) ? t / (double)n : nan("");      // skimage raises for a crop smaller than the window
+    out[1] = w ? s->x0 : 0; out[2] = h ? s->y0 : 0; out[3] = w; out[4] = h;
 }
 
 // ------------------------------------------------------------------------------------------------ rasteriser
@@ -226,6 +270,23 @@ extern "C" int arah_psnr(const float* pred, const float* gt, int64_t n, double* 
     const int nb = (int)(want < 1 ? 1 : (want > (size_t)PSNR_MAX_BLOCKS ? (size_t)PSNR_MAX_BLOCKS : want));
     ARAH_LAUNCH(k_sqdiff_partial, nb, BLK, st, pred, gt, (long long)n, (double*)workspace);
     ARAH_LAUNCH(k_psnr_finish, 1, BLK, st, (const double*)workspace, nb, (long long)n, mse_psnr);
+    ICU(cudaGetLastError());
+    return ARAH_OK;
+}
+
+extern "C" size_t arah_ssim_workspace(void) { return ialign(sizeof(SsimScratch)); }
+
+extern "C" int arah_ssim(const float* pred_image, const float* gt_image, const uint8_t* mask, int32_t H, int32_t W, double* out5, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    if (!pred_image || !gt_image || !mask || !out5 || !workspace) return arah_internal_fail(ARAH_EINVAL, "null argument");
+    if (bad_image(H, W)) return arah_internal_fail(ARAH_EINVAL, "bad image size");
+    if (workspace_bytes < arah_ssim_workspace()) return arah_internal_fail(ARAH_EINVAL, "workspace smaller than arah_ssim_workspace()");
+    cudaStream_t st = (cudaStream_t)stream;
+    SsimScratch* s = (SsimScratch*)workspace;
+    ARAH_LAUNCH(k_ssim_init, 1, 1, st, s);
+    ARAH_LAUNCH(k_ssim_rect, nblk((size_t)H * W), BLK, st, mask, H, W, s);
+    ARAH_LAUNCH(k_ssim_partial, SSIM_BLOCKS, BLK, st, pred_image, gt_image, W, s);
+    ARAH_LAUNCH(k_ssim_finish, 1, BLK, st, (const SsimScratch*)s, out5);
     ICU(cudaGetLastError());
     return ARAH_OK;
 }

@@ -147,4 +147,23 @@ ARAH_HD void face_normal_pixel(const float* a, const float* b, const float* c, f
     out[0] = to_unit(v[0]); out[1] = to_unit(v[1]); out[2] = to_unit(v[2]);
 }
 
+// SSIM of one channel at one pixel whose 7x7 window lies inside the image: skimage.metrics.structural_similarity with its defaults
+// as im2mesh/utils/eval.py:11-19 calls it (uniform window, sample covariance, float64 arithmetic, data_range 2 for float images,
+// K1 0.01, K2 0.03).  X, Y: [H][W][3] float32 images, (y, x) the window centre.
+constexpr int SSIM_WIN = 7, SSIM_PAD = 3;
+ARAH_HD double ssim_pixel(const float* X, const float* Y, int W, int y, int x, int ch) {
+    double sx = 0.0, sy = 0.0, sxx = 0.0, syy = 0.0, sxy = 0.0;
+    for (int dy = -SSIM_PAD; dy <= SSIM_PAD; ++dy)
+        for (int dx = -SSIM_PAD; dx <= SSIM_PAD; ++dx) {
+            const size_t i = ((size_t)(y + dy) * W + (x + dx)) * 3 + ch;
+            const double a = (double)X[i], b = (double)Y[i];
+            sx += a; sy += b; sxx += a * a; syy += b * b; sxy += a * b;
+        }
+    const double n = (double)(SSIM_WIN * SSIM_WIN), cov = n / (n - 1.0);
+    const double ux = sx / n, uy = sy / n;
+    const double vx = cov * (sxx / n - ux * ux), vy = cov * (syy / n - uy * uy), vxy = cov * (sxy / n - ux * uy);
+    const double C1 = (0.01 * 2.0) * (0.01 * 2.0), C2 = (0.03 * 2.0) * (0.03 * 2.0);
+    return ((2.0 * ux * uy + C1) * (2.0 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+}
+
 }  // namespace arah_img

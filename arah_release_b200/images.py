@@ -3,6 +3,7 @@
     fi = FrameImages(device)
     pred_pixels, pred_normals = fi.assemble(out['rgb_values'], out['points_cam'], rays['pix'], H, W)   # lightning_model.py:176-205
     mse, psnr = fi.psnr(out['rgb_values'], gt_rays)                                                     # :218-221, utils/eval.py:6-9
+    ssim = fi.ssim(pred_pixels, gt_pixels, image_mask)                                                  # :222, utils/eval.py:11-19
     maps = fi.normal_maps(verts_cano, faces, verts_posed, cam_rot, cam_trans, K)                        # models/__init__.py:226-309
     # maps: 'output_normal', 'normal_cano_front', 'normal_cano_back' — [1, H, W, 3] in [0, 1], the keys the reference adds
 
@@ -125,10 +126,33 @@ class FrameImages:
         m, p = self.psnr_device(pred, gt).tolist()                     # the one synchronisation (the reference returns a Python float)
         return m, p
 
+    def ssim_device(self, pred_pixels, gt_pixels, mask):
+        """-> float64 device tensor [5] = (ssim, x, y, w, h of the mask's bounding rectangle); no synchronisation."""
+        a = torch.as_tensor(pred_pixels, dtype=torch.float32).to(self.device).contiguous()
+        b = torch.as_tensor(gt_pixels, dtype=torch.float32).to(self.device).contiguous()
+        if a.dim() != 3 or a.shape[-1] != 3 or a.shape != b.shape:
+            raise _lib.ArahError('ssim: two [H, W, 3] images expected')
+        H, W = int(a.shape[0]), int(a.shape[1])
+        m = torch.as_tensor(mask).to(self.device).reshape(-1).to(torch.uint8).contiguous()
+        if m.numel() != H * W:
+            raise _lib.ArahError('ssim: mask size')
+        out = torch.empty(5, dtype=torch.float64, device=self.device)
+        ws = self._workspace('ssim', int(_lib.lib().arah_ssim_workspace()))
+        check(_lib.lib().arah_ssim(_ptr(a), _ptr(b), _ptr(m), H, W, _ptr(out), _ptr(ws), ws.numel(), self._stream))
+        self._keep_ssim = (a, b, m)
+        return out
+
+    def ssim(self, pred_pixels, gt_pixels, mask):
+        """`ssim_metric(pred_pixels, gt_pixels, bbox_mask)` (im2mesh/utils/eval.py:11-19) -> Python float."""
+        v = float(self.ssim_device(pred_pixels, gt_pixels, mask)[0].item())
+        if v != v:
+            raise ValueError('win_size exceeds image extent')            # what skimage raises for a crop smaller than 7 x 7
+        return v
+
     def validation_tail(self, model_outputs, batch):
         """The body of `LightningModel.validation_step` after the model call (lightning_model.py:176-229) minus SSIM / LPIPS:
         reads `batch['inputs.img_height' / 'inputs.img_width' / 'inputs.image_mask' / 'inputs']` and `model_outputs['rgb_values' /
-        'points_cam']` (or a ready 'output_normal') -> {'psnr' (float), 'rgb_pred', 'normal_pred', 'rgb_gt'} with the images
+        'points_cam']` (or a ready 'output_normal') -> {'psnr', 'ssim' (floats), 'rgb_pred', 'normal_pred', 'rgb_gt'} with the images
         channel-first [3, H, W] as the reference returns them (:225-227)."""
         H, W = int(batch['inputs.img_height'].item()), int(batch['inputs.img_width'].item())
         mask = torch.as_tensor(batch['inputs.image_mask']).to(self.device).reshape(-1)
@@ -144,7 +168,8 @@ class FrameImages:
         gt_pixels, _ = self.assemble(gt, None, pix, H, W, normals=False)
         # psnr_metric runs on the FULL ray lists, not on the [:n] slices (:218-221)
         psnr = self.psnr(model_outputs['rgb_values'].reshape(-1, 3), torch.as_tensor(batch['inputs']).reshape(-1, 3))[1]
-        return {'psnr': psnr, 'rgb_pred': pred_pixels.permute(2, 0, 1), 'normal_pred': pred_normals.permute(2, 0, 1), 'rgb_gt': gt_pixels.permute(2, 0, 1)}
+        ssim = self.ssim(pred_pixels, gt_pixels, mask)                            # :222 (LPIPS, a VGG network, stays with the caller)
+        return {'psnr': psnr, 'ssim': ssim, 'rgb_pred': pred_pixels.permute(2, 0, 1), 'normal_pred': pred_normals.permute(2, 0, 1), 'rgb_gt': gt_pixels.permute(2, 0, 1)}
 
     def rasterize(self, verts, faces, camera, H=512, W=512, zbuf=False):
         """-> pix_to_face [H,W] int32 (and zbuf [H,W] if asked)."""

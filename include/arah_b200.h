@@ -268,6 +268,13 @@ int arah_frame_images(const float* rgb, const float* points_cam, const int32_t* 
                       float* pred_normals, void* workspace, size_t workspace_bytes, void* stream);
 size_t arah_psnr_workspace(void);
 int arah_psnr(const float* pred, const float* gt, int64_t n, double* mse_psnr, void* workspace, size_t workspace_bytes, void* stream);
+/* arah_ssim (lightning_model.py:222, im2mesh/utils/eval.py:11-19): crop pred_image / gt_image [H][W][3] to cv2.boundingRect(mask [H*W]
+ *   bytes) and take skimage.metrics.structural_similarity(multichannel=True) with its defaults (uniform 7x7 window, sample covariance,
+ *   float64, data_range 2 for float images): out5[0] = SSIM (NaN if the crop is smaller than the window — skimage raises),
+ *   out5[1..4] = x, y, w, h of the rectangle; doubles on the device.  Bit-reproducible; no host synchronisation. */
+size_t arah_ssim_workspace(void);
+int arah_ssim(const float* pred_image, const float* gt_image, const uint8_t* mask, int32_t H, int32_t W, double* out5, void* workspace,
+              size_t workspace_bytes, void* stream);
 size_t arah_rasterize_mesh_workspace(int32_t n_verts, int32_t H, int32_t W);
 int arah_rasterize_mesh(const float* verts, int32_t n_verts, const int32_t* faces, int32_t n_faces, const ArahRasterCamera* cam, int32_t H,
                         int32_t W, int32_t* pix_to_face, float* zbuf, void* workspace, size_t workspace_bytes, void* stream);

@@ -210,3 +210,42 @@ def normal_maps(verts_cano, faces, verts_posed, cam_rot, cam_trans, K, H=512, W=
         p2f, _ = rasterize(project(verts_cano, fov_camera(R, T)), faces, H, W)
         out[name] = normal_image(verts_cano, faces, p2f, 1.0, None, 0.0)
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# (3) SSIM — lightning_model.py:222, im2mesh/utils/eval.py:11-19
+# --------------------------------------------------------------------------------------------------------------------
+def bounding_rect(mask):
+    """cv2.boundingRect(mask.astype(np.uint8)): (x, y, w, h) of the non-zero pixels of a 2-D mask; (0, 0, 0, 0) if there are none."""
+    ys, xs = np.nonzero(np.asarray(mask))
+    if len(ys) == 0:
+        return 0, 0, 0, 0
+    return int(xs.min()), int(ys.min()), int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1)
+
+
+def structural_similarity(X, Y, win_size=7, data_range=2.0, K1=0.01, K2=0.03):
+    """skimage.metrics.structural_similarity (0.18.1, environment.yml; ABSENT here — PARITY UNPINNED against skimage itself) for one
+    2-D channel with its defaults as the reference calls it: uniform 7x7 window, sample covariance, float64 arithmetic and — the
+    images being float32 without an explicit data_range — data_range = dtype range of float = 2.  Restated from its source with
+    the same scipy primitive (scipy.ndimage.uniform_filter, mode 'reflect'); the mean is taken over the image cropped by 3."""
+    from scipy.ndimage import uniform_filter
+    X, Y = np.asarray(X, np.float64), np.asarray(Y, np.float64)
+    if min(X.shape) < win_size:
+        raise ValueError('win_size exceeds image extent')
+    NP = win_size ** 2
+    cov_norm = NP / (NP - 1.0)
+    f = lambda a: uniform_filter(a, size=win_size)
+    ux, uy, uxx, uyy, uxy = f(X), f(Y), f(X * X), f(Y * Y), f(X * Y)
+    vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+    C1, C2 = (K1 * data_range) ** 2, (K2 * data_range) ** 2
+    S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+    pad = (win_size - 1) // 2
+    return float(S[pad:-pad, pad:-pad].mean(dtype=np.float64))
+
+
+def ssim_metric(img_pred, img_gt, mask_at_box):
+    """im2mesh/utils/eval.py:11-19: crop both [H,W,3] float32 images to the bounding rectangle of the mask, then
+    structural_similarity(multichannel=True) = mean of the per-channel values."""
+    x, y, w, h = bounding_rect(mask_at_box)
+    a, b = np.asarray(img_pred)[y:y + h, x:x + w], np.asarray(img_gt)[y:y + h, x:x + w]
+    return float(np.mean([structural_similarity(a[..., c], b[..., c]) for c in range(a.shape[-1])]))

@@ -93,6 +93,50 @@ def test_psnr_large_and_reproducible():
     assert abs(r1[1].item() + 10 * np.log10(mse64)) <= 1e-5
 
 
+def test_ssim_matches_oracle(light=False):
+    """arah_ssim against the oracle's restatement of skimage's structural_similarity (float64: 1e-10), the bounding rectangle exactly,
+    a crop smaller than the window -> ValueError like skimage.  (`light`: the subset the CPU emulator run executes.)"""
+    from oracle import images_oracle as io
+    fi = _fi()
+    rng = np.random.default_rng(4)
+    H, W = 72, 90
+    a = rng.random((H, W, 3)).astype(np.float32)
+    b = np.clip(a + 0.1 * rng.standard_normal(a.shape), 0, 1).astype(np.float32)
+    mask = np.zeros((H, W), bool)
+    mask[7:61, 11:80] = rng.random((54, 69)) < 0.6
+    mask[7, 30] = mask[60, 79] = mask[33, 11] = True
+    out = fi.ssim_device(_t(a), _t(b), _t(mask)).cpu().numpy()
+    assert tuple(int(v) for v in out[1:]) == io.bounding_rect(mask)
+    assert abs(out[0] - io.ssim_metric(a, b, mask)) <= 1e-10
+    small = np.zeros((H, W), bool); small[10:14, 10:40] = True
+    with pytest.raises(ValueError):
+        fi.ssim(_t(a), _t(b), _t(small))
+    if light:
+        return
+    assert abs(fi.ssim(_t(a), _t(a), _t(mask)) - 1.0) <= 1e-12
+    assert torch.equal(fi.ssim_device(_t(a), _t(b), _t(mask)), fi.ssim_device(_t(a), _t(b), _t(mask)))       # fixed reduction trees
+    full = np.ones((H, W), bool)
+    assert abs(fi.ssim(_t(a), _t(b), _t(full)) - io.ssim_metric(a, b, full)) <= 1e-10
+    with pytest.raises(ValueError):
+        fi.ssim(_t(a), _t(b), _t(np.zeros((H, W), bool)))
+
+
+def test_validation_tail_on_golden_batch(seed=2):
+    """`FrameImages.validation_tail` on the batch / model outputs the unmodified `validation_step` was run on."""
+    from oracle import images_oracle as io
+    fi = _fi()
+    g = load_images_golden(seed)
+    Hg, Wg, P = int(g['H']), int(g['W']), len(g['pix'])
+    outputs = {'rgb_values': _t(g['rgb']).view(1, P, 3), 'points_cam': _t(g['points_cam']).view(1, P, 3)}
+    batch = {'inputs.img_height': torch.tensor([Hg]), 'inputs.img_width': torch.tensor([Wg]), 'inputs.image_mask': _t(g['mask']).view(1, Hg, Wg),
+             'inputs': _t(g['gt']).view(1, P, 3)}
+    ev = fi.validation_tail(outputs, batch)
+    assert abs(ev['psnr'] - float(g['ref.psnr'])) <= 1e-5
+    assert abs(ev['ssim'] - io.ssim_metric(g['ref.rgb_pred'], g['ref.rgb_gt'], g['mask'])) <= 1e-10
+    assert np.array_equal(ev['rgb_pred'].permute(1, 2, 0).cpu().numpy(), g['ref.rgb_pred'])
+    assert np.abs(ev['normal_pred'].permute(1, 2, 0).cpu().numpy() - g['ref.normal_pred']).max() <= 1.2e-7
+
+
 CASES = [('hand', 48, 64), ('hand', 64, 40), ('torus', 72, 72), ('two_spheres', 64, 96), ('sphere', 33, 130)]
 
 

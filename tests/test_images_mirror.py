@@ -57,6 +57,20 @@ class ShimLib:
             o[0], o[1] = float(mse), -10.0 * np.log(float(mse)) / np.log(10.0)
         return 0
 
+    def arah_ssim_workspace(self):
+        return 4096
+
+    def arah_ssim(self, a, b, mask, H, W, out, ws, ws_bytes, stream):
+        X = np.ctypeslib.as_array(C.cast(a, FP), (H, W, 3)); Y = np.ctypeslib.as_array(C.cast(b, FP), (H, W, 3))
+        m = np.ctypeslib.as_array(C.cast(mask, C.POINTER(C.c_uint8)), (H, W))
+        o = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), (5,))
+        o[1:] = io.bounding_rect(m)
+        try:
+            o[0] = io.ssim_metric(X, Y, m)
+        except ValueError:
+            o[0] = np.nan
+        return 0
+
     def arah_rasterize_mesh_workspace(self, nv, H, W):
         return nv * 12 + 256 + H * W * 8
 

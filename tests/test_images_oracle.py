@@ -105,3 +105,36 @@ def test_normal_maps_of_a_sphere():
     # (-z in OpenCV camera coordinates), negated -> +z -> blue channel high; background -1 -> 0
     assert np.all(posed[0, 0] == 0.0)
     assert posed[32, 32, 2] > 0.95
+
+
+def test_ssim_oracle_against_brute_force_and_cv2():
+    """SSIM (skimage is absent: unpinned against it): the scipy-based restatement against a filter-free brute force, the bounding
+    rectangle against cv2.boundingRect itself, and the textbook properties (identical images -> 1, symmetric)."""
+    import cv2
+    from numpy.lib.stride_tricks import sliding_window_view as sw
+    rng = np.random.default_rng(0)
+    H, W = 40, 52
+    a = rng.random((H, W, 3)).astype(np.float32)
+    b = np.clip(a + 0.1 * rng.standard_normal(a.shape), 0, 1).astype(np.float32)
+    mask = np.zeros((H, W), bool)
+    mask[5:33, 9:47] = rng.random((28, 38)) < 0.7
+    mask[5, 20] = mask[32, 46] = mask[17, 9] = True
+    assert io.bounding_rect(mask) == tuple(cv2.boundingRect(mask.astype(np.uint8)))
+    assert io.bounding_rect(np.zeros((4, 4), bool)) == tuple(cv2.boundingRect(np.zeros((4, 4), np.uint8)))
+    x, y, w, h = io.bounding_rect(mask)
+
+    def brute(X, Y):
+        X, Y = X.astype(np.float64), Y.astype(np.float64)
+        m = lambda A: sw(A, (7, 7)).mean((-1, -2))
+        ux, uy, uxx, uyy, uxy = m(X), m(Y), m(X * X), m(Y * Y), m(X * Y)
+        cn = 49 / 48
+        vx, vy, vxy = cn * (uxx - ux * ux), cn * (uyy - uy * uy), cn * (uxy - ux * uy)
+        C1, C2 = 0.02 ** 2, 0.06 ** 2
+        return (((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))).mean()
+    ca, cb = a[y:y + h, x:x + w], b[y:y + h, x:x + w]
+    ref = float(np.mean([brute(ca[..., c], cb[..., c]) for c in range(3)]))
+    assert abs(io.ssim_metric(a, b, mask) - ref) <= 1e-12
+    assert abs(io.ssim_metric(a, a, mask) - 1.0) <= 1e-12
+    assert abs(io.ssim_metric(a, b, mask) - io.ssim_metric(b, a, mask)) <= 1e-12
+    with pytest.raises(ValueError):
+        io.ssim_metric(a, b, np.pad(np.ones((3, 9), bool), ((0, H - 3), (0, W - 9))))
