@@ -418,9 +418,12 @@ def image_tail_bench(net, frame, inp, steps=10, warmup=3, N=256):
     mesh = net.extract_canonical_mesh(inp, N=N)
     verts, faces, posed = mesh
     R, T, K = frame.pose[:3, :3], frame.pose[:3, 3], frame.K
-    ms = [[], [], []]
+    mask_img = torch.zeros(H * W, dtype=torch.uint8, device=dev)
+    mask_img[pix.long()] = 1
+    gtimg, _ = fi.assemble(gt, None, pix, H, W, normals=False)
+    ms = [[], [], [], []]
     for i in range(warmup + steps):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         e[0].record()
         pp, pn = fi.assemble(rgb, pts, pix, H, W)
         e[1].record()
@@ -428,11 +431,13 @@ def image_tail_bench(net, frame, inp, steps=10, warmup=3, N=256):
         e[2].record()
         maps = fi.normal_maps(verts, faces, posed, R, T, K, H, W)
         e[3].record()
+        ss = fi.ssim_device(pp, gtimg, mask_img)
+        e[4].record()
         torch.cuda.synchronize()
         if i >= warmup:
-            for k in range(3):
+            for k in range(4):
                 ms[k].append(e[k].elapsed_time(e[k + 1]))
-    m_img, m_psnr, m_maps = (float(np.median(x)) for x in ms)
+    m_img, m_psnr, m_maps, m_ssim = (float(np.median(x)) for x in ms)
     P, V, Fc, n = int(pix.numel()), int(verts.shape[0]), int(faces.shape[0]), H * W
     b_img = P * (12 + 12 + 4 + 24) + n * (12 + 12) + n * (12 + 12)          # rows in, scattered out, 2 clears, normals read + write
     b_psnr = 2 * 12 * P
@@ -446,11 +451,12 @@ def image_tail_bench(net, frame, inp, steps=10, warmup=3, N=256):
     ns = min(Fc, 4000)
     t = time.perf_counter(); io.rasterize(io.project(vh, io.opencv_camera(R, T, K, H, W)), fh[:ns], H, W); t_r = time.perf_counter() - t
     return {'workload': f'validation images + PSNR at {H}x{W} ({P} rays), 3 normal maps of the {N}^3 mesh ({V} verts, {Fc} faces)',
-            'ms_frame_images': m_img, 'ms_psnr': m_psnr, 'ms_normal_maps': m_maps, 'psnr_db': float(res[1].item()),
+            'ms_frame_images': m_img, 'ms_psnr': m_psnr, 'ms_normal_maps': m_maps, 'ms_ssim': m_ssim, 'psnr_db': float(res[1].item()),
+            'ssim': float(ss[0].item()),
             'frame_images_gbs': b_img / (m_img * 1e-3) / 1e9, 'psnr_gbs': b_psnr / (m_psnr * 1e-3) / 1e9, 'normal_maps_gbs': b_maps / (m_maps * 1e-3) / 1e9,
             'frac_of_hbm_peak': {'frame_images': b_img / (m_img * 1e-3) / 1e9 / pk['hbm_gbs'], 'psnr': b_psnr / (m_psnr * 1e-3) / 1e9 / pk['hbm_gbs'],
                                  'normal_maps': b_maps / (m_maps * 1e-3) / 1e9 / pk['hbm_gbs']},
-            'gpu_launches': 2 + 2 + 3 * 4, 'steps': steps, 'warmup': warmup,
+            'gpu_launches': 2 + 2 + 3 * 4 + 4, 'steps': steps, 'warmup': warmup,
             'note': 'a few MB per call: launch-latency-bound small kernels, timed through the Python mirror',
             'cpu_port': {'ms_frame_images': 1e3 * t_img, 'ms_psnr': 1e3 * t_psnr, 'ms_normal_maps_extrapolated': 1e3 * t_r * 3 * Fc / max(ns, 1),
                          'kind': 'oracle/images_oracle.py (numpy; python loop over faces)', 'sample': f'{ns} faces of one view timed, scaled to 3 views x {Fc} faces'}}
