@@ -104,3 +104,45 @@ def test_loss_kernels_on_emulator(on_emulator, monkeypatch, seed):
     import test_gpu_zx_loss as G
     monkeypatch.setattr(G, 'DEV', 'cpu')
     G.test_fused_loss_matches_reference(seed)
+
+
+def test_bench_image_tail_entry_runs_on_emulator(on_emulator, monkeypatch):
+    """bench.py::image_tail_bench end to end (its Python, the event bookkeeping, the byte accounting, the CPU-port leg) with a
+    stand-in renderer and the emulated library: a typo there would otherwise only show on the GPU box."""
+    import types
+    import bench
+    from arah_release_b200 import images
+    from helpers_images import iso_mesh, make_camera
+    H = W = 48
+    rng = np.random.default_rng(0)
+    mask = rng.random((H, W)) < 0.4
+    pix = np.flatnonzero(mask.reshape(-1))
+    P = len(pix)
+    v, f = iso_mesh('torus', 20)
+    R, T, K = make_camera(H, W)
+    T = T + np.array([0, 0, 2.6], np.float32)
+    pose = np.eye(4, dtype=np.float32); pose[:3, :3] = R; pose[:3, 3] = T
+    frame = types.SimpleNamespace(H=H, W=W, pix=pix.astype(np.int64), pose=pose, K=K)
+    out = {'rgb_values': torch.from_numpy(rng.random((1, P, 3)).astype(np.float32)), 'points_cam': torch.from_numpy(rng.random((1, P, 3)).astype(np.float32) + 2)}
+
+    class Net:
+        def __call__(self, inp):
+            return out
+
+        def extract_canonical_mesh(self, inp, N=256):
+            return torch.from_numpy(v), torch.from_numpy(f), torch.from_numpy(v + np.float32(0.01))
+
+    class Event:
+        def __init__(self, enable_timing=True):
+            pass
+
+        def record(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 1.0
+    monkeypatch.setattr(torch.cuda, 'Event', Event)
+    monkeypatch.setattr(images, 'FrameImages', lambda dev: on_emulator())
+    res = bench.image_tail_bench(Net(), frame, {}, steps=1, warmup=0, N=20)
+    assert res['ms_frame_images'] == 1.0 and res['ms_ssim'] == 1.0 and 0.0 < res['ssim'] <= 1.0 and res['psnr_db'] > 0
+    assert set(res['frac_of_hbm_peak']) == {'frame_images', 'psnr', 'normal_maps'} and res['cpu_port']['ms_frame_images'] > 0
