@@ -146,3 +146,27 @@ def test_bench_image_tail_entry_runs_on_emulator(on_emulator, monkeypatch):
     res = bench.image_tail_bench(Net(), frame, {}, steps=1, warmup=0, N=20)
     assert res['ms_frame_images'] == 1.0 and res['ms_ssim'] == 1.0 and 0.0 < res['ssim'] <= 1.0 and res['psnr_db'] > 0
     assert set(res['frac_of_hbm_peak']) == {'frame_images', 'psnr', 'normal_maps'} and res['cpu_port']['ms_frame_images'] > 0
+
+
+def test_render_normal_maps_of_the_drop_in_module_on_emulator(on_emulator, monkeypatch):
+    """`IDHRNetwork.render_normal_maps` (the `gen_cano_mesh` tail, models/__init__.py:226-309) with a given mesh: reads the reference's
+    camera keys, returns the reference's three output keys; values against the oracle."""
+    from arah_release_b200 import images, ref_layout as rl, synthetic as syn
+    from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
+    from helpers_images import iso_mesh, make_camera
+    from oracle import images_oracle as io
+    monkeypatch.setattr(images, 'FrameImages', lambda dev: on_emulator())
+    fr = syn.make_frame(8, 8, seed=0)
+    dev, rend, skin, _ = rl.modules_from_frame(fr, 'cpu')
+    net = IDHRNetwork(dev, rend, skin, BodyRayTracing(n_steps=64), cano_view_dirs=False).eval()
+    v, f = iso_mesh('two_spheres', 20)
+    posed = (v + np.float32(0.02)).astype(np.float32)
+    H, W = 40, 56
+    R, T, K = make_camera(H, W)
+    T = T + np.array([0, 0, 2.6], np.float32)
+    inp = {'cam_rot': torch.from_numpy(R).view(1, 3, 3), 'cam_trans': torch.from_numpy(T).view(1, 3), 'intrinsics': torch.from_numpy(K).view(1, 3, 3)}
+    maps = net.render_normal_maps(inp, image_size=(H, W), mesh=(torch.from_numpy(v), torch.from_numpy(f), torch.from_numpy(posed)))
+    ref = io.normal_maps(v, f, posed, R, T, K, H, W)
+    assert set(maps) == set(ref) == {'output_normal', 'normal_cano_front', 'normal_cano_back'}
+    for k in ref:
+        assert maps[k].shape == (1, H, W, 3) and np.array_equal(maps[k][0].numpy(), ref[k])
