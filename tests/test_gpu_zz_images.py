@@ -77,6 +77,32 @@ def test_frame_images_edge_cases():
         fi.psnr(torch.empty(0, device=DEV), torch.empty(0, device=DEV))
 
 
+def test_frame_images_full_size_512():
+    """BASELINE-size frame (512 x 512, ~1.3e5 bbox rays): the assembled images bit-exact against the oracle, plus size-independent
+    properties — scatter -> gather round trip, untouched background, value range, bit-identical re-runs."""
+    from oracle import images_oracle as io
+    H = W = 512
+    rng = np.random.default_rng(21)
+    yy, xx = np.mgrid[0:H, 0:W]
+    mask = ((yy - 250) / 230.0) ** 2 + ((xx - 260) / 140.0) ** 2 < 1.0
+    pix = np.flatnonzero(mask.reshape(-1)).astype(np.int32)
+    P = len(pix)
+    rgb = rng.random((P, 3)).astype(np.float32)
+    z = (3.0 + 0.3 * np.sin(xx / 17.0) * np.cos(yy / 23.0)).astype(np.float32)
+    pts = np.stack([(xx - 256) / 540.0 * z, (yy - 256) / 540.0 * z, z], -1).astype(np.float32).reshape(-1, 3)[pix]
+    pts[rng.random(P) < 0.2] = 0.0                                        # rays without a surface
+    fi = _fi()
+    pp, pn = fi.assemble(_t(rgb), _t(pts), _t(pix), H, W)
+    pp2, pn2 = fi.assemble(_t(rgb), _t(pts), _t(pix), H, W)
+    assert torch.equal(pp, pp2) and torch.equal(pn, pn2)
+    o_pp, o_pn = io.frame_images(rgb, pts, pix, H, W)
+    pp, pn = pp.cpu().numpy(), pn.cpu().numpy()
+    assert np.array_equal(pp, o_pp) and np.array_equal(pn, o_pn)
+    assert np.array_equal(pp.reshape(-1, 3)[pix], rgb)                    # round trip
+    assert not pp.reshape(-1, 3)[~mask.reshape(-1)].any()                 # background untouched
+    assert pn.min() >= 0.0 and pn.max() <= 1.0 and np.isfinite(pn).all()
+
+
 def test_psnr_large_and_reproducible():
     """786 432 floats (a 512 x 512 ray list): against float64 numpy, and bit-identical across runs (fixed reduction tree)."""
     fi = _fi()
