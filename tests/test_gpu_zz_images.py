@@ -145,6 +145,12 @@ def test_ssim_matches_oracle(light=False):
     assert abs(fi.ssim(_t(a), _t(b), _t(full)) - io.ssim_metric(a, b, full)) <= 1e-10
     with pytest.raises(ValueError):
         fi.ssim(_t(a), _t(b), _t(np.zeros((H, W), bool)))
+    # BASELINE-size images (512 x 512), an elliptic bounding-box mask
+    yy, xx = np.mgrid[0:512, 0:512]
+    big_mask = ((yy - 250) / 230.0) ** 2 + ((xx - 260) / 140.0) ** 2 < 1.0
+    A = rng.random((512, 512, 3)).astype(np.float32)
+    B = np.clip(A + 0.05 * rng.standard_normal(A.shape), 0, 1).astype(np.float32)
+    assert abs(fi.ssim(_t(A), _t(B), _t(big_mask)) - io.ssim_metric(A, B, big_mask)) <= 1e-10
 
 
 def test_validation_tail_on_golden_batch(seed=2):
