@@ -159,7 +159,7 @@ def test_normal_maps_plumbing(fi):
 
 
 @pytest.mark.parametrize('name', ['test_frame_images_edge_cases', 'test_psnr_large_and_reproducible', 'test_rasterize_degenerate_inputs',
-                                  'test_frame_images_full_size_512',
+                                  'test_frame_images_full_size_512', 'test_ssim_matches_oracle', 'test_validation_tail_on_golden_batch',
                                   'test_frame_images_match_reference_validation_step', 'test_rasterize_bit_exact_against_oracle'])
 def test_gpu_test_bodies_hold_on_the_host_shim(fi, monkeypatch, name):
     """The assertions of tests/test_gpu_zz_images.py, executed here with the device set to 'cpu' and the shim in place of the
