@@ -20,6 +20,7 @@
 #include "arah_corr_tc5.cuh"
 #include "arah_iso_init_tc.cuh"
 #include "arah_train_cuda.cuh"
+#include "arah_root.h"
 #include <stdlib.h>
 
 using namespace arah;
@@ -252,6 +253,14 @@ __global__ void __launch_bounds__(256, 1) k_umma_probe(const float* __restrict__
     if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+extern "C" int arah_debug_umma_f16(const float* A, const float* W, int32_t K, int32_t N, float* D, int32_t mode, void* stream) {
+    if (!A || !W || !D) return fail(ARAH_EINVAL, "null buffer");
+    if ((K != 64 && K != 128) || (N != 32 && N != 128 && N != 256)) return fail(ARAH_EINVAL, "K in {64,128}, N in {32,128,256}");
+    CU(root_init());
+    CU(root_probe_f16(A, W, K, N, D, mode, (cudaStream_t)stream));
+    return ARAH_OK;
+}
+
 extern "C" int arah_debug_umma_gemm(const float* A, const float* W, int32_t K, int32_t N, float* D, int32_t a_in_tmem, void* stream) {
     if (!A || !W || !D) return fail(ARAH_EINVAL, "null buffer");
     if (K <= 0 || K > 256 || (K % 32) != 0 || (N != 256 && N != 128)) return fail(ARAH_EINVAL, "K must be a multiple of 32 <= 256, N in {128,256}");
@@ -308,6 +317,8 @@ struct ArahHandle {
     int iso_init_tc = 1;       // k_iso_init_tc3: joint-search Jacobian initialisation on the tensor cores (forward mode, 4 rows per ray)
     int corr_interleave = 1;   // k_corr_tc5: the two tiles of a trip time-share the activation columns of TMEM (epilogue of one under the MMAs of the other)
     int corr_cluster = 1;      // 2-CTA clusters + weight multicast in the correspondence kernel (measured: -2 ms)
+    int corr_persist = 1;      // k_corr_persist: one persistent kernel with resident Broyden state (fp16 split precision) instead of 51 launches
+    SkinF16Dev skin16{};
     bool shade_cull_ran = false;
     int shade_cull = 1;        // exact alpha cull before the gradient / colour pass (k_alpha_cull)
     int shade_cluster = 0;     // same for shading (measured: +2 ms -- the kernel is not L2-bound; kept selectable)
@@ -354,6 +365,8 @@ static int alloc_arena(ArahHandle* h) {
     for (int l = 0; l < 5; ++l) reg(&h->tc_sdf3x[l], 8 * 256 * 32 * 2);
     for (int l = 0; l < 3; ++l) reg(&h->tc_skin_hid[l], 4 * 128 * 32 * 2);
     reg(&h->tc_skin_out, 4 * 32 * 32 * 2);
+    float *s16_hi = nullptr, *s16_lo = nullptr;
+    reg(&s16_hi, SKIN_F16_IMAGE_BYTES / 4); reg(&s16_lo, SKIN_F16_IMAGE_BYTES / 4); reg(&h->skin16.scale, 8);
     reg(&h->col_b[0], 256); reg(&h->col_b[1], 256); reg(&h->col_b[2], 256); reg(&h->col_b[3], 256); reg(&h->col_b[4], 256); reg(&h->col_b[5], 64);
     reg(&h->knn_sv, (size_t)((h->cfg.n_verts + 31) / 32) * 32 * 4); reg(&h->knn_cmin, (size_t)((h->cfg.n_verts + 31) / 32) * 4);
     reg(&h->knn_cmax, (size_t)((h->cfg.n_verts + 31) / 32) * 4);
@@ -365,6 +378,7 @@ static int alloc_arena(ArahHandle* h) {
     if (h->arena.ensure(off) != 0) return -1;
     for (auto& s : slots) *s.first = reinterpret_cast<float*>(static_cast<char*>(h->arena.p) + s.second);
     h->verts4 = reinterpret_cast<float4*>(static_cast<char*>(h->arena.p) + slots[slots.size() - 3].second);
+    h->skin16.hi = s16_hi; h->skin16.lo = s16_lo;
     return 0;
 }
 
@@ -440,6 +454,8 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_corr_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
     if (const char* e = getenv("ARAH_CORR_INTERLEAVE")) h->corr_interleave = atoi(e) != 0;
     if (const char* e = getenv("ARAH_CORR_CLUSTER")) h->corr_cluster = atoi(e) != 0;
+    if (const char* e = getenv("ARAH_CORR_PERSIST")) h->corr_persist = atoi(e) != 0;
+    CU(root_init());
     if (const char* e = getenv("ARAH_SHADE_CLUSTER")) h->shade_cluster = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_iso_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
@@ -551,6 +567,7 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
         for (int l = 1; l < 4; ++l) { k_pack_umma_x3<<<cdiv((size_t)4 * 128 * 32, 256), 256, 0, st>>>(f->skin_W[l], 128, h->tc_skin_hid[l - 1], 128, 128, 128, 4); ++npack; }
         k_pack_umma_x3<<<cdiv((size_t)4 * 32 * 32, 256), 256, 0, st>>>(f->skin_W[4], 128, h->tc_skin_out, 25, 32, 128, 4); ++npack;
         for (int l = 1; l < 6; ++l) { k_pack_umma_x3<<<cdiv((size_t)8 * 256 * 32, 256), 256, 0, st>>>(f->sdf_W[l], 256, h->tc_sdf3x[l - 1], 256, 256, 256, 8); ++npack; }
+        { long long n = 0; CU(root_pack_skin_f16(f->skin_W, h->skin16, st, &n)); npack += n; }
     }
     // pose buffers
     const cudaMemcpyKind kind = f->pose_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
@@ -692,9 +709,16 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     if (prof) CU(cudaEventRecord(h->ev[2], st));
     k_trace_finish<<<cdiv(P, 128), 128, 0, st>>>(fp, w); L();
     const unsigned g_knn_s = grid_min(cdiv(PS, 16), (size_t)nsm);
+    const bool persist = h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->corr_persist;
+    w.corr_seed = persist ? reinterpret_cast<CorrSeed*>(w.corr_state) : nullptr;
+    wk.corr_seed = w.corr_seed;
     k_knn_samples<<<g_knn_s, 512, sm_knn, st>>>(fp, h->knn, w); L();
     const unsigned g_smp_tiles = grid_min(cdiv(PS, TM), (size_t)2 * nsm);
-    if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
+    if (persist) {
+        long long n = 0;
+        CU(root_corr_persist(fp, h->skin_Wt[0], h->skin_b, h->skin16, wk, nsm, st, &n));
+        h->launches += n;
+    } else if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
         const unsigned g_tc = grid_min(cdiv(PS, UM), (size_t)nsm);
         for (int it = -1; it < BROYDEN_ITERS; ++it) {
             if (h->tc_engine >= 4 && h->corr_cluster) {

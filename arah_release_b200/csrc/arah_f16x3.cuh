@@ -1,0 +1,170 @@
+// arah_f16x3.cuh — split-precision tensor-core products on tcgen05 kind::f16 ("3xFP16"), sm_100a only.
+//
+// Root finding needs fp32-grade products (residuals resolve 1e-5 m).  Round 1 did that with 3xTF32: hi = RN_tf32(x),
+// lo = RN_tf32(x - hi), D = A_lo.B_hi + A_hi.B_lo + A_hi.B_hi — three kind::tf32 MMAs per useful one.  fp16 has the SAME
+// 11-bit significand as TF32, so the same split works with kind::f16, which issues at TWICE the TF32 rate (K = 16 per
+// instruction instead of 8), halves the weight bytes (4 B per weight for hi + lo instead of 8) and halves the TMEM columns of the
+// A operand (two K values per 32-bit column): a 128-wide activation tile is 64 + 64 columns, so TWO complete skinning tiles
+// (X_hi 64 | X_lo 64 | D 128 each) or one complete 256-wide SDF tile (X_hi 128 | X_lo 128 | D 256) fit in the 512 columns.
+// What fp16 lacks is exponent range (normal down to 6.1e-5, max 65504):
+//   * weights are pre-scaled per layer by a power of two (k_layer_scale: max |W| s in [128, 256)), the epilogue multiplies the
+//     accumulator by 1/s — exact;
+//   * activations here are sines (|x| <= 1) or softplus outputs of O(1); values below the normal range only lose RELATIVE
+//     precision, their absolute error stays <= 2^-25 = 3e-8, which is what a dot product sees.
+// Layout of one K-chunk (64 K values = one 128-byte swizzle row) of a weight image, N rows: byte offset
+//   (n / 8) * 1024 + (n % 8) * 128 + ((j ^ (n % 8)) * 16) + e * 2      for k = 64 kc + 8 j + e
+// i.e. the K-major SWIZZLE_128B canonical tile, pre-swizzled in global memory so that a chunk is one 1-D TMA bulk copy.
+// A in TMEM (.ts form): lane = row, column c of the operand holds K values 2c (low half-word) and 2c + 1 (high half-word).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "arah_tc2.cuh"
+
+namespace arah {
+
+constexpr int HK = 64;                       // K values per fp16 chunk
+
+// UMMA::InstrDescriptor for kind::f16: c_format F32 (1) @4, a/b_format F16 (0) @7/@10, K-major A and B, N>>3 @17, M>>4 @24
+__device__ __forceinline__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem], fp16 operands, fp32 accumulate; one instruction covers K = 16 (8 TMEM columns of A)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// write 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+// 32 fp32 values (K = k0 .. k0 + 31 of one row) -> 16 + 16 packed columns: hi = RN_f16(v), lo = RN_f16(v - hi)
+__device__ __forceinline__ void split_pack_f16(const float (&v)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);          // .x (low half-word) = even K
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+}
+// three-pass product of one 64-wide K-chunk: D (+)= X_lo.B_hi + X_hi.B_lo + X_hi.B_hi
+//   xh / xl: TMEM addresses of the chunk's 32 hi / lo columns; bh / bl: shared-memory addresses of the chunk's hi / lo images
+__device__ __forceinline__ void umma_f16x3_chunk(uint32_t td, uint32_t xh, uint32_t xl, uint32_t bh, uint32_t bl, uint32_t idesc, bool first) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t col = (uint32_t)(k * 8), ko = (uint32_t)(k * 32);
+        umma_f16_ts(td, xl + col, umma_smem_desc_sw128(bh + ko), idesc, (first && k == 0) ? 0u : 1u);
+        umma_f16_ts(td, xh + col, umma_smem_desc_sw128(bl + ko), idesc, 1u);
+        umma_f16_ts(td, xh + col, umma_smem_desc_sw128(bh + ko), idesc, 1u);
+    }
+}
+
+// ---- pack kernels (arah_set_frame) ----------------------------------------------------------------------------------------
+// out[0] = s = 2^e with max|W| * s in [128, 256) (1 if the layer is all zero / not finite), out[1] = 1 / s.  One block.
+__global__ void k_layer_scale(const float* __restrict__ W, int n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+        float s = 1.0f;
+        if (m > 0.f && m < 1e30f) { int ex; frexpf(m, &ex); s = ldexpf(1.0f, 8 - ex); }
+        out[0] = s; out[1] = 1.0f / s;
+    }
+}
+// src [N][src_ld] fp32 (reference layout [out][in]) -> hi / lo images, nchunks K-chunks of Npad rows (rows >= N, k >= K: zero)
+__global__ void k_pack_f16x2(const float* __restrict__ src, int src_ld, const float* __restrict__ scale, __half* __restrict__ dst_hi,
+                             __half* __restrict__ dst_lo, int N, int Npad, int K, int nchunks) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nchunks * Npad * HK) return;
+    const int kc = idx / (Npad * HK), rem = idx % (Npad * HK);
+    const int n = rem / HK, q = rem % HK, j = q >> 3, e = q & 7;
+    const int k = HK * kc + q;
+    float v = 0.f;
+    if (k < K && n < N) v = src[(size_t)n * src_ld + k] * scale[0];
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const size_t o = (size_t)kc * Npad * HK + (size_t)(n >> 3) * 512 + (n & 7) * 64 + ((j ^ (n & 7)) << 3) + e;
+    dst_hi[o] = h;
+    dst_lo[o] = l;
+}
+
+// ---- probe (tests/test_gpu_00_umma.py): D[128][N] = A[128][K] . W[N][K]^T through exactly the addressing the kernels use ----
+// mode bit 0: three-pass split product (else hi.hi only).  One CTA of 128 threads.  K in {64, 128}, N in {32, 128, 256}.
+__global__ void __launch_bounds__(128, 1) k_umma_f16_probe(const float* __restrict__ A, const __half* __restrict__ Whi, const __half* __restrict__ Wlo,
+                                                           const float* __restrict__ scale, int K, int N, float* __restrict__ D, int mode) {
+    extern __shared__ uint8_t raw_smem[];
+    const uint32_t base = (smem_u32(raw_smem) + 1023u) & ~1023u;
+    uint8_t* sm = raw_smem + (base - smem_u32(raw_smem));
+    const int nch = K / HK;
+    const uint32_t img = (uint32_t)N * HK * 2;                    // bytes per chunk image
+    uint8_t* sHi = sm;
+    uint8_t* sLo = sm + nch * img;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sLo + nch * img);   // [0] weights landed, [1] MMAs done
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(tslot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot;
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], 2u * nch * img);
+        bulk_g2s(sHi, Whi, nch * img, &bars[0]);
+        bulk_g2s(sLo, Wlo, nch * img, &bars[0]);
+    }
+    // A: row = tid; X_hi columns [0, K/2), X_lo columns [128, 128 + K/2), D columns [256, 256 + N)
+    const uint32_t trow = tbase + ((uint32_t)(32 * warp) << 16);
+    for (int c = 0; c < K / 32; ++c) {
+        float v[32];
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = A[(size_t)tid * K + 32 * c + i];
+        split_pack_f16(v, hi, lo);
+        tmem_st16(trow + 16u * c, hi);
+        tmem_st16(trow + 128u + 16u * c, lo);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        mbar_wait(&bars[0], 0);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_f16(UM, N);
+        for (int kc = 0; kc < nch; ++kc) {
+            const uint32_t bh = smem_u32(sHi) + kc * img, bl = smem_u32(sLo) + kc * img;
+            if (mode & 1) umma_f16x3_chunk(tbase + 256u, tbase + 32u * kc, tbase + 128u + 32u * kc, bh, bl, idesc, kc == 0);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_ts(tbase + 256u, tbase + 32u * kc + 8u * k, umma_smem_desc_sw128(bh + 32u * k), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+            }
+        }
+        umma_commit(&bars[1]);
+    }
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
+    const float inv = scale[1];
+    for (int b = 0; b < N / 32; ++b) {
+        float v[32];
+        tmem_ld32(trow + 256u + 32u * b, v);
+        for (int i = 0; i < 32; ++i) D[(size_t)tid * N + 32 * b + i] = v[i] * inv;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace arah

@@ -1,0 +1,68 @@
+// arah_root.cu — the persistent root-finding kernels (fp16 split-precision tensor-core engine) and their host launchers.
+#include "arah_root.h"
+
+#include "arah_corr_p.cuh"
+
+namespace arah {
+
+static inline unsigned cdiv_u(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+cudaError_t root_init() {
+    cudaError_t e = cudaFuncSetAttribute(k_corr_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_persist_smem_bytes());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_umma_f16_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * 256 * HK * 2 + 1024 + 64);
+}
+
+cudaError_t root_pack_skin_f16(const float* const W[5], const SkinF16Dev& dst, cudaStream_t st, long long* launches) {
+    __half* hi = reinterpret_cast<__half*>(dst.hi);
+    __half* lo = reinterpret_cast<__half*>(dst.lo);
+    for (int l = 1; l <= 4; ++l) {
+        const int N = (l < 4) ? 128 : 25, Npad = (l < 4) ? 128 : 32;
+        float* sc = dst.scale + 2 * (l - 1);
+        k_layer_scale<<<1, 1024, 0, st>>>(W[l], N * 128, sc);
+        const size_t off = (size_t)(l - 1) * 32768 / 2;             // halfs
+        k_pack_f16x2<<<cdiv_u((size_t)2 * Npad * HK, 256), 256, 0, st>>>(W[l], 128, sc, hi + off, lo + off, N, Npad, 128, 2);
+        if (launches) *launches += 2;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t root_corr_persist(const FrameParams& fp, const float* skin_Wt0, const float* const skin_b[5], const SkinF16Dev& img,
+                              const Work& w, int n_sms, cudaStream_t st, long long* launches) {
+    SkinF16 sk;
+    sk.Wt0 = skin_Wt0;
+    for (int l = 0; l < 5; ++l) sk.b[l] = skin_b[l];
+    sk.hi = reinterpret_cast<const __half*>(img.hi);
+    sk.lo = reinterpret_cast<const __half*>(img.lo);
+    sk.scale = img.scale;
+    const size_t PS = (size_t)w.P * w.S;
+    const unsigned g = (unsigned)((PS + 2 * UM - 1) / (2 * UM) < (size_t)n_sms ? (PS + 2 * UM - 1) / (2 * UM) : (size_t)n_sms);
+    k_corr_persist<<<g, CP_THREADS, corr_persist_smem_bytes(), st>>>(fp, sk, w);
+    const unsigned gc = (unsigned)((PS + 1023) / 1024 < (size_t)(4 * n_sms) ? (PS + 1023) / 1024 : (size_t)(4 * n_sms));
+    k_shade_compact<<<gc, 1024, 0, st>>>(w);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t root_probe_f16(const float* A, const float* W, int K, int N, float* D, int mode, cudaStream_t st) {
+    const int nch = K / HK;
+    __half* img = nullptr;
+    float* sc = nullptr;
+    cudaError_t e = cudaMalloc(&img, (size_t)2 * nch * N * HK * 2);
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&sc, 8);
+    if (e != cudaSuccess) { cudaFree(img); return e; }
+    __half* hi = img;
+    __half* lo = img + (size_t)nch * N * HK;
+    k_layer_scale<<<1, 1024, 0, st>>>(W, N * K, sc);
+    k_pack_f16x2<<<cdiv_u((size_t)nch * N * HK, 256), 256, 0, st>>>(W, K, sc, hi, lo, N, N, K, nch);
+    const int smem = 2 * nch * N * HK * 2 + 1024 + 64;
+    k_umma_f16_probe<<<1, 128, smem, st>>>(A, hi, lo, sc, K, N, D, mode);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(img);
+    cudaFree(sc);
+    return e;
+}
+
+}  // namespace arah

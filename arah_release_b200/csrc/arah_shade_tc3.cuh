@@ -31,9 +31,6 @@ __device__ __forceinline__ int seg_chunk(int order, int i) {
     if (order == 1) return (i >> 1) + ((i & 1) << 1);
     return i;
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // per-CTA parameter block: 3584 floats of first / last layer weights (+ 512 scratch) and, staged once instead of re-read from
 // L2 before every layer (a load + two CTA barriers per layer: 13 % of the SDF-only pass), the FiLM factors F, G of the six SDF

@@ -14,6 +14,9 @@ constexpr int TC_NSLOTS = 6;
 constexpr int TC_THREADS = 288;             // 8 compute warps + 1 producer warp
 
 __device__ __forceinline__ void cta_sync_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

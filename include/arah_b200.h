@@ -296,6 +296,12 @@ int arah_debug_phase_clocks(ArahHandle* h, uint64_t* out32, void* stream);
  * `.ts` MMA form); synchronises the stream. */
 int arah_debug_umma_gemm(const float* A, const float* W, int32_t K, int32_t N, float* D, int32_t a_in_tmem, void* stream);
 
+/* Debug/bring-up: the same product through the fp16 split-precision path of the persistent root-finding kernels
+ * (tcgen05 kind::f16, A in tensor memory as packed half pairs, weights as pre-scaled hi / lo chunk images;
+ * csrc/arah_f16x3.cuh).  K in {64, 128}, N in {32, 128, 256}; mode bit 0: three-pass split product
+ * (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32-grade) instead of hi.hi only; synchronises the stream. */
+int arah_debug_umma_f16(const float* A, const float* W, int32_t K, int32_t N, float* D, int32_t mode, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Training (BASELINE configs[2]; IDHRNetwork.forward with self.training == True,
  * renderer/implicit_differentiable_renderer.py:73-78,117-178,235-249, get_rbg_value_vol_sdf :261-396).
