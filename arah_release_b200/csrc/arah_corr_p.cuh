@@ -216,10 +216,12 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_corr_persist(FrameParams fp, 
         if (h == 0) {
             int it = __float_as_int(st[CS_IT * UM + r]);
             bool need = first_round;                                    // row wants a new sample
-            if (!first_round && it != CP_IDLE) {
-                float lgv[32];
+            float lgv[32];
+            if (!first_round) {                                         // warp-uniform: tcgen05.ld is a warp-collective instruction
                 tmem_ld32(tb + 128u, lgv);
                 tc_fence_before();
+            }
+            if (!first_round && it != CP_IDLE) {
                 float T12[12], g[3];
                 BroydenState<3> s;
                 {
