@@ -319,6 +319,9 @@ struct ArahHandle {
     int corr_cluster = 1;      // 2-CTA clusters + weight multicast in the correspondence kernel (measured: -2 ms)
     int corr_persist = 1;      // k_corr_persist: one persistent kernel with resident Broyden state (fp16 split precision) instead of 51 launches
     SkinF16Dev skin16{};
+    int trace_persist = 1;     // k_trace_persist: sphere tracing as one persistent kernel (1-NN + SDF per step, resident rays)
+    int iso_persist = 1;       // k_iso_persist: joint search as one persistent kernel
+    SdfF16Dev sdf16{};
     bool shade_cull_ran = false;
     int shade_cull = 1;        // exact alpha cull before the gradient / colour pass (k_alpha_cull)
     int shade_cluster = 0;     // same for shading (measured: +2 ms -- the kernel is not L2-bound; kept selectable)
@@ -367,6 +370,8 @@ static int alloc_arena(ArahHandle* h) {
     reg(&h->tc_skin_out, 4 * 32 * 32 * 2);
     float *s16_hi = nullptr, *s16_lo = nullptr;
     reg(&s16_hi, SKIN_F16_IMAGE_BYTES / 4); reg(&s16_lo, SKIN_F16_IMAGE_BYTES / 4); reg(&h->skin16.scale, 8);
+    float *d16_hi = nullptr, *d16_lo = nullptr;
+    reg(&d16_hi, SDF_F16_DEV_BYTES / 4); reg(&d16_lo, SDF_F16_DEV_BYTES / 4); reg(&h->sdf16.scale, 16);
     reg(&h->col_b[0], 256); reg(&h->col_b[1], 256); reg(&h->col_b[2], 256); reg(&h->col_b[3], 256); reg(&h->col_b[4], 256); reg(&h->col_b[5], 64);
     reg(&h->knn_sv, (size_t)((h->cfg.n_verts + 31) / 32) * 32 * 4); reg(&h->knn_cmin, (size_t)((h->cfg.n_verts + 31) / 32) * 4);
     reg(&h->knn_cmax, (size_t)((h->cfg.n_verts + 31) / 32) * 4);
@@ -379,6 +384,7 @@ static int alloc_arena(ArahHandle* h) {
     for (auto& s : slots) *s.first = reinterpret_cast<float*>(static_cast<char*>(h->arena.p) + s.second);
     h->verts4 = reinterpret_cast<float4*>(static_cast<char*>(h->arena.p) + slots[slots.size() - 3].second);
     h->skin16.hi = s16_hi; h->skin16.lo = s16_lo;
+    h->sdf16.hi = d16_hi; h->sdf16.lo = d16_lo;
     return 0;
 }
 
@@ -455,6 +461,9 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     if (const char* e = getenv("ARAH_CORR_INTERLEAVE")) h->corr_interleave = atoi(e) != 0;
     if (const char* e = getenv("ARAH_CORR_CLUSTER")) h->corr_cluster = atoi(e) != 0;
     if (const char* e = getenv("ARAH_CORR_PERSIST")) h->corr_persist = atoi(e) != 0;
+    if (const char* e = getenv("ARAH_TRACE_PERSIST")) h->trace_persist = atoi(e) != 0;
+    if (const char* e = getenv("ARAH_ISO_PERSIST")) h->iso_persist = atoi(e) != 0;
+    if (!root_trace_fits(cfg->n_verts)) h->trace_persist = 0;      // vertex index + weight ring must fit in 227 KB of shared memory
     CU(root_init());
     if (const char* e = getenv("ARAH_SHADE_CLUSTER")) h->shade_cluster = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
@@ -568,6 +577,7 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
         k_pack_umma_x3<<<cdiv((size_t)4 * 32 * 32, 256), 256, 0, st>>>(f->skin_W[4], 128, h->tc_skin_out, 25, 32, 128, 4); ++npack;
         for (int l = 1; l < 6; ++l) { k_pack_umma_x3<<<cdiv((size_t)8 * 256 * 32, 256), 256, 0, st>>>(f->sdf_W[l], 256, h->tc_sdf3x[l - 1], 256, 256, 256, 8); ++npack; }
         { long long n = 0; CU(root_pack_skin_f16(f->skin_W, h->skin16, st, &n)); npack += n; }
+        { long long n = 0; CU(root_pack_sdf_f16(f->sdf_W, h->sdf16, st, &n)); npack += n; }
     }
     // pose buffers
     const cudaMemcpyKind kind = f->pose_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
@@ -684,6 +694,15 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     k_trace_begin<<<cdiv(P, 256), 256, 0, st>>>(w); L();
     const unsigned g_ray_tiles = grid_min(cdiv(P, TM), (size_t)nsm);
     const unsigned g_knn_rays = grid_min(cdiv(P, 16), (size_t)nsm);        // >= one query per warp; idle blocks exit before staging
+    const bool tc_root = h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc;
+    SdfF16Host sh16;
+    sh16.Wt0 = h->sdf_Wt[0]; sh16.freq = h->sdf_freq; sh16.phase = h->sdf_phase; sh16.w6 = h->sdf_w6; sh16.b6 = h->sd.b6;
+    for (int l = 0; l < 6; ++l) sh16.b[l] = h->sdf_b[l];
+    if (tc_root && h->trace_persist) {
+        long long n = 0;
+        CU(root_trace_persist(fp, sh16, h->sdf16, h->knn, wk, nsm, st, &n));
+        h->launches += n;
+    } else
     for (int it = 0; it < TRACE_ITERS; ++it) {
         k_knn_rays<<<g_knn_rays, 512, sm_knn, st>>>(fp, h->knn, w, it); L();
         if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc)
@@ -699,6 +718,11 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     else
         k_iso_init<<<grid_min(cdiv(P, TM / 4), (size_t)nsm), 256, sm_sdf, st>>>(fp, w);
     L();
+    if (tc_root && h->iso_init_tc && h->iso_persist) {
+        long long n = 0;
+        CU(root_iso_persist(fp, sh16, h->sdf16, h->skin_Wt[0], h->skin_b, h->skin16, wk, nsm, st, &n));
+        h->launches += n;
+    } else
     for (int it = 0; it < BROYDEN_ITERS; ++it) {
         if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc)
             k_iso_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, h->sk, w, it);

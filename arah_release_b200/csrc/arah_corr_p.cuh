@@ -51,6 +51,63 @@ __device__ __forceinline__ bool named_sync_or(int id, int nthreads, bool pred) {
     return r != 0;
 }
 
+// ---- per-point phase helpers: the same formulas as arah_math.cuh (hierarchical_softmax, blend_T) with the MUFU forms of exp and
+// 1 / x (relative error ~2^-22, the noise floor of the split-precision MLP that produced the logits) and 128-bit loads of the bone
+// transforms; this phase sits on the critical path of a tile's iteration.
+__device__ __forceinline__ float fast_ex2(float x) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x)); return e; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.0f + fast_ex2(x * -1.4426950408889634f)); }
+__device__ __forceinline__ void fast_softmax3(const float* x, float* y) {
+    const float m = fmaxf(x[0], fmaxf(x[1], x[2]));
+    const float e0 = fast_ex2((x[0] - m) * 1.4426950408889634f), e1 = fast_ex2((x[1] - m) * 1.4426950408889634f),
+                e2 = fast_ex2((x[2] - m) * 1.4426950408889634f);
+    const float inv = fast_rcp(e0 + e1 + e2);
+    y[0] = e0 * inv; y[1] = e1 * inv; y[2] = e2 * inv;
+}
+// x: 25 logits already multiplied by 20 -> p: 24 weights (utils/utils.py:138-181)
+__device__ __forceinline__ void hierarchical_softmax_fast(const float* x, float* p) {
+    float sm[3];
+    fast_softmax3(x + 1, sm);
+    const float s0 = fast_sigmoid(x[0]);
+    p[0] = 1.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[1 + k] = p[0] * s0 * sm[k];
+    p[0] = p[0] * (1.0f - s0);
+#define ARAH_SPLITF(c, q, g) { const float s_ = fast_sigmoid(x[g]); p[c] = p[q] * s_; p[q] = p[q] * (1.0f - s_); }
+    ARAH_SPLITF(4, 1, 4) ARAH_SPLITF(5, 2, 5) ARAH_SPLITF(6, 3, 6)
+    ARAH_SPLITF(7, 4, 7) ARAH_SPLITF(8, 5, 8) ARAH_SPLITF(9, 6, 9)
+    ARAH_SPLITF(10, 7, 10) ARAH_SPLITF(11, 8, 11)
+    fast_softmax3(x + 12, sm);
+    {
+        const float s24 = fast_sigmoid(x[24]), p9 = p[9];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[12 + k] = p9 * s24 * sm[k];
+        p[9] = p9 * (1.0f - s24);
+    }
+    ARAH_SPLITF(15, 12, 15)
+    ARAH_SPLITF(16, 13, 16) ARAH_SPLITF(17, 14, 17)
+    ARAH_SPLITF(18, 16, 18) ARAH_SPLITF(19, 17, 19)
+    ARAH_SPLITF(20, 18, 20) ARAH_SPLITF(21, 19, 21)
+    ARAH_SPLITF(22, 20, 22) ARAH_SPLITF(23, 21, 23)
+#undef ARAH_SPLITF
+}
+// T12 = sum_j w_j B_j[:3,:] with B in shared memory ([24][16] floats, 16-byte aligned): same accumulation order as blend_T
+__device__ __forceinline__ void blend_T_smem(const float* w, const float* sB, float* T12) {
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const float4* B = reinterpret_cast<const float4*>(sB + j * 16);
+        const float4 b0 = B[0], b1 = B[1], b2 = B[2];
+        const float wj = w[j];
+        a0.x += wj * b0.x; a0.y += wj * b0.y; a0.z += wj * b0.z; a0.w += wj * b0.w;
+        a1.x += wj * b1.x; a1.y += wj * b1.y; a1.z += wj * b1.z; a1.w += wj * b1.w;
+        a2.x += wj * b2.x; a2.y += wj * b2.y; a2.z += wj * b2.z; a2.w += wj * b2.w;
+    }
+    T12[0] = a0.x; T12[1] = a0.y; T12[2] = a0.z; T12[3] = a0.w;
+    T12[4] = a1.x; T12[5] = a1.y; T12[6] = a1.z; T12[7] = a1.w;
+    T12[8] = a2.x; T12[9] = a2.y; T12[10] = a2.z; T12[11] = a2.w;
+}
+
 __global__ void __launch_bounds__(CP_THREADS, 1) k_corr_persist(FrameParams fp, SkinF16 sk, Work w) {
     extern __shared__ uint8_t raw_smem[];
     const int n_on = w.counters[C_ON];
@@ -73,14 +130,14 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_corr_persist(FrameParams fp, 
     uint64_t* wres = bars + 8;          // resident images landed
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 9);
     volatile int* tile_dead = reinterpret_cast<volatile int*>(tslot + 1);        // [2]
-    int* qstate = const_cast<int*>(tile_dead) + 2;                       // per tile [8]: blk_base[4], pos, nclaimed, exhausted, -
+    int* qstate = const_cast<int*>(tile_dead) + 2;                       // per tile [12]: blk_base[8], pos, nclaimed, exhausted, -
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], 8); mbar_init(&done[i], 1); }
         mbar_init(wres, 1);
         mbar_fence_init();
         tile_dead[0] = 0; tile_dead[1] = 0;
-        for (int i = 0; i < 16; ++i) qstate[i] = 0;
+        for (int i = 0; i < 24; ++i) qstate[i] = 0;
     }
     if (warp == 16) tmem_alloc(tslot, 512);
     for (int i = tid; i < 24 * 16; i += CP_THREADS) sB[i] = __ldg(fp.bone_T + i);
@@ -153,10 +210,10 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_corr_persist(FrameParams fp, 
     // ===== tile engines =====
     const int T = warp >> 3;                                            // tile of this warp
     const int q = warp & 3, h = (warp >> 2) & 1, r = 32 * q + lane;     // TMEM lane quarter, column half, row
-    const int bar_tile = 1 + T, bar_pp = 3 + T;
+    const int bar_tile = 1 + T;
     float* st = sState + T * CP_STATE_WORDS * UM;
     float (*xs)[4] = reinterpret_cast<float (*)[4]>(sXs + T * UM * 4);
-    int* qs = qstate + 8 * T;                                           // blk_base[4], pos, nclaimed, exhausted
+    int* qs = qstate + 12 * T;                                          // blk_base[8], pos, nclaimed, exhausted
     const uint32_t tb = tbase + 256u * T + ((uint32_t)(32 * q) << 16);  // this thread's TMEM row, tile base column
     uint32_t done_par = 0;
     int evals = 0;
@@ -190,26 +247,35 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_corr_persist(FrameParams fp, 
         }
         publish();
     };
-    // claim blocks of 128 on-samples until two full blocks lie ahead of the consumer position (one thread per tile)
-    auto claim_ahead = [&]() {
-        int nclaimed = qs[5];
-        const int pos = qs[4];
-        while (nclaimed * UM - pos < 3 * UM) {
+    // Work queue: blocks of 128 on-samples are claimed with one atomicAdd on a device-wide cursor by the tile's helper warp
+    // (tile-local warp 4, idle during the per-point phase) so that at least three full blocks always lie ahead of the position
+    // the row warps consume from; the seeds of a claimed block are prefetched into L2.  Claims made during a phase are
+    // published by the tile barrier that ends it.  blk ring: 8 slots, at most 6 blocks are alive at a time.
+    auto claim_ahead = [&]() {                          // all 32 lanes of the helper warp
+        int nclaimed = qs[9];
+        const int pos = *reinterpret_cast<volatile int*>(&qs[8]);
+        while (nclaimed * UM - pos < 5 * UM) {
             int b = -1;
-            if (!qs[6]) {
+            if (lane == 0 && !qs[10]) {
                 b = atomicAdd(&w.counters[C_CORR_CURSOR], UM);
-                if (b >= n_on) { b = -1; qs[6] = 1; }
+                if (b >= n_on) { b = -1; qs[10] = 1; }
             }
-            qs[nclaimed & 3] = b;
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= 0) {
+                const char* p0 = reinterpret_cast<const char*>(w.corr_seed + b);
+                for (int l = lane; l < (int)(UM * sizeof(CorrSeed) / 128); l += 32)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (size_t)l * 128));
+            }
+            if (lane == 0) qs[nclaimed & 7] = b;
             ++nclaimed;
         }
-        qs[5] = nclaimed;
+        if (lane == 0) qs[9] = nclaimed;
+        __syncwarp();
     };
     // ---- start: every row is idle and asks for a sample
-    if (h == 0) {
-        st[CS_IT * UM + r] = __int_as_float(CP_IDLE);
-        if (r == 0) claim_ahead();
-    }
+    if (h == 0) st[CS_IT * UM + r] = __int_as_float(CP_IDLE);
+    if (h == 1 && q == 0) claim_ahead();
+    named_sync(bar_tile, 2 * UM);
     bool first_round = true;
     while (true) {
         // =================== per-point phase (the 128 threads with h == 0 own one row each) ===================
@@ -229,8 +295,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_corr_persist(FrameParams fp, 
                     const float inv4 = sInv[3];
 #pragma unroll
                     for (int k = 0; k < 25; ++k) lg[k] = fmaf(lgv[k], inv4, sb[512 + k]) * 20.0f;
-                    hierarchical_softmax(lg, wj);
-                    blend_T(wj, sB, T12, nullptr);
+                    hierarchical_softmax_fast(lg, wj);
+                    blend_T_smem(wj, sB, T12);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) s.x[k] = st[(CS_X + k) * UM + r];
                     apply_T(T12, s.x, xb);
@@ -297,17 +363,15 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_corr_persist(FrameParams fp, 
                     need = true;
                 }
             }
-            if (r == 0) claim_ahead();
-            named_sync(bar_pp, UM);                                      // claimed blocks visible to the tile's four row warps
             // ---- re-fill the rows that finished
             {
                 const unsigned m = __ballot_sync(0xffffffffu, need);
                 int p0 = 0;
-                if (m && lane == (__ffs(m) - 1)) p0 = atomicAdd(&qs[4], __popc(m));
+                if (m && lane == (__ffs(m) - 1)) p0 = atomicAdd(&qs[8], __popc(m));
                 p0 = __shfl_sync(0xffffffffu, p0, m ? (__ffs(m) - 1) : 0);
                 if (need) {
                     const int p = p0 + __popc(m & ((1u << lane) - 1u));
-                    const int bb = qs[(p >> 7) & 3];
+                    const int bb = qs[(p >> 7) & 7];
                     const int idx = bb + (p & (UM - 1));
                     if (bb >= 0 && idx < n_on) {
                         const float4* sp = reinterpret_cast<const float4*>(w.corr_seed + idx);
@@ -331,6 +395,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_corr_persist(FrameParams fp, 
                 }
             }
         }
+        else if (q == 0) claim_ahead();                                  // helper warp: keep the block queue ahead
         first_round = false;
         pc.mark(5);
         // a tile lives while any of its rows has work (also publishes xs to the h == 1 warps)

@@ -2,6 +2,8 @@
 #include "arah_root.h"
 
 #include "arah_corr_p.cuh"
+#include "arah_iso_p.cuh"
+#include "arah_trace_p.cuh"
 
 namespace arah {
 
@@ -10,7 +12,62 @@ static inline unsigned cdiv_u(size_t a, size_t b) { return (unsigned)((a + b - 1
 cudaError_t root_init() {
     cudaError_t e = cudaFuncSetAttribute(k_corr_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_persist_smem_bytes());
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_iso_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso_persist_smem_bytes());
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_umma_f16_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * 256 * HK * 2 + 1024 + 64);
+}
+
+constexpr size_t MAX_DYN_SMEM = 232448;        // 227 KB per CTA on sm_100
+bool root_trace_fits(int n_verts) { return trace_persist_smem_bytes(n_verts) <= MAX_DYN_SMEM; }
+
+cudaError_t root_pack_sdf_f16(const float* const W[7], const SdfF16Dev& dst, cudaStream_t st, long long* launches) {
+    __half* hi = reinterpret_cast<__half*>(dst.hi);
+    __half* lo = reinterpret_cast<__half*>(dst.lo);
+    for (int l = 1; l <= 5; ++l) {
+        float* sc = dst.scale + 2 * (l - 1);
+        k_layer_scale<<<1, 1024, 0, st>>>(W[l], 256 * 256, sc);
+        const size_t off = (size_t)(l - 1) * 131072 / 2;            // halfs
+        k_pack_f16x2<<<cdiv_u((size_t)4 * 256 * HK, 256), 256, 0, st>>>(W[l], 256, sc, hi + off, lo + off, 256, 256, 256, 4);
+        if (launches) *launches += 2;
+    }
+    return cudaGetLastError();
+}
+
+static SdfF16 make_sdf16(const SdfF16Host& sh, const SdfF16Dev& img) {
+    SdfF16 sd;
+    sd.Wt0 = sh.Wt0; sd.freq = sh.freq; sd.phase = sh.phase; sd.w6 = sh.w6; sd.b6 = sh.b6;
+    for (int l = 0; l < 6; ++l) sd.b[l] = sh.b[l];
+    sd.hi = reinterpret_cast<const __half*>(img.hi); sd.lo = reinterpret_cast<const __half*>(img.lo); sd.scale = img.scale;
+    return sd;
+}
+
+cudaError_t root_trace_persist(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const KnnIndex& ix, const Work& w, int n_sms,
+                               cudaStream_t st, long long* launches) {
+    static int attr_for = -1;
+    const size_t smem = trace_persist_smem_bytes(fp.n_verts);
+    if (attr_for != (int)smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_trace_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_for = (int)smem;
+    }
+    const size_t tiles = ((size_t)w.P + UM - 1) / UM;
+    const unsigned g = (unsigned)(tiles < (size_t)n_sms ? tiles : (size_t)n_sms);
+    k_trace_persist<<<g, S16_THREADS, smem, st>>>(fp, make_sdf16(sh, img), ix, w);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t root_iso_persist(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const float* skin_Wt0, const float* const skin_b[5],
+                             const SkinF16Dev& skimg, const Work& w, int n_sms, cudaStream_t st, long long* launches) {
+    SkinF16 sk;
+    sk.Wt0 = skin_Wt0;
+    for (int l = 0; l < 5; ++l) sk.b[l] = skin_b[l];
+    sk.hi = reinterpret_cast<const __half*>(skimg.hi); sk.lo = reinterpret_cast<const __half*>(skimg.lo); sk.scale = skimg.scale;
+    const size_t tiles = ((size_t)w.P + UM - 1) / UM;
+    const unsigned g = (unsigned)(tiles < (size_t)n_sms ? tiles : (size_t)n_sms);
+    k_iso_persist<<<g, S16_THREADS, iso_persist_smem_bytes(), st>>>(fp, make_sdf16(sh, img), sk, w);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
 }
 
 cudaError_t root_pack_skin_f16(const float* const W[5], const SkinF16Dev& dst, cudaStream_t st, long long* launches) {

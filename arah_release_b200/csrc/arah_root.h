@@ -17,6 +17,24 @@ struct SkinF16Dev {
 };
 constexpr size_t SKIN_F16_IMAGE_BYTES = 3 * 32768 + 8192;
 
+// device images of the SDF hidden layers for the fp16 split-precision engine (arah_sdf16.cuh)
+struct SdfF16Dev {
+    void* hi;        // 5 x 128 KB
+    void* lo;
+    float* scale;    // [5][2]
+};
+constexpr size_t SDF_F16_DEV_BYTES = 5 * 131072;
+struct SdfF16Host {  // what the kernels need besides the images (device pointers into the frame arena)
+    const float* Wt0; const float* b[6]; const float* freq; const float* phase; const float* w6; float b6;
+};
+cudaError_t root_pack_sdf_f16(const float* const W[7], const SdfF16Dev& dst, cudaStream_t st, long long* launches);
+// sphere tracing of the rays listed in w.listA (k_trace_begin), persistent; false if the vertex index does not fit in shared memory
+bool root_trace_fits(int n_verts);
+cudaError_t root_trace_persist(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const KnnIndex& ix, const Work& w, int n_sms,
+                               cudaStream_t st, long long* launches);
+// joint search of the rays listed in w.listA (k_iso_prepare) whose state k_iso_init_tc3 has written, persistent
+cudaError_t root_iso_persist(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const float* skin_Wt0, const float* const skin_b[5],
+                             const SkinF16Dev& skimg, const Work& w, int n_sms, cudaStream_t st, long long* launches);
 // pack layers 1..4 of the skinning MLP (reference layout [out][in], fp32) into scaled fp16 hi / lo chunk images
 cudaError_t root_pack_skin_f16(const float* const W[5], const SkinF16Dev& dst, cudaStream_t st, long long* launches);
 // correspondence search of all on-samples (seeds in w.corr_seed) + the list of converged samples

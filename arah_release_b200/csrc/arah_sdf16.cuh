@@ -61,6 +61,13 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     return done != 0;
 }
 
+__device__ __forceinline__ bool cta_or_compute(bool pred) {                      // barrier 1 over the 256 compute threads + OR
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 1, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"((uint32_t)pred) : "memory");
+    return r != 0;
+}
+
 // ---- producer (one thread): ring position + what is still in flight -------------------------------------------------------
 struct S16Prod {
     uint32_t slot = 0, use = 0, issued = 0;
@@ -141,7 +148,7 @@ __device__ __forceinline__ void s16_ldg32(const float* __restrict__ p, float (&v
 // works on the 128 columns of its half h.  Returns this thread's partial of w6 . h5 (caller adds the two halves and b6).
 // inv5: 1 / scale of layers 1..5 (shared or global memory).
 __device__ __forceinline__ float s16_compute_sdf(const SdfF16& sd, float x, float y, float z, S16Ctl* c, uint32_t& done_par, uint32_t tbase,
-                                                 const float* inv5) {
+                                                 const float* inv5, PhaseClk* pc = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, h = (warp >> 2) & 1;
     const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
@@ -162,7 +169,7 @@ __device__ __forceinline__ float s16_compute_sdf(const SdfF16& sd, float x, floa
             const int j = 2 * h + jj;
             uint32_t hi0[16], lo0[16];
             float v[32];
-#pragma unroll 1
+#pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 const int col0 = 64 * j + 32 * hf;
                 float w0[32], w1[32], w2[32], pf[32], pb[32], pp[32];
@@ -178,6 +185,7 @@ __device__ __forceinline__ float s16_compute_sdf(const SdfF16& sd, float x, floa
             put(0, j, hi0, lo0, v);
         }
     }
+    if (pc) pc->mark(1);
     float dot = 0.f;
 #pragma unroll 1
     for (int L = 1; L <= 5; ++L) {
@@ -185,6 +193,7 @@ __device__ __forceinline__ float s16_compute_sdf(const SdfF16& sd, float x, floa
         done_par ^= 1u;
         __syncwarp();
         tc_fence_after();
+        if (pc) pc->mark(2);
         const int dreg = L & 1;
         const float inv = inv5[L - 1];
 #pragma unroll 1
@@ -192,7 +201,7 @@ __device__ __forceinline__ float s16_compute_sdf(const SdfF16& sd, float x, floa
             const int j = 2 * h + jj;
             uint32_t hi0[16], lo0[16];
             float v[32];
-#pragma unroll 1
+#pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 const int col0 = 64 * j + 32 * hf;
                 float pf[32], pb[32], pp[32];
@@ -210,6 +219,7 @@ __device__ __forceinline__ float s16_compute_sdf(const SdfF16& sd, float x, floa
             if (L < 5) put(dreg, j, hi0, lo0, v);          // in place: both halves of the chunk's accumulators have been read
         }
         if (L == 5) tc_fence_before();
+        if (pc) pc->mark(3);
     }
     return dot;
 }

@@ -21,13 +21,6 @@ __host__ __device__ constexpr size_t trace_persist_smem_bytes(int n_verts) {
     return (size_t)S16_NSLOTS * S16_SLOT_BYTES + knn_smem_bytes(n_verts) + (size_t)(TR_WORDS * UM + 2 * UM + 8) * 4 + sizeof(S16Ctl) + 64;
 }
 
-__device__ __forceinline__ bool cta_or_compute(bool pred) {                      // barrier 1 over the 256 compute threads + OR
-    uint32_t r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 1, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(r) : "r"((uint32_t)pred) : "memory");
-    return r != 0;
-}
-
 __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp, SdfF16 sd, KnnIndex ix, Work w) {
     extern __shared__ __align__(1024) uint8_t raw_smem[];
     const int n = w.counters[C_TRACE];                      // rays with near < far (k_trace_begin), listed in w.listA
@@ -117,6 +110,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
     bool live = cta_or_compute(tid < UM && __float_as_int(st[TR_RAY * UM + tid]) >= 0);
     if (tid == 0) { ctl->cont[0] = live ? 1 : 0; if (!live) ctl->stop = 1; __threadfence_block(); mbar_arrive(&ctl->go); }
     uint32_t e = 0;
+    PhaseClk pc; pc.start((tid == 32 && w.phase_clk) ? w.phase_clk + 16 : nullptr);      // [0] 1-NN, [1] layer 0, [2] MMA wait, [3] epilogues, [4] marching
     while (live) {
         // ---- nearest posed vertex + inverse NN skinning of the 16 rows of this warp (rows 16 warp .. 16 warp + 15)
         {
@@ -154,8 +148,9 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
             }
         }
         cta_sync_compute();
+        pc.mark(0);
         // ---- SDF of the 128 canonical points
-        const float dot = s16_compute_sdf(sd, st[TR_XN * UM + r], st[(TR_XN + 1) * UM + r], st[(TR_XN + 2) * UM + r], ctl, done_par, tbase, sInv);
+        const float dot = s16_compute_sdf(sd, st[TR_XN * UM + r], st[(TR_XN + 1) * UM + r], st[(TR_XN + 2) * UM + r], ctl, done_par, tbase, sInv, &pc);
         part[h][r] = dot;
         cta_sync_compute();
         // ---- marching logic (ray_tracing.py:228-241), one thread per row
@@ -190,6 +185,8 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
             row_live = __float_as_int(st[TR_RAY * UM + tid]) >= 0;
         }
         live = cta_or_compute(row_live);
+        pc.mark(4);
+        if (pc.dst) atomicAdd(pc.dst + 5, 1ull);                         // evaluations of this CTA
         ++e;
         if (tid == 0) { ctl->cont[e & 1u] = live ? 1 : 0; if (!live) ctl->stop = 1; __threadfence_block(); mbar_arrive(&ctl->go); }
     }

@@ -628,7 +628,7 @@ def run_ours(args):
                           'frac': (sum(corr_flops) / max(sum(corr_ms), 1e-9)) / 1e9 / pk['tf_sustained'], 'ms_per_step': float(np.mean(corr_ms)),
                           'share_of_step': float(sum(corr_ms) / (1e3 * t_dev))},
         'stages_ms_last_step': {k: stats_last[k] for k in ('ms_trace', 'ms_iso', 'ms_sample_corr', 'ms_shade', 'ms_composite', 'ms_total')},
-        'phase_cycles_last_step': {'corr': phase_clk[:6], 'shade': phase_clk[8:15], 'trace': phase_clk[16:21],
+        'phase_cycles_last_step': {'corr': phase_clk[:6], 'shade': phase_clk[8:15], 'trace': phase_clk[16:22],
                                    'note': 'SM cycles of one thread per CTA summed over CTAs/launches: corr = [gather, layer0, mma_wait, epilogue, out_layer, per_point]; '
                                            'shade = [setup+layer0, fwd_wait, fwd_epi, rev_wait, rev_epi, colour_inputs, colour_mlp]'},
         'counters_last_step': {k: stats_last[k] for k in ('rays', 'trace_sdf_evals', 'iso_rays', 'iso_g_evals', 'on_samples', 'corr_skin_evals',
