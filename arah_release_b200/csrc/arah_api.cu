@@ -322,6 +322,7 @@ struct ArahHandle {
     int trace_persist = 1;     // k_trace_persist: sphere tracing as one persistent kernel (1-NN + SDF per step, resident rays)
     int iso_persist = 1;       // k_iso_persist: joint search as one persistent kernel
     SdfF16Dev sdf16{};
+    int sdf_fwd16 = 1;         // k_sdf_fwd16: the SDF value compositing uses comes from a single-pass fp16 kernel over all converged samples
     bool shade_cull_ran = false;
     int shade_cull = 1;        // exact alpha cull before the gradient / colour pass (k_alpha_cull)
     int shade_cluster = 0;     // same for shading (measured: +2 ms -- the kernel is not L2-bound; kept selectable)
@@ -463,6 +464,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     if (const char* e = getenv("ARAH_CORR_PERSIST")) h->corr_persist = atoi(e) != 0;
     if (const char* e = getenv("ARAH_TRACE_PERSIST")) h->trace_persist = atoi(e) != 0;
     if (const char* e = getenv("ARAH_ISO_PERSIST")) h->iso_persist = atoi(e) != 0;
+    if (const char* e = getenv("ARAH_SDF_FWD16")) h->sdf_fwd16 = atoi(e) != 0;
     if (!root_trace_fits(cfg->n_verts)) h->trace_persist = 0;      // vertex index + weight ring must fit in 227 KB of shared memory
     CU(root_init());
     if (const char* e = getenv("ARAH_SHADE_CLUSTER")) h->shade_cluster = atoi(e) != 0;
@@ -782,9 +784,18 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
         else if (h->tc_engine >= 3) {
             const unsigned g = grid_min(cdiv(PS, UM), (size_t)nsm);
             h->shade_cull_ran = h->shade_cull != 0;
+            const bool fwd16 = h->sdf_fwd16 && h->cfg.root_mode == ARAH_ROOT_3XTF32;     // (the fp16 images are packed with the root engine's)
+            wk.shade_keep_sdf = fwd16 ? 1 : 0;
+            if (fwd16) {
+                // the SDF value of every converged sample (what compositing turns into sigma) in one fp16 single-pass sweep; the
+                // full pass below then only supplies colours, with or without the cull: both settings composite identical inputs
+                long long n = 0;
+                CU(root_sdf_fwd16(fp, sh16, h->sdf16, wk, nsm, st, &n));
+                h->launches += n;
+            }
             if (h->shade_cull) {
                 // exact alpha cull: SDF-only pass over all converged samples, alpha test, full shading of the survivors
-                k_shade_tc3<true><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk); L();
+                if (!fwd16) { k_shade_tc3<true><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk); L(); }
                 k_alpha_cull<<<cdiv(P, COMP_WARPS), 32 * COMP_WARPS, 0, st>>>(fp, w, w.listA); L();
                 Work w2 = wk;
                 w2.shade_list = w.listA; w2.shade_ctr = C_SHADE2;

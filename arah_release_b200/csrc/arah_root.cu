@@ -4,6 +4,7 @@
 #include "arah_corr_p.cuh"
 #include "arah_iso_p.cuh"
 #include "arah_trace_p.cuh"
+#include "arah_sdf_fwd16.cuh"
 
 namespace arah {
 
@@ -11,6 +12,8 @@ static inline unsigned cdiv_u(size_t a, size_t b) { return (unsigned)((a + b - 1
 
 cudaError_t root_init() {
     cudaError_t e = cudaFuncSetAttribute(k_corr_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_persist_smem_bytes());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sdf_fwd16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sdf_fwd16_smem_bytes());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_iso_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso_persist_smem_bytes());
     if (e != cudaSuccess) return e;
@@ -53,6 +56,15 @@ cudaError_t root_trace_persist(const FrameParams& fp, const SdfF16Host& sh, cons
     const size_t tiles = ((size_t)w.P + UM - 1) / UM;
     const unsigned g = (unsigned)(tiles < (size_t)n_sms ? tiles : (size_t)n_sms);
     k_trace_persist<<<g, S16_THREADS, smem, st>>>(fp, make_sdf16(sh, img), ix, w);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t root_sdf_fwd16(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const Work& w, int n_sms, cudaStream_t st,
+                           long long* launches) {
+    const size_t tiles = ((size_t)w.P * w.S + UM - 1) / UM;
+    const unsigned g = (unsigned)(tiles < (size_t)n_sms ? tiles : (size_t)n_sms);
+    k_sdf_fwd16<<<g, F16_THREADS, sdf_fwd16_smem_bytes(), st>>>(fp, make_sdf16(sh, img), w);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

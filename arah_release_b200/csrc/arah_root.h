@@ -32,6 +32,9 @@ cudaError_t root_pack_sdf_f16(const float* const W[7], const SdfF16Dev& dst, cud
 bool root_trace_fits(int n_verts);
 cudaError_t root_trace_persist(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const KnnIndex& ix, const Work& w, int n_sms,
                                cudaStream_t st, long long* launches);
+// SDF value (metres) of every sample of w.shade_list -> w.smp_sdf, single-pass fp16 tensor-core tiles (arah_sdf_fwd16.cuh)
+cudaError_t root_sdf_fwd16(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const Work& w, int n_sms, cudaStream_t st,
+                           long long* launches);
 // joint search of the rays listed in w.listA (k_iso_prepare) whose state k_iso_init_tc3 has written, persistent
 cudaError_t root_iso_persist(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const float* skin_Wt0, const float* const skin_b[5],
                              const SkinF16Dev& skimg, const Work& w, int n_sms, cudaStream_t st, long long* launches);

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
             pc.mark(2);                                           // forward epilogues
         }
         cta_sync_compute();
-        if (tid < UM && sl >= 0) w.smp_sdf[sl] = sdf_to_metres(part[0][tid][0] + part[1][tid][0] + tc.sdf_b6, fp.cmin, fp.cmax);
+        if (tid < UM && sl >= 0 && (SDF_ONLY || !w.shade_keep_sdf)) w.smp_sdf[sl] = sdf_to_metres(part[0][tid][0] + part[1][tid][0] + tc.sdf_b6, fp.cmin, fp.cmax);
         if (SDF_ONLY) { cta_sync_compute(); pc.mark(3); continue; }      // (part / xs are rewritten by the next tile)
         // ================= reverse pass =================
         float g3[3] = {0.f, 0.f, 0.f};
