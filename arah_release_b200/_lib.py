@@ -10,7 +10,7 @@ FP = C.c_void_p
 class ArahConfig(C.Structure):
     _fields_ = [('device', C.c_int32), ('n_steps', C.c_int32), ('near_samples', C.c_int32), ('far_samples', C.c_int32),
                 ('cano_view_dirs', C.c_int32), ('latent_dim', C.c_int32), ('n_verts', C.c_int32), ('max_rays', C.c_int32),
-                ('shade_mode', C.c_int32), ('root_mode', C.c_int32), ('shade_cull', C.c_int32)]
+                ('shade_mode', C.c_int32), ('root_mode', C.c_int32), ('shade_cull', C.c_int32), ('render_last_pt', C.c_int32)]
 
 
 class ArahFrame(C.Structure):

@@ -8,16 +8,8 @@
 #include "../../include/arah_b200.h"
 #include "arah_kernels.cuh"
 #include "arah_umma.cuh"
-#include "arah_shade_tc.cuh"
-#include "arah_corr_tc.cuh"
-#include "arah_shade_tc2.cuh"
-#include "arah_corr_tc2.cuh"
 #include "arah_shade_tc3.cuh"
-#include "arah_corr_tc3.cuh"
 #include "arah_sdf3x.cuh"
-#include "arah_shade_tc4.cuh"
-#include "arah_corr_tc4.cuh"
-#include "arah_corr_tc5.cuh"
 #include "arah_iso_init_tc.cuh"
 #include "arah_train_cuda.cuh"
 #include "arah_root.h"
@@ -315,8 +307,6 @@ struct ArahHandle {
     int trace_tc = 1;
     int knn_seed = 1;          // seeded per-lane 1-NN for runs of samples on one ray
     int iso_init_tc = 1;       // k_iso_init_tc3: joint-search Jacobian initialisation on the tensor cores (forward mode, 4 rows per ray)
-    int corr_interleave = 1;   // k_corr_tc5: the two tiles of a trip time-share the activation columns of TMEM (epilogue of one under the MMAs of the other)
-    int corr_cluster = 1;      // 2-CTA clusters + weight multicast in the correspondence kernel (measured: -2 ms)
     int corr_persist = 1;      // k_corr_persist: one persistent kernel with resident Broyden state (fp16 split precision) instead of 51 launches
     SkinF16Dev skin16{};
     int trace_persist = 1;     // k_trace_persist: sphere tracing as one persistent kernel (1-NN + SDF per step, resident rays)
@@ -325,7 +315,6 @@ struct ArahHandle {
     int sdf_fwd16 = 1;         // k_sdf_fwd16: the SDF value compositing uses comes from a single-pass fp16 kernel over all converged samples
     bool shade_cull_ran = false;
     int shade_cull = 1;        // exact alpha cull before the gradient / colour pass (k_alpha_cull)
-    int shade_cluster = 0;     // same for shading (measured: +2 ms -- the kernel is not L2-bound; kept selectable)
     // workspace
     DevBuf ws, scratch, io_in, io_out;
     Work w;
@@ -334,7 +323,6 @@ struct ArahHandle {
     int last_P = 0;
     int64_t pack_launches = 0;
     bool profile = false, profiled = false;
-    int tc_engine = 4;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // training (arah_train.h): raw reference-layout weight copies + the engine's saved activations
     bool training = false, train_traced = false;
@@ -344,6 +332,8 @@ struct ArahHandle {
     arah::train::Session<arah::train::CudaBK>* sess = nullptr;
     int col_d0 = 0;
 };
+
+extern "C" int arah_destroy(ArahHandle* h);
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -431,14 +421,14 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major < 10) return fail(ARAH_EINVAL, "arah_b200 needs an sm_100-class GPU");
     ArahHandle* h = new ArahHandle();
+    struct Guard { ArahHandle* h; ~Guard() { if (h) arah_destroy(h); } } guard{h};     // any early return below releases the handle and its buffers
     h->cfg = *cfg;
     h->n_sms = prop.multiProcessorCount;
-    if (const char* e = getenv("ARAH_TC_ENGINE")) { const int v = atoi(e); h->tc_engine = (v >= 1 && v <= 4) ? v : 4; }
     memset(&h->w, 0, sizeof(h->w));
-    if (alloc_arena(h) != 0) { delete h; return fail(ARAH_ENOMEM, "weight arena allocation failed"); }
-    if (ensure_workspace(h, cfg->max_rays > 0 ? cfg->max_rays : 4096) != 0) { h->arena.release(); delete h; return fail(ARAH_ENOMEM, "workspace allocation failed"); }
+    if (alloc_arena(h) != 0) return fail(ARAH_ENOMEM, "weight arena allocation failed");
+    if (ensure_workspace(h, cfg->max_rays > 0 ? cfg->max_rays : 4096) != 0) return fail(ARAH_ENOMEM, "workspace allocation failed");
     const size_t scr_fp32 = (size_t)7 * TM * SDF_H * 4, scr_tc = (size_t)TC_SCRATCH_FLOATS * 4;
-    if (h->scratch.ensure((size_t)h->n_sms * (scr_fp32 > scr_tc ? scr_fp32 : scr_tc)) != 0) { delete h; return fail(ARAH_ENOMEM, "scratch allocation failed"); }
+    if (h->scratch.ensure((size_t)h->n_sms * (scr_fp32 > scr_tc ? scr_fp32 : scr_tc)) != 0) return fail(ARAH_ENOMEM, "scratch allocation failed");
     h->w.scratch = (float*)h->scratch.p;
     CU(cudaFuncSetAttribute(k_trace_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SDF)));
     CU(cudaFuncSetAttribute(k_iso_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SDF)));
@@ -447,27 +437,16 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_corr_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SKIN)));
     CU(cudaFuncSetAttribute(k_eval_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SKIN)));
     CU(cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_shade_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc2_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_corr_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc2_smem_bytes()));
     CU(cudaFuncSetAttribute(k_shade_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_shade_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
     h->shade_cull = cfg->shade_cull == ARAH_CULL_OFF ? 0 : 1;
     if (const char* e = getenv("ARAH_SHADE_CULL")) h->shade_cull = atoi(e) != 0;
-    CU(cudaFuncSetAttribute(k_corr_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_shade_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_corr_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_corr_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_tc3_smem_bytes()));
-    if (const char* e = getenv("ARAH_CORR_INTERLEAVE")) h->corr_interleave = atoi(e) != 0;
-    if (const char* e = getenv("ARAH_CORR_CLUSTER")) h->corr_cluster = atoi(e) != 0;
     if (const char* e = getenv("ARAH_CORR_PERSIST")) h->corr_persist = atoi(e) != 0;
     if (const char* e = getenv("ARAH_TRACE_PERSIST")) h->trace_persist = atoi(e) != 0;
     if (const char* e = getenv("ARAH_ISO_PERSIST")) h->iso_persist = atoi(e) != 0;
     if (const char* e = getenv("ARAH_SDF_FWD16")) h->sdf_fwd16 = atoi(e) != 0;
     if (!root_trace_fits(cfg->n_verts)) h->trace_persist = 0;      // vertex index + weight ring must fit in 227 KB of shared memory
     CU(root_init());
-    if (const char* e = getenv("ARAH_SHADE_CLUSTER")) h->shade_cluster = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_iso_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_iso_init_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
@@ -479,6 +458,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+    guard.h = nullptr;
     *out = h;
     return ARAH_OK;
 }
@@ -528,9 +508,9 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     CU(cudaMemcpyAsync(h->sdf_w6, f->sdf_W[6], 256 * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(h->sdf_freq, f->sdf_freq, 6 * 256 * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(h->sdf_phase, f->sdf_phase, 6 * 256 * 4, cudaMemcpyDeviceToDevice, st));
-    // the scalar output bias travels as a kernel parameter: fetch it (4 bytes, the only D2H of set_frame)
-    float b6 = 0.f;
-    CU(cudaMemcpyAsync(&b6, f->sdf_b[6], 4, cudaMemcpyDeviceToHost, st));
+    // the scalar output bias stays on the device: kernels read it through a pointer (no D2H, no stream synchronisation here)
+    CU(cudaMemcpyAsync(h->d_b6, f->sdf_b[6], 4, cudaMemcpyDeviceToDevice, st));
+    const float* b6 = h->d_b6;
     // skinning
     tp(f->skin_W[0], 3, h->skin_Wt[0], 3, 128, 3, 128, 3, 0, 0);
     for (int l = 1; l < 4; ++l) tp(f->skin_W[l], 128, h->skin_Wt[l], 128, 128, 128, 128, 128, 0, 0);
@@ -595,7 +575,6 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
         h->have_smpl_w = true;
     }
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));       // b6 has landed; packing done (set_frame is once per frame, not per ray batch)
     FrameParams& fp = h->fp;
     for (int l = 0; l < 6; ++l) { fp.sdf_Wt[l] = h->sdf_Wt[l]; fp.sdf_W[l] = h->sdf_W[l]; fp.sdf_b[l] = h->sdf_b[l]; }
     fp.sdf_w6 = h->sdf_w6; fp.sdf_b6 = b6; fp.sdf_freq = h->sdf_freq; fp.sdf_phase = h->sdf_phase;
@@ -610,6 +589,7 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     fp.beta = f->beta;
     fp.n_steps = h->cfg.n_steps; fp.near_samples = h->cfg.near_samples; fp.far_samples = h->cfg.far_samples;
     fp.cano_view_dirs = h->cfg.cano_view_dirs;
+    fp.render_last_pt = h->cfg.render_last_pt ? 1 : 0;
     ShadeTC& tc = h->tc;
     tc.sdf_Wt0 = h->sdf_Wt[0]; tc.sdf_W0 = h->sdf_W[0]; tc.sdf_F = h->tc_F; tc.sdf_G = h->tc_G;
     for (int l = 0; l < 5; ++l) { tc.sdf_fwd[l] = h->tc_sdf_fwd[l]; tc.sdf_bwd[l] = h->tc_sdf_bwd[l]; }
@@ -696,7 +676,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     k_trace_begin<<<cdiv(P, 256), 256, 0, st>>>(w); L();
     const unsigned g_ray_tiles = grid_min(cdiv(P, TM), (size_t)nsm);
     const unsigned g_knn_rays = grid_min(cdiv(P, 16), (size_t)nsm);        // >= one query per warp; idle blocks exit before staging
-    const bool tc_root = h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc;
+    const bool tc_root = h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->trace_tc;
     SdfF16Host sh16;
     sh16.Wt0 = h->sdf_Wt[0]; sh16.freq = h->sdf_freq; sh16.phase = h->sdf_phase; sh16.w6 = h->sdf_w6; sh16.b6 = h->sd.b6;
     for (int l = 0; l < 6; ++l) sh16.b[l] = h->sdf_b[l];
@@ -707,7 +687,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     } else
     for (int it = 0; it < TRACE_ITERS; ++it) {
         k_knn_rays<<<g_knn_rays, 512, sm_knn, st>>>(fp, h->knn, w, it); L();
-        if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc)
+        if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->trace_tc)
             k_trace_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, wk, it);
         else
             k_trace_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it);
@@ -715,7 +695,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     }
     if (prof) CU(cudaEventRecord(h->ev[1], st));
     k_iso_prepare<<<cdiv(P, 256), 256, 0, st>>>(w); L();
-    if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc && h->iso_init_tc)
+    if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->trace_tc && h->iso_init_tc)
         k_iso_init_tc3<<<grid_min(cdiv(P, ISO_TC_PTS), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, h->sk, w);
     else
         k_iso_init<<<grid_min(cdiv(P, TM / 4), (size_t)nsm), 256, sm_sdf, st>>>(fp, w);
@@ -726,7 +706,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
         h->launches += n;
     } else
     for (int it = 0; it < BROYDEN_ITERS; ++it) {
-        if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->tc_engine >= 3 && h->trace_tc)
+        if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->trace_tc)
             k_iso_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, h->sk, w, it);
         else
             k_iso_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it);
@@ -744,44 +724,14 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
         long long n = 0;
         CU(root_corr_persist(fp, h->skin_Wt[0], h->skin_b, h->skin16, wk, nsm, st, &n));
         h->launches += n;
-    } else if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
-        const unsigned g_tc = grid_min(cdiv(PS, UM), (size_t)nsm);
-        for (int it = -1; it < BROYDEN_ITERS; ++it) {
-            if (h->tc_engine >= 4 && h->corr_cluster) {
-                cudaLaunchConfig_t lc{};
-                unsigned g = (g_tc + 1u) & ~1u;
-                if (g > (unsigned)(nsm & ~1)) g = (unsigned)(nsm & ~1);
-                lc.gridDim = dim3(g); lc.blockDim = dim3(TC3_THREADS); lc.dynamicSmemBytes = corr_tc3_smem_bytes(); lc.stream = st;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                lc.attrs = at; lc.numAttrs = 1;
-                if (h->corr_interleave) CU(cudaLaunchKernelEx(&lc, k_corr_tc5, fp, h->sk, wk, it));
-                else CU(cudaLaunchKernelEx(&lc, k_corr_tc4, fp, h->sk, wk, it));
-            }
-            else if (h->tc_engine >= 3) k_corr_tc3<<<g_tc, TC3_THREADS, corr_tc3_smem_bytes(), st>>>(fp, h->sk, wk, it);
-            else if (h->tc_engine == 2) k_corr_tc2<<<g_tc, TC_THREADS, corr_tc2_smem_bytes(), st>>>(fp, h->sk, wk, it);
-            else k_corr_tc<<<g_tc, 256, corr_tc_smem_bytes(), st>>>(fp, h->sk, w, it);
-            L();
-        }
     } else {
+        // per-iteration launches on fp32 FFMA tiles (root_mode fp32, or ARAH_CORR_PERSIST=0 for A/B runs)
         for (int it = -1; it < BROYDEN_ITERS; ++it) { k_corr_step<<<g_smp_tiles, 256, sm_skin, st>>>(fp, w, it); L(); }
     }
     if (prof) CU(cudaEventRecord(h->ev[3], st));
     if (trace_only) { CU(cudaGetLastError()); return ARAH_OK; }
     if (h->cfg.shade_mode == ARAH_SHADE_TF32) {
-        if (h->tc_engine >= 4 && h->shade_cluster) {
-            // 2-CTA clusters: the pair shares (multicasts) the weight stream
-            cudaLaunchConfig_t lc{};
-            unsigned g = grid_min(cdiv(PS, UM), (size_t)nsm);
-            g = (g + 1u) & ~1u;
-            if (g > (unsigned)(nsm & ~1)) g = (unsigned)(nsm & ~1);
-            lc.gridDim = dim3(g); lc.blockDim = dim3(TC3_THREADS); lc.dynamicSmemBytes = shade_tc3_smem_bytes(); lc.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            lc.attrs = at; lc.numAttrs = 1;
-            CU(cudaLaunchKernelEx(&lc, k_shade_tc4, fp, h->tc, wk));
-        }
-        else if (h->tc_engine >= 3) {
+        {
             const unsigned g = grid_min(cdiv(PS, UM), (size_t)nsm);
             h->shade_cull_ran = h->shade_cull != 0;
             const bool fwd16 = h->sdf_fwd16 && h->cfg.root_mode == ARAH_ROOT_3XTF32;     // (the fp16 images are packed with the root engine's)
@@ -803,8 +753,6 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
             } else
                 k_shade_tc3<false><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk);
         }
-        else if (h->tc_engine == 2) k_shade_tc2<<<grid_min(cdiv(PS, UM), (size_t)nsm), TC_THREADS, shade_tc2_smem_bytes(), st>>>(fp, h->tc, w);
-        else k_shade_tc<<<grid_min(cdiv(PS, UM), (size_t)nsm), 256, shade_tc_smem_bytes(), st>>>(fp, h->tc, w);
         L();
     }
     else { k_shade<<<grid_min(cdiv(PS, TM), (size_t)nsm), 256, shade_smem_bytes(), st>>>(fp, w); L(); }

@@ -113,7 +113,10 @@ __global__ void __launch_bounds__(BLK) k_ssim_rect(const uint8_t* __restrict__ m
 // one item = one interior pixel of the crop x one channel; fixed grid-stride partition, fp64, fixed trees: bit-reproducible
 __global__ void __launch_bounds__(BLK) k_ssim_partial(const float* __restrict__ X, const float* __restrict__ Y, int W, SsimScratch* s) {
     __shared__ double sh[BLK / 32];
-    const int x0 = s->x0, y0 = s->y0, iw = s->x1 - s->x0 + 1 - 2 * SSIM_PAD, ih = s->y1 - s->y0 + 1 - 2 * SSIM_PAD;
+    // empty mask: x0 = INT_MAX, x1 = -1 -- guard before subtracting (signed overflow otherwise), exactly as k_ssim_finish does
+    const int x0 = s->x0, y0 = s->y0;
+    const int w = (s->x1 >= s->x0) ? s->x1 - s->x0 + 1 : 0, h = (s->y1 >= s->y0) ? s->y1 - s->y0 + 1 : 0;
+    const int iw = w - 2 * SSIM_PAD, ih = h - 2 * SSIM_PAD;
     double acc = 0.0;
     if (iw > 0 && ih > 0) {
         const long long items = 3ll * iw * ih, stride = (long long)SSIM_BLOCKS * BLK;

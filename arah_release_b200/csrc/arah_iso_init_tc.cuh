@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_iso_init_tc3(FrameParams fp,
             float g0[4];
 #pragma unroll
             for (int k = 0; k < 3; ++k) g0[1 + k] = xb[k] - ((w.ray_dirs[3 * ray + k] * z0 + fp.cam_loc[k]) - fp.trans[k]);
-            g0[0] = sdf_to_metres(so4[0] + sd.b6, fp.cmin, fp.cmax);
+            g0[0] = sdf_to_metres(so4[0] + __ldg(sd.b6), fp.cmin, fp.cmax);
             BroydenState<4> st;
             broyden_begin<4>(st, u0, g0, Ji, w.ray_cur[ray].T);
             st.owner = ray;

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
                 for (int k = 0; k < 4; ++k) dx[k] = st[(IP_DX + k) * UM + tid];
 #pragma unroll
                 for (int k = 0; k < 25; ++k) lg32[k] = lgs[k * UM + tid];
-                iso_residual(fp, w, ray, s.x, lg32, part[0][tid] + part[1][tid] + sd.b6, g, T12);
+                iso_residual(fp, w, ray, s.x, lg32, part[0][tid] + part[1][tid] + __ldg(sd.b6), g, T12);
                 bool active = broyden_update<4>(s, dx, g, T12);
                 const int it = __float_as_int(st[IP_IT * UM + tid]);
                 if (it + 1 >= BROYDEN_ITERS) active = false;

@@ -722,8 +722,8 @@ __global__ void __launch_bounds__(256, 1) k_shade(FrameParams fp, Work w) {
 constexpr int COMP_WARPS = 4;
 // alpha of compacted sample e of a ray (implicit_differentiable_renderer.py:379-387); shared by k_composite and k_alpha_cull so
 // that both evaluate the identical fp32 expression
-__device__ __forceinline__ float sample_alpha(const float* cz, const float* cd, int e, int len, int S) {
-    const float dz = (e + 1 < len) ? (cz[e + 1] - cz[e]) : (1.0f / (float)S);     // :379-385
+__device__ __forceinline__ float sample_alpha(const float* cz, const float* cd, int e, int len, int S, int last_pt) {
+    const float dz = (e + 1 < len) ? (cz[e + 1] - cz[e]) : (last_pt ? 1e10f : 1.0f / (float)S);     // :379-385
     return 1.0f - expf(-cd[e] * dz);
 }
 
@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(32 * COMP_WARPS) k_alpha_cull(FrameParams fp, 
         int sl = 0;
         if (in) {
             sl = r * S + cs[e];
-            keep = sample_alpha(cz, cd, e, len, S) != 0.0f;
+            keep = sample_alpha(cz, cd, e, len, S, fp.render_last_pt) != 0.0f;
             if (!keep) { w.smp_rgb[3 * (size_t)sl] = 0.f; w.smp_rgb[3 * (size_t)sl + 1] = 0.f; w.smp_rgb[3 * (size_t)sl + 2] = 0.f; }
         }
         warp_append(keep, sl, out_list, &w.counters[C_SHADE2]);
@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(32 * COMP_WARPS) k_composite(FrameParams fp, W
         const int e = base + lane;
         const bool in = e < len;
         float alpha = 0.f;
-        if (in) alpha = sample_alpha(cz, cd, e, len, S);
+        if (in) alpha = sample_alpha(cz, cd, e, len, S, fp.render_last_pt);
         const float fac = in ? (1.0f - alpha + 1e-7f) : 1.0f;
         float incl = fac;
 #pragma unroll

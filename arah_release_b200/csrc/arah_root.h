@@ -25,7 +25,7 @@ struct SdfF16Dev {
 };
 constexpr size_t SDF_F16_DEV_BYTES = 5 * 131072;
 struct SdfF16Host {  // what the kernels need besides the images (device pointers into the frame arena)
-    const float* Wt0; const float* b[6]; const float* freq; const float* phase; const float* w6; float b6;
+    const float* Wt0; const float* b[6]; const float* freq; const float* phase; const float* w6; const float* b6;
 };
 cudaError_t root_pack_sdf_f16(const float* const W[7], const SdfF16Dev& dst, cudaStream_t st, long long* launches);
 // sphere tracing of the rays listed in w.listA (k_trace_begin), persistent; false if the vertex index does not fit in shared memory

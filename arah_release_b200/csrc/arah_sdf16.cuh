@@ -27,7 +27,7 @@ struct SdfF16 {
     const __half* lo;
     const float* scale;      // [5][2]: (s, 1 / s)
     const float* w6;
-    float b6;
+    const float* b6;         // [1] device scalar
 };
 constexpr size_t SDF_F16_IMAGE_BYTES = 5 * 131072;
 

@@ -13,9 +13,17 @@
 // (sin_cw): root finding keeps resolving 1e-5 m.
 #pragma once
 #include "arah_shade_tc3.cuh"
-#include "arah_corr_tc3.cuh"
 
 namespace arah {
+
+struct SkinTC {
+    const float* Wt0;      // [3][128]
+    const float* b[5];     // biases (b[4] padded to 32)
+    const float* hid[3];   // layers 1..3: 4 chunks of [hi | lo] images, N = 128
+    const float* out;      // layer 4: 4 chunks of [hi | lo] images, N = 32 (25 padded)
+};
+
+constexpr int LGS = 33;     // row stride of the logits staging tile: odd, so that row-per-lane accesses hit 32 different banks
 
 struct SdfTC {
     const float* Wt0;        // [3][256]
@@ -24,7 +32,7 @@ struct SdfTC {
     const float* phase;      // [6][256]
     const float* hid[5];     // layers 1..5: 8 chunks x [hi 32 KB | lo 32 KB]
     const float* w6;
-    float b6;
+    const float* b6;         // [1] device scalar
 };
 
 constexpr int S3_NSLOTS = 3;
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_trace_tc3(FrameParams fp, Sd
         if (tid < UM) {                                             // marching logic, identical to k_trace_iter
             bool still = false;
             if (ray >= 0) {
-                const float sdf = sdf_to_metres(part[0][tid] + part[1][tid] + sd.b6, fp.cmin, fp.cmax);
+                const float sdf = sdf_to_metres(part[0][tid] + part[1][tid] + __ldg(sd.b6), fp.cmin, fp.cmax);
                 float t = w.ray_t[ray];
                 const float far_ = w.near_far[2 * ray + 1];
                 const float sm = fminf(fmaxf(sdf, -0.1f), 0.1f);
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_sdf_grid_tc3(SdfTC sd, int N
         const float dot = s3_compute_sdf(sd, xs3, A_lo, bar, done_par, tbase);
         part[half][r] = dot;
         cta_sync_compute();
-        if (tid < UM && i < n_total) out[i] = part[0][tid] + part[1][tid] + sd.b6;
+        if (tid < UM && i < n_total) out[i] = part[0][tid] + part[1][tid] + __ldg(sd.b6);
         cta_sync_compute();
     }
     tc_fence_before();
@@ -461,7 +469,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_iso_tc3(FrameParams fp, SdfT
                 float g[4], T12[12], lg32[32];
 #pragma unroll
                 for (int k = 0; k < 25; ++k) lg32[k] = lg[k];
-                iso_residual(fp, w, ray, st.x, lg32, part[0][tid] + part[1][tid] + sd.b6, g, T12);
+                iso_residual(fp, w, ray, st.x, lg32, part[0][tid] + part[1][tid] + __ldg(sd.b6), g, T12);
                 active = broyden_update<4>(st, dx, g, T12);
                 if (iter + 1 >= BROYDEN_ITERS) active = false;
                 state_store(&w.iso_state[ray], st);

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_sdf_fwd16(FrameParams fp, Sd
         part[u][r] = dot;
         sync_epi();
         if (tid < UM && sl >= 0)
-            w.smp_sdf[sl] = sdf_to_metres(((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid])) + sd.b6, fp.cmin, fp.cmax);
+            w.smp_sdf[sl] = sdf_to_metres(((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid])) + __ldg(sd.b6), fp.cmin, fp.cmax);
         // (xs / part are rewritten only after the next sync_epi)
     }
     tc_fence_before();

@@ -1,4 +1,6 @@
-// arah_shade_tc3.cuh — k_shade_tc3: shading on tcgen05, engine v3 = v2 + chunk-granular overlap of MMA and epilogue.
+// arah_shade_tc3.cuh — k_shade_tc3: shading (SDF forward + reverse-mode gradient + colour MLP) on tcgen05, TF32 operands:
+// activations in tensor memory (.ts MMA form), pre-swizzled weight chunks through a 5-slot TMA ring fed by a producer warp,
+// chunk-granular overlap of MMA and epilogue.
 //
 // Roles (320 threads): warps 0-7 epilogue/compute, warp 8 TMA producer, warp 9 MMA issuer.
 // TMEM is split into two 256-column regions R0/R1.  For GEMM g the activations A live in one region and the accumulators
@@ -7,12 +9,35 @@
 // warp issues chunk c of the next GEMM as soon as ready[c] and the weight slot are there, writing the next D into the
 // region the previous A has vacated.  So layer l's epilogue and layer l+1's MMAs run concurrently, chunk by chunk; the
 // static per-tile program (18 GEMM segments, chunk order 0,4,1,5,.. = the order the two column-halves finish) is shared
-// by producer and issuer.  Arithmetic, scratch layout and results are those of k_shade_tc2.
+// by producer and issuer.
 #pragma once
-#include "arah_shade_tc2.cuh"
+#include <cuda_bf16.h>
+
+#include "arah_kernels.cuh"
+#include "arah_tc2.cuh"
 
 namespace arah {
 
+struct ShadeTC {
+    const float* sdf_Wt0;      // [3][256]
+    const float* sdf_W0;       // [256][3]
+    const float* sdf_F;        // [6][256]  30 f
+    const float* sdf_G;        // [6][256]  30 (f b + phi)
+    const float* sdf_fwd[5];   // layers 1..5, swizzled chunks of B[n=out][k=in]
+    const float* sdf_bwd[5];   // layers 1..5, swizzled chunks of B[n=in][k=out]
+    const float* sdf_w6;       // [256]
+    const float* sdf_b6;       // [1] device scalar
+    const float* col0;         // 10 chunks, N=256: k = [feat 256 | x,PE,n 33 | pad]
+    const float* col1;         // 8 chunks
+    const float* col2;         // 8 chunks, N=128
+    const float* col3b;        // 4 chunks (lin2 output part of the skip layer)
+    const float* col3a;        // 10 chunks (network-input part)
+    const float* col4;         // 8 chunks
+    const float* col_W5;       // [3][256]
+    const float* col_b[6];
+};
+
+constexpr int TC_SCRATCH_FLOATS = 6 * UM * 256 / 2 + UM * 256;     // bf16 cos factors + fp32 feature, in float units
 constexpr int TC3_THREADS = 320;
 constexpr int TC3_NSLOTS = 5;
 constexpr int TC3_NSEG = 18;      // 5 forward + 5 reverse + lin0 (2) + lin1 + lin2 + lin3 (3) + lin4
@@ -273,7 +298,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_shade_tc3(FrameParams fp, Sh
             pc.mark(2);                                           // forward epilogues
         }
         cta_sync_compute();
-        if (tid < UM && sl >= 0 && (SDF_ONLY || !w.shade_keep_sdf)) w.smp_sdf[sl] = sdf_to_metres(part[0][tid][0] + part[1][tid][0] + tc.sdf_b6, fp.cmin, fp.cmax);
+        if (tid < UM && sl >= 0 && (SDF_ONLY || !w.shade_keep_sdf)) w.smp_sdf[sl] = sdf_to_metres(part[0][tid][0] + part[1][tid][0] + __ldg(tc.sdf_b6), fp.cmin, fp.cmax);
         if (SDF_ONLY) { cta_sync_compute(); pc.mark(3); continue; }      // (part / xs are rewritten by the next tile)
         // ================= reverse pass =================
         float g3[3] = {0.f, 0.f, 0.f};

@@ -206,7 +206,7 @@ struct FrameParams {
     const float* sdf_W[6];       // l=0: [256][3]; l=1..5: [256][256]
     const float* sdf_b[6];
     const float* sdf_w6;         // [256]
-    float sdf_b6;
+    const float* sdf_b6;         // [1] device scalar
     const float* sdf_freq;       // [6][256]
     const float* sdf_phase;      // [6][256]
     // skinning MLP (metaavatar/models/decoder.py:201-233), weight-norm folded
@@ -229,6 +229,7 @@ struct FrameParams {
     int n_verts;
     float trans[3], cmin, cmax, center[3], cam_loc[3], pose[16], beta;
     int n_steps, near_samples, far_samples, cano_view_dirs;
+    int render_last_pt;          // last interval of a ray is 1e10 instead of 1 / n_steps (implicit_differentiable_renderer.py:380-381)
 };
 
 __device__ __forceinline__ void normalize3(const FrameParams& fp, const float* p, float* q) {
@@ -320,7 +321,7 @@ __device__ __forceinline__ void sdf_tile_forward(const FrameParams& fp, const fl
 #pragma unroll
         for (int r = 1; r < 8; ++r) if (lane == r) v = y[r];
         const bool is_value = (MODE == PLAIN) || ((lane & 3) == 0);
-        out[warp * 8 + lane] = is_value ? (v + fp.sdf_b6) : v;
+        out[warp * 8 + lane] = is_value ? (v + __ldg(fp.sdf_b6)) : v;
     }
 }
 

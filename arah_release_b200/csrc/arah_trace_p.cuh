@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
             const int ray = __float_as_int(st[TR_RAY * UM + tid]);
             bool need = false;
             if (ray >= 0) {
-                const float sdf = sdf_to_metres(part[0][tid] + part[1][tid] + sd.b6, fp.cmin, fp.cmax);
+                const float sdf = sdf_to_metres(part[0][tid] + part[1][tid] + __ldg(sd.b6), fp.cmin, fp.cmax);
                 float t = st[TR_T * UM + tid];
                 const float far_ = st[TR_FAR * UM + tid];
                 const float sm = fminf(fmaxf(sdf, -0.1f), 0.1f);

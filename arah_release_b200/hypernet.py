@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import ArahHyperWeights, ArahSdfParams, check
-from . import ref_layout as rl
+from . import containers as rl
 
 IN_CH = [3, 256, 256, 256, 256, 256, 256]
 OUT_CH = [256, 256, 256, 256, 256, 256, 1]

@@ -124,10 +124,18 @@ class IDHRLoss(nn.Module):
         aux = {'device': dev, 'n_rays': N, 'body_mask': body, 'network_body_mask': u8(model_outputs['network_body_mask']),
                'off_surface_mask': u8(model_outputs['off_surface_mask']), 'rgb_gt': None, 'sampled_weights': None}
         on = lambda w: w > 0
+        # the kernels index every per-ray array up to n_rays: a row-count mismatch (an indexing error in the reference) must not
+        # become an out-of-bounds device access here
+        for name in ('network_body_mask', 'off_surface_mask'):
+            if int(aux[name].numel()) != N:
+                raise _lib.ArahError('%s has %d rays but body_mask %d' % (name, int(aux[name].numel()), N))
         rgb = sdf_out = gth = off_sdf = ins_sdf = pw = None
         if on(self.rgb_weight):
             rgb = rgb_all[0, :_MAX_RAYS]
             aux['rgb_gt'] = ground_truth['rgb'][0, :_MAX_RAYS].detach().to(dev, torch.float32).contiguous()
+            if rgb.shape[0] != N or rgb.shape[-1] != 3 or tuple(aux['rgb_gt'].shape) != tuple(rgb.shape):
+                raise _lib.ArahError('rgb term: rgb_values %s / rgb ground truth %s do not match the %d rays of body_mask'
+                                     % (tuple(rgb.shape), tuple(aux['rgb_gt'].shape), N))
         if on(self.mask_weight):
             sdf_out = model_outputs['sdf_output'][0].reshape(-1)                # NOT cut to 2048 by the reference (:143)
             if sdf_out.numel() != N:

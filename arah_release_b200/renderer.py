@@ -22,6 +22,8 @@ import ctypes as C
 import os
 import weakref
 
+from collections import OrderedDict
+
 import torch
 import torch.nn as nn
 
@@ -88,7 +90,7 @@ class ArahRenderer:
     """Thin RAII wrapper around an ArahHandle (one per device/stream; not thread-safe)."""
 
     def __init__(self, device, n_steps=64, near_samples=16, far_samples=16, cano_view_dirs=True, latent_dim=128,
-                 n_verts=N_VERTS_DEFAULT, max_rays=65536, shade_mode=None, root_mode=None, shade_cull=None):
+                 n_verts=N_VERTS_DEFAULT, max_rays=65536, shade_mode=None, root_mode=None, shade_cull=None, render_last_pt=False):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.ArahError('the ARAH hot path only exists as CUDA kernels; got device %s' % device)
@@ -103,7 +105,7 @@ class ArahRenderer:
         self.cfg = ArahConfig(device=self.device.index or 0, n_steps=n_steps, near_samples=near_samples,
                               far_samples=far_samples, cano_view_dirs=int(bool(cano_view_dirs)), latent_dim=latent_dim,
                               n_verts=n_verts, max_rays=max_rays, shade_mode=mode, root_mode=rmode,
-                              shade_cull=0 if (shade_cull is None or shade_cull) else 1)
+                              shade_cull=0 if (shade_cull is None or shade_cull) else 1, render_last_pt=int(bool(render_last_pt)))
         self.shade_cull = bool(self.cfg.shade_cull == 0) and os.environ.get('ARAH_SHADE_CULL', '1') != '0'
         self._h = C.c_void_p()
         check(_lib.lib().arah_create(C.byref(self.cfg), C.byref(self._h)))
@@ -170,7 +172,7 @@ class ArahRenderer:
 
     def set_frame_from_modules(self, sdf_network, skinning_model, rendering_network, deviation_network, inputs,
                                pose_on_host=False):
-        """Read weights out of modules laid out like the reference's (see ref_layout.py) + the input dict."""
+        """Read weights out of modules laid out like the reference's (tools/ref_layout.py builds such modules for tests and bench.py) + the input dict."""
         sdf_W, sdf_b = [], []
         freq, phase = [], []
         if len(sdf_network) != 7:
@@ -201,15 +203,28 @@ class ArahRenderer:
             if pe != 'latent':
                 raise _lib.ArahError("only color_pose_encoder 'latent' (or None) is implemented")
             latent = inputs['pose_cond']['latent_code'].reshape(-1)
-        beta = float(torch.linalg.norm(deviation_network.variance.detach()).item())
-        cam_loc = inputs['cam_loc'].reshape(-1, 3)[0].tolist()
+        # ---- per-frame scalars without stalling the stream more than once.  beta = |variance| changes only with an optimiser step:
+        # cached against the parameter's version counter.  The geometry scalars come from `inputs['host_scalars']` when the caller
+        # still has the host values the dataset produced (no device read-back at all); otherwise ONE batched device -> host copy.
+        var = deviation_network.variance
+        key = (var.data_ptr(), var._version)
+        if getattr(self, '_beta_key', None) != key:
+            self._beta = float(torch.linalg.norm(var.detach()).item())
+            self._beta_key = key
+        beta = self._beta
+        hs = inputs.get('host_scalars')
+        if hs is not None:
+            trans, cmin, cmax = [float(v) for v in hs['trans']], float(hs['coord_min']), float(hs['coord_max'])
+            center, cam_loc, pose = [float(v) for v in hs['center']], [float(v) for v in hs['cam_loc']], [float(v) for v in hs['pose']]
+        else:
+            flat = torch.cat([inputs['trans'].reshape(-1)[:3].float(), inputs['coord_min'].reshape(-1)[:1].float(), inputs['coord_max'].reshape(-1)[:1].float(),
+                              inputs['center'].reshape(-1)[:3].float(), inputs['cam_loc'].reshape(-1)[:3].float(), inputs['pose'].reshape(-1)[:16].float()]).tolist()
+            trans, cmin, cmax, center, cam_loc, pose = flat[0:3], flat[3], flat[4], flat[5:8], flat[8:11], flat[11:27]
         self.set_frame(sdf_W=sdf_W, sdf_b=sdf_b, sdf_freq=torch.stack(freq), sdf_phase=torch.stack(phase), skin_W=skin_W,
                        skin_b=skin_b, col_W=col_W, col_b=col_b, latent=latent, beta=beta,
                        bone_transforms=inputs['bone_transforms'][0], smpl_verts=inputs['smpl_verts'][0],
-                       smpl_weights=inputs['skinning_weights'][0], trans=inputs['trans'].reshape(-1)[:3].tolist(),
-                       coord_min=float(inputs['coord_min'].reshape(-1)[0]), coord_max=float(inputs['coord_max'].reshape(-1)[0]),
-                       center=inputs['center'].reshape(-1)[:3].tolist(), cam_loc=cam_loc,
-                       pose=inputs['pose'].reshape(-1, 16)[0].tolist(), pose_on_host=pose_on_host)
+                       smpl_weights=inputs['skinning_weights'][0], trans=trans, coord_min=cmin, coord_max=cmax,
+                       center=center, cam_loc=cam_loc, pose=pose, pose_on_host=pose_on_host)
 
     # ------------------------------------------------------------------ render
     def render(self, ray_dirs, near_far, want_weights=False):
@@ -510,8 +525,20 @@ class BodyRayTracing(nn.Module):
         owner = self._owner() if self._owner is not None else None
         if owner is None:
             raise _lib.ArahError('BodyRayTracing must be owned by an IDHRNetwork (it shares its renderer handle)')
-        return owner._trace_only(sdf_network, cam_loc, ray_directions, body_bounds_intersections, smpl_verts,
-                                       skinning_weights, bone_transforms, trans, coord_min, coord_max, center, train=not eval_mode)
+        if isinstance(vol_feat, OrderedDict):
+            # query_weights / forward_skinning normalise with (x - loc) * sc_factor for this kind of skinning decoder
+            # (root_finding_utils.py:66-72); the kernels implement the plain coord_min / coord_max normalisation only
+            raise _lib.ArahError('vol_feat as an OrderedDict (the (x - loc) * sc_factor normalisation branch) is not supported')
+        out = owner._trace_only(sdf_network, cam_loc, ray_directions, body_bounds_intersections, smpl_verts,
+                                skinning_weights, bone_transforms, trans, coord_min, coord_max, center, train=not eval_mode)
+        if self.sample_bg_pts > 0 and not eval_mode:
+            # background depths for a NeRF background model (ray_tracing.py:375-378; IDHRNetwork drops them again, :108-110):
+            # far / flip(linspace(1e-3, 1 - 1 / (n + 1), n)) per ray
+            n = self.sample_bg_pts
+            zo = torch.linspace(1e-3, 1.0 - 1.0 / (n + 1.0), n, device=ray_directions.device, dtype=torch.float32).view(1, 1, -1)
+            zo = body_bounds_intersections[..., 1:] / torch.flip(zo, dims=[-1])
+            out = out[:4] + ((out[4], zo),) + out[5:]
+        return out
 
     def draw_jitter(self, P):
         """The three uniform draws of ray_sampler in training mode, in the reference's order and shapes and — like the
@@ -542,8 +569,6 @@ class IDHRNetwork(nn.Module):
         self.train_skinning_net = train_skinning_net
         self.render_last_pt = render_last_pt
         self.low_vram = low_vram
-        if render_last_pt:
-            raise _lib.ArahError('render_last_pt=True is not implemented (no shipped config sets it, configs/default.yaml:52)')
         if isinstance(ray_tracer, BodyRayTracing):
             object.__setattr__(ray_tracer, '_owner', weakref.ref(self))
         self._renderers = {}
@@ -557,7 +582,7 @@ class IDHRNetwork(nn.Module):
             r = ArahRenderer(device, n_steps=rt.n_steps, near_samples=rt.near_surface_vol_samples,
                              far_samples=rt.far_surface_vol_samples, cano_view_dirs=self.cano_view_dirs,
                              latent_dim=latent_dim, n_verts=n_verts, shade_mode=self.shade_mode, root_mode=self.root_mode,
-                             shade_cull=self.shade_cull)
+                             shade_cull=self.shade_cull, render_last_pt=self.render_last_pt)
             self._renderers[key] = r
         return r
 
@@ -600,6 +625,8 @@ class IDHRNetwork(nn.Module):
         ray_dirs = input['ray_dirs']
         device = ray_dirs.device
         batch_size, P, _ = ray_dirs.shape
+        if self.render_last_pt:
+            raise _lib.ArahError('render_last_pt=True is implemented for the eval render only (the training engine composites with 1 / n_steps)')
         r = self._prepare(input, training=True)
         sdf_p, skin_p, col_p = self._param_tensors(input)
         pose_cond = input.get('pose_cond', {})
@@ -624,6 +651,9 @@ class IDHRNetwork(nn.Module):
                     view = ray_dirs + vn
             else:
                 view = torch.zeros_like(ray_dirs)
+        if ray_dirs.requires_grad or input['cam_loc'].requires_grad:
+            # model.train_cameras = True: the reference lets d rgb / d view_dir flow into the camera extrinsics; no such gradient here
+            raise _lib.ArahError('gradients with respect to ray_dirs / cam_loc (train_cameras) are not implemented')
         rgb, ws = _ShadeFn.apply(r, view[0].detach(), view_orig[0].detach(), ray_augm, self.train_skinning_net, *(sdf_p + skin_p + col_p))
         # regularisers (:73-78,117-140)
         out_extra = {}

@@ -43,6 +43,9 @@ def parse():
     ap.add_argument('--no-train-step', action='store_true', help='skip the BASELINE configs[2] training-step measurement')
     ap.add_argument('--no-mesh', action='store_true', help='skip the canonical-mesh (row f1) measurement')
     ap.add_argument('--train-rays', type=int, default=2048, help='rays per training step (configs/default.yaml:13-14: 1024 fg + 1024 bg)')
+    ap.add_argument('--seq-frames', type=int, default=258, help='frames of the BASELINE configs[3] sequence entry (0 = skip)')
+    ap.add_argument('--seq-lattice', type=int, default=256, help='lattice side of the canonical mesh extracted per sequence frame (0 = no normal maps)')
+    ap.add_argument('--no-h36m', action='store_true', help='skip the BASELINE configs[4] entry (1024x1024, 128 near samples)')
     return ap.parse_args()
 
 
@@ -100,6 +103,25 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def host_threads():
+    """Every host core this process may run on: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which must not
+    shrink the CPU arm (the reference's CPU path uses all cores)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def workload_config(size, frame, gpus, ours=True, sample=None):
+    """`config` of the JSON line: the SAME keys in both arms."""
+    return {'workload': f'ZJU-377-like {size}x{size} novel-view render, fp32 storage (BASELINE configs[1])', 'rays_per_frame': int(frame.P),
+            'n_steps': int(frame.n_steps), 'near_far_samples': [int(frame.near_samples), int(frame.far_samples)],
+            'parallelism': f'frames sharded over {gpus} GPU(s), 1 frame/rank/step' if ours else 'rank 0 only, all host cores (OpenMP over rays)',
+            'l2': '256 MB memset between timed steps' if ours else 'n/a (CPU arm)',
+            'timing': 'CUDA events on the launching stream, per step, summed; max over ranks' if ours else 'perf_counter around each step',
+            'sample': sample or 'all bbox rays of the frame, every step'}
+
+
 def make_frames(size, n_frames, first):
     from arah_release_b200 import synthetic as syn
     return [syn.make_frame(size, size, seed=0, frame_idx=first + i) for i in range(n_frames)]
@@ -116,7 +138,7 @@ def algorithmic_flops(st):
 def cpu_rate(frame, seconds, threads=0):
     """rays/s of the oracle port (oracle/arah_oracle.c, all host threads) on a bounded random ray sample of the frame."""
     from oracle import oracle as orc
-    nthr = orc.num_threads() if threads <= 0 else threads
+    nthr = host_threads() if threads <= 0 else threads
     rng = np.random.default_rng(0)
     n0 = min(frame.P, 64 * nthr)
     sel = rng.choice(frame.P, size=n0, replace=False)
@@ -149,7 +171,7 @@ def run_reference(args):
         return
     from oracle import oracle as orc
     frame = make_frames(args.size, 1, 0)[0]
-    nthr = orc.num_threads()
+    nthr = host_threads()
     rng = np.random.default_rng(0)
     # bounded sample per step, sized so that the whole run stays within a few minutes
     t = time.perf_counter()
@@ -171,8 +193,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'rays/sec at 512x512 ZJU-377 render', 'value': val, 'unit': 'rays/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'ZJU-377-like {args.size}x{args.size} novel-view render, fp32 (BASELINE configs[1])', 'rays_per_frame': frame.P,
-                       'n_steps': frame.n_steps, 'near_far_samples': [frame.near_samples, frame.far_samples]},
+            'config': workload_config(args.size, frame, args.gpus, ours=False,
+                                      sample=f'{n} random bbox rays of the frame per step (value = rays timed / seconds: the reference cost is linear in P)'),
             'cpu_baseline': {'value': val, 'unit': 'rays/s', 'cores': nthr, 'kind': 'port',
                              'sample': f'{n} random bbox rays of the frame per step; oracle/arah_oracle.c (C restatement of the reference '
                                        f'algorithm, OpenMP over rays); the Python reference cannot travel to this box'},
@@ -186,7 +208,8 @@ def train_step_bench(args, dev, frame, steps=5, warmup=3, variant='torch'):
     evaluations) + IDHRLoss-style loss + backward to every parameter tensor, on `--train-rays` random bbox rays of the frame
     (BASELINE configs[2]: 1024 + 1024 rays, train_skinning_net).  Secondary metric; the headline stays the 512x512 render."""
     import torch
-    from arah_release_b200 import ref_layout as rl, synthetic as syn
+    from arah_release_b200 import synthetic as syn
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     rng = np.random.default_rng(0)
     sel = np.sort(rng.choice(frame.P, size=min(args.train_rays, frame.P), replace=False))
@@ -269,7 +292,9 @@ def train_step_bench(args, dev, frame, steps=5, warmup=3, variant='torch'):
             'shaded_samples': int(samples), 'ms_per_step': tot, 'ms_forward_incl_tracer': float(np.mean(ms['forward'])),
             'ms_backward': float(np.mean(ms['backward'])), 'rays_per_s': P / tot * 1e3, 'steps': steps, 'warmup': warmup,
             'gpu_launches_per_step': int(launches), 'loss': float(loss.detach()),
-            'algorithmic_tflops_differentiable_part': 2.0 * mac / (tot * 1e-3) / 1e12}
+            'algorithmic_tflops_differentiable_part': 2.0 * mac / (tot * 1e-3) / 1e12,
+            'frac_of_bf16_peak': 2.0 * mac / (tot * 1e-3) / 1e12 / peaks()['tf_sustained'],
+            'note': 'tracer (persistent kernels) + hand-written forward/backward GEMM chains; latency-bound at 2048 rays'}
 
 
 # ------------------------------------------------------------------------------------------------ canonical mesh (row f1)
@@ -462,11 +487,164 @@ def image_tail_bench(net, frame, inp, steps=10, warmup=3, N=256):
                          'kind': 'oracle/images_oracle.py (numpy; python loop over faces)', 'sample': f'{ns} faces of one view timed, scaled to 3 views x {Fc} faces'}}
 
 
+
+# ------------------------------------------------------------------------------------------------ per-stage rooflines
+def stage_table(stats, t_dev, pk, r):
+    """Algorithmic and executed FLOPs of every stage of the timed steps against the measured bf16 peak."""
+    n = len(stats)
+    S = lambda k: float(sum(st[k] for st in stats))
+    cull_ran = bool(r.shade_cull and r.shade_mode == 'tf32')
+    shaded, culled = S('shaded_samples'), (S('culled_samples') if cull_ran else 0.0)
+    rows = {
+        'trace': ('k_trace_persist (1-NN + inverse NN skinning + SDF per marching step)', 'ms_trace', 2.0 * S('trace_sdf_evals') * MAC_SDF, None),
+        'iso': ('k_iso_init_tc3 + k_iso_persist (joint search: skinning MLP + SDF per Broyden step)', 'ms_iso',
+                2.0 * (S('iso_rays') * (4 * MAC_SKIN + 2 * MAC_SDF) + S('iso_g_evals') * (MAC_SKIN + MAC_SDF)), None),
+        # the reference evaluates g twice at the start of every search (J init + g(x0)); the kernel evaluates it once
+        'sample_corr': ('k_knn_samples + k_corr_persist (per-sample correspondence search, skinning MLP in 3xfp16 split precision)', 'ms_sample_corr',
+                        2.0 * S('corr_skin_evals') * MAC_SKIN, 2.0 * (S('corr_skin_evals') - S('on_samples')) * MAC_SKIN),
+        'shade': ('k_sdf_fwd16 + k_alpha_cull + k_shade_tc3 (SDF value of all samples in fp16; gradient + colour MLP of the alpha != 0 samples in tf32)',
+                  'ms_shade', 2.0 * shaded * (2 * MAC_SDF + MAC_COL),
+                  2.0 * ((shaded * MAC_SDF if cull_ran else 0.0) + (shaded - culled) * (2 * MAC_SDF + MAC_COL))),
+    }
+    main = {'trace': 'k_trace_persist', 'iso': 'k_iso_persist', 'sample_corr': 'k_corr_persist', 'shade': 'k_shade_tc3'}
+    out = {}
+    for k, (name, msk, alg, ex) in rows.items():
+        ms = S(msk)
+        ex = alg if ex is None else ex
+        out[k] = {'kernel': name, 'main_kernel': main[k], 'ms_per_step': ms / n, 'share_of_step': ms / (1e3 * t_dev),
+                  'algorithmic_flops_per_step': alg / n, 'executed_flops_per_step': ex / n,
+                  'achieved': alg / max(ms, 1e-9) / 1e9, 'frac': alg / max(ms, 1e-9) / 1e9 / pk['tf_sustained'],
+                  'executed_tflops': ex / max(ms, 1e-9) / 1e9, 'executed_frac': ex / max(ms, 1e-9) / 1e9 / pk['tf_sustained']}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ configs[3]: sharded sequence
+def sequence_bench(args, dev, net, world, rank):
+    """BASELINE configs[3] (test.py:71-80, lightning_model.py:306-360): a novel-pose sequence, frame i -> rank i mod N, per frame the
+    render, the canonical mesh + three normal maps (gen_cano_mesh=True) and the uint8 image; one gather of the images at the end.
+    Device time per frame from CUDA events (frame preparation on the host is the dataset's job and stays outside), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from tools import ref_layout as rl, sharding as sh, synthetic as syn
+    mine = sh.frames_for_rank(args.seq_frames, rank, world)
+    t_render = t_mesh = 0.0
+    rays = 0
+    images = {}
+    t_wall = time.perf_counter()
+    H = W = args.size
+    for fi in mine:
+        f = syn.make_frame(args.size, args.size, seed=0, frame_idx=fi)
+        inp = rl.inputs_from_frame(f, rl.sdf_network_from_frame(f, dev), dev)
+        pix = torch.from_numpy(f.pix).to(dev)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        out = net(inp)
+        images[fi] = sh.to_image_u8(out['rgb_values'][0], pix, f.H, f.W)
+        e[1].record()
+        if args.seq_lattice > 0:
+            inp2 = dict(inp, cam_rot=torch.from_numpy(f.pose[:3, :3].copy()).view(1, 3, 3), cam_trans=torch.from_numpy(f.pose[:3, 3].copy()).view(1, 3),
+                        intrinsics=torch.from_numpy(f.K).view(1, 3, 3))
+            net.render_normal_maps(inp2, N=args.seq_lattice, image_size=(f.H, f.W))
+        e[2].record()
+        torch.cuda.synchronize()
+        t_render += e[0].elapsed_time(e[1]) / 1e3
+        t_mesh += e[1].elapsed_time(e[2]) / 1e3
+        rays += f.P
+    t_wall = time.perf_counter() - t_wall
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    g0 = time.perf_counter()
+    gathered = sh.gather_frames(images, args.seq_frames, H=H, W=W, device=dev)
+    torch.cuda.synchronize()
+    t_gather = time.perf_counter() - g0
+    per_rank = [[t_render, t_mesh, t_wall, float(rays), t_gather]]
+    if world > 1:
+        tl = torch.tensor(per_rank[0], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(tl) for _ in range(world)]
+        dist.all_gather(allt, tl)
+        per_rank = [[float(v) for v in x] for x in allt]
+    if rank != 0:
+        return None
+    tr, tm = max(x[0] for x in per_rank), max(x[0] + x[1] for x in per_rank)
+    rays_all = sum(x[3] for x in per_rank)
+    return {'workload': f'{args.seq_frames}-frame synthetic novel-pose sequence at {args.size}x{args.size} (BASELINE configs[3]), frame i -> rank i mod {world}',
+            'frames': args.seq_frames, 'n_gpus': world, 'rays': int(rays_all),
+            'seconds_render_only': tr, 'rays_per_s_render_only': rays_all / tr, 'frames_per_s_render_only': args.seq_frames / tr,
+            'seconds_with_normal_maps': tm, 'frames_per_s_with_normal_maps': args.seq_frames / tm, 'normal_maps_lattice': args.seq_lattice,
+            'mesh_branch_share': (tm - tr) / tm if tm > 0 else None,
+            'seconds_gather_uint8': max(x[4] for x in per_rank), 'gathered_images': None if gathered is None else len(gathered),
+            'seconds_wall_incl_host_frame_prep': max(x[2] for x in per_rank),
+            'per_rank_seconds_device': [x[0] + x[1] for x in per_rank],
+            'timing': 'CUDA events per frame around render (+ uint8 image) and around mesh extraction + 3 normal maps, summed per rank, max over ranks'}
+
+
+# ------------------------------------------------------------------------------------------------ configs[4]: 1024^2, 128 near samples
+def h36m_bench(dev, pk, steps=3, warmup=2):
+    """BASELINE configs[4] (im2mesh/config.py:225, ray_tracing.py:336,346): 1024x1024, n_steps 160, 128 near-surface samples, canonical view
+    directions: ~10^6 rays x 160 sample slots, the HBM / MLP stress case."""
+    import torch
+    from arah_release_b200 import synthetic as syn
+    from tools import ref_layout as rl
+    from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
+    fr = syn.make_frame(1024, 1024, seed=4, n_steps=160, near_samples=128, far_samples=16, cano_view_dirs=True, beta=0.003)
+    dvn, rend, skin, sdf = rl.modules_from_frame(fr, dev)
+    net = IDHRNetwork(dvn, rend, skin, BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples, far_surface_vol_samples=fr.far_samples),
+                      cano_view_dirs=True).eval()
+    inp = rl.inputs_from_frame(fr, sdf, dev)
+    free0 = torch.cuda.mem_get_info(dev)[0]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        net(inp)
+    rr = net._last[0]
+    rr.set_profiling(True)
+    ms, sts = [], []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); net(inp); e1.record()
+        sts.append(rr.stats())
+        ms.append(e0.elapsed_time(e1))
+    free1 = torch.cuda.mem_get_info(dev)[0]
+    m = float(np.mean(ms))
+    stt = stage_table(sts, sum(ms) / 1e3, pk, rr)
+    st = sts[-1]
+    return {'workload': '1024x1024, n_steps 160, 128 near + 16 far samples, cano_view_dirs (BASELINE configs[4])', 'rays': int(fr.P),
+            'ms_per_frame': m, 'rays_per_s': fr.P / m * 1e3, 'steps': steps, 'warmup': warmup,
+            'stages_ms': {k: st[k] for k in ('ms_trace', 'ms_iso', 'ms_sample_corr', 'ms_shade', 'ms_composite')},
+            'counters': {k: st[k] for k in ('on_samples', 'corr_skin_evals', 'shaded_samples', 'culled_samples', 'hit_rays')},
+            'roofline_stages': {k: {'ms_per_step': v['ms_per_step'], 'frac': v['frac'], 'executed_frac': v['executed_frac']} for k, v in stt.items()},
+            'device_memory_in_use_gb': (free0 - free1) / 2 ** 30 + 0.25, 'gpu_launches_per_frame': int(st['kernel_launches'])}
+
+
+# ------------------------------------------------------------------------------------------------ configs[2]: CPU leg of the training step
+def train_step_cpu(frame, rays=192, seed=0):
+    """One training step of the CPU port (oracle/arah_oracle.c training-mode tracer on all host threads + oracle/train_oracle.py, the torch
+    fp32 autograd restatement pinned to the unmodified reference by tests/golden/train_*.npz) on a bounded ray sample."""
+    import copy
+    import torch
+    from arah_release_b200 import synthetic as syn
+    from oracle import oracle as orc, train_oracle as to
+    torch.set_num_threads(host_threads())
+    rng = np.random.default_rng(1)
+    sel = np.sort(rng.choice(frame.P, size=min(rays, frame.P), replace=False))
+    fr = copy.copy(frame)
+    fr.ray_dirs, fr.near_far, fr.pix = frame.ray_dirs[sel], frame.near_far[sel], frame.pix[sel]
+    aux = syn.train_aux_points(fr, seed=seed)
+    t = time.perf_counter()
+    c = orc.render(fr, train_noise=orc.train_noise(fr, seed), threads=host_threads())
+    trace = {k[len('trace.'):]: v for k, v in c.items() if k.startswith('trace.')}
+    to.train_step(fr, aux, trace, seed, train_skinning_net=True)
+    dt = time.perf_counter() - t
+    return {'value': fr.P / dt, 'unit': 'rays/s', 'cores': host_threads(), 'kind': 'port',
+            'sample': f'{fr.P} rays of the frame, one forward + backward in {dt:.1f} s (C tracer + torch autograd restatement)'}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from arah_release_b200 import ref_layout as rl
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -521,24 +699,15 @@ def run_ours(args):
     if rank == 0:
         clk.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    shade_ms, shade_flops, shade_flops_ref, step_flops, stats_last = [], [], [], [], None
-    corr_ms, corr_flops = [], []
+    step_flops, stats_last, stage_acc = [], None, []
     for k in range(args.steps):
         flush.zero_()                                   # L2 flush between timed iterations (outside the event pair)
         ev[k][0].record()
         step_device(args.warmup + k)
         ev[k][1].record()
         st = r.stats()                                  # syncs; counters + stage events of this step
-        shade_ms.append(st['ms_shade'])
-        # executed work of the shading stage: with the exact alpha cull every converged sample gets an SDF-only forward pass and
-        # only the survivors (alpha != 0) the full SDF fwd + gradient + colour pass; without it all samples get the full pass
-        culled, shaded = st.get('culled_samples', 0), st['shaded_samples']
-        cull_ran = r.shade_cull and r.shade_mode == 'tf32'
-        shade_flops.append(2.0 * ((shaded * MAC_SDF if cull_ran else 0) + (shaded - culled) * (2 * MAC_SDF + MAC_COL)))
-        shade_flops_ref.append(2.0 * shaded * (2 * MAC_SDF + MAC_COL))
         step_flops.append(algorithmic_flops(st))
-        corr_ms.append(st['ms_sample_corr'])
-        corr_flops.append(2.0 * st['corr_skin_evals'] * MAC_SKIN)
+        stage_acc.append(st)
         stats_last = st
         phase_clk = r.phase_clocks()
     barrier()
@@ -568,15 +737,26 @@ def run_ours(args):
     h2d = P0 * 20 + 24 * 16 * 4 + f0.smpl_verts.size * 4 + f0.smpl_weights.size * 4
     d2h = P0 * (12 + 1 + 12)
 
-    # ---------------- reduce over ranks: MAX time, SUM rays
+    # ---------------- reduce over ranks: MAX time, SUM rays; per-rank spread of the device time
+    per_rank_ms = [1e3 * t_dev / args.steps]
     if world > 1:
-        t = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tl = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(tl) for _ in range(world)]
+        dist.all_gather(allt, tl)
+        per_rank_ms = [1e3 * float(x[0]) / args.steps for x in allt]
+        t_dev, t_e2e = max(float(x[0]) for x in allt), max(float(x[1]) for x in allt)
         n = torch.tensor([float(rays_timed)], device=dev, dtype=torch.float64)
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
-        t_dev, t_e2e, rays_all = float(t[0]), float(t[1]), float(n[0])
+        rays_all = float(n[0])
     else:
         rays_all = float(rays_timed)
+    # ---------------- BASELINE configs[3]: the 258-frame sequence sharded over the ranks (every rank takes part)
+    seq = None
+    if args.seq_frames > 0:
+        try:
+            seq = sequence_bench(args, dev, net, world, rank)
+        except Exception as ex:
+            seq = {'error': repr(ex)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -590,50 +770,51 @@ def run_ours(args):
             ours0 = (o0['rgb_values'][0].cpu().numpy(), o0['network_body_mask'][0].cpu().numpy())
         except Exception:
             ours0 = None
-    ach = (sum(shade_flops) / max(sum(shade_ms), 1e-9)) / 1e9          # FLOP/ms -> TFLOP/s
-    traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'k_shade_tc3_traffic.json' if r.shade_mode == 'tf32' else 'k_shade_traffic.json')
+    # ---------------- rooflines: every stage against the measured bf16 peak; the stage with the largest share is `roofline`
+    stt = stage_table(stage_acc, t_dev, pk, r)
+    dom = max(stt, key=lambda k: stt[k]['ms_per_step'])
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+            tj = json.load(open(tp))
+            traffic = tj.get(stt[dom]['main_kernel'], {}).get('dram_bytes_per_launch')
+            traffic_src = tj.get('_source')
         except Exception:
             traffic = None
+    roof = dict(stt[dom])
+    roof.update({'bound': 'tensor', 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'peak_source': pk['src'] + ' bf16 cuBLAS sustained (MEASURED_PEAKS.json)',
+                 'stage': dom, 'traffic': traffic, 'traffic_source': traffic_src,
+                 'note': 'achieved = ALGORITHMIC flops (SURVEY §8d formula through the device counters; a split-precision product counts once) / '
+                         'stage time from CUDA events recorded inside the library at stage boundaries'})
+    exec_flops = sum(v['executed_flops_per_step'] for v in stt.values())
     line = {
         'metric': 'rays/sec at 512x512 ZJU-377 render', 'value': rays_all / t_dev, 'unit': 'rays/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'ZJU-377-like {args.size}x{args.size} novel-view render, fp32 (BASELINE configs[1])',
-                   'rays_per_frame': P0, 'n_steps': f0.n_steps, 'near_far_samples': [f0.near_samples, f0.far_samples],
-                   'parallelism': f'frames sharded over {args.gpus} GPU(s), 1 frame/rank/step', 'l2': '256 MB memset between timed steps',
-                   'precision': f'fp32 storage/accumulate; shading MLP operands {r.shade_mode}; root finding (sphere tracing, joint search, correspondences) {r.root_mode}',
-                   'timing': 'CUDA events on the launching stream, per step, summed; max over ranks'},
+        'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'fp32 storage/accumulate; tensor-core operands: tf32 (colour + gradient), fp16 (SDF value), 3xfp16 split ~ fp32 (all root finding)'
+                 if r.shade_mode == 'tf32' else 'f32', 'data': 'synthetic',
+        'config': workload_config(args.size, f0, args.gpus),
         'e2e': {'value': rays_all / t_e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'api': 'arah_set_frame(pose_on_host) + arah_render_host via IDHRNetwork host wrapper'},
         'gpu_launches': int((stats_last['kernel_launches'] + stats_last['pack_launches']) * args.steps),
+        'gpu_launches_per_frame': {'render': int(stats_last['kernel_launches']), 'set_frame_packing': int(stats_last['pack_launches'])},
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': f'shading stage: k_shade_tc3<sdf-only> + k_alpha_cull + k_shade_tc3 (SDF fwd + reverse-mode grad + colour MLP; tcgen05 {r.shade_mode} operands, fp32 accumulate in TMEM)'
-                     if r.shade_mode == 'tf32' else 'k_shade (fp32 FFMA tiles)',
-                     'achieved': ach, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf_sustained'],
-                     'peak_source': pk['src'] + ' bf16 cuBLAS sustained (MEASURED_PEAKS.json)', 'traffic': traffic,
-                     'algorithmic_flops_per_launch': float(np.mean(shade_flops)), 'ms_per_launch': float(np.mean(shade_ms)),
-                     'kernel_share_of_step': float(sum(shade_ms) / (1e3 * t_dev)),
-                     'exact_alpha_cull': {'enabled': bool(r.shade_cull and r.shade_mode == 'tf32'), 'culled_samples': int(stats_last.get('culled_samples', 0)),
-                                          'shaded_samples': int(stats_last['shaded_samples']),
-                                          'reference_equivalent_tflops': float(sum(shade_flops_ref) / max(sum(shade_ms), 1e-9) / 1e9),
-                                          'note': 'achieved counts EXECUTED flops only (SDF-only pass over all converged samples + full pass over '
-                                                  'samples with alpha != 0); reference_equivalent counts the full pass for every sample as the reference executes it'},
-                     'whole_step_tflops_reference_equivalent': float(sum(step_flops) / t_dev / 1e12)},
-        'roofline_corr': {'bound': 'tensor', 'kernel': f'k_knn_samples + 51 x k_corr_tc3 (per-sample correspondence search; skinning MLP {r.root_mode}: 3 TF32 products count as 1 useful)',
-                          'achieved': (sum(corr_flops) / max(sum(corr_ms), 1e-9)) / 1e9, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-                          'frac': (sum(corr_flops) / max(sum(corr_ms), 1e-9)) / 1e9 / pk['tf_sustained'], 'ms_per_step': float(np.mean(corr_ms)),
-                          'share_of_step': float(sum(corr_ms) / (1e3 * t_dev))},
+        'roofline': roof,
+        'roofline_stages': stt,
+        'whole_step_executed_frac': exec_flops / (1e3 * t_dev / args.steps * 1e-3) / 1e12 / pk['tf_sustained'],
+        'whole_step_tflops_reference_equivalent': float(sum(step_flops) / t_dev / 1e12),
+        'per_rank_ms_per_step': {'min': min(per_rank_ms), 'max': max(per_rank_ms), 'mean': float(np.mean(per_rank_ms)), 'all': per_rank_ms},
         'stages_ms_last_step': {k: stats_last[k] for k in ('ms_trace', 'ms_iso', 'ms_sample_corr', 'ms_shade', 'ms_composite', 'ms_total')},
         'phase_cycles_last_step': {'corr': phase_clk[:6], 'shade': phase_clk[8:15], 'trace': phase_clk[16:22],
-                                   'note': 'SM cycles of one thread per CTA summed over CTAs/launches: corr = [gather, layer0, mma_wait, epilogue, out_layer, per_point]; '
-                                           'shade = [setup+layer0, fwd_wait, fwd_epi, rev_wait, rev_epi, colour_inputs, colour_mlp]'},
+                                   'note': 'SM cycles of one thread per CTA summed over CTAs/launches: corr = [-, layer0, mma_wait, epilogue, out_layer, per_point]; '
+                                           'shade = [setup+layer0, fwd_wait, fwd_epi, rev_wait, rev_epi, colour_inputs, colour_mlp]; '
+                                           'trace = [1-NN, layer0, mma_wait, epilogue, marching, evaluations]'},
         'counters_last_step': {k: stats_last[k] for k in ('rays', 'trace_sdf_evals', 'iso_rays', 'iso_g_evals', 'on_samples', 'corr_skin_evals',
-                                                           'shaded_samples', 'hit_rays', 'vol_rays')},
+                                                           'shaded_samples', 'culled_samples', 'hit_rays', 'vol_rays')},
     }
+    if seq is not None:
+        line['sequence258'] = seq
     if args.gpus == 1 and not args.no_train_step:
         try:
             line['train_step'] = train_step_bench(args, dev, f0)
@@ -665,6 +846,13 @@ def run_ours(args):
             line['train_step'].update(train_step_bench(args, dev, f0, variant='fused'))
         except Exception as ex:
             line['train_step']['fused_loss_error'] = repr(ex)[:300]
+    if args.gpus == 1 and not args.no_h36m:
+        try:
+            del net
+            torch.cuda.empty_cache()
+            line['h36m_1024'] = h36m_bench(dev, pk)
+        except Exception as ex:
+            line['h36m_1024'] = {'error': repr(ex)[:300]}
     if args.gpus == 1 and not args.no_cpu_baseline:
         v, cores, n, dt, sel, o_cpu = cpu_rate(f0, args.cpu_sample_seconds)
         line['cpu_baseline'] = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
@@ -674,6 +862,12 @@ def run_ours(args):
                 line['parity'] = parity_on_sample(ours0[0], ours0[1], sel, o_cpu)
             except Exception as ex:
                 line['parity'] = {'error': repr(ex)[:300]}
+        if not args.no_train_step and isinstance(line.get('train_step'), dict) and 'error' not in line['train_step']:
+            try:
+                line['train_step']['cpu_baseline'] = train_step_cpu(f0)
+                line['train_step']['speedup_vs_cpu_port'] = line['train_step']['rays_per_s'] / line['train_step']['cpu_baseline']['value']
+            except Exception as ex:
+                line['train_step']['cpu_baseline'] = {'error': repr(ex)[:300]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -39,16 +39,21 @@ typedef struct ArahConfig {
     int32_t latent_dim;           /* colour-net per-frame latent (128; 0 = none) */
     int32_t n_verts;              /* SMPL vertices (6890) */
     int32_t max_rays;             /* initial workspace size in rays (grown on demand) */
-    int32_t shade_mode;           /* ARAH_SHADE_TF32 (default 0): shading MLPs on tcgen05 tensor cores, TF32 operands,
-                                   * fp32 accumulate; ARAH_SHADE_FP32 (1): fp32 FFMA tiles (bit-for-bit the oracle's
-                                   * arithmetic order).  Root finding is fp32 in both modes. */
-    int32_t root_mode;            /* ARAH_ROOT_3XTF32 (default 0): the skinning MLP of the per-sample correspondence search on
-                                   * tcgen05 in split precision (hi/lo TF32, 3 products ~ fp32); ARAH_ROOT_FP32 (1): fp32
-                                   * FFMA tiles.  Residual bookkeeping, Jacobians and Broyden updates are fp32 in both. */
+    int32_t shade_mode;           /* ARAH_SHADE_TF32 (default 0): shading MLPs on tcgen05 tensor cores (gradient + colour: TF32
+                                   * operands; the SDF value compositing uses: fp16 operands), fp32 accumulate;
+                                   * ARAH_SHADE_FP32 (1): fp32 FFMA tiles (bit-for-bit the oracle's arithmetic order).
+                                   * Independent of root_mode. */
+    int32_t root_mode;            /* ARAH_ROOT_3XTF32 (default 0; the name is historical): every MLP of the root-finding stages
+                                   * (sphere tracing, joint search, per-sample correspondence search) on tcgen05 in split
+                                   * precision (hi/lo fp16 or TF32 operands, 3 products ~ one fp32 product), persistent kernels;
+                                   * ARAH_ROOT_FP32 (1): fp32 FFMA tiles, one launch per iteration.  Residual bookkeeping,
+                                   * Jacobians and Broyden updates are fp32 in both. */
     int32_t shade_cull;           /* ARAH_CULL_EXACT (default 0): with shade_mode TF32, converged samples whose compositing alpha is
                                    * exactly 0.0f in fp32 skip the SDF-gradient + colour pass — their weight alpha * T is 0, so no
                                    * output bit can depend on their colour (results are bit-identical to ARAH_CULL_OFF, see
                                    * tests/test_gpu_parity.py::test_alpha_cull_is_exact); ARAH_CULL_OFF (1): shade every sample. */
+    int32_t render_last_pt;       /* IDHRNetwork(render_last_pt=...), implicit_differentiable_renderer.py:380-381: != 0 gives the last
+                                   * converged sample of a ray the interval 1e10 (opaque beyond it) instead of 1 / n_steps */
 } ArahConfig;
 #define ARAH_CULL_EXACT 0
 #define ARAH_CULL_OFF 1

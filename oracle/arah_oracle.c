@@ -50,6 +50,7 @@ typedef struct {
     int32_t n_verts;
     float trans[3], cmin, cmax, center[3], cam_loc[3], pose[16];
     int32_t n_steps, near_samples, far_samples, cano_view_dirs;
+    int32_t render_last_pt;                        /* implicit_differentiable_renderer.py:380-381: last interval 1e10 instead of 1 / n_steps */
 } OracleFrame;
 
 typedef struct {
@@ -622,7 +623,7 @@ static void render_ray(const OracleFrame *f, const Packed *p, const float *d, fl
     }
     float rgb[3] = {0, 0, 0}, wsum = 0.0f, Tr = 1.0f;
     for (int k = 0; k < len; ++k) {
-        float dz = (k + 1 < len) ? (cz[k + 1] - cz[k]) : (1.0f / (float)S);     /* :379-385 */
+        float dz = (k + 1 < len) ? (cz[k + 1] - cz[k]) : (f->render_last_pt ? 1e10f : 1.0f / (float)S);     /* :379-385 */
         const float alpha = 1.0f - expf(-cden[k] * dz);
         const float w = alpha * Tr;
         Tr = Tr * (1.0f - alpha + 1e-7f);

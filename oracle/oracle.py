@@ -25,7 +25,7 @@ class OracleFrame(C.Structure):
                 ('trans', C.c_float * 3), ('cmin', C.c_float), ('cmax', C.c_float), ('center', C.c_float * 3),
                 ('cam_loc', C.c_float * 3), ('pose', C.c_float * 16),
                 ('n_steps', C.c_int32), ('near_samples', C.c_int32), ('far_samples', C.c_int32),
-                ('cano_view_dirs', C.c_int32)]
+                ('cano_view_dirs', C.c_int32), ('render_last_pt', C.c_int32)]
 
 
 class OracleOut(C.Structure):
@@ -113,6 +113,7 @@ def make_frame(frame):
     of.near_samples = frame.near_samples
     of.far_samples = frame.far_samples
     of.cano_view_dirs = int(frame.cano_view_dirs)
+    of.render_last_pt = int(bool(getattr(frame, 'render_last_pt', False)))
     return of, keep
 
 

@@ -1,7 +1,7 @@
 // host_math_test.cpp — compiles arah_math.cuh (the per-point math the kernels run) for the HOST so that
 // tests/test_host_math.py can check it on CPU against independent implementations (torch / the reference's broyden()).
 #include <cstring>
-#include "arah_math.cuh"
+#include "../../arah_release_b200/csrc/arah_math.cuh"
 
 using namespace arah;
 

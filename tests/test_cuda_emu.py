@@ -151,7 +151,8 @@ def test_bench_image_tail_entry_runs_on_emulator(on_emulator, monkeypatch):
 def test_render_normal_maps_of_the_drop_in_module_on_emulator(on_emulator, monkeypatch):
     """`IDHRNetwork.render_normal_maps` (the `gen_cano_mesh` tail, models/__init__.py:226-309) with a given mesh: reads the reference's
     camera keys, returns the reference's three output keys; values against the oracle."""
-    from arah_release_b200 import images, ref_layout as rl, synthetic as syn
+    from arah_release_b200 import images, synthetic as syn
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     from helpers_images import iso_mesh, make_camera
     from oracle import images_oracle as io

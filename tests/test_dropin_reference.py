@@ -67,7 +67,8 @@ def test_reference_get_model_builds_with_our_classes(name, monkeypatch):
     assert (tr.n_steps, tr.near_surface_vol_samples, tr.far_surface_vol_samples) == (m['n_steps'], m['near_surface_samples'], m['far_surface_samples'])
     assert model.idhr_network.cano_view_dirs == m['cano_view_dirs']
     # no CPU path behind the reference's module tree either
-    from arah_release_b200 import ref_layout as rl, synthetic as syn
+    from arah_release_b200 import synthetic as syn
+    from tools import ref_layout as rl
     fr = syn.make_frame(8, 8, seed=0)
     with pytest.raises(_lib.ArahError):
         model.idhr_network.eval()(rl.inputs_from_frame(fr, rl.sdf_network_from_frame(fr, 'cpu'), 'cpu'))

@@ -56,7 +56,8 @@ def test_hypernetwork_matches_reference_and_oracle(seed):
 
 def test_hypernetwork_feeds_the_renderer():
     """decoder from the hypernetwork kernel -> IDHRNetwork on the device == the same SDF parameters uploaded from the host."""
-    from arah_release_b200 import ref_layout as rl, synthetic as syn
+    from arah_release_b200 import synthetic as syn
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     fr = syn.make_frame(16, 16, seed=3)
     sd, dec = _decoder(0, False)

@@ -14,7 +14,7 @@ DEV = 'cuda:0'
 
 
 def _net(fr, root_mode):
-    from arah_release_b200 import ref_layout as rl
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
     tracer = BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples, far_surface_vol_samples=fr.far_samples)

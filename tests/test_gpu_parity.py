@@ -13,7 +13,7 @@ DEV = 'cuda:0'
 
 
 def _build(fr, shade_mode='fp32', root_mode=None):
-    from arah_release_b200 import ref_layout as rl
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
     tracer = BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples, far_surface_vol_samples=fr.far_samples)
@@ -214,7 +214,7 @@ def test_alpha_cull_is_exact(name):
     fr, ref, _ = load_golden(name)
     outs, stats = [], []
     for cull in (True, False):
-        from arah_release_b200 import ref_layout as rl
+        from tools import ref_layout as rl
         from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
         dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
         tracer = BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples, far_surface_vol_samples=fr.far_samples)
@@ -230,7 +230,8 @@ def test_alpha_cull_is_exact(name):
 
 
 def test_alpha_cull_is_exact_full_size_512():
-    from arah_release_b200 import ref_layout as rl, synthetic as syn
+    from arah_release_b200 import synthetic as syn
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     fr = syn.make_frame(512, 512, seed=0)
     res = []
@@ -262,7 +263,7 @@ def test_full_size_properties_h36m_1024():
     rgb = rgb1.cpu().numpy()
     assert np.isfinite(rgb).all() and rgb.min() >= 0 and rgb.max() <= 1.0 + 1e-5
     # exact alpha cull on vs off: bit-identical at this size too
-    from arah_release_b200 import ref_layout as rl
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
     tracer = BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples, far_surface_vol_samples=fr.far_samples)

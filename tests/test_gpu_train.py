@@ -13,7 +13,7 @@ DEV = 'cuda:0'
 
 
 def build_net(fr, train_skinning_net, leaves=True, train_mode='fp32'):
-    from arah_release_b200 import ref_layout as rl
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
     sdf_leaves = {}
@@ -35,7 +35,7 @@ def build_net(fr, train_skinning_net, leaves=True, train_mode='fp32'):
 
 
 def train_inputs(fr, sdf, aux):
-    from arah_release_b200 import ref_layout as rl
+    from tools import ref_layout as rl
     inp = rl.inputs_from_frame(fr, sdf, DEV)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
     inp['pose_cond']['latent_code'] = inp['pose_cond']['latent_code'].clone().requires_grad_(True)

@@ -248,7 +248,7 @@ def test_normal_maps_full_size_512():
 def test_gen_cano_mesh_end_to_end():
     """extract_canonical_mesh -> skinned vertices -> the three normal maps, all on the GPU (models/__init__.py:203-311)."""
     from helpers import load_golden
-    from arah_release_b200 import ref_layout as rl
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     from oracle import images_oracle as io
     fr, _, _ = load_golden('zju377_24x24_s0')

@@ -10,13 +10,14 @@ import torch
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 CSRC = os.path.join(ROOT, 'arah_release_b200', 'csrc')
-SO = os.path.join(CSRC, 'libhost_math_test.so')
+NATIVE = os.path.join(ROOT, 'tests', 'native')
+SO = os.path.join(NATIVE, 'libhost_math_test.so')
 FP = C.POINTER(C.c_float)
 
 
 @pytest.fixture(scope='module')
 def hm():
-    src = os.path.join(CSRC, 'host_math_test.cpp')
+    src = os.path.join(NATIVE, 'host_math_test.cpp')
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, 'arah_math.cuh'))):
         cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
         subprocess.check_call([cxx, '-O2', '-std=c++17', '-x', 'c++', '-shared', '-fPIC', '-o', SO, src])

@@ -138,6 +138,31 @@ def test_mirror_matches_reference_through_shim(criterion_factory, seed):
         assert not grads['rgb_values'][2048:].any()
 
 
+def test_mirror_rejects_row_count_mismatch(criterion_factory):
+    """Every per-ray tensor must have body_mask's row count: the kernels index all of them up to n_rays (a mismatch
+    that raises an indexing error in the reference must not become an out-of-bounds device access)."""
+    from arah_release_b200 import _lib
+    cfg, cut, full, ref = load_loss_golden(LOSS_SEEDS[0])
+    crit = criterion_factory(cfg)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).unsqueeze(0)
+
+    def outputs(**short):
+        mo = {'rgb_values': t(full['rgb_values']), 'sdf_output': t(full['sdf_output']), 'network_body_mask': t(full['network_body_mask']),
+              'body_mask': t(full['body_mask']), 'off_surface_mask': t(full['off_surface_mask']), 'surface_normals': None,
+              'grad_theta': torch.from_numpy(full['grad_theta']), 'off_surface_sdf': torch.from_numpy(full['off_surface_sdf']),
+              'inside_sdf': torch.from_numpy(full['inside_sdf']), 'pred_weights': t(full['pred_weights']), 'sdf_params': [t(p) for p in full['sdf_params']]}
+        for k, n in short.items():
+            mo[k] = mo[k][:, :n]
+        return mo
+    gt = {'rgb': t(full['rgb_gt']), 'sampled_weights': t(full['sampled_weights'])}
+    n = full['body_mask'].shape[0]
+    for key in ('rgb_values', 'network_body_mask', 'off_surface_mask'):
+        with pytest.raises(_lib.ArahError):
+            crit(outputs(**{key: n - 3}), gt)
+    with pytest.raises(_lib.ArahError):
+        crit(outputs(), {'rgb': t(full['rgb_gt'])[:, :n - 3], 'sampled_weights': gt['sampled_weights']})
+
+
 @pytest.mark.parametrize('seed', LOSS_SEEDS)
 def test_gpu_test_body_holds_on_the_host_shim(hl, monkeypatch, seed):
     """The assertions of tests/test_gpu_zx_loss.py::test_fused_loss_matches_reference, executed with the device set to 'cpu' and the

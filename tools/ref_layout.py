@@ -1,4 +1,4 @@
-"""Parameter containers with the reference's module / state_dict layout, WITHOUT any forward computation.
+"""Test / bench scaffolding: parameter containers with the reference's module / state_dict layout, WITHOUT any forward computation.
 
 On the GPU box /root/reference does not exist, so tests and bench.py need something that *looks* like the modules the
 reference hands to the renderer (attribute names, tensor shapes, weight-norm parametrisation) to exercise the drop-in
@@ -13,26 +13,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-
-class _NoForward(nn.Module):
-    def forward(self, *a, **k):
-        raise RuntimeError(f'{type(self).__name__} is a parameter container; the ARAH hot path runs in libarah_b200.so only')
-
-
-class BatchLinearFiLM(_NoForward):
-    def __init__(self, weights, biases, freq, phase_shift):
-        super().__init__()
-        self.weights, self.biases, self.freq, self.phase_shift = weights, biases, freq, phase_shift
-
-
-class BatchLinear(_NoForward):
-    def __init__(self, weights, biases):
-        super().__init__()
-        self.weights, self.biases = weights, biases
-
-
-class Sine(_NoForward):
-    pass
+from arah_release_b200.containers import BatchLinear, BatchLinearFiLM, Sine, _NoForward  # noqa: F401
 
 
 class WNLinear(_NoForward):
@@ -113,4 +94,9 @@ def inputs_from_frame(frame, sdf_network, device):
         'coord_max': t(np.array([frame.coord_max])).view(1, 1, 1), 'center': t(frame.center).view(1, 1, 3),
         'minimal_shape': t(frame.minimal_shape).view(1, -1, 3), 'sdf_network': sdf_network,
         'pose_cond': {'latent_code': t(frame.latent).view(1, -1)},
+        # host copies of the per-frame scalars (the dataset has them before .cuda()): lets the renderer skip the device read-back
+        'host_scalars': {'trans': [float(v) for v in np.asarray(frame.trans).reshape(-1)[:3]], 'coord_min': float(frame.coord_min),
+                         'coord_max': float(frame.coord_max), 'center': [float(v) for v in np.asarray(frame.center).reshape(-1)[:3]],
+                         'cam_loc': [float(v) for v in np.asarray(frame.cam_loc).reshape(-1)[:3]],
+                         'pose': [float(v) for v in np.asarray(frame.pose).reshape(-1)[:16]]},
     }

@@ -30,7 +30,7 @@ def main():
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
-    from arah_release_b200 import ref_layout as rl, sharding as sh, synthetic as syn
+    from tools import ref_layout as rl, sharding as sh, synthetic as syn
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     world, rank, local = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
@@ -70,7 +70,7 @@ def main():
         t = torch.tensor([secs], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         n = torch.tensor([float(rays)], device=dev, dtype=torch.float64); dist.all_reduce(n, op=dist.ReduceOp.SUM)
         secs, rays = float(t[0]), float(n[0])
-    gathered = sh.gather_frames(images, a.frames) if a.gather and images else None
+    gathered = sh.gather_frames(images, a.frames, H=a.size, W=a.size, device=dev) if a.gather else None
     if rank == 0:
         print(json.dumps({'workload': f'{a.frames}-frame synthetic novel-pose sequence at {a.size}x{a.size}, frames sharded over {world} GPU(s)',
                           'frames': a.frames, 'rays': int(rays), 'seconds': secs, 'rays_per_s': rays / secs, 'frames_per_s': a.frames / secs,
