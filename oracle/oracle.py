@@ -48,8 +48,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()                      # (re)compile when the .so is missing or older than its sources
         _lib = C.CDLL(_SO)
         _lib.arah_oracle_render.argtypes = [C.POINTER(OracleFrame), FP, FP, C.c_int, C.POINTER(OracleOut), C.c_int]
         _lib.arah_oracle_render_train.argtypes = [C.POINTER(OracleFrame), FP, FP, C.c_int, C.POINTER(OracleOut), C.c_int, FP, FP, FP]

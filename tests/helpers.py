@@ -86,3 +86,28 @@ def check_render(out, ref, label='', tol=TOL, stages=True):
     st['points_cam_linf'] = float(np.abs(ref['points_cam'][pc_both] - out['points_cam'][pc_both]).max()) if pc_both.any() else 0.0
     assert st['points_cam_linf'] <= 2 * tol['depth_linf'], (label, st)
     return st
+
+
+EXTRA_WSUM_CASES = ['wsum_zju377_24x24_s0', 'wsum_cano_20x20_s1']
+EXTRA_LASTPT_CASE = 'lastpt_16x16_s3'
+
+
+def load_extra(name):
+    """Fixtures of oracle/gen_golden_extra.py: (frame, reference arrays, meta); frame.render_last_pt is set from the recipe."""
+    from arah_release_b200 import synthetic as syn
+    z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False)
+    meta = json.loads(str(z['meta']))
+    fr = syn.make_frame(**meta['make_frame'])
+    fr.render_last_pt = bool(meta['render_last_pt'])
+    assert fr.P == meta['P']
+    return fr, {k: z[k] for k in z.files if k != 'meta'}, meta
+
+
+def check_weights_sum(ws, ref, label='', atol=1e-4, max_outliers=0.002):
+    """Eval weights_sum (implicit_differentiable_renderer.py:392) against the reference at 1e-4 on rays both sides put in the volume
+    mask; rays whose converged-sample set differs by a borderline sample may deviate and must be rare."""
+    m = ref['network_body_mask'].astype(bool)
+    d = np.abs(np.asarray(ws, np.float64)[m] - ref['weights_sum'].astype(np.float64)[m])
+    frac = float((d > atol).mean()) if d.size else 0.0
+    assert frac <= max_outliers, (label, frac, float(d.max()))
+    return {'wsum_linf_inliers': float(d[d <= atol].max()) if (d <= atol).any() else 0.0, 'wsum_outlier_frac': frac}

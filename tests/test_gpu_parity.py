@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_CASES, TOL, check_render, load_golden, psnr
+from helpers import (EXTRA_LASTPT_CASE, EXTRA_WSUM_CASES, GOLDEN_CASES, TOL, check_render, check_weights_sum, load_extra, load_golden,
+                     psnr)
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -17,7 +18,7 @@ def _build(fr, shade_mode='fp32', root_mode=None):
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     dev, rend, skin, sdf = rl.modules_from_frame(fr, DEV)
     tracer = BodyRayTracing(n_steps=fr.n_steps, near_surface_vol_samples=fr.near_samples, far_surface_vol_samples=fr.far_samples)
-    net = IDHRNetwork(dev, rend, skin, tracer, cano_view_dirs=fr.cano_view_dirs, shade_mode=shade_mode,
+    net = IDHRNetwork(dev, rend, skin, tracer, cano_view_dirs=fr.cano_view_dirs, shade_mode=shade_mode, render_last_pt=getattr(fr, 'render_last_pt', False),
                       root_mode=root_mode if root_mode is not None else ('fp32' if shade_mode == 'fp32' else '3xtf32')).eval()
     inputs = rl.inputs_from_frame(fr, sdf, DEV)
     return net, inputs
@@ -304,3 +305,62 @@ def test_knn_seed_is_exact(monkeypatch):
         res.append((out['rgb_values'].clone(), tr[3].clone(), tr[5].clone(), tr[6].clone(), net.stats()['corr_skin_evals']))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
     assert torch.equal(res[0][3], res[1][3]) and res[0][4] == res[1][4]
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'tf32'])
+@pytest.mark.parametrize('name', EXTRA_WSUM_CASES)
+def test_eval_weights_sum_matches_reference(name, mode):
+    """Eval weights_sum (arah_render's optional output) against the unmodified reference at 1e-4."""
+    fr, ref, _ = load_extra(name)
+    net, inputs = _build(fr, mode)
+    r = net._prepare(inputs)
+    rgb, mask, pc, ws = r.render(inputs['ray_dirs'][0], inputs['body_bounds_intersections'][0], want_weights=True)
+    torch.cuda.synchronize()
+    assert (mask.cpu().numpy() != ref['network_body_mask'].astype(bool)).mean() <= TOL['ray_mask_mismatch']
+    atol = 1e-4 if mode == 'fp32' else 5e-4                  # tensor-core mode: the SDF value carries 11-bit operands
+    print(name, mode, check_weights_sum(ws.cpu().numpy(), ref, label=name, atol=atol))
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'tf32'])
+def test_render_last_pt_matches_reference(mode):
+    """IDHRNetwork(render_last_pt=True), implicit_differentiable_renderer.py:380-381, against a fixture of the unmodified reference."""
+    fr, ref, _ = load_extra(EXTRA_LASTPT_CASE)
+    net, inputs = _build(fr, mode)
+    assert net.render_last_pt
+    r = net._prepare(inputs)
+    rgb, mask, pc, ws = r.render(inputs['ray_dirs'][0], inputs['body_bounds_intersections'][0], want_weights=True)
+    torch.cuda.synchronize()
+    assert psnr(rgb.cpu().numpy(), ref['rgb_values']) >= (60.0 if mode == 'fp32' else 55.0)
+    print('last_pt', mode, check_weights_sum(ws.cpu().numpy(), ref, label='last_pt', atol=1e-4 if mode == 'fp32' else 5e-4))
+    fr.render_last_pt = False
+    net2, _ = _build(fr, mode)
+    ws2 = net2._prepare(inputs).render(inputs['ray_dirs'][0], inputs['body_bounds_intersections'][0], want_weights=True)[3]
+    assert float((ws2 - ws).abs().max()) > 1e-3                # the switch matters on this frame
+
+
+def test_512_frame_16k_rays_against_the_oracle():
+    """BASELINE configs[1] size: 16 384 random rays of the 512x512 frame, rendered inside the full batch, against the CPU oracle
+    (pinned to the unmodified reference by tests/golden): colour, volume mask, hit mask, depth."""
+    from arah_release_b200 import synthetic as syn
+    from oracle import oracle as orc
+    fr = syn.make_frame(512, 512, seed=0)
+    net, inputs = _build(fr, 'tf32')
+    out = net(inputs)
+    tr = net.tracer_outputs()
+    torch.cuda.synchronize()
+    sel = np.sort(np.random.default_rng(7).choice(fr.P, size=16384, replace=False))
+    o = orc.render(fr, ray_dirs=fr.ray_dirs[sel], near_far=fr.near_far[sel], stages=False)
+    rgb = out['rgb_values'][0].cpu().numpy()[sel]
+    ps = psnr(rgb, o['rgb_values'])
+    gt = np.clip(o['rgb_values'] + np.random.default_rng(123).normal(scale=0.03, size=o['rgb_values'].shape), 0, 1)
+    dps = abs(psnr(rgb, gt) - psnr(o['rgb_values'], gt))
+    hit = tr[1][0].cpu().numpy()[sel].astype(bool)
+    ho = o['trace.network_body_mask'].astype(bool)
+    both = hit & ho
+    depth = float(np.abs(tr[2][0].cpu().numpy()[sel][both] - o['trace.dists'][both]).max())
+    vol = (out['network_body_mask'][0].cpu().numpy()[sel] != o['network_body_mask'].astype(bool)).mean()
+    print(f'512x512, 16384 rays vs oracle: PSNR {ps:.1f} dB, dPSNR {dps:.2e} dB, hit-mask mismatch {(hit != ho).mean():.2e}, '
+          f'volume-mask mismatch {vol:.2e}, depth Linf {depth:.2e} m on {int(both.sum())} common hits')
+    assert ps >= 55.0 and dps <= TOL['dpsnr_max']
+    assert (hit != ho).mean() <= TOL['ray_mask_mismatch'] and vol <= TOL['ray_mask_mismatch']
+    assert depth <= TOL['depth_linf']

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from helpers import GOLDEN_CASES, check_render, load_golden
+from helpers import EXTRA_LASTPT_CASE, EXTRA_WSUM_CASES, GOLDEN_CASES, check_render, check_weights_sum, load_extra, load_golden, psnr
 
 
 @pytest.mark.parametrize('name', GOLDEN_CASES)
@@ -82,3 +82,26 @@ def test_oracle_matches_reference_no_normal_colour_mode():
     for mode, width in (('no_normal', 414), ('no_view_dir', 390)):
         W = np.random.default_rng(0).normal(size=(5, width)).astype(np.float32)
         assert np.array_equal(R._expand_color_weight(torch.from_numpy(W), mode).numpy(), syn.expand_color_weight(W, mode))
+
+
+@pytest.mark.parametrize('name', EXTRA_WSUM_CASES)
+def test_oracle_eval_weights_sum_matches_reference(name):
+    """Eval weights_sum, the second output of get_rbg_value_vol_sdf (SURVEY §7 minimum slice: 1e-4)."""
+    from oracle import oracle as orc
+    fr, ref, meta = load_extra(name)
+    out = orc.render(fr, threads=0, stages=False)
+    assert (out['network_body_mask'].astype(bool) != ref['network_body_mask'].astype(bool)).mean() <= 0.002
+    print(name, check_weights_sum(out['weights_sum'], ref, label=name))
+
+
+def test_oracle_render_last_pt_matches_reference():
+    """IDHRNetwork(render_last_pt=True): the last converged sample of a ray gets the interval 1e10 (:380-381)."""
+    from oracle import oracle as orc
+    fr, ref, meta = load_extra(EXTRA_LASTPT_CASE)
+    assert fr.render_last_pt
+    out = orc.render(fr, threads=0, stages=False)
+    assert psnr(out['rgb_values'], ref['rgb_values']) >= 60.0
+    print('last_pt', check_weights_sum(out['weights_sum'], ref, label='last_pt'))
+    fr.render_last_pt = False                               # and the switch matters on this frame
+    off = orc.render(fr, threads=0, stages=False)
+    assert np.abs(off['weights_sum'] - out['weights_sum']).max() > 1e-3
