@@ -312,6 +312,7 @@ struct ArahHandle {
     int trace_persist = 1;     // k_trace_persist: sphere tracing as one persistent kernel (1-NN + SDF per step, resident rays)
     int iso_persist = 1;       // k_iso_persist: joint search as one persistent kernel
     SdfF16Dev sdf16{};
+    int grid16 = 1;            // k_sdf_grid16: the canonical lattice on the fp16 split-precision engine
     int sdf_fwd16 = 1;         // k_sdf_fwd16: the SDF value compositing uses comes from a single-pass fp16 kernel over all converged samples
     bool shade_cull_ran = false;
     int shade_cull = 1;        // exact alpha cull before the gradient / colour pass (k_alpha_cull)
@@ -445,6 +446,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     if (const char* e = getenv("ARAH_TRACE_PERSIST")) h->trace_persist = atoi(e) != 0;
     if (const char* e = getenv("ARAH_ISO_PERSIST")) h->iso_persist = atoi(e) != 0;
     if (const char* e = getenv("ARAH_SDF_FWD16")) h->sdf_fwd16 = atoi(e) != 0;
+    if (const char* e = getenv("ARAH_GRID16")) h->grid16 = atoi(e) != 0;
     if (!root_trace_fits(cfg->n_verts)) h->trace_persist = 0;      // vertex index + weight ring must fit in 227 KB of shared memory
     CU(root_init());
     CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
@@ -899,7 +901,12 @@ extern "C" int arah_sdf_grid(ArahHandle* h, int32_t N, float* sdf, void* stream)
     CU(cudaSetDevice(h->cfg.device));
     const float voxel = (float)(2.0 / (double)(N - 1));
     const long long n = (long long)N * N * N;
-    if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
+    if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->grid16) {
+        SdfF16Host sh16;
+        sh16.Wt0 = h->sdf_Wt[0]; sh16.freq = h->sdf_freq; sh16.phase = h->sdf_phase; sh16.w6 = h->sdf_w6; sh16.b6 = h->sd.b6;
+        for (int l = 0; l < 6; ++l) sh16.b[l] = h->sdf_b[l];
+        CU(root_sdf_grid16(sh16, h->sdf16, N, voxel, n, sdf, h->n_sms, st));
+    } else if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
         const unsigned g = grid_min(cdiv((size_t)n, UM), (size_t)h->n_sms);
         k_sdf_grid_tc3<<<g, TC3_THREADS, trace_tc3_smem_bytes(), st>>>(h->sd, N, voxel, n, sdf);
     } else {

@@ -20,7 +20,7 @@ enum { IS_X = 0, IS_J = 4, IS_GX = 20, IS_UPD = 24, IS_BX = 28, IS_BT = 32, IS_B
 static_assert(sizeof(BroydenState<4>) == IP_STATE_WORDS * 4, "state words");
 
 __host__ __device__ constexpr size_t iso_persist_smem_bytes() {
-    return (size_t)S16_NSLOTS * S16_SLOT_BYTES + (size_t)(IP_WORDS * UM + 25 * UM + 2 * UM + 3 * 128 + 5 * 128 + 16) * 4 + sizeof(S16Ctl) + 64;
+    return (size_t)S16_NSLOTS * S16_SLOT_BYTES + (size_t)(IP_WORDS * UM + 25 * UM + 4 * UM + 3 * 128 + 5 * 128 + 16) * 4 + sizeof(S16Ctl) + 64;
 }
 
 __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, SdfF16 sd, SkinF16 sk, Work w) {
@@ -32,13 +32,13 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
     float* st = reinterpret_cast<float*>(ring + S16_NSLOTS * S16_SLOT_BYTES);      // [IP_WORDS][128]
     float* lgs = st + IP_WORDS * UM;                                               // [25][128] logits (incl. bias)
     float (*part)[UM] = reinterpret_cast<float (*)[UM]>(lgs + 25 * UM);
-    float* sW0 = reinterpret_cast<float*>(part) + 2 * UM;                          // skinning layer 0 [3][128]
+    float* sW0 = reinterpret_cast<float*>(part) + 4 * UM;                          // skinning layer 0 [3][128]
     float* sb = sW0 + 3 * 128;                                                     // skinning biases 4 x 128, then 32
     float* sInv = sb + 5 * 128;                                                    // [0..3] skinning layers 1..4, [4..8] SDF layers 1..5
     S16Ctl* ctl = reinterpret_cast<S16Ctl*>(sInv + 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s16_ctl_init(ctl);
-    if (warp == 9) tmem_alloc(&ctl->tslot, 512);
+    if (warp == 17) tmem_alloc(&ctl->tslot, 512);
     for (int i = tid; i < 3 * 128; i += S16_THREADS) sW0[i] = __ldg(sk.Wt0 + i);
     for (int i = tid; i < 4 * 128; i += S16_THREADS) sb[i] = __ldg(sk.b[i >> 7] + (i & 127));
     if (tid < 32) sb[512 + tid] = __ldg(sk.b[4] + tid);
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
     tc_fence_after();
     const uint32_t tbase = ctl->tslot;
 
-    if (warp == 8) {                                        // ===== TMA producer: skinning images then SDF images, per evaluation =====
+    if (warp == 16) {                                       // ===== TMA producer: skinning images then SDF images, per evaluation =====
         if (lane == 0) {
             S16Prod p;
             bool ok = true;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
         }
         return;
     }
-    if (warp == 9) {                                        // ===== MMA issuer =====
+    if (warp == 17) {                                       // ===== MMA issuer =====
         if (lane == 0) {
             S16Mma m;
             uint32_t skpar = 0;
@@ -106,12 +106,12 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
             }
         }
         __syncwarp();
-        asm volatile("bar.sync 2, 288;" ::: "memory");
+        s16_sync_exit();
         tmem_dealloc(tbase, 512);
         return;
     }
     // ===== compute warps =====
-    const int q = warp & 3, h = warp >> 2, r = 32 * q + lane;
+    const int q = warp & 3, u = warp >> 2, r = 32 * q + lane;        // TMEM lane quarter, column quarter, row
     const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
     uint32_t done_par = 0;
     int evals = 0;
@@ -163,15 +163,14 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
         if (__float_as_int(st[IP_RAY * UM + tid]) >= 0) advance();
         else { st[(IP_XN) * UM + tid] = 0.f; st[(IP_XN + 1) * UM + tid] = 0.f; st[(IP_XN + 2) * UM + tid] = 0.f; }
     }
-    bool live = cta_or_compute(tid < UM && __float_as_int(st[IP_RAY * UM + tid]) >= 0);
+    bool live = s16_sync_or(tid < UM && __float_as_int(st[IP_RAY * UM + tid]) >= 0);
     if (tid == 0) { ctl->cont[0] = live ? 1 : 0; if (!live) ctl->stop = 1; __threadfence_block(); mbar_arrive(&ctl->go); }
     uint32_t e = 0;
     while (live) {
         const float x = st[IP_XN * UM + r], y = st[(IP_XN + 1) * UM + r], z = st[(IP_XN + 2) * UM + r];
         // ---- skinning MLP (layer 0 on the FP32 pipe, layers 1..4 on the tensor cores)
-#pragma unroll 1
-        for (int b = 0; b < 2; ++b) {
-            const int col0 = 64 * h + 32 * b;
+        {
+            const int col0 = 32 * u;
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -185,9 +184,8 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
         for (int l = 1; l < 4; ++l) {
             wait_done();
             const float inv = sInv[l - 1];
-#pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
-                const int col0 = 64 * h + 32 * b;
+            {
+                const int col0 = 32 * u;
                 float v[32];
                 tmem_ld32(trow + 128u + (uint32_t)col0, v);
 #pragma unroll
@@ -197,7 +195,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
             publish_sk();
         }
         wait_done();
-        if (h == 0) {                                                   // logits of row r (= tid for the row threads)
+        if (u == 0) {                                                   // logits of row r (= tid for the row threads)
             float v[32];
             tmem_ld32(trow + 128u, v);
             const float inv4 = sInv[3];
@@ -205,12 +203,12 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
             for (int k = 0; k < 25; ++k) lgs[k * UM + r] = fmaf(v[k], inv4, sb[512 + k]);
         }
         tc_fence_before();
-        cta_sync_compute();                                             // tensor memory is free for the SDF
+        s16_sync();                                                     // tensor memory is free for the SDF
         tc_fence_after();
         // ---- SDF
         const float dot = s16_compute_sdf(sd, x, y, z, ctl, done_par, tbase, sInv + 4);
-        part[h][r] = dot;
-        cta_sync_compute();
+        part[u][r] = dot;
+        s16_sync();
         // ---- residual + Broyden update, one thread per row
         bool row_live = false;
         if (tid < UM) {
@@ -226,7 +224,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
                 for (int k = 0; k < 4; ++k) dx[k] = st[(IP_DX + k) * UM + tid];
 #pragma unroll
                 for (int k = 0; k < 25; ++k) lg32[k] = lgs[k * UM + tid];
-                iso_residual(fp, w, ray, s.x, lg32, part[0][tid] + part[1][tid] + __ldg(sd.b6), g, T12);
+                iso_residual(fp, w, ray, s.x, lg32, ((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid])) + __ldg(sd.b6), g, T12);
                 bool active = broyden_update<4>(s, dx, g, T12);
                 const int it = __float_as_int(st[IP_IT * UM + tid]);
                 if (it + 1 >= BROYDEN_ITERS) active = false;
@@ -240,13 +238,13 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
             row_live = __float_as_int(st[IP_RAY * UM + tid]) >= 0;
             if (row_live) advance();
         }
-        live = cta_or_compute(row_live);
+        live = s16_sync_or(row_live);
         ++e;
         if (tid == 0) { ctl->cont[e & 1u] = live ? 1 : 0; if (!live) ctl->stop = 1; __threadfence_block(); mbar_arrive(&ctl->go); }
     }
     warp_stat_add(evals, &w.counters[C_STAT_ISO_EVALS]);
     tc_fence_before();
-    asm volatile("bar.sync 2, 288;" ::: "memory");
+    s16_sync_exit();
 }
 
 }  // namespace arah

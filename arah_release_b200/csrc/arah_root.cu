@@ -5,6 +5,7 @@
 #include "arah_iso_p.cuh"
 #include "arah_trace_p.cuh"
 #include "arah_sdf_fwd16.cuh"
+#include "arah_grid16.cuh"
 
 namespace arah {
 
@@ -14,6 +15,8 @@ cudaError_t root_init() {
     cudaError_t e = cudaFuncSetAttribute(k_corr_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_persist_smem_bytes());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sdf_fwd16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sdf_fwd16_smem_bytes());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sdf_grid16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sdf_grid16_smem_bytes());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_iso_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso_persist_smem_bytes());
     if (e != cudaSuccess) return e;
@@ -66,6 +69,13 @@ cudaError_t root_sdf_fwd16(const FrameParams& fp, const SdfF16Host& sh, const Sd
     const unsigned g = (unsigned)(tiles < (size_t)n_sms ? tiles : (size_t)n_sms);
     k_sdf_fwd16<<<g, F16_THREADS, sdf_fwd16_smem_bytes(), st>>>(fp, make_sdf16(sh, img), w);
     if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t root_sdf_grid16(const SdfF16Host& sh, const SdfF16Dev& img, int N, float voxel, long long n, float* out, int n_sms, cudaStream_t st) {
+    const size_t tiles = (size_t)((n + UM - 1) / UM);
+    const unsigned g = (unsigned)(tiles < (size_t)n_sms ? tiles : (size_t)n_sms);
+    k_sdf_grid16<<<g, S16_THREADS, sdf_grid16_smem_bytes(), st>>>(make_sdf16(sh, img), N, voxel, n, out);
     return cudaGetLastError();
 }
 

@@ -35,6 +35,8 @@ cudaError_t root_trace_persist(const FrameParams& fp, const SdfF16Host& sh, cons
 // SDF value (metres) of every sample of w.shade_list -> w.smp_sdf, single-pass fp16 tensor-core tiles (arah_sdf_fwd16.cuh)
 cudaError_t root_sdf_fwd16(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const Work& w, int n_sms, cudaStream_t st,
                            long long* launches);
+// canonical SDF lattice (row f1): raw network output at the N^3 lattice points of [-1, 1]^3
+cudaError_t root_sdf_grid16(const SdfF16Host& sh, const SdfF16Dev& img, int N, float voxel, long long n, float* out, int n_sms, cudaStream_t st);
 // joint search of the rays listed in w.listA (k_iso_prepare) whose state k_iso_init_tc3 has written, persistent
 cudaError_t root_iso_persist(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const float* skin_Wt0, const float* const skin_b[5],
                              const SkinF16Dev& skimg, const Work& w, int n_sms, cudaStream_t st, long long* launches);

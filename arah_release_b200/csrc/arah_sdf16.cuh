@@ -3,10 +3,10 @@
 // (sphere tracing, joint search) and of the canonical SDF lattice.
 //
 // Everything lives in tensor memory now.  TMEM = two 256-column regions R0 / R1.  The activations of layer L sit in one region
-// as four K-chunks of 64 values: chunk j -> columns [64 j, 64 j + 32) hi | [64 j + 32, 64 j + 64) lo (two K values per column);
-// the accumulators of layer L go to the other region.  The epilogue turns D into the next layer's operand IN PLACE, chunk by
-// chunk (a thread reads the 64 accumulator columns of a chunk, then overwrites them with 32 hi + 32 lo columns) and arrives on
-// the chunk's `ready` barrier; the MMA warp starts chunk j of the next layer as soon as ready[j] and the weight images are
+// as four K-chunks of 64 values: chunk j, K-step k -> columns [64 j + 16 k, +8) hi | [64 j + 16 k + 8, +8) lo (two K values per column);
+// the accumulators of layer L go to the other region.  The epilogue turns D into the next layer's operand IN PLACE: sixteen
+// compute warps, four per TMEM lane quarter; warp (q, u) reads accumulator columns [64 j + 16 u, +16) of chunk j and overwrites
+// them with 8 hi + 8 lo operand columns (K-step u of chunk j), then arrives on the chunk's `ready` barrier; the MMA warp starts chunk j of the next layer as soon as ready[j] and the weight images are
 // there and writes the new accumulators into the region the previous operand vacated: layer L's epilogue and layer L + 1's MMAs
 // overlap chunk by chunk, exactly as in round 1's engine — but at twice the MMA rate, with half the weight bytes, and without
 // the 128 KB shared-memory copy of A_lo, which frees the room for the 1-NN vertex index in the tracing kernel.
@@ -33,14 +33,16 @@ constexpr size_t SDF_F16_IMAGE_BYTES = 5 * 131072;
 
 constexpr int S16_NSLOTS = 3;
 constexpr int S16_SLOT_BYTES = 32768;
-constexpr int S16_THREADS = 320;         // 8 compute warps, producer warp, MMA warp
+constexpr int S16_WARPS = 16;            // compute warps: q = warp & 3 -> TMEM lane quarter, u = warp >> 2 -> 16 columns of every K-chunk
+constexpr int S16_CTHREADS = 32 * S16_WARPS;
+constexpr int S16_THREADS = S16_CTHREADS + 64;   // + producer warp (16) + MMA warp (17)
 
 struct S16Ctl {                          // shared-memory control block
     uint64_t full[S16_NSLOTS], empty[S16_NSLOTS];
-    uint64_t ready[4];                   // SDF operand chunk j written (4 warp arrivals)
+    uint64_t ready[4];                   // SDF operand chunk j written (one arrival per compute warp)
     uint64_t done;                       // a layer's accumulators are complete
     uint64_t go;                         // compute -> MMA warp: decision about the next evaluation is in cont[]
-    uint64_t ready_sk;                   // skinning operand written by all 8 warps (joint search only)
+    uint64_t ready_sk;                   // skinning operand written by all compute warps (joint search only)
     uint32_t tslot;
     volatile int stop;                   // compute -> producer: no further evaluation
     volatile int cont[2];
@@ -48,12 +50,12 @@ struct S16Ctl {                          // shared-memory control block
 
 __device__ __forceinline__ void s16_ctl_init(S16Ctl* c) {      // one thread
     for (int i = 0; i < S16_NSLOTS; ++i) { mbar_init(&c->full[i], 1); mbar_init(&c->empty[i], 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(&c->ready[i], 4);
-    mbar_init(&c->done, 1); mbar_init(&c->go, 1); mbar_init(&c->ready_sk, 8);
+    for (int i = 0; i < 4; ++i) mbar_init(&c->ready[i], S16_WARPS);
+    mbar_init(&c->done, 1); mbar_init(&c->go, 1); mbar_init(&c->ready_sk, S16_WARPS);
     mbar_fence_init();
     c->stop = 0; c->cont[0] = 0; c->cont[1] = 0;
 }
-__device__ __forceinline__ int s16_chunk(int i) { return (i >> 1) + ((i & 1) << 1); }      // 0, 2, 1, 3: the order the two column halves finish
+__device__ __forceinline__ int s16_chunk(int i) { return i; }                                  // every warp finishes chunk 0 first, then 1, 2, 3
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -61,12 +63,14 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     return done != 0;
 }
 
-__device__ __forceinline__ bool cta_or_compute(bool pred) {                      // barrier 1 over the 256 compute threads + OR
+__device__ __forceinline__ void s16_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }      // the 16 compute warps
+__device__ __forceinline__ bool s16_sync_or(bool pred) {                         // same barrier + OR of a predicate
     uint32_t r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 1, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 1, 512, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(r) : "r"((uint32_t)pred) : "memory");
     return r != 0;
 }
+__device__ __forceinline__ void s16_sync_exit() { asm volatile("bar.sync 2, 544;" ::: "memory"); } // compute warps + MMA warp: TMEM is idle
 
 // ---- producer (one thread): ring position + what is still in flight -------------------------------------------------------
 struct S16Prod {
@@ -114,14 +118,14 @@ __device__ __forceinline__ void s16_mma_sdf(uint8_t* ring, S16Ctl* c, S16Mma& m,
             const int ch = s16_chunk(i);
             mbar_wait(&c->ready[ch], (m.rpar >> ch) & 1u);
             m.rpar ^= (1u << ch);
-            const uint32_t xh = ta + 64u * ch, xl = xh + 32u;
+            const uint32_t xh = ta + 64u * ch, xl = xh + 8u;                     // K-step k: hi at xh + 16 k, lo 8 columns behind
             mbar_wait(&c->full[m.slot], m.use & 1u);                           // B_hi(ch)
             tc_fence_after();
             uint32_t b = smem_u32(ring + m.slot * S16_SLOT_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                umma_f16_ts(td, xl + 8u * k, umma_smem_desc_sw128(b + 32u * k), idesc, (i > 0 || k > 0) ? 1u : 0u);    // X_lo . B_hi
-                umma_f16_ts(td, xh + 8u * k, umma_smem_desc_sw128(b + 32u * k), idesc, 1u);                            // X_hi . B_hi
+                umma_f16_ts(td, xl + 16u * k, umma_smem_desc_sw128(b + 32u * k), idesc, (i > 0 || k > 0) ? 1u : 0u);   // X_lo . B_hi
+                umma_f16_ts(td, xh + 16u * k, umma_smem_desc_sw128(b + 32u * k), idesc, 1u);                           // X_hi . B_hi
             }
             umma_commit(&c->empty[m.slot]);
             if (++m.slot == S16_NSLOTS) { m.slot = 0; ++m.use; }
@@ -129,7 +133,7 @@ __device__ __forceinline__ void s16_mma_sdf(uint8_t* ring, S16Ctl* c, S16Mma& m,
             tc_fence_after();
             b = smem_u32(ring + m.slot * S16_SLOT_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ts(td, xh + 8u * k, umma_smem_desc_sw128(b + 32u * k), idesc, 1u);    // X_hi . B_lo
+            for (int k = 0; k < 4; ++k) umma_f16_ts(td, xh + 16u * k, umma_smem_desc_sw128(b + 32u * k), idesc, 1u);   // X_hi . B_lo
             umma_commit(&c->empty[m.slot]);
             if (++m.slot == S16_NSLOTS) { m.slot = 0; ++m.use; }
         }
@@ -138,26 +142,44 @@ __device__ __forceinline__ void s16_mma_sdf(uint8_t* ring, S16Ctl* c, S16Mma& m,
 }
 
 // ---- compute warps --------------------------------------------------------------------------------------------------------------
-// 32 consecutive per-column parameters as 8 LDG.128
-__device__ __forceinline__ void s16_ldg32(const float* __restrict__ p, float (&v)[32]) {
+// 16 consecutive per-column parameters as 4 LDG.128
+__device__ __forceinline__ void s16_ldg16(const float* __restrict__ p, float (&v)[16]) {
     const float4* q = reinterpret_cast<const float4*>(p);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const float4 t = __ldg(q + j); v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w; }
+    for (int j = 0; j < 4; ++j) { const float4 t = __ldg(q + j); v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w; }
 }
-// SDF of the row of this thread (TMEM lane 32 q + lane) at the normalised point (x, y, z): all 8 compute warps call it; a thread
-// works on the 128 columns of its half h.  Returns this thread's partial of w6 . h5 (caller adds the two halves and b6).
+__device__ __forceinline__ void s16_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// SDF of the row of this thread (TMEM lane 32 q + lane) at the normalised point (x, y, z): all 16 compute warps call it; warp
+// (q, u) works on columns [64 j + 16 u, 64 j + 16 u + 16) of every K-chunk j, so chunk j of the next layer is complete after a
+// quarter of the epilogue.  In place: the 16 accumulator columns just read become 8 hi + 8 lo operand columns.
+// Returns this thread's partial of w6 . h5 over its 64 columns (caller adds the four u-parts and b6).
 // inv5: 1 / scale of layers 1..5 (shared or global memory).
 __device__ __forceinline__ float s16_compute_sdf(const SdfF16& sd, float x, float y, float z, S16Ctl* c, uint32_t& done_par, uint32_t tbase,
                                                  const float* inv5, PhaseClk* pc = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, h = (warp >> 2) & 1;
+    const int q = warp & 3, u = (warp >> 2) & 3;
     const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
-    // operand chunk j of region `reg` from the activations v0 (K = 64 j ..) and v1 (K = 64 j + 32 ..)
-    auto put = [&](int reg, int j, const uint32_t (&hi0)[16], const uint32_t (&lo0)[16], const float (&v1)[32]) {
-        uint32_t hi1[16], lo1[16];
-        split_pack_f16(v1, hi1, lo1);
-        const uint32_t a = trow + 256u * reg + 64u * j;
-        tmem_st16(a, hi0); tmem_st16(a + 16u, hi1); tmem_st16(a + 32u, lo0); tmem_st16(a + 48u, lo1);
+    auto put = [&](int reg, int j, const float (&v)[16]) {
+        uint32_t p[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+            p[i] = *reinterpret_cast<const uint32_t*>(&h);
+            p[8 + i] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        tmem_st16(trow + 256u * reg + 64u * j + 16u * u, p);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -165,24 +187,17 @@ __device__ __forceinline__ float s16_compute_sdf(const SdfF16& sd, float x, floa
     };
     {   // layer 0 (K = 3) on the FP32 pipe
 #pragma unroll 1
-        for (int jj = 0; jj < 2; ++jj) {
-            const int j = 2 * h + jj;
-            uint32_t hi0[16], lo0[16];
-            float v[32];
+        for (int j = 0; j < 4; ++j) {
+            const int col0 = 64 * j + 16 * u;
+            float v[16], w0[16], w1[16], w2[16], pf[16], pb[16], pp[16];
+            s16_ldg16(sd.Wt0 + col0, w0); s16_ldg16(sd.Wt0 + 256 + col0, w1); s16_ldg16(sd.Wt0 + 512 + col0, w2);
+            s16_ldg16(sd.freq + col0, pf); s16_ldg16(sd.b[0] + col0, pb); s16_ldg16(sd.phase + col0, pp);
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int col0 = 64 * j + 32 * hf;
-                float w0[32], w1[32], w2[32], pf[32], pb[32], pp[32];
-                s16_ldg32(sd.Wt0 + col0, w0); s16_ldg32(sd.Wt0 + 256 + col0, w1); s16_ldg32(sd.Wt0 + 512 + col0, w2);
-                s16_ldg32(sd.freq + col0, pf); s16_ldg32(sd.b[0] + col0, pb); s16_ldg32(sd.phase + col0, pp);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float a = fmaf(w2[i], z, fmaf(w1[i], y, w0[i] * x));
-                    v[i] = sin_cw(30.0f * (pf[i] * (a + pb[i]) + pp[i]));
-                }
-                if (hf == 0) split_pack_f16(v, hi0, lo0);
+            for (int i = 0; i < 16; ++i) {
+                const float a = fmaf(w2[i], z, fmaf(w1[i], y, w0[i] * x));
+                v[i] = sin_cw(30.0f * (pf[i] * (a + pb[i]) + pp[i]));
             }
-            put(0, j, hi0, lo0, v);
+            put(0, j, v);
         }
     }
     if (pc) pc->mark(1);
@@ -197,26 +212,19 @@ __device__ __forceinline__ float s16_compute_sdf(const SdfF16& sd, float x, floa
         const int dreg = L & 1;
         const float inv = inv5[L - 1];
 #pragma unroll 1
-        for (int jj = 0; jj < 2; ++jj) {
-            const int j = 2 * h + jj;
-            uint32_t hi0[16], lo0[16];
-            float v[32];
+        for (int j = 0; j < 4; ++j) {
+            const int col0 = 64 * j + 16 * u;
+            float v[16], pf[16], pb[16], pp[16];
+            s16_ldg16(sd.freq + L * 256 + col0, pf); s16_ldg16(sd.b[L] + col0, pb); s16_ldg16(sd.phase + L * 256 + col0, pp);
+            s16_tmem_ld16(trow + 256u * dreg + (uint32_t)col0, v);
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int col0 = 64 * j + 32 * hf;
-                float pf[32], pb[32], pp[32];
-                s16_ldg32(sd.freq + L * 256 + col0, pf); s16_ldg32(sd.b[L] + col0, pb); s16_ldg32(sd.phase + L * 256 + col0, pp);
-                tmem_ld32(trow + 256u * dreg + (uint32_t)col0, v);
+            for (int i = 0; i < 16; ++i) v[i] = sin_cw(30.0f * (pf[i] * (v[i] * inv + pb[i]) + pp[i]));
+            if (L < 5) put(dreg, j, v);
+            else {
+                s16_ldg16(sd.w6 + col0, pf);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = sin_cw(30.0f * (pf[i] * (v[i] * inv + pb[i]) + pp[i]));
-                if (L < 5) { if (hf == 0) split_pack_f16(v, hi0, lo0); }
-                else {
-                    s16_ldg32(sd.w6 + col0, pf);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) dot = fmaf(v[i], pf[i], dot);
-                }
+                for (int i = 0; i < 16; ++i) dot = fmaf(v[i], pf[i], dot);
             }
-            if (L < 5) put(dreg, j, hi0, lo0, v);          // in place: both halves of the chunk's accumulators have been read
         }
         if (L == 5) tc_fence_before();
         if (pc) pc->mark(3);

@@ -8,7 +8,7 @@
 // 128 canonical points on the tensor cores (arah_sdf16.cuh) and advances the rays (:228-241).  A ray that has converged,
 // diverged or used its 50 steps is written back and its row is re-filled from the device-wide list of rays at once, so the tile
 // stays full while rays are left; every ray runs exactly the step sequence of the reference (rays are independent).
-// Warps: 0-7 compute (row work + epilogues), 8 TMA producer (runs ahead speculatively, stops on the `stop` flag), 9 MMA issuer.
+// Warps: 0-15 compute (row work + epilogues), 16 TMA producer (runs ahead speculatively, stops on the `stop` flag), 17 MMA issuer.
 #pragma once
 #include "arah_sdf16.cuh"
 
@@ -18,7 +18,7 @@ namespace arah {
 enum { TR_RAY = 0, TR_T = 1, TR_FAR = 2, TR_D = 3, TR_IT = 6, TR_S = 7, TR_T12 = 8, TR_XN = 20, TR_WORDS = 23 };
 
 __host__ __device__ constexpr size_t trace_persist_smem_bytes(int n_verts) {
-    return (size_t)S16_NSLOTS * S16_SLOT_BYTES + knn_smem_bytes(n_verts) + (size_t)(TR_WORDS * UM + 2 * UM + 8) * 4 + sizeof(S16Ctl) + 64;
+    return (size_t)S16_NSLOTS * S16_SLOT_BYTES + knn_smem_bytes(n_verts) + (size_t)(TR_WORDS * UM + 4 * UM + 8) * 4 + sizeof(S16Ctl) + 64;
 }
 
 __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp, SdfF16 sd, KnnIndex ix, Work w) {
@@ -30,18 +30,18 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
     float4* sknn = reinterpret_cast<float4*>(ring + S16_NSLOTS * S16_SLOT_BYTES);
     float* st = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sknn) + knn_smem_bytes(fp.n_verts));
     float (*part)[UM] = reinterpret_cast<float (*)[UM]>(st + TR_WORDS * UM);
-    float* sInv = reinterpret_cast<float*>(part) + 2 * UM;                        // [5] (+3 pad)
+    float* sInv = reinterpret_cast<float*>(part) + 4 * UM;                        // [5] (+3 pad)
     S16Ctl* ctl = reinterpret_cast<S16Ctl*>(sInv + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s16_ctl_init(ctl);
-    if (warp == 9) tmem_alloc(&ctl->tslot, 512);
+    if (warp == 17) tmem_alloc(&ctl->tslot, 512);
     if (tid < 5) sInv[tid] = __ldg(sd.scale + 2 * tid + 1);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = ctl->tslot;
 
-    if (warp == 8) {                                        // ===== TMA producer =====
+    if (warp == 16) {                                       // ===== TMA producer =====
         if (lane == 0) {
             S16Prod p;
             while (s16_produce_sdf(ring, ctl, p, sd, true)) {}
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
         }
         return;
     }
-    if (warp == 9) {                                        // ===== MMA issuer =====
+    if (warp == 17) {                                       // ===== MMA issuer =====
         if (lane == 0) {
             S16Mma m;
             for (uint32_t e = 0;; ++e) {
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
             }
         }
         __syncwarp();
-        asm volatile("bar.sync 2, 288;" ::: "memory");      // compute warps are out of tensor memory
+        s16_sync_exit();                                    // compute warps are out of tensor memory
         tmem_dealloc(tbase, 512);
         return;
     }
@@ -68,10 +68,10 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
     KnnSmem kk;
     {
         const int nv = ix.nc * KNN_CLUSTER, ns = (ix.nc + KNN_SUPER - 1) / KNN_SUPER;
-        for (int v = tid; v < nv; v += 256) sknn[v] = __ldg(ix.sv + v);
-        for (int c = tid; c < ix.nc; c += 256) { sknn[nv + c] = __ldg(ix.cmin + c); sknn[nv + ix.nc + c] = __ldg(ix.cmax + c); }
-        cta_sync_compute();
-        for (int g = tid; g < ns; g += 256) {
+        for (int v = tid; v < nv; v += S16_CTHREADS) sknn[v] = __ldg(ix.sv + v);
+        for (int c = tid; c < ix.nc; c += S16_CTHREADS) { sknn[nv + c] = __ldg(ix.cmin + c); sknn[nv + ix.nc + c] = __ldg(ix.cmax + c); }
+        s16_sync();
+        for (int g = tid; g < ns; g += S16_CTHREADS) {
             float4 mn = make_float4(1e30f, 1e30f, 1e30f, 0.f), mx = make_float4(-1e30f, -1e30f, -1e30f, 0.f);
             for (int c = g * KNN_SUPER; c < min(ix.nc, (g + 1) * KNN_SUPER); ++c) {
                 const float4 a = sknn[nv + c], b = sknn[nv + ix.nc + c];
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
         }
         kk.sv = sknn; kk.cmin = sknn + nv; kk.cmax = sknn + nv + ix.nc; kk.smin = sknn + nv + 2 * ix.nc; kk.smax = kk.smin + ns; kk.nc = ix.nc; kk.ns = ns;
     }
-    const int q = warp & 3, h = warp >> 2, r = 32 * q + lane;           // TMEM row of this thread (SDF epilogues)
+    const int q = warp & 3, u = warp >> 2, r = 32 * q + lane;           // TMEM row of this thread / its 16 columns per chunk (SDF epilogues)
     uint32_t done_par = 0;
     int evals = 0;
     // row `tid` (tid < 128) asks for a ray: warp-aggregated claim on the list cursor
@@ -107,15 +107,15 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
         }
     };
     if (tid < UM) refill(true);
-    bool live = cta_or_compute(tid < UM && __float_as_int(st[TR_RAY * UM + tid]) >= 0);
+    bool live = s16_sync_or(tid < UM && __float_as_int(st[TR_RAY * UM + tid]) >= 0);
     if (tid == 0) { ctl->cont[0] = live ? 1 : 0; if (!live) ctl->stop = 1; __threadfence_block(); mbar_arrive(&ctl->go); }
     uint32_t e = 0;
     PhaseClk pc; pc.start((tid == 32 && w.phase_clk) ? w.phase_clk + 16 : nullptr);      // [0] 1-NN, [1] layer 0, [2] MMA wait, [3] epilogues, [4] marching
     while (live) {
-        // ---- nearest posed vertex + inverse NN skinning of the 16 rows of this warp (rows 16 warp .. 16 warp + 15)
+        // ---- nearest posed vertex + inverse NN skinning of the 8 rows of this warp (rows 8 warp .. 8 warp + 7)
         {
-            const int row = 16 * warp + (lane & 15);
-            const bool mine_row = lane < 16;
+            const int row = 8 * warp + (lane & 7);
+            const bool mine_row = lane < 8;
             const int ray = __float_as_int(st[TR_RAY * UM + row]);
             float x[3] = {0.f, 0.f, 0.f};
             if (ray >= 0) {
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
             }
             int mine = 0;
 #pragma unroll 1
-            for (int r4 = 0; r4 < 16; r4 += 4) {                         // four queries at a time, one per octet (knn_warp_batches)
+            for (int r4 = 0; r4 < 8; r4 += 4) {                          // four queries at a time, one per octet (knn_warp_batches)
                 const int qi = r4 + (lane >> 3);
                 const float qx = __shfl_sync(0xffffffffu, x[0], qi), qy = __shfl_sync(0xffffffffu, x[1], qi), qz = __shfl_sync(0xffffffffu, x[2], qi);
                 const bool qv = __shfl_sync(0xffffffffu, (int)(ray >= 0), qi) != 0;
@@ -147,19 +147,19 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
                 for (int k = 0; k < 3; ++k) st[(TR_XN + k) * UM + row] = xn[k];
             }
         }
-        cta_sync_compute();
+        s16_sync();
         pc.mark(0);
         // ---- SDF of the 128 canonical points
         const float dot = s16_compute_sdf(sd, st[TR_XN * UM + r], st[(TR_XN + 1) * UM + r], st[(TR_XN + 2) * UM + r], ctl, done_par, tbase, sInv, &pc);
-        part[h][r] = dot;
-        cta_sync_compute();
+        part[u][r] = dot;
+        s16_sync();
         // ---- marching logic (ray_tracing.py:228-241), one thread per row
         bool row_live = false;
         if (tid < UM) {
             const int ray = __float_as_int(st[TR_RAY * UM + tid]);
             bool need = false;
             if (ray >= 0) {
-                const float sdf = sdf_to_metres(part[0][tid] + part[1][tid] + __ldg(sd.b6), fp.cmin, fp.cmax);
+                const float sdf = sdf_to_metres(((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid])) + __ldg(sd.b6), fp.cmin, fp.cmax);
                 float t = st[TR_T * UM + tid];
                 const float far_ = st[TR_FAR * UM + tid];
                 const float sm = fminf(fmaxf(sdf, -0.1f), 0.1f);
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
             refill(need);
             row_live = __float_as_int(st[TR_RAY * UM + tid]) >= 0;
         }
-        live = cta_or_compute(row_live);
+        live = s16_sync_or(row_live);
         pc.mark(4);
         if (pc.dst) atomicAdd(pc.dst + 5, 1ull);                         // evaluations of this CTA
         ++e;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
     }
     warp_stat_add(evals, &w.counters[C_STAT_TRACE_EVALS]);
     tc_fence_before();
-    asm volatile("bar.sync 2, 288;" ::: "memory");
+    s16_sync_exit();
 }
 
 }  // namespace arah

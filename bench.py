@@ -525,7 +525,8 @@ def sequence_bench(args, dev, net, world, rank):
     Device time per frame from CUDA events (frame preparation on the host is the dataset's job and stays outside), max over ranks."""
     import torch
     import torch.distributed as dist
-    from tools import ref_layout as rl, sharding as sh, synthetic as syn
+    from arah_release_b200 import sharding as sh, synthetic as syn
+    from tools import ref_layout as rl
     mine = sh.frames_for_rank(args.seq_frames, rank, world)
     t_render = t_mesh = 0.0
     rays = 0

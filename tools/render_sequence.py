@@ -30,7 +30,8 @@ def main():
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
-    from tools import ref_layout as rl, sharding as sh, synthetic as syn
+    from arah_release_b200 import sharding as sh, synthetic as syn
+    from tools import ref_layout as rl
     from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
     world, rank, local = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
