@@ -305,7 +305,7 @@ struct ArahHandle {
     float* tc_sdf3x[5];
     SdfTC sd;
     int trace_tc = 1;
-    int knn_seed = 0;          // 1: round 1's seeded per-lane 1-NN for runs of samples on one ray (A/B); 0: quad-cooperative scan (knn_scan_quad)
+    int knn_seed = 1;          // seeded per-lane 1-NN for runs of samples on one ray
     int iso_init_tc = 1;       // k_iso_init_tc3: joint-search Jacobian initialisation on the tensor cores (forward mode, 4 rows per ray)
     int corr_persist = 1;      // k_corr_persist: one persistent kernel with resident Broyden state (fp16 split precision) instead of 51 launches
     SkinF16Dev skin16{};

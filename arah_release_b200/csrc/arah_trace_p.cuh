@@ -123,13 +123,15 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
 #pragma unroll
                 for (int k = 0; k < 3; ++k) x[k] = st[(TR_D + k) * UM + row] * t + fp.cam_loc[k];
             }
-            int mine;
-            {                                                            // eight queries at once, one per quad (knn_scan_quad)
-                const int qi = lane >> 2;
+            int mine = 0;
+#pragma unroll 1
+            for (int r4 = 0; r4 < 8; r4 += 4) {                          // four queries at a time, one per octet (knn_warp_batches)
+                const int qi = r4 + (lane >> 3);
                 const float qx = __shfl_sync(0xffffffffu, x[0], qi), qy = __shfl_sync(0xffffffffu, x[1], qi), qz = __shfl_sync(0xffffffffu, x[2], qi);
                 const bool qv = __shfl_sync(0xffffffffu, (int)(ray >= 0), qi) != 0;
-                const int idx = knn_scan_quad(kk, qx, qy, qz, qv);
-                mine = __shfl_sync(0xffffffffu, idx, 4 * (lane & 7));    // lane l < 8 takes the result of query l
+                const int idx = knn_scan_octet(kk, qx, qy, qz, qv);
+                const int got = __shfl_sync(0xffffffffu, idx, (lane & 3) * 8);
+                if ((lane >> 2) == (r4 >> 2)) mine = got;
             }
             float xn[3] = {0.f, 0.f, 0.f};
             if (mine_row && ray >= 0) {

@@ -376,97 +376,6 @@ __device__ __forceinline__ int knn_scan_octet(const KnnSmem& k, float x, float y
     return bi;
 }
 
-// Quad form: the warp works on EIGHT queries at once, 4 lanes each (all 4 lanes of a quad hold the same query).  The search is
-// split into a short sequential part and a bulk part without dependences:
-//   1. the closest super box, the closest cluster box inside it, a scan of that cluster -> an upper bound bd0 on the nearest
-//      distance (two quad reductions);
-//   2. every super box whose distance is <= bd0 has its 8 cluster boxes tested; the clusters with distance <= bd0 are the
-//      candidates (any cluster that holds the nearest vertex — or a vertex at the same distance — has box distance <= the
-//      nearest distance <= bd0);
-//   3. the candidates are scanned with a per-lane running best, no reduction per cluster; one quad reduction at the end.
-// Exact: same fp32 distance expression as the brute force, lexicographic (distance, original index) minimum, hence the
-// lowest index on ties.  ~10x fewer instructions per query than the octet form (no ballots, no per-cluster butterflies), which
-// scanned candidates one by one while tightening the bound.
-__device__ __forceinline__ void knn_quad_argmin(float& d, int& id) {
-#pragma unroll
-    for (int o = 2; o > 0; o >>= 1) {
-        const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
-        const int i2 = __shfl_xor_sync(0xffffffffu, id, o);
-        if (d2 < d || (d2 == d && i2 < id)) { d = d2; id = i2; }
-    }
-}
-__device__ __forceinline__ int knn_scan_quad(const KnnSmem& k, float x, float y, float z, bool valid) {
-    const int lane = threadIdx.x & 31, s = lane & 3;
-    // this lane's 8 vertices of cluster c (interleaved: a quad reads 64 contiguous bytes per step)
-    auto scan_part = [&](int c, float& bd, int& bi) {
-#pragma unroll
-        for (int i = 0; i < KNN_CLUSTER / 4; ++i) {
-            const float4 p = k.sv[c * KNN_CLUSTER + 4 * i + s];
-            const float dx = x - p.x, dy = y - p.y, dz = z - p.z;
-            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const int id = __float_as_int(p.w);
-            if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
-        }
-    };
-    // ---- 1. closest super box -> closest cluster in it -> first bound
-    float lb0 = INFINITY;
-    int s0 = 0x7fffffff;
-    for (int g = s; g < k.ns; g += 4) {
-        const float lb = box_dist2(k.smin[g], k.smax[g], x, y, z);
-        if (lb < lb0) { lb0 = lb; s0 = g; }
-    }
-    knn_quad_argmin(lb0, s0);
-    if (s0 >= k.ns) s0 = 0;                                   // every box at infinite distance (NaN / inf query): any cluster
-    float lc = INFINITY;
-    int c0 = 0x7fffffff;
-#pragma unroll
-    for (int j = 0; j < KNN_SUPER / 4; ++j) {
-        const int c = s0 * KNN_SUPER + s + 4 * j;
-        if (c < k.nc) {
-            const float lb = box_dist2(k.cmin[c], k.cmax[c], x, y, z);
-            if (lb < lc) { lc = lb; c0 = c; }
-        }
-    }
-    knn_quad_argmin(lc, c0);
-    if (c0 >= k.nc) c0 = s0 * KNN_SUPER;
-    float bd = INFINITY;
-    int bi = 0x7fffffff;
-    if (valid) scan_part(c0, bd, bi);
-    float thr = bd;
-    {
-        int ti = bi;
-        knn_quad_argmin(thr, ti);
-    }
-    thr *= 1.000001f;                                          // the box distance is a lower bound computed in the same fp32 form: 1-ulp-safe margin
-    // ---- 2. candidate clusters: lane s tests the super boxes s, s + 4, ...; 8 mask bits per super box
-    unsigned long long cand = 0ull;                            // bit 8 t + b: cluster b of this lane's t-th super box (ns <= 32 -> t < 8)
-    if (valid) {
-        int t = 0;
-        for (int g = s; g < k.ns; g += 4, ++t) {
-            if (box_dist2(k.smin[g], k.smax[g], x, y, z) > thr) continue;
-#pragma unroll
-            for (int b = 0; b < KNN_SUPER; ++b) {
-                const int c = g * KNN_SUPER + b;
-                if (c < k.nc && c != c0 && box_dist2(k.cmin[c], k.cmax[c], x, y, z) <= thr) cand |= 1ull << (8 * t + b);
-            }
-        }
-    }
-    // ---- 3. bulk scan: the quad walks the four lanes' candidate lists one after the other
-#pragma unroll 1
-    for (int o = 0; o < 4; ++o) {
-        unsigned lo = __shfl_sync(0xffffffffu, (unsigned)cand, (lane & ~3) | o), hi = __shfl_sync(0xffffffffu, (unsigned)(cand >> 32), (lane & ~3) | o);
-        while (__any_sync(0xffffffffu, (lo | hi) != 0u)) {
-            if (lo | hi) {
-                const int bit = lo ? (__ffs(lo) - 1) : (32 + __ffs(hi) - 1);
-                if (lo) lo &= lo - 1; else hi &= hi - 1;
-                scan_part((o + 4 * (bit >> 3)) * KNN_SUPER + (bit & 7), bd, bi);
-            }
-        }
-    }
-    knn_quad_argmin(bd, bi);
-    return bi;
-}
-
 // Batch driver: a warp takes `B` consecutive queries (B = 1..32 so that every warp of the grid has work when few queries are
 // left); lane l loads query l, the queries are scanned cooperatively one after the other, lane l finishes query l.
 // Measured (B200, 15 M queries): with a full warp of queries the per-lane scan (knn_scan, 32 queries in SIMT) is ~3x
@@ -487,15 +396,8 @@ __device__ __forceinline__ void knn_warp_batches(const KnnSmem& kk, int n, int B
         float x[3] = {0.f, 0.f, 0.f};
         if (lane < cnt) load(i0 + lane, x);
         int mine = 0;
-        if (B > COOP_MAX_B) {                                    // full warps: eight queries at a time, one per quad
-#pragma unroll 1
-            for (int p = 0; p < 4; ++p) {
-                const int qi = 8 * p + (lane >> 2);
-                const float qx = __shfl_sync(0xffffffffu, x[0], qi), qy = __shfl_sync(0xffffffffu, x[1], qi), qz = __shfl_sync(0xffffffffu, x[2], qi);
-                const int idx = knn_scan_quad(kk, qx, qy, qz, qi < cnt);
-                const int got = __shfl_sync(0xffffffffu, idx, 4 * (lane & 7));         // result of query 8 p + (lane & 7)
-                if ((lane >> 3) == p) mine = got;
-            }
+        if (B > COOP_MAX_B) {
+            if (lane < cnt) mine = knn_scan(kk, x[0], x[1], x[2]);
         } else {
             if (cnt >= 3) {                                     // four queries at a time, one per octet
                 for (int r4 = 0; r4 < cnt; r4 += 4) {

@@ -8,10 +8,14 @@ import csv
 import io
 import json
 import re
+import os
 import subprocess
 import sys
 from collections import defaultdict
 
+EXTRA = {'lts__t_sectors_srcunit_tex_op_read.sum.per_second', 'l1tex__m_xbar2l1tex_read_bytes.sum', 'l1tex__m_xbar2l1tex_read_bytes.sum.per_second',
+         'lts__t_sector_hit_rate.pct', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active'}
 KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
@@ -46,6 +50,41 @@ def launches(src, dst):
     print(open(dst).read())
 
 
+def csvpage(src, dst, traffic_json=None):
+    """`ncu -i x.ncu-rep --page raw --csv` output (made on the GPU box) -> markdown table per kernel + optional traffic JSON."""
+    rd = list(csv.reader(open(src)))
+    hdr, units, data = rd[0], rd[1], rd[2:]
+    traffic = {'_source': f'ncu --set full --clock-control none, one launch per kernel ({src})'}
+    with open(dst, 'w') as f:
+        f.write(f'# ncu --set full summary ({src})\n\nOne launch per kernel inside a steady-state bench.py frame; numbers under ncu are never bench values.\n\n')
+        for row in data:
+            d = dict(zip(hdr, row))
+            u = dict(zip(hdr, units))
+            name = re.sub(r'\(.*', '', d.get('Kernel Name', '?')).strip()
+            f.write(f"## {name}  (ID {d.get('ID')})\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for k in hdr:
+                if any(k == x or k.startswith(x) for x in KEYS) or ('issue_stalled' in k and k.endswith('per_issue_active.ratio')) or k in EXTRA:
+                    f.write(f'| {k} | {d[k]} | {u[k]} |\n')
+            f.write('\n')
+            try:
+                scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+                rb = float(d['dram__bytes_read.sum'].replace(',', '')) * scale.get(u['dram__bytes_read.sum'], 1)
+                wb = float(d['dram__bytes_write.sum'].replace(',', '')) * scale.get(u['dram__bytes_write.sum'], 1)
+                key = name.replace('void ', '').replace('arah::', '').split('<')[0]
+                if key not in traffic:
+                    traffic[key] = {'dram_bytes_per_launch': rb + wb, 'dram_read': rb, 'dram_write': wb, 'ms': d.get('gpu__time_duration.sum'),
+                                    'tensor_pipe_pct': d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')}
+            except Exception:
+                pass
+    if traffic_json:
+        old = {}
+        if os.path.exists(traffic_json):
+            old = json.load(open(traffic_json))
+        old.update(traffic)
+        json.dump(old, open(traffic_json, 'w'), indent=1)
+    print(open(dst).read()[:2500])
+
+
 def rep(src, dst, traffic_json=None):
     out = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rd = list(csv.reader(io.StringIO(out)))
@@ -76,5 +115,7 @@ def rep(src, dst, traffic_json=None):
 if __name__ == '__main__':
     if sys.argv[1] == 'launches':
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == 'csv':
+        csvpage(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
     else:
         rep(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
