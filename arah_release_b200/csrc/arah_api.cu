@@ -306,6 +306,7 @@ struct ArahHandle {
     SdfTC sd;
     int trace_tc = 1;
     int knn_seed = 1;          // seeded per-lane 1-NN for runs of samples on one ray
+    int trace_knn = 1;         // k_trace_persist: seeded one-row-per-lane 1-NN (0: octet form)
     int iso_init_tc = 1;       // k_iso_init_tc3: joint-search Jacobian initialisation on the tensor cores (forward mode, 4 rows per ray)
     int corr_persist = 1;      // k_corr_persist: one persistent kernel with resident Broyden state (fp16 split precision) instead of 51 launches
     SkinF16Dev skin16{};
@@ -454,6 +455,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_iso_init_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     if (const char* e = getenv("ARAH_ISO_INIT_TC")) h->iso_init_tc = atoi(e) != 0;
     if (const char* e = getenv("ARAH_KNN_SEED")) h->knn_seed = atoi(e) != 0;
+    if (const char* e = getenv("ARAH_TRACE_KNN")) h->trace_knn = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_sdf_grid_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     if (const char* e = getenv("ARAH_TRACE_TC")) h->trace_tc = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
@@ -672,6 +674,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     CU(cudaMemsetAsync(w.counters, 0, C_COUNT * 4, st));
     w.shade_ctr = C_SHADE;
     w.knn_seed = h->knn_seed;
+    w.trace_knn = h->trace_knn;
     Work wk = w;                      // kernels get the phase-clock pointer only while profiling
     if (prof) CU(cudaMemsetAsync(w.phase_clk, 0, 32 * 8, st)); else wk.phase_clk = nullptr;
     if (prof) CU(cudaEventRecord(h->ev[0], st));

@@ -15,7 +15,7 @@
 namespace arah {
 
 // per-row words, SoA in shared memory: word f of row r at st[f * 128 + r]
-enum { TR_RAY = 0, TR_T = 1, TR_FAR = 2, TR_D = 3, TR_IT = 6, TR_S = 7, TR_T12 = 8, TR_XN = 20, TR_WORDS = 23 };
+enum { TR_RAY = 0, TR_T = 1, TR_FAR = 2, TR_D = 3, TR_IT = 6, TR_S = 7, TR_T12 = 8, TR_XN = 20, TR_SLOT = 23, TR_WORDS = 24 };
 
 __host__ __device__ constexpr size_t trace_persist_smem_bytes(int n_verts) {
     return (size_t)S16_NSLOTS * S16_SLOT_BYTES + knn_smem_bytes(n_verts) + (size_t)(TR_WORDS * UM + 4 * UM + 8) * 4 + sizeof(S16Ctl) + 64;
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
 #pragma unroll
                 for (int k = 0; k < 3; ++k) st[(TR_D + k) * UM + tid] = w.ray_dirs[3 * ray + k];
                 st[TR_IT * UM + tid] = __int_as_float(0);
+                st[TR_SLOT * UM + tid] = __int_as_float(-1);               // no previous nearest vertex yet
             }
             st[TR_RAY * UM + tid] = __int_as_float(ray);
         }
@@ -112,8 +113,32 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
     uint32_t e = 0;
     PhaseClk pc; pc.start((tid == 32 && w.phase_clk) ? w.phase_clk + 16 : nullptr);      // [0] 1-NN, [1] layer 0, [2] MMA wait, [3] epilogues, [4] marching
     while (live) {
-        // ---- nearest posed vertex + inverse NN skinning of the 8 rows of this warp (rows 8 warp .. 8 warp + 7)
-        {
+        // ---- nearest posed vertex + inverse NN skinning.  Two shapes (w.trace_knn): 1 = one row per lane on warps 0-3, the exact
+        // scan seeded with the row's previous winner (a marching ray moves little between steps, so the first bound is tight);
+        // 0 = four rows at a time per warp, 8 lanes each (octet form), all 16 warps
+        if (w.trace_knn) {
+            if (tid < UM) {
+                const int ray = __float_as_int(st[TR_RAY * UM + tid]);
+                float xn[3] = {0.f, 0.f, 0.f};
+                if (ray >= 0) {
+                    const float t = st[TR_T * UM + tid];
+                    float x[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) x[k] = st[(TR_D + k) * UM + tid] * t + fp.cam_loc[k];
+                    int slot = __float_as_int(st[TR_SLOT * UM + tid]);
+                    const int idx = knn_scan_seeded(kk, x[0], x[1], x[2], slot);
+                    st[TR_SLOT * UM + tid] = __int_as_float(slot);
+                    float T12[12], s_, xh[3];
+                    nn_inverse_skinning(fp, idx, x, T12, &s_, xh);
+                    normalize3(fp, xh, xn);
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) st[(TR_T12 + k) * UM + tid] = T12[k];
+                    st[TR_S * UM + tid] = s_;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) st[(TR_XN + k) * UM + tid] = xn[k];
+            }
+        } else {
             const int row = 8 * warp + (lane & 7);
             const bool mine_row = lane < 8;
             const int ray = __float_as_int(st[TR_RAY * UM + row]);

@@ -55,6 +55,7 @@ struct Work {
     int* shade_list;          // [P*S]
     int* counters;            // [C_COUNT]
     int knn_seed;             // k_knn_samples: seed each query of a run with the previous winner (exact; switchable for A/B)
+    int trace_knn;            // k_trace_persist: 1 = seeded one-row-per-lane 1-NN, 0 = octet form (exact both; switchable for A/B)
     int shade_ctr;            // counter slot holding the length of shade_list for the tensor-core shading kernel (C_SHADE / C_SHADE2)
     int shade_keep_sdf;       // full shading pass leaves smp_sdf alone (k_sdf_fwd16 has written the value compositing uses)
     float* scratch;           // shade kernel: per-CTA [7][TM][256]
