@@ -305,8 +305,8 @@ struct ArahHandle {
     float* tc_sdf3x[5];
     SdfTC sd;
     int trace_tc = 1;
-    int knn_seed = 1;          // seeded per-lane 1-NN for runs of samples on one ray
-    int trace_knn = 1;         // k_trace_persist: seeded one-row-per-lane 1-NN (0: octet form)
+    int knn_seed = 2;          // k_knn_samples: 2 = ray-major seeded per-lane 1-NN, 1 = runs of 4 on-samples (round 1), 0 = unseeded
+    int trace_knn = 0;         // k_trace_persist: 0 = octet-cooperative 1-NN (measured faster), 1 = seeded one-row-per-lane scan
     int iso_init_tc = 1;       // k_iso_init_tc3: joint-search Jacobian initialisation on the tensor cores (forward mode, 4 rows per ray)
     int corr_persist = 1;      // k_corr_persist: one persistent kernel with resident Broyden state (fp16 split precision) instead of 51 launches
     SkinF16Dev skin16{};
@@ -392,6 +392,7 @@ static int ensure_workspace(ArahHandle* h, int P) {
     const size_t o_z = take(PS * 4), o_xn = take(PS * 12), o_T = take(PS * 48), o_sc = take(PS), o_sdf = take(PS * 4), o_rgb = take(PS * 12);
     const size_t o_cs = take(PS * sizeof(BroydenState<3>));
     const size_t o_la = take(PS * 4), o_lb = take(PS * 4), o_on = take(PS * 4), o_sh = take(PS * 4), o_ctr = take(C_COUNT * 4 + 64), o_clk = take(32 * 8);
+    const size_t o_rb = take(cap * 4);
     if (h->ws.ensure(off) != 0) return -1;
     char* b = static_cast<char*>(h->ws.p);
     Work& w = h->w;
@@ -401,7 +402,7 @@ static int ensure_workspace(ArahHandle* h, int P) {
     w.ray_pnorm = (float*)(b + o_pn); w.z_vals = (float*)(b + o_z); w.smp_xn = (float*)(b + o_xn); w.smp_T = (float*)(b + o_T);
     w.smp_conv = (uint8_t*)(b + o_sc); w.smp_sdf = (float*)(b + o_sdf); w.smp_rgb = (float*)(b + o_rgb);
     w.corr_state = (BroydenState<3>*)(b + o_cs); w.listA = (int*)(b + o_la); w.listB = (int*)(b + o_lb);
-    w.on_list = (int*)(b + o_on); w.shade_list = (int*)(b + o_sh); w.counters = (int*)(b + o_ctr);
+    w.on_list = (int*)(b + o_on); w.shade_list = (int*)(b + o_sh); w.counters = (int*)(b + o_ctr); w.ray_on_base = (int*)(b + o_rb);
     w.phase_clk = (unsigned long long*)(b + o_clk);
     h->cap_rays = cap;
     return 0;
@@ -454,7 +455,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_iso_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_iso_init_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     if (const char* e = getenv("ARAH_ISO_INIT_TC")) h->iso_init_tc = atoi(e) != 0;
-    if (const char* e = getenv("ARAH_KNN_SEED")) h->knn_seed = atoi(e) != 0;
+    if (const char* e = getenv("ARAH_KNN_SEED")) h->knn_seed = atoi(e);
     if (const char* e = getenv("ARAH_TRACE_KNN")) h->trace_knn = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_sdf_grid_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     if (const char* e = getenv("ARAH_TRACE_TC")) h->trace_tc = atoi(e) != 0;

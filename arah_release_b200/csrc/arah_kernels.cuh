@@ -423,6 +423,7 @@ __global__ void k_trace_finish(FrameParams fp, Work w) {
     int base = 0;
     if (lane == 0 && total) base = atomicAdd(&w.counters[C_ON], total);
     base = __shfl_sync(0xffffffffu, base, 0) + incl - count;
+    if (r < w.P) w.ray_on_base[r] = base;
     for (int i = 0; i < count; ++i) w.on_list[base + i] = r * w.S + i;
 }
 
@@ -454,6 +455,27 @@ __global__ void __launch_bounds__(512, 1) k_knn_samples(FrameParams fp, KnnIndex
         st.best_n = 0.f; st.owner = w.on_list[i]; st.g_evals = 0;
         state_store(&w.corr_state[i], st);
     };
+    if (B == 32 && w.knn_seed == 2) {
+        // throughput regime, ray-major: a lane walks ALL on-samples of one ray front to back, each query seeded with the previous
+        // winner; the lanes of a warp hold adjacent rays (adjacent pixels), so at every step their queries lie within centimetres
+        // of each other and scan the same clusters: the per-lane search stays converged (round 1's run-of-4 mapping put two whole
+        // rays, ~2 m of depth range, into one warp)
+        const int total = gridDim.x * blockDim.x;
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < w.P; r += total) {
+            const int cnt = w.ray_conv[r] ? (fp.near_samples + 1 + fp.far_samples) : w.S;
+            const int base = w.ray_on_base[r];
+            const float d0 = w.ray_dirs[3 * r], d1 = w.ray_dirs[3 * r + 1], d2 = w.ray_dirs[3 * r + 2];
+            const float* zr = w.z_vals + (size_t)r * w.S;
+            int slot = -1;
+            for (int i = 0; i < cnt; ++i) {
+                const float z = zr[i];
+                const float x[3] = {d0 * z + fp.cam_loc[0], d1 * z + fp.cam_loc[1], d2 * z + fp.cam_loc[2]};
+                const int idx = knn_scan_seeded(kk, x[0], x[1], x[2], slot);
+                finish(base + i, x, idx);
+            }
+        }
+        return;
+    }
     if (B == 32 && w.knn_seed) {
         // throughput regime: a lane walks a run of KNN_RUN consecutive on-samples (neighbours on one ray), each query seeded by
         // the previous winner while the ray stays the same

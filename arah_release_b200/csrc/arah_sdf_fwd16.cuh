@@ -34,21 +34,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// the same load without the wait: the data may be used only after tmem_ld16_wait(r), which also ties the registers to the wait so
-// that the compiler cannot move a use in front of it
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
-                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :: "memory");
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
@@ -151,7 +136,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_sdf_fwd16(FrameParams fp, Sd
         }
         tmem_st8(trow + 256u * reg + 64u * j + 16u * u, p);
     };
-    // the warp's share of chunk j is in tensor memory: called one batch later, when the store has long completed
+    // the warp's share of chunk j is in tensor memory
     auto publish = [&](int j) {
         tmem_st_wait();
         tc_fence_before();
@@ -174,15 +159,19 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_sdf_fwd16(FrameParams fp, Sd
                 const int col0 = 64 * j + 16 * u;
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int cc = col0 + i;
-                    const float a = fmaf(sW0[512 + cc], z, fmaf(sW0[256 + cc], y, sW0[cc] * x));
-                    v[i] = __sinf(fmaf(a, sF[cc], sG[cc]));
+                for (int i4 = 0; i4 < 4; ++i4) {                          // 128-bit shared-memory loads: LDS and MUFU share the MIO queue
+                    const int cc = col0 + 4 * i4;
+                    const float4 wx = *reinterpret_cast<const float4*>(sW0 + cc), wy = *reinterpret_cast<const float4*>(sW0 + 256 + cc),
+                                 wz = *reinterpret_cast<const float4*>(sW0 + 512 + cc), f4 = *reinterpret_cast<const float4*>(sF + cc),
+                                 g4 = *reinterpret_cast<const float4*>(sG + cc);
+                    v[4 * i4 + 0] = __sinf(fmaf(fmaf(wz.x, z, fmaf(wy.x, y, wx.x * x)), f4.x, g4.x));
+                    v[4 * i4 + 1] = __sinf(fmaf(fmaf(wz.y, z, fmaf(wy.y, y, wx.y * x)), f4.y, g4.y));
+                    v[4 * i4 + 2] = __sinf(fmaf(fmaf(wz.z, z, fmaf(wy.z, y, wx.z * x)), f4.z, g4.z));
+                    v[4 * i4 + 3] = __sinf(fmaf(fmaf(wz.w, z, fmaf(wy.w, y, wx.w * x)), f4.w, g4.w));
                 }
-                if (j > 0) publish(j - 1);
                 put(0, j, v);
+                publish(j);
             }
-            publish(3);
         }
         float dot = 0.f;
 #pragma unroll 1
@@ -194,27 +183,28 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_sdf_fwd16(FrameParams fp, Sd
             const int dreg = L & 1;
             const float* F = sF + L * 256;
             const float* G = sG + L * 256;
-            // software pipeline over the four 16-column batches: the load of batch j + 1 is in flight while batch j is converted, and
-            // batch j is published (store complete -> arrive) after batch j + 1 has been converted
-            uint32_t raw[2][16];
-            tmem_ld16_issue(trow + 256u * dreg + (uint32_t)(16 * u), raw[0]);
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < 4; ++j) {
                 const int col0 = 64 * j + 16 * u;
-                tmem_ld16_wait(raw[j & 1]);
-                if (j < 3) tmem_ld16_issue(trow + 256u * dreg + (uint32_t)(col0 + 64), raw[(j + 1) & 1]);
                 float v[16];
+                tmem_ld16(trow + 256u * dreg + (uint32_t)col0, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __sinf(fmaf(__uint_as_float(raw[j & 1][i]), F[col0 + i], G[col0 + i]));
-                if (L < 5) {
-                    if (j > 0) publish(j - 1);
-                    put(dreg, j, v);                 // in place: the 8 packed columns lie inside the 16 just read
-                } else {
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const float4 f4 = *reinterpret_cast<const float4*>(F + col0 + 4 * i4), g4 = *reinterpret_cast<const float4*>(G + col0 + 4 * i4);
+                    v[4 * i4 + 0] = __sinf(fmaf(v[4 * i4 + 0], f4.x, g4.x));
+                    v[4 * i4 + 1] = __sinf(fmaf(v[4 * i4 + 1], f4.y, g4.y));
+                    v[4 * i4 + 2] = __sinf(fmaf(v[4 * i4 + 2], f4.z, g4.z));
+                    v[4 * i4 + 3] = __sinf(fmaf(v[4 * i4 + 3], f4.w, g4.w));
+                }
+                if (L < 5) { put(dreg, j, v); publish(j); }      // in place: the 8 packed columns lie inside the 16 just read
+                else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) dot = fmaf(v[i], sW6[col0 + i], dot);
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(sW6 + col0 + 4 * i4);
+                        dot = fmaf(v[4 * i4 + 3], w4.w, fmaf(v[4 * i4 + 2], w4.z, fmaf(v[4 * i4 + 1], w4.y, fmaf(v[4 * i4], w4.x, dot))));
+                    }
                 }
             }
-            if (L < 5) publish(3);
         }
         tc_fence_before();
         part[u][r] = dot;

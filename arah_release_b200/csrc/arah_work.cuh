@@ -52,9 +52,11 @@ struct Work {
     CorrSeed* corr_seed;          // [P*S]   persistent kernel (aliases corr_state's storage); null selects corr_state
     int* listA; int* listB;   // [P*S]
     int* on_list;             // [P*S] sample slot index of the k-th on-sample
+    int* ray_on_base;         // [P]   position of the ray's first on-sample in on_list (its on-samples are consecutive)
     int* shade_list;          // [P*S]
     int* counters;            // [C_COUNT]
-    int knn_seed;             // k_knn_samples: seed each query of a run with the previous winner (exact; switchable for A/B)
+    int knn_seed;             // k_knn_samples: 2 = one ray per lane, every sample seeded by the previous one (default); 1 = runs of 4
+                              // on-samples per lane; 0 = unseeded batches (all exact; switchable for A/B)
     int trace_knn;            // k_trace_persist: 1 = seeded one-row-per-lane 1-NN, 0 = octet form (exact both; switchable for A/B)
     int shade_ctr;            // counter slot holding the length of shade_list for the tensor-core shading kernel (C_SHADE / C_SHADE2)
     int shade_keep_sdf;       // full shading pass leaves smp_sdf alone (k_sdf_fwd16 has written the value compositing uses)
