@@ -74,7 +74,7 @@ EXPORTS = ['arah_last_error', 'arah_version', 'arah_create', 'arah_destroy', 'ar
            'arah_render_host', 'arah_get_trace', 'arah_get_stats', 'arah_eval_sdf', 'arah_eval_skin', 'arah_debug_umma_gemm', 'arah_debug_umma_f16', 'arah_debug_phase_clocks',
            'arah_set_training', 'arah_train_trace', 'arah_train_shade_forward', 'arah_train_shade_backward', 'arah_train_sdf_forward',
            'arah_train_sdf_backward', 'arah_train_skin_forward', 'arah_train_skin_backward', 'arah_debug_train_gemm',
-           'arah_sdf_grid', 'arah_marching_cubes', 'arah_mc_case_table', 'arah_debug_knn', 'arah_marching_cubes_workspace',
+           'arah_sdf_grid', 'arah_sdf_grid_banded', 'arah_marching_cubes', 'arah_mc_case_table', 'arah_debug_knn', 'arah_marching_cubes_workspace',
            'arah_hyper_forward', 'arah_hyper_workspace', 'arah_pose_smpl', 'arah_frame_rays', 'arah_frame_rays_workspace',
            'arah_frame_images', 'arah_frame_images_workspace', 'arah_psnr', 'arah_psnr_workspace', 'arah_rasterize_mesh',
            'arah_rasterize_mesh_workspace', 'arah_face_normal_image', 'arah_idhr_loss', 'arah_idhr_loss_workspace', 'arah_ssim', 'arah_ssim_workspace']
@@ -141,6 +141,7 @@ def lib():
     L.arah_debug_train_gemm.argtypes = [C.c_int32, C.c_int32, C.c_int32, FP, C.c_int64, C.c_int64, FP, C.c_int64, C.c_int64, FP, C.c_int32, FP,
                                         C.c_int32, C.c_int32, C.c_void_p]
     L.arah_sdf_grid.argtypes = [C.c_void_p, C.c_int32, FP, C.c_void_p]
+    L.arah_sdf_grid_banded.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, FP, FP, C.c_void_p]
     L.arah_marching_cubes.argtypes = [FP, C.c_int32, C.c_float, C.c_float, C.POINTER(C.c_float), FP, C.c_int32, FP, C.c_int32, FP, FP, C.c_size_t, C.c_void_p]
     L.arah_marching_cubes_workspace.argtypes = [C.c_int32]
     L.arah_marching_cubes_workspace.restype = C.c_size_t

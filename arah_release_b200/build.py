@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, 'csrc')
 INC = os.path.join(ROOT, 'include')
 OBJ = os.path.join(ROOT, 'build')
 SO = os.path.join(HERE, 'libarah_b200.so')
-SOURCES = ['arah_api.cu', 'arah_root.cu', 'arah_mesh.cu', 'arah_hyper.cu', 'arah_rays.cu', 'arah_image.cu', 'arah_loss.cu']
+SOURCES = ['arah_api.cu', 'arah_root.cu', 'arah_shade.cu', 'arah_mesh.cu', 'arah_hyper.cu', 'arah_rays.cu', 'arah_image.cu', 'arah_loss.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
 

@@ -13,6 +13,7 @@
 #include "arah_iso_init_tc.cuh"
 #include "arah_train_cuda.cuh"
 #include "arah_root.h"
+#include "arah_shade.h"
 #include <stdlib.h>
 
 using namespace arah;
@@ -314,6 +315,8 @@ struct ArahHandle {
     int iso_persist = 1;       // k_iso_persist: joint search as one persistent kernel
     SdfF16Dev sdf16{};
     int grid16 = 1;            // k_sdf_grid16: the canonical lattice on the fp16 split-precision engine
+    int shade16 = 1;           // k_shade16: gradient + colour pass with fp16 operands (kind::f16) instead of round 1's TF32 k_shade_tc3
+    Shade16Dev shade16_img{};
     int sdf_fwd16 = 1;         // k_sdf_fwd16: the SDF value compositing uses comes from a single-pass fp16 kernel over all converged samples
     bool shade_cull_ran = false;
     int shade_cull = 1;        // exact alpha cull before the gradient / colour pass (k_alpha_cull)
@@ -365,6 +368,8 @@ static int alloc_arena(ArahHandle* h) {
     reg(&s16_hi, SKIN_F16_IMAGE_BYTES / 4); reg(&s16_lo, SKIN_F16_IMAGE_BYTES / 4); reg(&h->skin16.scale, 8);
     float *d16_hi = nullptr, *d16_lo = nullptr;
     reg(&d16_hi, SDF_F16_DEV_BYTES / 4); reg(&d16_lo, SDF_F16_DEV_BYTES / 4); reg(&h->sdf16.scale, 16);
+    float *sh16_bwd = nullptr, *sh16_col = nullptr;
+    reg(&sh16_bwd, SHADE16_BWD_DEV_BYTES / 4); reg(&sh16_col, SHADE16_COL_DEV_BYTES / 4);
     reg(&h->col_b[0], 256); reg(&h->col_b[1], 256); reg(&h->col_b[2], 256); reg(&h->col_b[3], 256); reg(&h->col_b[4], 256); reg(&h->col_b[5], 64);
     reg(&h->knn_sv, (size_t)((h->cfg.n_verts + 31) / 32) * 32 * 4); reg(&h->knn_cmin, (size_t)((h->cfg.n_verts + 31) / 32) * 4);
     reg(&h->knn_cmax, (size_t)((h->cfg.n_verts + 31) / 32) * 4);
@@ -378,6 +383,7 @@ static int alloc_arena(ArahHandle* h) {
     h->verts4 = reinterpret_cast<float4*>(static_cast<char*>(h->arena.p) + slots[slots.size() - 3].second);
     h->skin16.hi = s16_hi; h->skin16.lo = s16_lo;
     h->sdf16.hi = d16_hi; h->sdf16.lo = d16_lo;
+    h->shade16_img.bwd = sh16_bwd; h->shade16_img.col = sh16_col;
     return 0;
 }
 
@@ -449,6 +455,8 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     if (const char* e = getenv("ARAH_ISO_PERSIST")) h->iso_persist = atoi(e) != 0;
     if (const char* e = getenv("ARAH_SDF_FWD16")) h->sdf_fwd16 = atoi(e) != 0;
     if (const char* e = getenv("ARAH_GRID16")) h->grid16 = atoi(e) != 0;
+    if (const char* e = getenv("ARAH_SHADE16")) h->shade16 = atoi(e) != 0;
+    CU(shade16_init());
     if (!root_trace_fits(cfg->n_verts)) h->trace_persist = 0;      // vertex index + weight ring must fit in 227 KB of shared memory
     CU(root_init());
     CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
@@ -565,6 +573,7 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
         for (int l = 1; l < 6; ++l) { k_pack_umma_x3<<<cdiv((size_t)8 * 256 * 32, 256), 256, 0, st>>>(f->sdf_W[l], 256, h->tc_sdf3x[l - 1], 256, 256, 256, 8); ++npack; }
         { long long n = 0; CU(root_pack_skin_f16(f->skin_W, h->skin16, st, &n)); npack += n; }
         { long long n = 0; CU(root_pack_sdf_f16(f->sdf_W, h->sdf16, st, &n)); npack += n; }
+        if (h->cfg.shade_mode == ARAH_SHADE_TF32 && h->shade16) { long long n = 0; CU(shade16_pack(f->sdf_W, f->col_W, din, h->shade16_img, st, &n)); npack += n; }
     }
     // pose buffers
     const cudaMemcpyKind kind = f->pose_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
@@ -742,6 +751,14 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
             h->shade_cull_ran = h->shade_cull != 0;
             const bool fwd16 = h->sdf_fwd16 && h->cfg.root_mode == ARAH_ROOT_3XTF32;     // (the fp16 images are packed with the root engine's)
             wk.shade_keep_sdf = fwd16 ? 1 : 0;
+            // fp16 operands for the gradient + colour pass (the forward images are the root engine's, so root_mode must have packed them)
+            const bool use16 = h->shade16 && h->cfg.root_mode == ARAH_ROOT_3XTF32;
+            Shade16Host s16h{};
+            if (use16) {
+                s16h.sdf_Wt0 = h->sdf_Wt[0]; s16h.sdf_W0 = h->sdf_W[0]; s16h.sdf_F = h->tc_F; s16h.sdf_G = h->tc_G; s16h.sdf_scale = h->sdf16.scale;
+                s16h.sdf_fwd_hi = h->sdf16.hi; s16h.sdf_w6 = h->sdf_w6; s16h.sdf_b6 = h->d_b6; s16h.col_W5 = h->col_W5;
+                for (int l = 0; l < 6; ++l) s16h.col_b[l] = h->col_b[l];
+            }
             if (fwd16) {
                 // the SDF value of every converged sample (what compositing turns into sigma) in one fp16 single-pass sweep; the
                 // full pass below then only supplies colours, with or without the cull: both settings composite identical inputs
@@ -755,11 +772,11 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
                 k_alpha_cull<<<cdiv(P, COMP_WARPS), 32 * COMP_WARPS, 0, st>>>(fp, w, w.listA); L();
                 Work w2 = wk;
                 w2.shade_list = w.listA; w2.shade_ctr = C_SHADE2;
-                k_shade_tc3<false><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, w2);
-            } else
-                k_shade_tc3<false><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk);
+                if (use16) { long long n = 0; CU(shade16_launch(fp, s16h, h->shade16_img, w2, g, st, &n)); h->launches += n; }
+                else { k_shade_tc3<false><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, w2); L(); }
+            } else if (use16) { long long n = 0; CU(shade16_launch(fp, s16h, h->shade16_img, wk, g, st, &n)); h->launches += n; }
+            else { k_shade_tc3<false><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk); L(); }
         }
-        L();
     }
     else { k_shade<<<grid_min(cdiv(PS, TM), (size_t)nsm), 256, shade_smem_bytes(), st>>>(fp, w); L(); }
     if (prof) CU(cudaEventRecord(h->ev[4], st));
@@ -925,6 +942,26 @@ extern "C" int arah_sdf_grid(ArahHandle* h, int32_t N, float* sdf, void* stream)
         }
     }
     CU(cudaGetLastError());
+    return ARAH_OK;
+}
+
+
+extern "C" int arah_sdf_grid_banded(ArahHandle* h, int32_t N, float level, float eps, float* sdf, int32_t* stats, void* stream) {
+    if (!h || !h->frame_set) return fail(ARAH_ESTATE, "arah_set_frame first");
+    if (N < 2 || N > 1024) return fail(ARAH_EINVAL, "lattice side must be in [2, 1024]");
+    if (!sdf || !stats) return fail(ARAH_EINVAL, "null buffer");
+    if (!(eps >= 0.f)) return fail(ARAH_EINVAL, "eps must be >= 0");
+    if (h->cfg.root_mode != ARAH_ROOT_3XTF32) return fail(ARAH_ESTATE, "the banded lattice needs root_mode 3xTF32 (fp16 weight images); use arah_sdf_grid");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)N * N * N;
+    if (h->io_in.ensure(align_up(n, 256) + n * 4) != 0) return fail(ARAH_ENOMEM, "lattice flag / list allocation failed");
+    uint8_t* flag = (uint8_t*)h->io_in.p;
+    int* list = (int*)(flag + align_up(n, 256));
+    SdfF16Host sh16;
+    sh16.Wt0 = h->sdf_Wt[0]; sh16.freq = h->sdf_freq; sh16.phase = h->sdf_phase; sh16.w6 = h->sdf_w6; sh16.b6 = h->sd.b6;
+    for (int l = 0; l < 6; ++l) sh16.b[l] = h->sdf_b[l];
+    CU(root_sdf_grid_banded(sh16, h->sdf16, N, (float)(2.0 / (double)(N - 1)), level, eps, sdf, flag, list, stats, h->n_sms, st, nullptr));
     return ARAH_OK;
 }
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ void umma_f16x3_chunk(uint32_t td, uint32_t xh, uint3
 
 // ---- pack kernels (arah_set_frame) ----------------------------------------------------------------------------------------
 // out[0] = s = 2^e with max|W| * s in [128, 256) (1 if the layer is all zero / not finite), out[1] = 1 / s.  One block.
-__global__ void k_layer_scale(const float* __restrict__ W, int n, float* __restrict__ out) {
+static __global__ void k_layer_scale(const float* __restrict__ W, int n, float* __restrict__ out) {
     __shared__ float red[32];
     float m = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
@@ -83,7 +83,7 @@ __global__ void k_layer_scale(const float* __restrict__ W, int n, float* __restr
     }
 }
 // src [N][src_ld] fp32 (reference layout [out][in]) -> hi / lo images, nchunks K-chunks of Npad rows (rows >= N, k >= K: zero)
-__global__ void k_pack_f16x2(const float* __restrict__ src, int src_ld, const float* __restrict__ scale, __half* __restrict__ dst_hi,
+static __global__ void k_pack_f16x2(const float* __restrict__ src, int src_ld, const float* __restrict__ scale, __half* __restrict__ dst_hi,
                              __half* __restrict__ dst_lo, int N, int Npad, int K, int nchunks) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nchunks * Npad * HK) return;
@@ -99,9 +99,26 @@ __global__ void k_pack_f16x2(const float* __restrict__ src, int src_ld, const fl
     dst_lo[o] = l;
 }
 
+// single fp16 image (no split, no scale) with the column permutation / transpose options of k_pack_umma (arah_api.cu):
+//   B[n][k] = src[n][col(k)]  (or src[col(k)][n] when transpose_src), col(k) = k < split ? k + off_lo : k - split + off_hi; 0 beyond K
+static __global__ void k_pack_f16(const float* __restrict__ src, int src_ld, __half* __restrict__ dst, int N, int K, int nchunks, int split,
+                           int off_lo, int off_hi, int transpose_src) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nchunks * N * HK) return;
+    const int kc = idx / (N * HK), rem = idx % (N * HK);
+    const int n = rem / HK, q = rem % HK, j = q >> 3, e = q & 7;
+    const int k = HK * kc + q;
+    float v = 0.f;
+    if (k < K) {
+        const int col = (k < split) ? (k + off_lo) : (k - split + off_hi);
+        v = transpose_src ? src[(size_t)col * src_ld + n] : src[(size_t)n * src_ld + col];
+    }
+    dst[(size_t)kc * N * HK + (size_t)(n >> 3) * 512 + (n & 7) * 64 + ((j ^ (n & 7)) << 3) + e] = __float2half_rn(v);
+}
+
 // ---- probe (tests/test_gpu_00_umma.py): D[128][N] = A[128][K] . W[N][K]^T through exactly the addressing the kernels use ----
 // mode bit 0: three-pass split product (else hi.hi only).  One CTA of 128 threads.  K in {64, 128}, N in {32, 128, 256}.
-__global__ void __launch_bounds__(128, 1) k_umma_f16_probe(const float* __restrict__ A, const __half* __restrict__ Whi, const __half* __restrict__ Wlo,
+static __global__ void __launch_bounds__(128, 1) k_umma_f16_probe(const float* __restrict__ A, const __half* __restrict__ Whi, const __half* __restrict__ Wlo,
                                                            const float* __restrict__ scale, int K, int N, float* __restrict__ D, int mode) {
     extern __shared__ uint8_t raw_smem[];
     const uint32_t base = (smem_u32(raw_smem) + 1023u) & ~1023u;

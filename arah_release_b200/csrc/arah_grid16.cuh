@@ -10,8 +10,13 @@ namespace arah {
 
 __host__ __device__ constexpr size_t sdf_grid16_smem_bytes() { return (size_t)S16_NSLOTS * S16_SLOT_BYTES + (size_t)(4 * UM + 8) * 4 + sizeof(S16Ctl) + 64; }
 
-__global__ void __launch_bounds__(S16_THREADS, 1) k_sdf_grid16(SdfF16 sd, int N, float voxel, long long n_total, float* __restrict__ out) {
+// list != nullptr (the refinement pass of the banded lattice): the points are list[0 .. *list_n) (lattice indices); a refined
+// value that differs from the coarse value already in out[] by more than eps counts into *violations.
+__global__ void __launch_bounds__(S16_THREADS, 1) k_sdf_grid16(SdfF16 sd, int N, float voxel, long long n_total_, float* __restrict__ out,
+                                                               const int* __restrict__ list, const int* __restrict__ list_n, float eps,
+                                                               int* __restrict__ violations) {
     extern __shared__ __align__(1024) uint8_t raw_smem[];
+    const long long n_total = list ? (long long)*list_n : n_total_;
     const long long ntiles = (n_total + UM - 1) / UM;
     if ((long long)blockIdx.x >= ntiles) return;
     if (smem_u32(raw_smem) & 1023u) __trap();
@@ -41,9 +46,10 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_sdf_grid16(SdfF16 sd, int N,
     const int q = warp & 3, u = warp >> 2, r = 32 * q + lane;
     uint32_t done_par = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long i = tile * UM + r;                  // the lattice point of this thread's row
+        const long long e = tile * UM + r;                  // the lattice point of this thread's row
+        const long long i = (list && e < n_total) ? (long long)list[e] : e;
         float x = 0.f, y = 0.f, z = 0.f;
-        if (i < n_total) {
+        if (e < n_total) {
             const int iz = (int)(i % N), iy = (int)((i / N) % N), ix = (int)(i / ((long long)N * N));
             x = __fadd_rn(__fmul_rn((float)ix, voxel), -1.0f);
             y = __fadd_rn(__fmul_rn((float)iy, voxel), -1.0f);
@@ -52,11 +58,41 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_sdf_grid16(SdfF16 sd, int N,
         const float dot = s16_compute_sdf(sd, x, y, z, ctl, done_par, tbase, sInv);
         part[u][r] = dot;
         s16_sync();
-        if (u == 0 && i < n_total) out[i] = ((part[0][r] + part[1][r]) + (part[2][r] + part[3][r])) + __ldg(sd.b6);
+        if (u == 0 && e < n_total) {
+            const float val = ((part[0][r] + part[1][r]) + (part[2][r] + part[3][r])) + __ldg(sd.b6);
+            if (list && !(fabsf(val - out[i]) <= eps)) atomicAdd(violations, 1);
+            out[i] = val;
+        }
         s16_sync();                                         // part is rewritten by the next tile
     }
     tc_fence_before();
     s16_sync_exit();
+}
+
+// ---- banded lattice: which points need the split-precision value ------------------------------------------------------------
+// A cell can contribute to the iso-surface only if its 8 corner values straddle `level`.  With |coarse - exact| <= eps at every
+// point, a cell whose coarse corner values satisfy min - eps > level or max + eps < level cannot straddle it, and all its corners
+// keep the sign (relative to level) of their exact values.  Every other cell gets all 8 corners refined, so marching cubes sees
+// exact values wherever it interpolates and exact signs everywhere: its output is bit-identical to that of the full lattice.
+__global__ void k_grid_band_flag(const float* __restrict__ vol, int N, float level, float eps, uint8_t* __restrict__ flag) {
+    const int iz = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y, ix = blockIdx.z;
+    if (iz >= N - 1) return;
+    const size_t b = ((size_t)ix * N + iy) * N + iz, sx = (size_t)N * N, sy = (size_t)N;
+    const size_t o[8] = {b, b + 1, b + sy, b + sy + 1, b + sx, b + sx + 1, b + sx + sy, b + sx + sy + 1};
+    float mn = 3.4e38f, mx = -3.4e38f;
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { const float v = vol[o[c]]; mn = fminf(mn, v); mx = fmaxf(mx, v); finite = finite && (fabsf(v) < 3.0e38f); }
+    if (!finite || (mn - eps <= level && level <= mx + eps)) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) flag[o[c]] = 1;
+    }
+}
+__global__ void k_grid_band_list(const uint8_t* __restrict__ flag, int n, int* __restrict__ list, int* __restrict__ counter) {
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {     // warp-uniform trip count (n rounded up by the caller)
+        const int i = base + threadIdx.x;
+        warp_append(i < n && flag[i] != 0, i, list, counter);
+    }
 }
 
 }  // namespace arah

@@ -67,7 +67,7 @@ cudaError_t root_sdf_fwd16(const FrameParams& fp, const SdfF16Host& sh, const Sd
                            long long* launches) {
     const size_t tiles = ((size_t)w.P * w.S + UM - 1) / UM;
     const unsigned g = (unsigned)(tiles < (size_t)n_sms ? tiles : (size_t)n_sms);
-    k_sdf_fwd16<<<g, F16_THREADS, sdf_fwd16_smem_bytes(), st>>>(fp, make_sdf16(sh, img), w);
+    k_sdf_fwd16<<<g, F16_THREADS, sdf_fwd16_smem_bytes(), st>>>(fp, make_sdf16(sh, img), w, Fwd16Grid{0, 0.f, 0, nullptr});
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -75,7 +75,29 @@ cudaError_t root_sdf_fwd16(const FrameParams& fp, const SdfF16Host& sh, const Sd
 cudaError_t root_sdf_grid16(const SdfF16Host& sh, const SdfF16Dev& img, int N, float voxel, long long n, float* out, int n_sms, cudaStream_t st) {
     const size_t tiles = (size_t)((n + UM - 1) / UM);
     const unsigned g = (unsigned)(tiles < (size_t)n_sms ? tiles : (size_t)n_sms);
-    k_sdf_grid16<<<g, S16_THREADS, sdf_grid16_smem_bytes(), st>>>(make_sdf16(sh, img), N, voxel, n, out);
+    k_sdf_grid16<<<g, S16_THREADS, sdf_grid16_smem_bytes(), st>>>(make_sdf16(sh, img), N, voxel, n, out, nullptr, nullptr, 0.f, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t root_sdf_grid_banded(const SdfF16Host& sh, const SdfF16Dev& img, int N, float voxel, float level, float eps, float* out,
+                                 uint8_t* flag, int* list, int* stats, int n_sms, cudaStream_t st, long long* launches) {
+    const int n = N * N * N;                                       // N <= 1024 (checked by the caller): fits an int
+    const size_t tiles = ((size_t)n + UM - 1) / UM;
+    const unsigned g = (unsigned)(tiles < (size_t)n_sms ? tiles : (size_t)n_sms);
+    cudaError_t e = cudaMemsetAsync(flag, 0, (size_t)n, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(stats, 0, 2 * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    // 1. every lattice point in one fp16 pass
+    FrameParams fp0{};
+    Work w0{};
+    k_sdf_fwd16<<<g, F16_THREADS, sdf_fwd16_smem_bytes(), st>>>(fp0, make_sdf16(sh, img), w0, Fwd16Grid{N, voxel, n, out});
+    // 2. corners of the cells that may straddle the level, as a list
+    k_grid_band_flag<<<dim3(cdiv_u((size_t)N - 1, 128), N - 1, N - 1), 128, 0, st>>>(out, N, level, eps, flag);
+    k_grid_band_list<<<4 * n_sms, 256, 0, st>>>(flag, n, list, stats);
+    // 3. those points again in split precision (grid: the list length is only known on the device; idle CTAs exit at once)
+    k_sdf_grid16<<<g, S16_THREADS, sdf_grid16_smem_bytes(), st>>>(make_sdf16(sh, img), N, voxel, 0, out, list, stats, eps, stats + 1);
+    if (launches) *launches += 4;
     return cudaGetLastError();
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdint.h>
 
 #include "arah_work.cuh"
 
@@ -37,6 +38,11 @@ cudaError_t root_sdf_fwd16(const FrameParams& fp, const SdfF16Host& sh, const Sd
                            long long* launches);
 // canonical SDF lattice (row f1): raw network output at the N^3 lattice points of [-1, 1]^3
 cudaError_t root_sdf_grid16(const SdfF16Host& sh, const SdfF16Dev& img, int N, float voxel, long long n, float* out, int n_sms, cudaStream_t st);
+// the lattice marching cubes needs (arah_sdf_grid_banded): one fp16 pass over all points, then split precision for the corners of
+// every cell whose coarse values lie within eps of straddling `level`.  flag: N^3 bytes, list: N^3 ints, stats: 2 ints
+// (refined points, refined points whose coarse value was off by more than eps) — all device scratch of the caller.
+cudaError_t root_sdf_grid_banded(const SdfF16Host& sh, const SdfF16Dev& img, int N, float voxel, float level, float eps, float* out,
+                                 uint8_t* flag, int* list, int* stats, int n_sms, cudaStream_t st, long long* launches);
 // joint search of the rays listed in w.listA (k_iso_prepare) whose state k_iso_init_tc3 has written, persistent
 cudaError_t root_iso_persist(const FrameParams& fp, const SdfF16Host& sh, const SdfF16Dev& img, const float* skin_Wt0, const float* const skin_b[5],
                              const SkinF16Dev& skimg, const Work& w, int n_sms, cudaStream_t st, long long* launches);

@@ -39,10 +39,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
-// sdf_out == nullptr: write w.smp_sdf[slot] (metres) for the slots of w.shade_list[0 .. counters[C_SHADE]).
-__global__ void __launch_bounds__(F16_THREADS, 1) k_sdf_fwd16(FrameParams fp, SdfF16 sd, Work w) {
+// Lattice mode (arah_grid16.cuh, the coarse pass of the banded lattice): the points are the first `n` lattice points of an N^3
+// lattice and the RAW network output goes to out[i].
+struct Fwd16Grid { int N; float voxel; int n; float* out; };
+
+// g.out == nullptr: write w.smp_sdf[slot] (metres) for the slots of w.shade_list[0 .. counters[C_SHADE]).
+__global__ void __launch_bounds__(F16_THREADS, 1) k_sdf_fwd16(FrameParams fp, SdfF16 sd, Work w, Fwd16Grid g) {
     extern __shared__ __align__(1024) uint8_t raw_smem[];
-    const int n = w.counters[C_SHADE];
+    const int n = g.out ? g.n : w.counters[C_SHADE];
     const int ntiles = (n + UM - 1) / UM;
     if ((int)blockIdx.x >= ntiles) return;
     if (smem_u32(raw_smem) & 1023u) __trap();
@@ -148,7 +152,15 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_sdf_fwd16(FrameParams fp, Sd
         if (tid < UM) {
             const int i = tile * UM + tid;
             float xn[3] = {0.f, 0.f, 0.f};
-            if (i < n) { sl = w.shade_list[i]; xn[0] = w.smp_xn[3 * (size_t)sl]; xn[1] = w.smp_xn[3 * (size_t)sl + 1]; xn[2] = w.smp_xn[3 * (size_t)sl + 2]; }
+            if (i < n) {
+                if (g.out) {                                        // lattice coordinates with the reference's arithmetic (sdf_meshing.py:25-38)
+                    sl = i;
+                    const int iz = i % g.N, iy = (i / g.N) % g.N, ix = i / (g.N * g.N);
+                    xn[0] = __fadd_rn(__fmul_rn((float)ix, g.voxel), -1.0f);
+                    xn[1] = __fadd_rn(__fmul_rn((float)iy, g.voxel), -1.0f);
+                    xn[2] = __fadd_rn(__fmul_rn((float)iz, g.voxel), -1.0f);
+                } else { sl = w.shade_list[i]; xn[0] = w.smp_xn[3 * (size_t)sl]; xn[1] = w.smp_xn[3 * (size_t)sl + 1]; xn[2] = w.smp_xn[3 * (size_t)sl + 2]; }
+            }
             xs[tid][0] = xn[0]; xs[tid][1] = xn[1]; xs[tid][2] = xn[2]; xs[tid][3] = 0.f;
         }
         sync_epi();
@@ -209,8 +221,11 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_sdf_fwd16(FrameParams fp, Sd
         tc_fence_before();
         part[u][r] = dot;
         sync_epi();
-        if (tid < UM && sl >= 0)
-            w.smp_sdf[sl] = sdf_to_metres(((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid])) + __ldg(sd.b6), fp.cmin, fp.cmax);
+        if (tid < UM && sl >= 0) {
+            const float raw = ((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid])) + __ldg(sd.b6);
+            if (g.out) g.out[sl] = raw;
+            else w.smp_sdf[sl] = sdf_to_metres(raw, fp.cmin, fp.cmax);
+        }
         // (xs / part are rewritten only after the next sync_epi)
     }
     tc_fence_before();

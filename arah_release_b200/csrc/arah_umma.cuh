@@ -199,5 +199,8 @@ __device__ __forceinline__ float softplus100_fast(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
     return fmaf(l, 0.006931471805599453f, fmaxf(x, 0.0f));
 }
+// (Round 2 tried moving the logarithm of every second element to the FP32 pipe, e P(e) with a degree-6 polynomial, to relieve the
+// MUFU unit in k_corr_persist: one MUFU less but four FP32 instructions more per element made the kernel 1.3 ms SLOWER — the
+// epilogues are as much issue-bound as MUFU-bound.  Reverted.)
 
 }  // namespace arah

@@ -31,6 +31,9 @@ from . import _lib
 from ._lib import ArahConfig, ArahFrame, ArahStats, ArahTrainGrads, check
 
 N_VERTS_DEFAULT = 6890
+# Error bound assumed for the fp16 pass of the banded lattice (raw network output units): ~10x the largest deviation measured on
+# the 256^3 fixtures (tests/test_gpu_mesh.py prints it); the library checks the bound on every refined point at run time.
+BAND_EPS = 0.02
 
 
 def _ptr(t):
@@ -360,6 +363,28 @@ class ArahRenderer:
         check(_lib.lib().arah_sdf_grid(self._h, int(N), _ptr(out), self.stream))
         return out
 
+    def sdf_grid_banded(self, N=256, level=0.0, eps=BAND_EPS):
+        """The lattice for a caller that only extracts the `level` iso-surface from it (include/arah_b200.h, arah_sdf_grid_banded):
+        one fp16 pass over all N^3 points, split precision for the corners of every cell within eps of straddling the level.
+        Returns (vol [N, N, N], stats int32[2] = [points refined, refined points whose coarse value was off by more than eps]),
+        both on the device; marching_cubes(vol, level) equals marching_cubes(sdf_grid(N), level) bit for bit while stats[1] == 0."""
+        out = torch.empty(N, N, N, device=self.device)
+        stats = torch.zeros(2, dtype=torch.int32, device=self.device)
+        check(_lib.lib().arah_sdf_grid_banded(self._h, int(N), float(level), float(eps), _ptr(out), _ptr(stats), self.stream))
+        return out, stats
+
+    def canonical_mesh(self, N=256, level=0.0, voxel_size=None, origin=(-1.0, -1.0, -1.0)):
+        """SDF lattice + iso-surface (utils/sdf_meshing.py:13-114) -> device (verts, faces).  Tensor-core modes use the banded
+        lattice and fall back to the full-precision one if its run-time error check fires (never observed)."""
+        if self.root_mode != '3xtf32' or os.environ.get('ARAH_GRID_BANDED', '1') == '0':
+            return self.marching_cubes(self.sdf_grid(N), level=level, voxel_size=voxel_size, origin=origin)
+        vol, stats = self.sdf_grid_banded(N, level=level)
+        verts, faces = self.marching_cubes(vol, level=level, voxel_size=voxel_size, origin=origin)     # (synchronises: counts)
+        self.last_band_stats = [int(v) for v in stats.tolist()]
+        if self.last_band_stats[1] != 0:
+            verts, faces = self.marching_cubes(self.sdf_grid(N), level=level, voxel_size=voxel_size, origin=origin)
+        return verts, faces
+
     def marching_cubes(self, vol, level=0.0, voxel_size=None, origin=(-1.0, -1.0, -1.0), max_verts=None, max_faces=None):
         """utils/sdf_meshing.py:69-114 on the GPU: (verts [nv, 3] float32, faces [nf, 3] int32), both device tensors.
         One host synchronisation (the vertex / face counts size the result)."""
@@ -389,8 +414,7 @@ def create_mesh_vertices_and_faces(renderer, N=256, max_batch=64 ** 3, offset=No
     """Drop-in for im2mesh.utils.sdf_meshing.create_mesh_vertices_and_faces (utils/sdf_meshing.py:13-66) with the frame's
     ArahRenderer in place of the `decoder` module: SDF lattice on the tensor cores, iso-surface on the GPU; returns numpy
     (mesh_points [nv, 3], faces [nf, 3]) like the reference.  `max_batch` is accepted and ignored (no chunking needed)."""
-    vol = renderer.sdf_grid(N)
-    verts, faces = renderer.marching_cubes(vol, level=0.0, voxel_size=2.0 / (N - 1), origin=(-1.0, -1.0, -1.0))
+    verts, faces = renderer.canonical_mesh(N, level=0.0, voxel_size=2.0 / (N - 1), origin=(-1.0, -1.0, -1.0))
     if scale is not None:
         verts = verts / scale
     if offset is not None:
@@ -708,8 +732,7 @@ class IDHRNetwork(nn.Module):
         frame's SDF (normalised coordinates) and its posed vertices `forward_skinning(unnormalize(verts)) + trans`.
         Returns device tensors (verts [nv,3], faces [nf,3] int32, points_bar [nv,3])."""
         r = self._prepare(input)
-        vol = r.sdf_grid(N)
-        verts, faces = r.marching_cubes(vol)
+        verts, faces = r.canonical_mesh(N)
         cmin, cmax = input['coord_min'].reshape(-1)[0], input['coord_max'].reshape(-1)[0]
         pts_hat = (verts / 2.0 + 0.5) * 1.1 * (cmax - cmin) + cmin - 0.05 * (cmax - cmin) + input['center'].reshape(1, 3)
         _, x_bar = r.eval_skin(pts_hat)

@@ -305,17 +305,26 @@ def mesh_extract_bench(net, frame, steps=3, warmup=2, N=256):
     import torch
     from oracle import oracle as orc
     r = net._last[0]
-    ms_g, ms_m = [], []
+    banded = r.root_mode == '3xtf32'
+    ms_g, ms_m, ms_full = [], [], []
+    stats = None
     for i in range(warmup + steps):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record()
-        vol = r.sdf_grid(N)
+        # what the mesh branch runs: the banded lattice (fp16 pass + split precision near the surface) where the fp16 images exist
+        if banded:
+            vol, stats = r.sdf_grid_banded(N)
+        else:
+            vol = r.sdf_grid(N)
         e[1].record()
         v, f = r.marching_cubes(vol, max_verts=1 << 20, max_faces=1 << 21)
         e[2].record()
+        full = r.sdf_grid(N)                 # every point in split precision (round 1's lattice), for comparison
+        e[3].record()
         torch.cuda.synchronize()
         if i >= warmup:
-            ms_g.append(e[0].elapsed_time(e[1])); ms_m.append(e[1].elapsed_time(e[2]))
+            ms_g.append(e[0].elapsed_time(e[1])); ms_m.append(e[1].elapsed_time(e[2])); ms_full.append(e[2].elapsed_time(e[3]))
+    del full
     pk = peaks()
     g, m = float(np.mean(ms_g)), float(np.mean(ms_m))
     mc_bytes = 4.0 * N ** 3 + 12.0 * v.shape[0] + 12.0 * f.shape[0]
@@ -328,7 +337,11 @@ def mesh_extract_bench(net, frame, steps=3, warmup=2, N=256):
             'n_verts': int(v.shape[0]), 'n_faces': int(f.shape[0]),
             'sdf_grid_tflops_useful': 2.0 * MAC_SDF * N ** 3 / (g * 1e-3) / 1e12, 'sdf_grid_frac_of_bf16_peak': 2.0 * MAC_SDF * N ** 3 / (g * 1e-3) / 1e12 / pk['tf_sustained'],
             'marching_cubes_gbs': mc_bytes / (m * 1e-3) / 1e9, 'marching_cubes_frac_of_hbm_peak': mc_bytes / (m * 1e-3) / 1e9 / pk['hbm_gbs'],
-            'gpu_launches': 5, 'steps': steps, 'warmup': warmup,
+            'gpu_launches': 8 if banded else 5, 'steps': steps, 'warmup': warmup,
+            'lattice': ('banded: fp16 pass over all points, split precision for the corners of cells within eps of the level; marching-cubes '
+                        'output bit-identical to the full lattice (tests/test_gpu_mesh.py)') if banded else 'full precision',
+            'banded_stats': [int(x) for x in stats.tolist()] if stats is not None else None,
+            'ms_sdf_grid_full_split_precision': float(np.mean(ms_full)),
             'cpu_port': {'ms_marching_cubes_1core': 1e3 * t_mc, 'ms_sdf_grid_extrapolated': 1e3 * t_sdf * (N / 64.0) ** 3, 'cores': orc.num_threads(),
                          'sample': '64^3 lattice points timed, scaled by (N/64)^3'}}
 

@@ -169,6 +169,15 @@ int arah_eval_skin(ArahHandle* h, const float* x_hat, int32_t n, float* weights,
  *   this step to skimage 0.18.1 `marching_cubes_lewiner` (absent here: parity against it is unpinned; the checker is
  *   oracle/mc_oracle.c, a CPU restatement of the same published scheme).  Works on the current device; no handle needed. */
 int arah_sdf_grid(ArahHandle* h, int32_t N, float* sdf, void* stream);
+/* arah_sdf_grid_banded: the same lattice for the caller that only feeds it to arah_marching_cubes at `level`
+ *   (utils/sdf_meshing.py:59-114 does exactly that), in two precisions.  Every point is evaluated in one fp16 tensor-core pass;
+ *   every cell whose eight coarse corner values satisfy min - eps <= level <= max + eps has all its corners re-evaluated in split
+ *   precision (bit-identical to arah_sdf_grid's values).  As long as the coarse error stays below eps, marching cubes finds exact
+ *   values wherever it interpolates and exact signs everywhere else, so its vertices and faces are bit-identical to those of the
+ *   full-precision lattice.  stats (device, 2 x int32): [0] points refined, [1] refined points whose coarse value was off by more
+ *   than eps — a run-time check of the bound on the ~2 % of the lattice nearest the surface; non-zero means: call arah_sdf_grid.
+ *   Values far from the level keep their fp16-pass accuracy (~1e-3).  Needs root_mode ARAH_ROOT_3XTF32. */
+int arah_sdf_grid_banded(ArahHandle* h, int32_t N, float level, float eps, float* sdf, int32_t* stats, void* stream);
 int arah_marching_cubes(const float* sdf, int32_t N, float level, float voxel_size, const float* origin3 /* host [3] */,
                         float* verts, int32_t max_verts, int32_t* faces, int32_t max_faces, int32_t* counts,
                         void* workspace /* device, 16-byte aligned */, size_t workspace_bytes, void* stream);

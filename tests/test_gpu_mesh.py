@@ -42,6 +42,48 @@ def test_sdf_grid_matches_oracle(root_mode, atol):
         assert (np.sign(g.cpu().numpy()) != np.sign(ref)).mean() < 2e-3
 
 
+@pytest.mark.parametrize('N,level', [(17, 0.0), (48, 0.0), (256, 0.0), (128, 0.03)])
+def test_banded_lattice_gives_the_full_lattice_mesh(N, level):
+    """arah_sdf_grid_banded: fp16 pass + split precision near the level.  Marching cubes must not be able to tell it from the
+    full split-precision lattice (bit-identical vertices and faces), the run-time bound check must stay silent, and the refined
+    points must carry exactly arah_sdf_grid's values."""
+    from arah_release_b200.renderer import BAND_EPS
+    fr, _, _ = load_golden('zju377_24x24_s0')
+    net, inputs = _net(fr, '3xtf32')
+    r = net._prepare(inputs)
+    full = r.sdf_grid(N)
+    vol, stats = r.sdf_grid_banded(N, level=level)
+    torch.cuda.synchronize()
+    n_ref, n_bad = (int(v) for v in stats.tolist())
+    diff = (vol - full).abs()
+    print(f'banded lattice N={N} level={level}: refined {n_ref} of {N ** 3} points ({n_ref / N ** 3:.2%}), '
+          f'max |fp16 pass - split precision| = {float(diff.max()):.2e} (eps {BAND_EPS})')
+    assert n_bad == 0
+    assert float(diff.max()) <= 0.5 * BAND_EPS                 # the assumed bound holds with a factor of two to spare
+    assert n_ref == int((diff == 0).sum()) or n_ref <= int((diff == 0).sum())     # refined points are bit-equal to arah_sdf_grid
+    near = (full - level).abs() <= 0.25 * BAND_EPS
+    assert bool((diff[near] == 0).all())                        # everything close to the level was refined
+    if N >= 128:
+        assert n_ref < 0.10 * N ** 3
+    v0, f0 = r.marching_cubes(full, level=level)
+    v1, f1 = r.marching_cubes(vol, level=level)
+    torch.cuda.synchronize()
+    assert torch.equal(f0, f1) and torch.equal(v0, v1)
+    v2, f2 = r.canonical_mesh(N, level=level)
+    assert torch.equal(f0, f2) and torch.equal(v0, v2) and r.last_band_stats[1] == 0
+
+
+def test_banded_lattice_bound_check_fires():
+    """With eps = 0 the coarse values are (almost) never within the bound: the run-time check must report it."""
+    fr, _, _ = load_golden('zju377_24x24_s0')
+    net, inputs = _net(fr, '3xtf32')
+    r = net._prepare(inputs)
+    vol, stats = r.sdf_grid_banded(48, eps=0.0)
+    torch.cuda.synchronize()
+    n_ref, n_bad = (int(v) for v in stats.tolist())
+    assert n_ref > 0 and n_bad > 0.5 * n_ref
+
+
 @pytest.mark.parametrize('N', [2, 3, 31, 64])
 def test_marching_cubes_bit_exact_vs_oracle(N):
     from oracle import oracle as orc
