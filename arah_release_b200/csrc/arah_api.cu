@@ -8,7 +8,6 @@
 #include "../../include/arah_b200.h"
 #include "arah_kernels.cuh"
 #include "arah_umma.cuh"
-#include "arah_shade_tc3.cuh"
 #include "arah_sdf3x.cuh"
 #include "arah_iso_init_tc.cuh"
 #include "arah_train_cuda.cuh"
@@ -298,26 +297,17 @@ struct ArahHandle {
     float* bone_T; float4* verts4; float* verts3; float* smpl_w;
     float* knn_sv; float* knn_cmin; float* knn_cmax; KnnIndex knn;
     // tensor-core shading: pre-swizzled chunk images (arah_umma.cuh)
-    float* tc_sdf_fwd[5]; float* tc_sdf_bwd[5]; float* tc_F; float* tc_G;
-    float* tc_col0; float* tc_col1; float* tc_col2; float* tc_col3b; float* tc_col3a; float* tc_col4;
-    ShadeTC tc;
+    float* tc_F; float* tc_G;  // FiLM factors 30 f, 30 (f b + phi) of the six SDF layers (k_pack_film)
     float* tc_skin_hid[3]; float* tc_skin_out;
     SkinTC sk;
     float* tc_sdf3x[5];
     SdfTC sd;
-    int trace_tc = 1;
-    int knn_seed = 2;          // k_knn_samples: 2 = ray-major seeded per-lane 1-NN, 1 = runs of 4 on-samples (round 1), 0 = unseeded
+    int knn_seed = 2;          // k_knn_samples: 2 = ray-major seeded per-lane 1-NN for full frames, runs of 4 for small batches; 3 = always ray-major; 1 = runs of 4 on-samples (round 1); 0 = unseeded
     int trace_knn = 0;         // k_trace_persist: 0 = octet-cooperative 1-NN (measured faster), 1 = seeded one-row-per-lane scan
-    int iso_init_tc = 1;       // k_iso_init_tc3: joint-search Jacobian initialisation on the tensor cores (forward mode, 4 rows per ray)
-    int corr_persist = 1;      // k_corr_persist: one persistent kernel with resident Broyden state (fp16 split precision) instead of 51 launches
     SkinF16Dev skin16{};
     int trace_persist = 1;     // k_trace_persist: sphere tracing as one persistent kernel (1-NN + SDF per step, resident rays)
-    int iso_persist = 1;       // k_iso_persist: joint search as one persistent kernel
     SdfF16Dev sdf16{};
-    int grid16 = 1;            // k_sdf_grid16: the canonical lattice on the fp16 split-precision engine
-    int shade16 = 1;           // k_shade16: gradient + colour pass with fp16 operands (kind::f16) instead of round 1's TF32 k_shade_tc3
     Shade16Dev shade16_img{};
-    int sdf_fwd16 = 1;         // k_sdf_fwd16: the SDF value compositing uses comes from a single-pass fp16 kernel over all converged samples
     bool shade_cull_ran = false;
     int shade_cull = 1;        // exact alpha cull before the gradient / colour pass (k_alpha_cull)
     // workspace
@@ -357,10 +347,7 @@ static int alloc_arena(ArahHandle* h) {
     reg(&h->skin_Wt[4], 128 * 32); reg(&h->skin_b[4], 32);
     reg(&h->col_Wt0, COL_IN_PAD * 256); reg(&h->col_Wt1, 256 * 256); reg(&h->col_Wt2, 256 * 128);
     reg(&h->col_Wt3a, COL_IN_PAD * 256); reg(&h->col_Wt3b, 128 * 256); reg(&h->col_Wt4, 256 * 256); reg(&h->col_W5, 3 * 256);
-    for (int l = 0; l < 5; ++l) { reg(&h->tc_sdf_fwd[l], 256 * 256); reg(&h->tc_sdf_bwd[l], 256 * 256); }
     reg(&h->tc_F, 6 * 256); reg(&h->tc_G, 6 * 256);
-    reg(&h->tc_col0, 10 * 256 * 32); reg(&h->tc_col1, 256 * 256); reg(&h->tc_col2, 8 * 128 * 32); reg(&h->tc_col3b, 4 * 256 * 32);
-    reg(&h->tc_col3a, 10 * 256 * 32); reg(&h->tc_col4, 256 * 256);
     for (int l = 0; l < 5; ++l) reg(&h->tc_sdf3x[l], 8 * 256 * 32 * 2);
     for (int l = 0; l < 3; ++l) reg(&h->tc_skin_hid[l], 4 * 128 * 32 * 2);
     reg(&h->tc_skin_out, 4 * 32 * 32 * 2);
@@ -436,7 +423,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     memset(&h->w, 0, sizeof(h->w));
     if (alloc_arena(h) != 0) return fail(ARAH_ENOMEM, "weight arena allocation failed");
     if (ensure_workspace(h, cfg->max_rays > 0 ? cfg->max_rays : 4096) != 0) return fail(ARAH_ENOMEM, "workspace allocation failed");
-    const size_t scr_fp32 = (size_t)7 * TM * SDF_H * 4, scr_tc = (size_t)TC_SCRATCH_FLOATS * 4;
+    const size_t scr_fp32 = (size_t)7 * TM * SDF_H * 4, scr_tc = shade16_scratch_bytes_per_cta();
     if (h->scratch.ensure((size_t)h->n_sms * (scr_fp32 > scr_tc ? scr_fp32 : scr_tc)) != 0) return fail(ARAH_ENOMEM, "scratch allocation failed");
     h->w.scratch = (float*)h->scratch.p;
     CU(cudaFuncSetAttribute(k_trace_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SDF)));
@@ -446,27 +433,16 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     CU(cudaFuncSetAttribute(k_corr_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SKIN)));
     CU(cudaFuncSetAttribute(k_eval_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(LDA_SKIN)));
     CU(cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_shade_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_shade_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_tc3_smem_bytes()));
     h->shade_cull = cfg->shade_cull == ARAH_CULL_OFF ? 0 : 1;
     if (const char* e = getenv("ARAH_SHADE_CULL")) h->shade_cull = atoi(e) != 0;
-    if (const char* e = getenv("ARAH_CORR_PERSIST")) h->corr_persist = atoi(e) != 0;
     if (const char* e = getenv("ARAH_TRACE_PERSIST")) h->trace_persist = atoi(e) != 0;
-    if (const char* e = getenv("ARAH_ISO_PERSIST")) h->iso_persist = atoi(e) != 0;
-    if (const char* e = getenv("ARAH_SDF_FWD16")) h->sdf_fwd16 = atoi(e) != 0;
-    if (const char* e = getenv("ARAH_GRID16")) h->grid16 = atoi(e) != 0;
-    if (const char* e = getenv("ARAH_SHADE16")) h->shade16 = atoi(e) != 0;
     CU(shade16_init());
     if (!root_trace_fits(cfg->n_verts)) h->trace_persist = 0;      // vertex index + weight ring must fit in 227 KB of shared memory
     CU(root_init());
     CU(cudaFuncSetAttribute(k_trace_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
-    CU(cudaFuncSetAttribute(k_iso_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
     CU(cudaFuncSetAttribute(k_iso_init_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
-    if (const char* e = getenv("ARAH_ISO_INIT_TC")) h->iso_init_tc = atoi(e) != 0;
     if (const char* e = getenv("ARAH_KNN_SEED")) h->knn_seed = atoi(e);
     if (const char* e = getenv("ARAH_TRACE_KNN")) h->trace_knn = atoi(e) != 0;
-    CU(cudaFuncSetAttribute(k_sdf_grid_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_tc3_smem_bytes()));
-    if (const char* e = getenv("ARAH_TRACE_TC")) h->trace_tc = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
@@ -550,30 +526,22 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     CU(cudaMemcpyAsync(h->col_b[2], f->col_b[2], 128 * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(h->col_b[4], f->col_b[4], 256 * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(h->col_b[5], f->col_b[5], 3 * 4, cudaMemcpyDeviceToDevice, st));
-    if (h->cfg.shade_mode == ARAH_SHADE_TF32) {
-        auto up = [&](const float* src, int ld, float* dst, int N, int K, int nchunks, int split, int lo, int hi, int transpose) {
-            k_pack_umma<<<cdiv((size_t)nchunks * N * 32, 256), 256, 0, st>>>(src, ld, dst, N, K, nchunks, split, lo, hi, transpose);
-            ++npack;
-        };
-        for (int l = 1; l < 6; ++l) {
-            up(f->sdf_W[l], 256, h->tc_sdf_fwd[l - 1], 256, 256, 8, 256, 0, 0, 0);
-            up(f->sdf_W[l], 256, h->tc_sdf_bwd[l - 1], 256, 256, 8, 256, 0, 0, 1);
-        }
+    const bool tc_shade = h->cfg.shade_mode == ARAH_SHADE_TF32, tc_root = h->cfg.root_mode == ARAH_ROOT_3XTF32;
+    if (tc_shade || tc_root) { long long n = 0; CU(root_pack_sdf_f16(f->sdf_W, h->sdf16, st, &n)); npack += n; }      // fp16 hi / lo images of the SDF
+    if (tc_shade) {
         for (int l = 0; l < 6; ++l) { k_pack_film<<<1, 256, 0, st>>>(f->sdf_b[l], f->sdf_freq + l * 256, f->sdf_phase + l * 256, h->tc_F + l * 256, h->tc_G + l * 256); ++npack; }
-        up(f->col_W[0], din, h->tc_col0, 256, COL_IN, 10, 256, 33, 0, 0);
-        up(f->col_W[1], 256, h->tc_col1, 256, 256, 8, 256, 0, 0, 0);
-        up(f->col_W[2], 256, h->tc_col2, 128, 256, 8, 256, 0, 0, 0);
-        up(f->col_W[3], din + 128, h->tc_col3b, 256, 128, 4, 128, din, 0, 0);
-        up(f->col_W[3], din + 128, h->tc_col3a, 256, COL_IN, 10, 256, 33, 0, 0);
-        up(f->col_W[4], 256, h->tc_col4, 256, 256, 8, 256, 0, 0, 0);
+        long long n = 0;
+        CU(shade16_pack(f->sdf_W, f->col_W, din, h->shade16_img, st, &n));
+        npack += n;
     }
-    if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
+    if (tc_root) {
+        // 3xTF32 images: k_iso_init_tc3 (both MLPs) and the k_trace_tc3 fallback
         for (int l = 1; l < 4; ++l) { k_pack_umma_x3<<<cdiv((size_t)4 * 128 * 32, 256), 256, 0, st>>>(f->skin_W[l], 128, h->tc_skin_hid[l - 1], 128, 128, 128, 4); ++npack; }
         k_pack_umma_x3<<<cdiv((size_t)4 * 32 * 32, 256), 256, 0, st>>>(f->skin_W[4], 128, h->tc_skin_out, 25, 32, 128, 4); ++npack;
         for (int l = 1; l < 6; ++l) { k_pack_umma_x3<<<cdiv((size_t)8 * 256 * 32, 256), 256, 0, st>>>(f->sdf_W[l], 256, h->tc_sdf3x[l - 1], 256, 256, 256, 8); ++npack; }
-        { long long n = 0; CU(root_pack_skin_f16(f->skin_W, h->skin16, st, &n)); npack += n; }
-        { long long n = 0; CU(root_pack_sdf_f16(f->sdf_W, h->sdf16, st, &n)); npack += n; }
-        if (h->cfg.shade_mode == ARAH_SHADE_TF32 && h->shade16) { long long n = 0; CU(shade16_pack(f->sdf_W, f->col_W, din, h->shade16_img, st, &n)); npack += n; }
+        long long n = 0;
+        CU(root_pack_skin_f16(f->skin_W, h->skin16, st, &n));
+        npack += n;
     }
     // pose buffers
     const cudaMemcpyKind kind = f->pose_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
@@ -604,13 +572,6 @@ extern "C" int arah_set_frame(ArahHandle* h, const ArahFrame* f, void* stream_) 
     fp.n_steps = h->cfg.n_steps; fp.near_samples = h->cfg.near_samples; fp.far_samples = h->cfg.far_samples;
     fp.cano_view_dirs = h->cfg.cano_view_dirs;
     fp.render_last_pt = h->cfg.render_last_pt ? 1 : 0;
-    ShadeTC& tc = h->tc;
-    tc.sdf_Wt0 = h->sdf_Wt[0]; tc.sdf_W0 = h->sdf_W[0]; tc.sdf_F = h->tc_F; tc.sdf_G = h->tc_G;
-    for (int l = 0; l < 5; ++l) { tc.sdf_fwd[l] = h->tc_sdf_fwd[l]; tc.sdf_bwd[l] = h->tc_sdf_bwd[l]; }
-    tc.sdf_w6 = h->sdf_w6; tc.sdf_b6 = b6;
-    tc.col0 = h->tc_col0; tc.col1 = h->tc_col1; tc.col2 = h->tc_col2; tc.col3b = h->tc_col3b; tc.col3a = h->tc_col3a; tc.col4 = h->tc_col4;
-    tc.col_W5 = h->col_W5;
-    for (int l = 0; l < 6; ++l) tc.col_b[l] = h->col_b[l];
     SdfTC& sd = h->sd;
     sd.Wt0 = h->sdf_Wt[0]; sd.freq = h->sdf_freq; sd.phase = h->sdf_phase; sd.w6 = h->sdf_w6; sd.b6 = b6;
     for (int l = 0; l < 6; ++l) sd.b[l] = h->sdf_b[l];
@@ -689,94 +650,75 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     if (prof) CU(cudaMemsetAsync(w.phase_clk, 0, 32 * 8, st)); else wk.phase_clk = nullptr;
     if (prof) CU(cudaEventRecord(h->ev[0], st));
     k_trace_begin<<<cdiv(P, 256), 256, 0, st>>>(w); L();
-    const unsigned g_ray_tiles = grid_min(cdiv(P, TM), (size_t)nsm);
     const unsigned g_knn_rays = grid_min(cdiv(P, 16), (size_t)nsm);        // >= one query per warp; idle blocks exit before staging
-    const bool tc_root = h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->trace_tc;
+    // root_mode 3xTF32: the persistent tensor-core kernels (fp16 split precision); fp32: one FFMA-tile launch per iteration
+    const bool tc_root = h->cfg.root_mode == ARAH_ROOT_3XTF32;
     SdfF16Host sh16;
-    sh16.Wt0 = h->sdf_Wt[0]; sh16.freq = h->sdf_freq; sh16.phase = h->sdf_phase; sh16.w6 = h->sdf_w6; sh16.b6 = h->sd.b6;
+    sh16.Wt0 = h->sdf_Wt[0]; sh16.freq = h->sdf_freq; sh16.phase = h->sdf_phase; sh16.w6 = h->sdf_w6; sh16.b6 = h->d_b6;
     for (int l = 0; l < 6; ++l) sh16.b[l] = h->sdf_b[l];
     if (tc_root && h->trace_persist) {
         long long n = 0;
         CU(root_trace_persist(fp, sh16, h->sdf16, h->knn, wk, nsm, st, &n));
         h->launches += n;
-    } else
-    for (int it = 0; it < TRACE_ITERS; ++it) {
-        k_knn_rays<<<g_knn_rays, 512, sm_knn, st>>>(fp, h->knn, w, it); L();
-        if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->trace_tc)
-            k_trace_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, wk, it);
-        else
-            k_trace_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it);
-        L();
+    } else {
+        // fp32 mode, or the vertex index does not fit next to the persistent kernel's weight ring (n_verts > ~7000; ARAH_TRACE_PERSIST=0
+        // forces this path in the tests): one 1-NN + one SDF launch per sphere-tracing step
+        for (int it = 0; it < TRACE_ITERS; ++it) {
+            k_knn_rays<<<g_knn_rays, 512, sm_knn, st>>>(fp, h->knn, w, it); L();
+            if (tc_root) k_trace_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, wk, it);
+            else k_trace_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it);
+            L();
+        }
     }
     if (prof) CU(cudaEventRecord(h->ev[1], st));
     k_iso_prepare<<<cdiv(P, 256), 256, 0, st>>>(w); L();
-    if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->trace_tc && h->iso_init_tc)
-        k_iso_init_tc3<<<grid_min(cdiv(P, ISO_TC_PTS), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, h->sk, w);
-    else
-        k_iso_init<<<grid_min(cdiv(P, TM / 4), (size_t)nsm), 256, sm_sdf, st>>>(fp, w);
-    L();
-    if (tc_root && h->iso_init_tc && h->iso_persist) {
+    if (tc_root) {
+        k_iso_init_tc3<<<grid_min(cdiv(P, ISO_TC_PTS), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, h->sk, w); L();
         long long n = 0;
         CU(root_iso_persist(fp, sh16, h->sdf16, h->skin_Wt[0], h->skin_b, h->skin16, wk, nsm, st, &n));
         h->launches += n;
-    } else
-    for (int it = 0; it < BROYDEN_ITERS; ++it) {
-        if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->trace_tc)
-            k_iso_tc3<<<grid_min(cdiv(P, UM), (size_t)nsm), TC3_THREADS, trace_tc3_smem_bytes(), st>>>(fp, h->sd, h->sk, w, it);
-        else
-            k_iso_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it);
-        L();
+    } else {
+        k_iso_init<<<grid_min(cdiv(P, TM / 4), (size_t)nsm), 256, sm_sdf, st>>>(fp, w); L();
+        for (int it = 0; it < BROYDEN_ITERS; ++it) { k_iso_iter<<<grid_min(cdiv(P, TM), (size_t)2 * nsm), 256, sm_sdf, st>>>(fp, w, it); L(); }
     }
     if (prof) CU(cudaEventRecord(h->ev[2], st));
     k_trace_finish<<<cdiv(P, 128), 128, 0, st>>>(fp, w); L();
     const unsigned g_knn_s = grid_min(cdiv(PS, 16), (size_t)nsm);
-    const bool persist = h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->corr_persist;
-    w.corr_seed = persist ? reinterpret_cast<CorrSeed*>(w.corr_state) : nullptr;
+    w.corr_seed = tc_root ? reinterpret_cast<CorrSeed*>(w.corr_state) : nullptr;
     wk.corr_seed = w.corr_seed;
     k_knn_samples<<<g_knn_s, 512, sm_knn, st>>>(fp, h->knn, w); L();
-    const unsigned g_smp_tiles = grid_min(cdiv(PS, TM), (size_t)2 * nsm);
-    if (persist) {
+    if (tc_root) {
         long long n = 0;
         CU(root_corr_persist(fp, h->skin_Wt[0], h->skin_b, h->skin16, wk, nsm, st, &n));
         h->launches += n;
     } else {
-        // per-iteration launches on fp32 FFMA tiles (root_mode fp32, or ARAH_CORR_PERSIST=0 for A/B runs)
+        const unsigned g_smp_tiles = grid_min(cdiv(PS, TM), (size_t)2 * nsm);
         for (int it = -1; it < BROYDEN_ITERS; ++it) { k_corr_step<<<g_smp_tiles, 256, sm_skin, st>>>(fp, w, it); L(); }
     }
     if (prof) CU(cudaEventRecord(h->ev[3], st));
     if (trace_only) { CU(cudaGetLastError()); return ARAH_OK; }
     if (h->cfg.shade_mode == ARAH_SHADE_TF32) {
-        {
-            const unsigned g = grid_min(cdiv(PS, UM), (size_t)nsm);
-            h->shade_cull_ran = h->shade_cull != 0;
-            const bool fwd16 = h->sdf_fwd16 && h->cfg.root_mode == ARAH_ROOT_3XTF32;     // (the fp16 images are packed with the root engine's)
-            wk.shade_keep_sdf = fwd16 ? 1 : 0;
-            // fp16 operands for the gradient + colour pass (the forward images are the root engine's, so root_mode must have packed them)
-            const bool use16 = h->shade16 && h->cfg.root_mode == ARAH_ROOT_3XTF32;
-            Shade16Host s16h{};
-            if (use16) {
-                s16h.sdf_Wt0 = h->sdf_Wt[0]; s16h.sdf_W0 = h->sdf_W[0]; s16h.sdf_F = h->tc_F; s16h.sdf_G = h->tc_G; s16h.sdf_scale = h->sdf16.scale;
-                s16h.sdf_fwd_hi = h->sdf16.hi; s16h.sdf_w6 = h->sdf_w6; s16h.sdf_b6 = h->d_b6; s16h.col_W5 = h->col_W5;
-                for (int l = 0; l < 6; ++l) s16h.col_b[l] = h->col_b[l];
-            }
-            if (fwd16) {
-                // the SDF value of every converged sample (what compositing turns into sigma) in one fp16 single-pass sweep; the
-                // full pass below then only supplies colours, with or without the cull: both settings composite identical inputs
-                long long n = 0;
-                CU(root_sdf_fwd16(fp, sh16, h->sdf16, wk, nsm, st, &n));
-                h->launches += n;
-            }
-            if (h->shade_cull) {
-                // exact alpha cull: SDF-only pass over all converged samples, alpha test, full shading of the survivors
-                if (!fwd16) { k_shade_tc3<true><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk); L(); }
-                k_alpha_cull<<<cdiv(P, COMP_WARPS), 32 * COMP_WARPS, 0, st>>>(fp, w, w.listA); L();
-                Work w2 = wk;
-                w2.shade_list = w.listA; w2.shade_ctr = C_SHADE2;
-                if (use16) { long long n = 0; CU(shade16_launch(fp, s16h, h->shade16_img, w2, g, st, &n)); h->launches += n; }
-                else { k_shade_tc3<false><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, w2); L(); }
-            } else if (use16) { long long n = 0; CU(shade16_launch(fp, s16h, h->shade16_img, wk, g, st, &n)); h->launches += n; }
-            else { k_shade_tc3<false><<<g, TC3_THREADS, shade_tc3_smem_bytes(), st>>>(fp, h->tc, wk); L(); }
+        // tensor-core shading (11-bit operands: fp16 images; round 1 used TF32, hence the mode's name)
+        const unsigned g = grid_min(cdiv(PS, UM), (size_t)nsm);
+        h->shade_cull_ran = h->shade_cull != 0;
+        wk.shade_keep_sdf = 1;
+        Shade16Host s16h{};
+        s16h.sdf_Wt0 = h->sdf_Wt[0]; s16h.sdf_W0 = h->sdf_W[0]; s16h.sdf_F = h->tc_F; s16h.sdf_G = h->tc_G; s16h.sdf_scale = h->sdf16.scale;
+        s16h.sdf_fwd_hi = h->sdf16.hi; s16h.sdf_w6 = h->sdf_w6; s16h.sdf_b6 = h->d_b6; s16h.col_W5 = h->col_W5;
+        for (int l = 0; l < 6; ++l) s16h.col_b[l] = h->col_b[l];
+        // 1. the SDF value of every converged sample (what compositing turns into sigma) in one fp16 single-pass sweep; the gradient +
+        //    colour pass below then only supplies colours, with or without the cull: both settings composite identical inputs
+        long long n = 0;
+        CU(root_sdf_fwd16(fp, sh16, h->sdf16, wk, nsm, st, &n));
+        Work w2 = wk;
+        if (h->shade_cull) {
+            // 2. exact alpha cull: samples whose alpha is exactly 0 cannot influence any output bit (arah_kernels.cuh)
+            k_alpha_cull<<<cdiv(P, COMP_WARPS), 32 * COMP_WARPS, 0, st>>>(fp, w, w.listA); L();
+            w2.shade_list = w.listA; w2.shade_ctr = C_SHADE2;
         }
+        // 3. SDF gradient + colour of the survivors
+        CU(shade16_launch(fp, s16h, h->shade16_img, w2, g, st, &n));
+        h->launches += n;
     }
     else { k_shade<<<grid_min(cdiv(PS, TM), (size_t)nsm), 256, shade_smem_bytes(), st>>>(fp, w); L(); }
     if (prof) CU(cudaEventRecord(h->ev[4], st));
@@ -922,14 +864,11 @@ extern "C" int arah_sdf_grid(ArahHandle* h, int32_t N, float* sdf, void* stream)
     CU(cudaSetDevice(h->cfg.device));
     const float voxel = (float)(2.0 / (double)(N - 1));
     const long long n = (long long)N * N * N;
-    if (h->cfg.root_mode == ARAH_ROOT_3XTF32 && h->grid16) {
+    if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
         SdfF16Host sh16;
-        sh16.Wt0 = h->sdf_Wt[0]; sh16.freq = h->sdf_freq; sh16.phase = h->sdf_phase; sh16.w6 = h->sdf_w6; sh16.b6 = h->sd.b6;
+        sh16.Wt0 = h->sdf_Wt[0]; sh16.freq = h->sdf_freq; sh16.phase = h->sdf_phase; sh16.w6 = h->sdf_w6; sh16.b6 = h->d_b6;
         for (int l = 0; l < 6; ++l) sh16.b[l] = h->sdf_b[l];
         CU(root_sdf_grid16(sh16, h->sdf16, N, voxel, n, sdf, h->n_sms, st));
-    } else if (h->cfg.root_mode == ARAH_ROOT_3XTF32) {
-        const unsigned g = grid_min(cdiv((size_t)n, UM), (size_t)h->n_sms);
-        k_sdf_grid_tc3<<<g, TC3_THREADS, trace_tc3_smem_bytes(), st>>>(h->sd, N, voxel, n, sdf);
     } else {
         // fp32 FFMA tiles: lattice points are staged in chunks of 64^3 (the reference's own max_batch, sdf_meshing.py:14)
         const int chunk = 64 * 64 * 64;
@@ -959,7 +898,7 @@ extern "C" int arah_sdf_grid_banded(ArahHandle* h, int32_t N, float level, float
     uint8_t* flag = (uint8_t*)h->io_in.p;
     int* list = (int*)(flag + align_up(n, 256));
     SdfF16Host sh16;
-    sh16.Wt0 = h->sdf_Wt[0]; sh16.freq = h->sdf_freq; sh16.phase = h->sdf_phase; sh16.w6 = h->sdf_w6; sh16.b6 = h->sd.b6;
+    sh16.Wt0 = h->sdf_Wt[0]; sh16.freq = h->sdf_freq; sh16.phase = h->sdf_phase; sh16.w6 = h->sdf_w6; sh16.b6 = h->d_b6;
     for (int l = 0; l < 6; ++l) sh16.b[l] = h->sdf_b[l];
     CU(root_sdf_grid_banded(sh16, h->sdf16, N, (float)(2.0 / (double)(N - 1)), level, eps, sdf, flag, list, stats, h->n_sms, st, nullptr));
     return ARAH_OK;

@@ -455,7 +455,9 @@ __global__ void __launch_bounds__(512, 1) k_knn_samples(FrameParams fp, KnnIndex
         st.best_n = 0.f; st.owner = w.on_list[i]; st.g_evals = 0;
         state_store(&w.corr_state[i], st);
     };
-    if (B == 32 && w.knn_seed == 2) {
+    // (2 = default: ray-major only when the rays fill at least half of the grid's lanes — a 2048-ray training batch would leave
+    // 97 % of them idle and walk 64 samples serially per lane; 3 = always, for the tests)
+    if (B == 32 && (w.knn_seed == 3 || (w.knn_seed == 2 && 2 * w.P >= (int)(gridDim.x * blockDim.x)))) {
         // throughput regime, ray-major: a lane walks ALL on-samples of one ray front to back, each query seeded with the previous
         // winner; the lanes of a warp hold adjacent rays (adjacent pixels), so at every step their queries lie within centimetres
         // of each other and scan the same clusters: the per-lane search stays converged (round 1's run-of-4 mapping put two whole
@@ -751,7 +753,7 @@ __device__ __forceinline__ float sample_alpha(const float* cz, const float* cd, 
 
 // Exact alpha cull.  A converged sample whose alpha is EXACTLY 0.0f has compositing weight alpha * T == 0, so its colour (and
 // the SDF gradient that only feeds the colour network) cannot influence any output bit: rgb += 0 * c.  Given smp_sdf of every
-// converged sample (k_shade_tc3<true>), this kernel recomputes alpha with k_composite's own expression and builds the list of
+// converged sample (k_sdf_fwd16), this kernel recomputes alpha with k_composite's own expression and builds the list of
 // samples that still need the full shading pass; culled samples get rgb = 0 (k_composite multiplies it by 0).  Far from the
 // surface sigma = exp(-sdf/beta)/(2 beta) underflows quickly: ~80 % of the samples of a bounding-box frame are culled.
 __global__ void __launch_bounds__(32 * COMP_WARPS) k_alpha_cull(FrameParams fp, Work w, int* __restrict__ out_list) {

@@ -1,9 +1,10 @@
 // arah_sdf3x.cuh — the 256-wide FiLM-SIREN SDF on tcgen05 in split precision (3xTF32 ~ fp32) for the ROOT-FINDING
-// kernels (sphere tracing k_trace_tc3, joint search k_iso_tc3), engine v3 roles (8 epilogue warps, TMA producer warp,
+// kernels of round 1 that are still in use (k_trace_tc3: sphere tracing when the vertex index does not fit next to the persistent
+// kernel's weight ring; k_iso_init_tc3: Jacobian initialisation of the joint search), engine v3 roles (8 epilogue warps, TMA producer warp,
 // MMA-issuer warp, per-chunk ready barriers).
 //
 // A 256-wide layer needs A_hi (256 cols) + A_lo (256 cols) + D (256 cols) = 768 TMEM columns, TMEM has 512.  So:
-//   A_hi : TMEM, ping-pongs with D between the two 256-column regions (in-place D -> A_hi, as in k_shade_tc3),
+//   A_hi : TMEM, ping-pongs with D between the two 256-column regions (in-place D -> A_hi),
 //   A_lo : shared memory, 8 K-chunks x 16 KB, SWIZZLE_128B K-major (the SS form of tcgen05.mma reads it),
 //   B    : per K-chunk two 32 KB images [B_hi], [B_lo] through a 3-slot ring,
 //   D   += A_lo(smem).B_hi + A_hi(tmem).B_hi        (when B_hi(c) has landed)
@@ -12,9 +13,18 @@
 // The activation math is the fp32 FFMA kernels' own formula sin(30 (f (acc + b) + phi)) with a 1-2 ulp Cody-Waite sine
 // (sin_cw): root finding keeps resolving 1e-5 m.
 #pragma once
-#include "arah_shade_tc3.cuh"
+#include "arah_tc2.cuh"
+#include "arah_work.cuh"
 
 namespace arah {
+
+constexpr int TC3_THREADS = 320;      // 8 epilogue warps + TMA producer warp + MMA-issuer warp
+// order in which the K-chunks of a 256- (order 0) / 128-wide (order 1) operand become ready: the two column halves finish alternately
+__device__ __forceinline__ int seg_chunk(int order, int i) {
+    if (order == 0) return (i >> 1) + ((i & 1) << 2);
+    if (order == 1) return (i >> 1) + ((i & 1) << 1);
+    return i;
+}
 
 struct SkinTC {
     const float* Wt0;      // [3][128]
@@ -237,73 +247,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_trace_tc3(FrameParams fp, Sd
     if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
-// =====================================================================================================================
-// k_sdf_grid_tc3: the canonical SDF sampled on the N^3 lattice over [-1,1]^3 (utils/sdf_meshing.py:13-58).
-// The lattice coordinates are generated in the kernel with the reference's own arithmetic (index * voxel_size + origin, one
-// fp32 rounding per operation, sdf_meshing.py:25-38); out[(ix*N + iy)*N + iz] = raw network output (what `decoder(model_input)`
-// returns, :49-54).  n0/n1 bound the linear index range of this launch (chunked by the caller only for the fp32 fallback).
-__global__ void __launch_bounds__(TC3_THREADS, 1) k_sdf_grid_tc3(SdfTC sd, int N, float voxel, long long n_total, float* __restrict__ out) {
-    extern __shared__ __align__(1024) uint8_t raw_smem[];
-    const long long ntiles = (n_total + UM - 1) / UM;
-    if ((long long)blockIdx.x >= ntiles) return;
-    if (smem_u32(raw_smem) & 1023u) __trap();
-    float* A_lo = reinterpret_cast<float*>(raw_smem);
-    float* ring = A_lo + S3_ALO_FLOATS;
-    float* xs3 = ring + S3_RING_FLOATS;
-    float (*part)[UM] = reinterpret_cast<float (*)[UM]>(xs3 + UM * 3);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs3 + UM * 3 + 2 * UM);
-    S3Bars bar; bar.full = bars; bar.empty = bars + S3_NSLOTS; bar.ready = bars + 2 * S3_NSLOTS; bar.done = bar.ready + 8;
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar.done + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int i = 0; i < S3_NSLOTS; ++i) { mbar_init(&bar.full[i], 1); mbar_init(&bar.empty[i], 1); }
-        for (int i = 0; i < 8; ++i) mbar_init(&bar.ready[i], 4);
-        mbar_init(bar.done, 1);
-        mbar_fence_init();
-    }
-    if (warp == 0) tmem_alloc(tslot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tbase = *tslot;
-    if (warp == 8) {
-        if (lane == 0) { uint32_t slot = 0, use = 0; for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) s3_produce_sdf(ring, bar, slot, use, sd); }
-        return;
-    }
-    if (warp == 9) {
-        if (lane == 0) { uint32_t slot = 0, use = 0, rpar = 0; for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) s3_mma_sdf(ring, A_lo, bar, slot, use, rpar, tbase); }
-        return;
-    }
-    const int half = warp >> 2, r = 32 * (warp & 3) + lane;
-    uint32_t done_par = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long i = tile * UM + tid;
-        if (tid < UM) {
-            float x = 0.f, y = 0.f, z = 0.f;
-            if (i < n_total) {
-                const int iz = (int)(i % N), iy = (int)((i / N) % N), ix = (int)(i / ((long long)N * N));
-                x = __fadd_rn(__fmul_rn((float)ix, voxel), -1.0f);
-                y = __fadd_rn(__fmul_rn((float)iy, voxel), -1.0f);
-                z = __fadd_rn(__fmul_rn((float)iz, voxel), -1.0f);
-            }
-            xs3[3 * tid] = x; xs3[3 * tid + 1] = y; xs3[3 * tid + 2] = z;
-        }
-        cta_sync_compute();
-        const float dot = s3_compute_sdf(sd, xs3, A_lo, bar, done_par, tbase);
-        part[half][r] = dot;
-        cta_sync_compute();
-        if (tid < UM && i < n_total) out[i] = part[0][tid] + part[1][tid] + __ldg(sd.b6);
-        cta_sync_compute();
-    }
-    tc_fence_before();
-    cta_sync_compute();
-    if (warp == 0) tmem_dealloc(tbase, 512);
-}
-
-}  // namespace arah
-
-namespace arah {
-
 // ---- skinning MLP (3xTF32) on the same 3-slot ring / barrier set, for the joint-search kernel -----------------------------
 // TMEM: X hi [0,128) | lo [128,256), accumulators ping-pong Da = [256,384) / Db = [384,512) (as k_corr_tc3).
 __device__ __forceinline__ void s3_produce_skin(float* ring, const S3Bars& bar, uint32_t& slot, uint32_t& use, const SkinTC& sk) {
@@ -337,151 +280,6 @@ __device__ __forceinline__ void s3_mma_skin(float* ring, const S3Bars& bar, uint
         }
         umma_commit(bar.done);
     }
-}
-// compute warps: logits[r][0..31] for the 128 rows in xs3
-__device__ __forceinline__ void s3_compute_skin(const SkinTC& sk, const float* xs3, const S3Bars& bar, uint32_t& done_par, uint32_t tbase, float (*logits)[LGS]) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, half = warp >> 2, r = 32 * q + lane;
-    const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
-    auto put = [&](int chunk, const float (&v)[32]) {
-        a_tmem_store_split(trow + 32u * chunk, trow + 128u + 32u * chunk, v);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar.ready[chunk]);
-    };
-    auto wait_done = [&]() { mbar_wait(bar.done, done_par); done_par ^= 1u; __syncwarp(); tc_fence_after(); };
-    {
-        const float x = xs3[3 * r], y = xs3[3 * r + 1], z = xs3[3 * r + 2];
-#pragma unroll 1
-        for (int b = 0; b < 2; ++b) {
-            const int col0 = 64 * half + 32 * b;
-            float h[32], w0[32], w1[32], w2[32], pb[32];
-            ldg32(sk.Wt0 + col0, w0); ldg32(sk.Wt0 + 128 + col0, w1); ldg32(sk.Wt0 + 256 + col0, w2); ldg32(sk.b[0] + col0, pb);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) h[i] = softplus100_fast(fmaf(w2[i], z, fmaf(w1[i], y, w0[i] * x)) + pb[i]);
-            put(col0 / 32, h);
-        }
-    }
-    for (int l = 1; l < 4; ++l) {
-        wait_done();
-        const uint32_t tD = trow + ((l & 1) ? 256u : 384u);
-#pragma unroll 1
-        for (int b = 0; b < 2; ++b) {
-            const int col0 = 64 * half + 32 * b;
-            float v[32], pb[32];
-            ldg32(sk.b[l] + col0, pb);
-            tmem_ld32(tD + (uint32_t)col0, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = softplus100_fast(v[i] + pb[i]);
-            put(col0 / 32, v);
-        }
-    }
-    wait_done();
-    if (half == 0) {
-        float v[32], pb[32];
-        ldg32(sk.b[4], pb);
-        tmem_ld32(trow + 384u, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) logits[r][i] = v[i] + pb[i];
-    }
-    tc_fence_before();
-}
-
-// =====================================================================================================================
-// k_iso_tc3: one joint-search Broyden step (root_finding_utils.py:426-461 + broyden.py:47-76), 128 rays per tile:
-// skinning MLP then SDF, both 3xTF32; residual, Jacobian update and bookkeeping fp32 as in k_iso_iter.
-__global__ void __launch_bounds__(TC3_THREADS, 1) k_iso_tc3(FrameParams fp, SdfTC sd, SkinTC sk, Work w, int iter) {
-    extern __shared__ __align__(1024) uint8_t raw_smem[];
-    const int n = w.counters[C_ISO + iter];
-    if ((int)blockIdx.x * UM >= n) return;
-    if (smem_u32(raw_smem) & 1023u) __trap();
-    float* A_lo = reinterpret_cast<float*>(raw_smem);
-    float (*logits)[LGS] = reinterpret_cast<float (*)[LGS]>(A_lo);        // aliases A_lo: only alive between the two MLPs
-    float* ring = A_lo + S3_ALO_FLOATS;
-    float* xs3 = ring + S3_RING_FLOATS;
-    float (*part)[UM] = reinterpret_cast<float (*)[UM]>(xs3 + UM * 3);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs3 + UM * 3 + 2 * UM);
-    S3Bars bar; bar.full = bars; bar.empty = bars + S3_NSLOTS; bar.ready = bars + 2 * S3_NSLOTS; bar.done = bar.ready + 8;
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar.done + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int i = 0; i < S3_NSLOTS; ++i) { mbar_init(&bar.full[i], 1); mbar_init(&bar.empty[i], 1); }
-        for (int i = 0; i < 8; ++i) mbar_init(&bar.ready[i], 4);
-        mbar_init(bar.done, 1);
-        mbar_fence_init();
-    }
-    if (warp == 0) tmem_alloc(tslot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tbase = *tslot;
-    const int ntiles = (n + UM - 1) / UM;
-    if (warp == 8) {
-        if (lane == 0) {
-            uint32_t slot = 0, use = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) { s3_produce_skin(ring, bar, slot, use, sk); s3_produce_sdf(ring, bar, slot, use, sd); }
-        }
-        return;
-    }
-    if (warp == 9) {
-        if (lane == 0) {
-            uint32_t slot = 0, use = 0, rpar = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) { s3_mma_skin(ring, bar, slot, use, rpar, tbase); s3_mma_sdf(ring, A_lo, bar, slot, use, rpar, tbase); }
-        }
-        return;
-    }
-    const int half = warp >> 2, r = 32 * (warp & 3) + lane;
-    uint32_t done_par = 0;
-    const int* list = (iter & 1) ? w.listB : w.listA;
-    int* next = (iter & 1) ? w.listA : w.listB;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int ray = -1;
-        BroydenState<4> st;
-        float dx[4];
-        if (tid < UM) {
-            const int i = tile * UM + tid;
-            float xn[3] = {0.f, 0.f, 0.f};
-            if (i < n) {
-                ray = list[i];
-                state_load(st, &w.iso_state[ray]);
-                broyden_advance<4>(st, dx);
-                normalize3(fp, st.x, xn);
-            }
-            xs3[3 * tid] = xn[0]; xs3[3 * tid + 1] = xn[1]; xs3[3 * tid + 2] = xn[2];
-        }
-        cta_sync_compute();
-        s3_compute_skin(sk, xs3, bar, done_par, tbase, logits);
-        cta_sync_compute();
-        tc_fence_after();
-        float lg[25];
-        if (tid < UM) {
-#pragma unroll
-            for (int k = 0; k < 25; ++k) lg[k] = logits[tid][k];
-        }
-        cta_sync_compute();                                            // logits consumed: A_lo may be overwritten
-        const float dot = s3_compute_sdf(sd, xs3, A_lo, bar, done_par, tbase);
-        part[half][r] = dot;
-        cta_sync_compute();
-        if (tid < UM) {
-            bool active = false;
-            if (ray >= 0) {
-                float g[4], T12[12], lg32[32];
-#pragma unroll
-                for (int k = 0; k < 25; ++k) lg32[k] = lg[k];
-                iso_residual(fp, w, ray, st.x, lg32, part[0][tid] + part[1][tid] + __ldg(sd.b6), g, T12);
-                active = broyden_update<4>(st, dx, g, T12);
-                if (iter + 1 >= BROYDEN_ITERS) active = false;
-                state_store(&w.iso_state[ray], st);
-            }
-            if (iter + 1 < BROYDEN_ITERS) warp_append(active, ray, next, &w.counters[C_ISO + iter + 1]);
-            warp_stat_add(ray >= 0 ? 1 : 0, &w.counters[C_STAT_ISO_EVALS]);
-        }
-        cta_sync_compute();
-    }
-    tc_fence_before();
-    cta_sync_compute();
-    if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
 }  // namespace arah

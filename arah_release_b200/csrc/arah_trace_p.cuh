@@ -148,16 +148,21 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_trace_persist(FrameParams fp
 #pragma unroll
                 for (int k = 0; k < 3; ++k) x[k] = st[(TR_D + k) * UM + row] * t + fp.cam_loc[k];
             }
-            int mine = 0;
+            // TR_SLOT holds the cluster of the row's previous nearest vertex (-1 on the first step): the seed of this step's scan
+            const int seed = (ray >= 0) ? __float_as_int(st[TR_SLOT * UM + row]) : -1;
+            int mine = 0, mine_c = -1;
 #pragma unroll 1
             for (int r4 = 0; r4 < 8; r4 += 4) {                          // four queries at a time, one per octet (knn_warp_batches)
                 const int qi = r4 + (lane >> 3);
                 const float qx = __shfl_sync(0xffffffffu, x[0], qi), qy = __shfl_sync(0xffffffffu, x[1], qi), qz = __shfl_sync(0xffffffffu, x[2], qi);
                 const bool qv = __shfl_sync(0xffffffffu, (int)(ray >= 0), qi) != 0;
-                const int idx = knn_scan_octet(kk, qx, qy, qz, qv);
-                const int got = __shfl_sync(0xffffffffu, idx, (lane & 3) * 8);
-                if ((lane >> 2) == (r4 >> 2)) mine = got;
+                const int qs = __shfl_sync(0xffffffffu, seed, qi);
+                int wc = -1;
+                const int idx = knn_scan_octet(kk, qx, qy, qz, qv, qv ? qs : 0, &wc);
+                const int got = __shfl_sync(0xffffffffu, idx, (lane & 3) * 8), got_c = __shfl_sync(0xffffffffu, wc, (lane & 3) * 8);
+                if ((lane >> 2) == (r4 >> 2)) { mine = got; mine_c = got_c; }
             }
+            if (mine_row && ray >= 0) st[TR_SLOT * UM + row] = __int_as_float(mine_c);
             float xn[3] = {0.f, 0.f, 0.f};
             if (mine_row && ray >= 0) {
                 float T12[12], s_, xh[3];

@@ -311,10 +311,13 @@ __device__ __forceinline__ void knn_octet_argmin(float& d, int& id) {
         if (d2 < d || (d2 == d && i2 < id)) { d = d2; id = i2; }
     }
 }
-__device__ __forceinline__ int knn_scan_octet(const KnnSmem& k, float x, float y, float z, bool valid) {
+// seed_c (octet-uniform): cluster of the query's previous winner, or < 0 — a marching ray moves little between steps, so scanning
+// that cluster first gives a tight bound and the search for the best box is skipped (still exact: every cluster whose box is
+// within the bound is scanned below).  *win_c receives the winner's cluster.
+__device__ __forceinline__ int knn_scan_octet(const KnnSmem& k, float x, float y, float z, bool valid, int seed_c = -1, int* win_c = nullptr) {
     const int lane = threadIdx.x & 31, sub = lane & 7, oct = lane >> 3;
     float bd = INFINITY;
-    int bi = 0x7fffffff;
+    int bi = 0x7fffffff, bc = 0;
     // executed by ALL 32 lanes (the butterfly uses full-mask shuffles); `on` is octet-uniform: does this octet scan cluster c
     auto scan = [&](int c, bool on) {
         float d = INFINITY;
@@ -330,21 +333,25 @@ __device__ __forceinline__ int knn_scan_octet(const KnnSmem& k, float x, float y
             }
         }
         knn_octet_argmin(d, id);
-        if (on && (d < bd || (d == bd && id < bi))) { bd = d; bi = id; }
+        if (on && (d < bd || (d == bd && id < bi))) { bd = d; bi = id; bc = c; }
     };
-    // ---- best super box, best cluster in it
-    float lb0 = INFINITY;
-    int s0 = 0x7fffffff;
-    for (int g = sub; g < k.ns; g += 8) {
-        const float lb = box_dist2(k.smin[g], k.smax[g], x, y, z);
-        if (lb < lb0) { lb0 = lb; s0 = g; }
+    int c0 = seed_c;
+    if (__any_sync(0xffffffffu, seed_c < 0)) {
+        // ---- best super box, best cluster in it (for the octets without a seed)
+        float lb0 = INFINITY;
+        int s0 = 0x7fffffff;
+        for (int g = sub; g < k.ns; g += 8) {
+            const float lb = box_dist2(k.smin[g], k.smax[g], x, y, z);
+            if (lb < lb0) { lb0 = lb; s0 = g; }
+        }
+        knn_octet_argmin(lb0, s0);
+        if (s0 >= k.ns) s0 = 0;
+        int cb = s0 * KNN_SUPER + sub;
+        float lc = (cb < k.nc) ? box_dist2(k.cmin[cb], k.cmax[cb], x, y, z) : INFINITY;
+        knn_octet_argmin(lc, cb);
+        if (cb >= k.nc) cb = s0 * KNN_SUPER;
+        if (seed_c < 0) c0 = cb;
     }
-    knn_octet_argmin(lb0, s0);
-    if (s0 >= k.ns) s0 = 0;
-    int c0 = s0 * KNN_SUPER + sub;
-    float lc = (c0 < k.nc) ? box_dist2(k.cmin[c0], k.cmax[c0], x, y, z) : INFINITY;
-    knn_octet_argmin(lc, c0);
-    if (c0 >= k.nc) c0 = s0 * KNN_SUPER;
     scan(c0, valid);
     // ---- every other cluster that can still hold a closer vertex, super box by super box
     const int ns8 = (k.ns + 7) & ~7;
@@ -376,6 +383,7 @@ __device__ __forceinline__ int knn_scan_octet(const KnnSmem& k, float x, float y
             }
         }
     }
+    if (win_c) *win_c = bc;
     return bi;
 }
 

@@ -515,11 +515,11 @@ def stage_table(stats, t_dev, pk, r):
         # the reference evaluates g twice at the start of every search (J init + g(x0)); the kernel evaluates it once
         'sample_corr': ('k_knn_samples + k_corr_persist (per-sample correspondence search, skinning MLP in 3xfp16 split precision)', 'ms_sample_corr',
                         2.0 * S('corr_skin_evals') * MAC_SKIN, 2.0 * (S('corr_skin_evals') - S('on_samples')) * MAC_SKIN),
-        'shade': ('k_sdf_fwd16 + k_alpha_cull + k_shade_tc3 (SDF value of all samples in fp16; gradient + colour MLP of the alpha != 0 samples in tf32)',
+        'shade': ('k_sdf_fwd16 + k_alpha_cull + k_shade16 (SDF value of all samples; gradient + colour MLP of the alpha != 0 samples; fp16 operands)',
                   'ms_shade', 2.0 * shaded * (2 * MAC_SDF + MAC_COL),
                   2.0 * ((shaded * MAC_SDF if cull_ran else 0.0) + (shaded - culled) * (2 * MAC_SDF + MAC_COL))),
     }
-    main = {'trace': 'k_trace_persist', 'iso': 'k_iso_persist', 'sample_corr': 'k_corr_persist', 'shade': 'k_shade_tc3'}
+    main = {'trace': 'k_trace_persist', 'iso': 'k_iso_persist', 'sample_corr': 'k_corr_persist', 'shade': 'k_shade16'}
     out = {}
     for k, (name, msk, alg, ex) in rows.items():
         ms = S(msk)
@@ -806,7 +806,7 @@ def run_ours(args):
         'metric': 'rays/sec at 512x512 ZJU-377 render', 'value': rays_all / t_dev, 'unit': 'rays/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'fp32 storage/accumulate; tensor-core operands: tf32 (colour + gradient), fp16 (SDF value), 3xfp16 split ~ fp32 (all root finding)'
+        'dtype': 'fp32 storage/accumulate; tensor-core operands: fp16 (SDF value, gradient, colour), 3xfp16 split ~ fp32 (all root finding)'
                  if r.shade_mode == 'tf32' else 'f32', 'data': 'synthetic',
         'config': workload_config(args.size, f0, args.gpus),
         'e2e': {'value': rays_all / t_e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),

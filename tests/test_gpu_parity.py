@@ -63,15 +63,38 @@ def test_render_matches_reference_golden(name, mode):
     fr, ref, meta = load_golden(name)
     net, inputs = _build(fr, mode)
     out = _render_dict(net, inputs)
-    # 'fp32' = every MLP on fp32 FFMA tiles (the oracle's arithmetic); 'tf32' = tensor cores: shading in TF32, all root
-    # finding (sphere tracing, joint search, correspondences) in 3xTF32 split precision -> same masks/depths, colours
-    # within TF32 operand rounding
+    # 'fp32' = every MLP on fp32 FFMA tiles (the oracle's arithmetic); 'tf32' = tensor cores: shading with 11-bit operands (fp16
+    # images; TF32 in round 1, hence the name), all root finding (sphere tracing, joint search, correspondences) in split
+    # precision -> same masks/depths, colours within the operand rounding
     tol = dict(TOL, rgb_psnr_min=55.0) if mode == 'tf32' else TOL
     st = check_render(out, ref, label=name + ':' + mode, tol=tol)
     stats = net.stats()
     assert stats['rays'] == fr.P and stats['kernel_launches'] > 0
     assert stats['vol_rays'] == int(out['network_body_mask'].sum())
     print(name, mode, st, stats)
+
+
+@pytest.mark.parametrize('shade_mode,root_mode', [('tf32', 'fp32'), ('fp32', '3xtf32')])
+def test_mixed_precision_modes_match_reference(shade_mode, root_mode):
+    """The two mode switches are independent: tensor-core shading over fp32 root finding (the fp16 images are packed for the
+    shading kernels alone) and fp32 shading over tensor-core root finding."""
+    fr, ref, _ = load_golden('zju377_24x24_s0')
+    net, inputs = _build(fr, shade_mode, root_mode)
+    out = _render_dict(net, inputs)
+    tol = dict(TOL, rgb_psnr_min=55.0) if shade_mode == 'tf32' else TOL
+    print(shade_mode, root_mode, check_render(out, ref, label=f'{shade_mode}/{root_mode}', tol=tol))
+
+
+def test_per_step_sphere_tracing_path_matches_reference(monkeypatch):
+    """ARAH_TRACE_PERSIST=0 forces the path taken when the vertex index does not fit next to the persistent kernel's weight ring
+    (n_verts > ~7000): one k_knn_rays + k_trace_tc3 launch per sphere-tracing step."""
+    monkeypatch.setenv('ARAH_TRACE_PERSIST', '0')
+    fr, ref, _ = load_golden('zju377_24x24_s0')
+    net, inputs = _build(fr, 'tf32')
+    out = _render_dict(net, inputs)
+    st = check_render(out, ref, label='per-step tracing', tol=dict(TOL, rgb_psnr_min=55.0))
+    assert net.stats()['kernel_launches'] > 100            # 2 x 50 launches instead of one
+    print('per-step tracing', st)
 
 
 @pytest.mark.parametrize('name', GOLDEN_CASES[:1])
@@ -296,15 +319,15 @@ def test_knn_seed_is_exact(monkeypatch):
     from arah_release_b200 import synthetic as syn
     fr = syn.make_frame(96, 96, seed=5)
     res = []
-    for seed_on in ('1', '0'):
+    for seed_on in ('3', '2', '1', '0'):          # ray-major (forced), default (runs of 4 at this size), runs of 4, unseeded
         monkeypatch.setenv('ARAH_KNN_SEED', seed_on)
         net, inputs = _build(fr, 'tf32')
         out = net(inputs)
         tr = net.tracer_outputs()
         torch.cuda.synchronize()
         res.append((out['rgb_values'].clone(), tr[3].clone(), tr[5].clone(), tr[6].clone(), net.stats()['corr_skin_evals']))
-    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
-    assert torch.equal(res[0][3], res[1][3]) and res[0][4] == res[1][4]
+    for other in res[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(res[0][:4], other[:4])) and res[0][4] == other[4]
 
 
 @pytest.mark.parametrize('mode', ['fp32', 'tf32'])

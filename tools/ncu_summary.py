@@ -72,7 +72,9 @@ def csvpage(src, dst, traffic_json=None):
                 wb = float(d['dram__bytes_write.sum'].replace(',', '')) * scale.get(u['dram__bytes_write.sum'], 1)
                 key = name.replace('void ', '').replace('arah::', '').split('<')[0]
                 if key not in traffic:
-                    traffic[key] = {'dram_bytes_per_launch': rb + wb, 'dram_read': rb, 'dram_write': wb, 'ms': d.get('gpu__time_duration.sum'),
+                    tscale = {'ns': 1e-6, 'nsecond': 1e-6, 'us': 1e-3, 'usecond': 1e-3, 'ms': 1.0, 'msecond': 1.0, 's': 1e3, 'second': 1e3}
+                    ms = float(d['gpu__time_duration.sum'].replace(',', '')) * tscale.get(u['gpu__time_duration.sum'], 1.0)
+                    traffic[key] = {'dram_bytes_per_launch': rb + wb, 'dram_read': rb, 'dram_write': wb, 'ms': ms,
                                     'tensor_pipe_pct': d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')}
             except Exception:
                 pass
@@ -83,6 +85,45 @@ def csvpage(src, dst, traffic_json=None):
         old.update(traffic)
         json.dump(old, open(traffic_json, 'w'), indent=1)
     print(open(dst).read()[:2500])
+
+
+def table(srcs, dst):
+    """Several raw-page CSVs -> one compact markdown table, one row per distinct kernel (its first captured launch)."""
+    cols = [('ms', 'gpu__time_duration.sum'), ('grid', 'launch__grid_size'), ('block', 'launch__block_size'), ('regs', 'launch__registers_per_thread'),
+            ('smem KB', 'launch__shared_mem_per_block_dynamic'), ('tensor %', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'),
+            ('XU %', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'), ('FMA %', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active'),
+            ('issue %', 'smsp__issue_active.avg.pct_of_peak_sustained_active'), ('DRAM %', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'),
+            ('DRAM rd', 'dram__bytes_read.sum'), ('DRAM wr', 'dram__bytes_write.sum'), ('L2->SM', 'l1tex__m_xbar2l1tex_read_bytes.sum.per_second')]
+    seen = set()
+    with open(dst, 'w') as f:
+        f.write('# ncu --set full --clock-control none: one launch per kernel (' + ', '.join(srcs) + ')\n\n'
+                'Numbers under ncu are never bench values; times are cold-cache and serialised.  Units as ncu prints them.\n\n')
+        f.write('| kernel | ' + ' | '.join(c for c, _ in cols) + ' |\n|---|' + '---:|' * len(cols) + '\n')
+        for src in srcs:
+            rd = list(csv.reader(open(src)))
+            hdr, units, data = rd[0], rd[1], rd[2:]
+            u = dict(zip(hdr, units))
+            for row in data:
+                d = dict(zip(hdr, row))
+                name = re.sub(r'\(.*', '', d.get('Kernel Name', '?')).strip().replace('void ', '')
+                name = re.sub(r'^(arah\w*::)+', '', name)
+                if name in seen:
+                    continue
+                seen.add(name)
+                cells = []
+                for c, k in cols:
+                    v = d.get(k, '')
+                    try:
+                        x = float(v.replace(',', ''))
+                        v = f'{x:.3g}' if abs(x) < 1000 else f'{x:.0f}'
+                    except Exception:
+                        pass
+                    unit = u.get(k, '')
+                    if c in ('ms', 'DRAM rd', 'DRAM wr', 'L2->SM') and unit not in ('', '%'):
+                        v += ' ' + unit.replace('second', 's').replace('byte', 'B')
+                    cells.append(v)
+                f.write(f'| `{name}` | ' + ' | '.join(cells) + ' |\n')
+    print(open(dst).read())
 
 
 def rep(src, dst, traffic_json=None):
@@ -115,6 +156,8 @@ def rep(src, dst, traffic_json=None):
 if __name__ == '__main__':
     if sys.argv[1] == 'launches':
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == 'table':
+        table(sys.argv[2:-1], sys.argv[-1])
     elif sys.argv[1] == 'csv':
         csvpage(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
     else:
