@@ -696,7 +696,11 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
         for (int it = -1; it < BROYDEN_ITERS; ++it) { k_corr_step<<<g_smp_tiles, 256, sm_skin, st>>>(fp, w, it); L(); }
     }
     if (prof) CU(cudaEventRecord(h->ev[3], st));
-    if (trace_only) { CU(cudaGetLastError()); return ARAH_OK; }
+    if (trace_only) {                                  // (training: the shading runs in arah_train.h; stage events stay well defined)
+        if (prof) { CU(cudaEventRecord(h->ev[4], st)); CU(cudaEventRecord(h->ev[5], st)); }
+        CU(cudaGetLastError());
+        return ARAH_OK;
+    }
     if (h->cfg.shade_mode == ARAH_SHADE_TF32) {
         // tensor-core shading (11-bit operands: fp16 images; round 1 used TF32, hence the mode's name)
         const unsigned g = grid_min(cdiv(PS, UM), (size_t)nsm);

@@ -284,6 +284,16 @@ def train_step_bench(args, dev, frame, steps=5, warmup=3, variant='torch'):
         st = net.stats()
         launches, samples = st['kernel_launches'], st['shaded_samples']
     tot = float(np.mean(ms['total']))
+    tracer_ms = None
+    try:                                   # where the forward's tracer part goes (one extra, untimed step with the library's stage events)
+        r = net._last[0]
+        r.set_profiling(True)
+        net(inp)
+        stp = r.stats()
+        tracer_ms = {k: stp[k] for k in ('ms_trace', 'ms_iso', 'ms_sample_corr')}
+        r.set_profiling(False)
+    except Exception as ex:
+        tracer_ms = {'error': repr(ex)[:200]}
     # algorithmic MACs of the differentiable part per sample: SDF fwd + input-gradient sweep + their second- and first-order
     # backward (4 data GEMM sweeps + 2 weight-gradient sweeps), colour net fwd + data + weight gradient, skinning net value +
     # 3 tangents + backward
@@ -291,7 +301,7 @@ def train_step_bench(args, dev, frame, steps=5, warmup=3, variant='torch'):
     return {'workload': f'{P} rays of the ZJU-377-like frame, train_skinning_net, fp32 (BASELINE configs[2] shape)', 'rays': int(P),
             'shaded_samples': int(samples), 'ms_per_step': tot, 'ms_forward_incl_tracer': float(np.mean(ms['forward'])),
             'ms_backward': float(np.mean(ms['backward'])), 'rays_per_s': P / tot * 1e3, 'steps': steps, 'warmup': warmup,
-            'gpu_launches_per_step': int(launches), 'loss': float(loss.detach()),
+            'gpu_launches_per_step': int(launches), 'loss': float(loss.detach()), 'tracer_stages_ms': tracer_ms,
             'algorithmic_tflops_differentiable_part': 2.0 * mac / (tot * 1e-3) / 1e12,
             'frac_of_bf16_peak': 2.0 * mac / (tot * 1e-3) / 1e12 / peaks()['tf_sustained'],
             'note': 'tracer (persistent kernels) + hand-written forward/backward GEMM chains; latency-bound at 2048 rays'}
