@@ -1,19 +1,23 @@
 #!/bin/bash
-# Quick A/B of one env switch on the GPU box: parity tests with the new setting, then the bench line with the switch on and off.
-# Usage: tools/gpu_ab.sh <tag> <ENV_NAME>
-TAG=${1:-ab}; VAR=${2:-ARAH_CORR_INTERLEAVE}
+# A/B of one library switch: tools/gpu_ab.sh <tag> <ENV_NAME> [values...]   (default values: 1 0)
+TAG=${1:-ab}
+NAME=${2:-ARAH_RAY_ORDER}
+shift 2
+VALS=${@:-1 0}
 mkdir -p gpurun_out
-timeout -s KILL 420 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log
-tail -4 gpurun_out/${TAG}_pytest.log
-for v in 1 0; do
-  env ${VAR}=$v timeout -s KILL 300 python bench.py --steps 5 --warmup 3 --no-train-step --no-mesh --no-cpu-baseline > gpurun_out/${TAG}_bench_$v.json 2> gpurun_out/${TAG}_bench_$v.err; echo "bench ${VAR}=$v rc=$?"
-  python - <<EOF
-import json
+timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q -k "not h36m_1024" > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log
+grep -a "passed\|failed\|Error\|error" gpurun_out/${TAG}_pytest.log | tail -5
+for v in $VALS; do
+env $NAME=$v timeout 900 python bench.py --steps 5 --warmup 3 --no-train-step --no-cpu-baseline --no-mesh --seq-frames 0 --no-h36m > gpurun_out/${TAG}_bench_$v.json 2> gpurun_out/${TAG}_bench_$v.err; echo "bench $NAME=$v rc=$?"
+V=$v TAG=$TAG python - <<'PY'
+import json, os
+v, t = os.environ['V'], os.environ['TAG']
 try:
-    d=json.loads(open('gpurun_out/${TAG}_bench_$v.json').read().splitlines()[0])
-    print('${VAR}=$v', round(d['value']), 'rays/s', round(d['ms_per_step'],2), 'ms', d['stages_ms_last_step'])
-    print(' corr phases', d['phase_cycles_last_step']['corr'])
+    d=json.loads(open(f'gpurun_out/{t}_bench_{v}.json').read().strip().splitlines()[-1])
+    print(v, round(d['value']), round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), {a: round(x,2) for a,x in d['stages_ms_last_step'].items()}, d['gpu_launches_per_frame'])
+    print('  trace phases', d['phase_cycles_last_step'].get('trace'))
 except Exception as e:
-    print('no bench line', e)
-EOF
+    print('parse failed', e)
+PY
+tail -2 gpurun_out/${TAG}_bench_$v.err
 done
