@@ -444,7 +444,7 @@ extern "C" int arah_create(const ArahConfig* cfg, ArahHandle** out) {
     if (const char* e = getenv("ARAH_KNN_SEED")) h->knn_seed = atoi(e);
     if (const char* e = getenv("ARAH_TRACE_KNN")) h->trace_knn = atoi(e) != 0;
     CU(cudaFuncSetAttribute(k_knn_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
-    CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
+    CU(cudaFuncSetAttribute(k_knn_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(knn_smem_bytes(cfg->n_verts) + knn_quarter_smem_bytes(cfg->n_verts))));
     CU(cudaFuncSetAttribute(k_knn_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(cfg->n_verts)));
     CU(cudaFuncSetAttribute(k_knn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
     guard.h = nullptr;
@@ -686,7 +686,7 @@ static int render_device(ArahHandle* h, const float* ray_dirs, const float* near
     const unsigned g_knn_s = grid_min(cdiv(PS, 16), (size_t)nsm);
     w.corr_seed = tc_root ? reinterpret_cast<CorrSeed*>(w.corr_state) : nullptr;
     wk.corr_seed = w.corr_seed;
-    k_knn_samples<<<g_knn_s, 512, sm_knn, st>>>(fp, h->knn, w); L();
+    k_knn_samples<<<g_knn_s, 512, sm_knn + knn_quarter_smem_bytes(fp.n_verts), st>>>(fp, h->knn, w); L();
     if (tc_root) {
         long long n = 0;
         CU(root_corr_persist(fp, h->skin_Wt[0], h->skin_b, h->skin16, wk, nsm, st, &n));

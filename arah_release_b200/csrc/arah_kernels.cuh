@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(512, 1) k_knn_samples(FrameParams fp, KnnIndex
     if (blockIdx.x == 0 && threadIdx.x == 0) w.counters[C_CORR] = n;
     const int B = knn_batch_size<KNN_COOP_SAMPLES>(n);
     if ((int)(blockIdx.x * (blockDim.x >> 5)) * B >= n) return;
-    const KnnSmem kk = load_knn(sv, ix);
+    KnnSmem kk = load_knn(sv, ix);
+    load_knn_quarters(sv + knn_smem_bytes(fp.n_verts) / 16, kk);
     auto finish = [&](int i, const float* x, int idx) {
         BroydenState<3> st;
         float s_, xh[3];

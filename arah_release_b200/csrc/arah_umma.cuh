@@ -201,6 +201,8 @@ __device__ __forceinline__ float softplus100_fast(float x) {
 }
 // (Round 2 tried moving the logarithm of every second element to the FP32 pipe, e P(e) with a degree-6 polynomial, to relieve the
 // MUFU unit in k_corr_persist: one MUFU less but four FP32 instructions more per element made the kernel 1.3 ms SLOWER — the
-// epilogues are as much issue-bound as MUFU-bound.  Reverted.)
+// epilogues are as much issue-bound as MUFU-bound.  Reverted.  Also tried: a warp-voted shortcut — for |x| >= 0.1675 the function
+// returns max(x, 0) bit-exactly (1 + e rounds to 1), and two thirds of the (warp, hidden unit) pairs of the synthetic frame qualify —
+// but a vote + uniform branch per element serialises the 32 independent MUFU chains the straight-line code overlaps: 31.9 -> 40.3 ms.)
 
 }  // namespace arah

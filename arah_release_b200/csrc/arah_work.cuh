@@ -140,7 +140,12 @@ __device__ __forceinline__ uint32_t morton_spread10(uint32_t v) {
     return v;
 }
 
-struct KnnSmem { const float4* sv; const float4* cmin; const float4* cmax; const float4* smin; const float4* smax; int nc, ns; };
+struct KnnSmem {
+    const float4* sv; const float4* cmin; const float4* cmax; const float4* smin; const float4* smax; int nc, ns;
+    const float4* qmin = nullptr; const float4* qmax = nullptr;      // optional: boxes of the four 8-vertex quarters of every cluster (load_knn_quarters)
+};
+constexpr int KNN_QUARTER = 8;
+__host__ __device__ constexpr size_t knn_quarter_smem_bytes(int n_verts) { return (size_t)((n_verts + KNN_CLUSTER - 1) / KNN_CLUSTER) * 4 * 32; }
 __device__ __forceinline__ KnnSmem load_knn(float4* smem, const KnnIndex& ix) {
     const int nv = ix.nc * KNN_CLUSTER, ns = (ix.nc + KNN_SUPER - 1) / KNN_SUPER;
     for (int v = threadIdx.x; v < nv; v += blockDim.x) smem[v] = __ldg(ix.sv + v);
@@ -159,6 +164,22 @@ __device__ __forceinline__ KnnSmem load_knn(float4* smem, const KnnIndex& ix) {
     __syncthreads();
     KnnSmem k; k.sv = smem; k.cmin = smem + nv; k.cmax = smem + nv + ix.nc; k.smin = smem + nv + 2 * ix.nc; k.smax = k.smin + ns; k.nc = ix.nc; k.ns = ns;
     return k;
+}
+// Quarter boxes: the vertices of a cluster are Morton-sorted, so 8 consecutive ones are compact.  A cluster whose box passes the
+// bound test usually only grazes the search ball: testing its four quarter boxes first (4 tests) replaces the scan of 32 vertices
+// by that of the 8 or 16 that can matter.  `q` points at 8 * nc float4 of shared memory behind the index; call after load_knn.
+__device__ __forceinline__ void load_knn_quarters(float4* q, KnnSmem& k) {
+    for (int b = threadIdx.x; b < 4 * k.nc; b += blockDim.x) {
+        float4 mn = make_float4(1e30f, 1e30f, 1e30f, 0.f), mx = make_float4(-1e30f, -1e30f, -1e30f, 0.f);
+        for (int v = b * KNN_QUARTER; v < (b + 1) * KNN_QUARTER; ++v) {
+            const float4 p = k.sv[v];
+            mn.x = fminf(mn.x, p.x); mn.y = fminf(mn.y, p.y); mn.z = fminf(mn.z, p.z);
+            mx.x = fmaxf(mx.x, p.x); mx.y = fmaxf(mx.y, p.y); mx.z = fmaxf(mx.z, p.z);
+        }
+        q[b] = mn; q[4 * k.nc + b] = mx;
+    }
+    __syncthreads();
+    k.qmin = q; k.qmax = q + 4 * k.nc;
 }
 __device__ __forceinline__ float box_dist2(const float4 mn, const float4 mx, float x, float y, float z) {
     const float dx = fmaxf(fmaxf(mn.x - x, x - mx.x), 0.f), dy = fmaxf(fmaxf(mn.y - y, y - mx.y), 0.f), dz = fmaxf(fmaxf(mn.z - z, z - mx.z), 0.f);
@@ -211,15 +232,22 @@ __device__ __forceinline__ int knn_scan(const KnnSmem& k, float x, float y, floa
 __device__ __forceinline__ int knn_scan_seeded(const KnnSmem& k, float x, float y, float z, int& slot) {
     float bd = INFINITY;
     int bi = 0x7fffffff, bs = 0;
-    auto scan = [&](int c) {
+    auto scan_range = [&](int v0, int v1) {
 #pragma unroll 8
-        for (int v = c * KNN_CLUSTER; v < (c + 1) * KNN_CLUSTER; ++v) {
+        for (int v = v0; v < v1; ++v) {
             const float4 p = k.sv[v];
             const float dx = x - p.x, dy = y - p.y, dz = z - p.z;
             const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             const int id = __float_as_int(p.w);
             if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bs = v; }
         }
+    };
+    auto scan = [&](int c) {
+        if (k.qmin) {
+#pragma unroll 1
+            for (int q = 4 * c; q < 4 * c + 4; ++q)
+                if (box_dist2(k.qmin[q], k.qmax[q], x, y, z) <= bd * 1.000001f) scan_range(q * KNN_QUARTER, (q + 1) * KNN_QUARTER);
+        } else scan_range(c * KNN_CLUSTER, (c + 1) * KNN_CLUSTER);
     };
     if (slot >= 0) {
         const float4 p = k.sv[slot];
