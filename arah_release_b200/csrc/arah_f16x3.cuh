@@ -67,6 +67,26 @@ __device__ __forceinline__ void umma_f16x3_chunk(uint32_t td, uint32_t xh, uint3
 
 // ---- pack kernels (arah_set_frame) ----------------------------------------------------------------------------------------
 // out[0] = s = 2^e with max|W| * s in [128, 256) (1 if the layer is all zero / not finite), out[1] = 1 / s.  One block.
+// (one block per layer: blockIdx.x selects the job, so the five SDF / four skinning layers of a frame cost one launch each set)
+struct ScaleJobs { const float* W[8]; int n[8]; float* out[8]; };
+static __global__ void k_layer_scales(ScaleJobs jobs) {
+    const float* __restrict__ W = jobs.W[blockIdx.x];
+    const int n = jobs.n[blockIdx.x];
+    float* __restrict__ out = jobs.out[blockIdx.x];
+    __shared__ float red[32];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+        float s = 1.0f;
+        if (m > 0.f && m < 1e30f) { int ex; frexpf(m, &ex); s = ldexpf(1.0f, 8 - ex); }
+        out[0] = s; out[1] = 1.0f / s;
+    }
+}
 static __global__ void k_layer_scale(const float* __restrict__ W, int n, float* __restrict__ out) {
     __shared__ float red[32];
     float m = 0.f;

@@ -29,12 +29,14 @@ bool root_trace_fits(int n_verts) { return trace_persist_smem_bytes(n_verts) <= 
 cudaError_t root_pack_sdf_f16(const float* const W[7], const SdfF16Dev& dst, cudaStream_t st, long long* launches) {
     __half* hi = reinterpret_cast<__half*>(dst.hi);
     __half* lo = reinterpret_cast<__half*>(dst.lo);
+    ScaleJobs jobs{};
+    for (int l = 1; l <= 5; ++l) { jobs.W[l - 1] = W[l]; jobs.n[l - 1] = 256 * 256; jobs.out[l - 1] = dst.scale + 2 * (l - 1); }
+    k_layer_scales<<<5, 1024, 0, st>>>(jobs);
+    if (launches) *launches += 1;
     for (int l = 1; l <= 5; ++l) {
-        float* sc = dst.scale + 2 * (l - 1);
-        k_layer_scale<<<1, 1024, 0, st>>>(W[l], 256 * 256, sc);
         const size_t off = (size_t)(l - 1) * 131072 / 2;            // halfs
-        k_pack_f16x2<<<cdiv_u((size_t)4 * 256 * HK, 256), 256, 0, st>>>(W[l], 256, sc, hi + off, lo + off, 256, 256, 256, 4);
-        if (launches) *launches += 2;
+        k_pack_f16x2<<<cdiv_u((size_t)4 * 256 * HK, 256), 256, 0, st>>>(W[l], 256, dst.scale + 2 * (l - 1), hi + off, lo + off, 256, 256, 256, 4);
+        if (launches) *launches += 1;
     }
     return cudaGetLastError();
 }
@@ -117,13 +119,15 @@ cudaError_t root_iso_persist(const FrameParams& fp, const SdfF16Host& sh, const 
 cudaError_t root_pack_skin_f16(const float* const W[5], const SkinF16Dev& dst, cudaStream_t st, long long* launches) {
     __half* hi = reinterpret_cast<__half*>(dst.hi);
     __half* lo = reinterpret_cast<__half*>(dst.lo);
+    ScaleJobs jobs{};
+    for (int l = 1; l <= 4; ++l) { jobs.W[l - 1] = W[l]; jobs.n[l - 1] = ((l < 4) ? 128 : 25) * 128; jobs.out[l - 1] = dst.scale + 2 * (l - 1); }
+    k_layer_scales<<<4, 1024, 0, st>>>(jobs);
+    if (launches) *launches += 1;
     for (int l = 1; l <= 4; ++l) {
         const int N = (l < 4) ? 128 : 25, Npad = (l < 4) ? 128 : 32;
-        float* sc = dst.scale + 2 * (l - 1);
-        k_layer_scale<<<1, 1024, 0, st>>>(W[l], N * 128, sc);
         const size_t off = (size_t)(l - 1) * 32768 / 2;             // halfs
-        k_pack_f16x2<<<cdiv_u((size_t)2 * Npad * HK, 256), 256, 0, st>>>(W[l], 128, sc, hi + off, lo + off, N, Npad, 128, 2);
-        if (launches) *launches += 2;
+        k_pack_f16x2<<<cdiv_u((size_t)2 * Npad * HK, 256), 256, 0, st>>>(W[l], 128, dst.scale + 2 * (l - 1), hi + off, lo + off, N, Npad, 128, 2);
+        if (launches) *launches += 1;
     }
     return cudaGetLastError();
 }
