@@ -1,23 +1,20 @@
 // arah_shade16.cuh — k_shade16: gradient + colour pass of the samples that survive the exact alpha cull (SDF forward, reverse-mode
 // gradient, colour MLP; renderer/implicit_differentiable_renderer.py:311-361) on tcgen05 kind::f16.
 //
-// Same program as k_shade_tc3 (round 1: TF32 operands) — 18 GEMM segments per 128-sample tile, activations in tensor memory,
-// in-place D -> A epilogues, weight chunks through a 5-slot TMA ring fed by a producer warp, MMA-issuer warp — with fp16 operands:
-// fp16 has TF32's 11-bit significand, issues at twice the rate and halves the weight stream, and k_shade_tc3 was bound by exactly
-// that stream (9.2 TB/s L2 -> SM, profiles/r02_render_kernels_ncu.md).  No weight scaling is needed for a single-pass product:
-// values below fp16's normal range keep an absolute error <= 2^-25, far below the 2^-11 relative operand rounding of everything
-// else (the forward SDF layers reuse the pre-scaled hi images of the root-finding engine; their 1/s is folded into F).
-// Layout of the A operand in a 256-column region (two K values per column):
-//   map 0 (written by a 256-wide epilogue / layer 0 / the feature refill): K-chunk c (64 values) at columns 128 (c >> 1) + 32 (c & 1),
-//         chunk 4 (the 33 colour inputs x | PE(view) | normal, zero padded) at columns 64..95;
-//   map 1 (written by the 128-wide epilogue of lin2): K-chunk c at columns 64 c.
-// In place: a thread reads 32 accumulator columns and overwrites 16 columns that lie inside what it has already read.
-// Per-CTA scratch (global, L2 resident): the cos factors of layers 0..4 and the feature vector, both as fp16 (393 KB per CTA;
-// round 1 kept six layers as bf16 plus an fp32 feature, 524 KB).  A line is discarded from L2 after its last read
-// (discard.global.L2), so the dirty scratch lines are dropped instead of being written back to HBM.
+// 18 GEMM segments per 128-sample tile (5 forward + 5 reverse SDF layers, lin0 (2), lin1, lin2, lin3 (3), lin4), activations in
+// tensor memory, weight chunks (64 K-values x N rows of fp16, pre-swizzled) through a 5-slot TMA ring fed by a producer warp, an
+// MMA-issuer warp, and SIXTEEN epilogue warps laid out like the root-finding engine (arah_sdf16.cuh): four per TMEM lane quarter;
+// warp (q, u) owns accumulator columns [64 j + 16 u, +16) of every K-chunk j and overwrites them IN PLACE with the 8 packed fp16
+// columns of K-step u of the next operand's chunk j, then arrives on ready[j]: chunk j of the next GEMM can start after a quarter
+// of the epilogue.  (Round 1's TF32 kernel and the first fp16 version had eight epilogue warps with 128 columns per thread.)
+// fp16 has TF32's 11-bit significand, issues at twice the rate and halves the weight stream.  No weight scaling is needed for a
+// single-pass product: values below fp16's normal range keep an absolute error <= 2^-25 (the forward SDF layers reuse the
+// pre-scaled hi images of the root-finding engine; their 1 / s is applied to the accumulator).
+// Operand columns of a 256-column region: K-step (j, k) of a 256- or 128-wide activation at [64 j + 16 k, +8); the 33 colour inputs
+// x | PE(view) | normal (zero padded to 64 = one K-chunk) sit in the gaps of chunk 0: K-step k at [16 k + 8, +8).
+// Per-CTA scratch (global, L2 resident): the cos factors of layers 0..4 and the feature vector as fp16, 393 KB per CTA; a line is
+// discarded from L2 after its last read (discard.global.L2), so dirty scratch lines are dropped instead of written back to HBM.
 #pragma once
-#include <cuda_bf16.h>
-
 #include "arah_f16x3.cuh"
 #include "arah_tc2.cuh"
 #include "arah_work.cuh"
@@ -45,11 +42,13 @@ struct Shade16 {
 };
 constexpr size_t SHADE16_BWD_BYTES = 5 * 131072, SHADE16_COL_BYTES = (size_t)(5 + 4 + 2 + 5 + 4) * 32768 + 4 * 16384;
 
-constexpr int SH16_THREADS = 320;
+constexpr int SH16_WARPS = 16;
+constexpr int SH16_CTHREADS = 32 * SH16_WARPS;
+constexpr int SH16_THREADS = SH16_CTHREADS + 64;          // + producer warp (16) + MMA warp (17)
 constexpr int SH16_NSLOTS = 5;
 constexpr int SH16_NSEG = 18;
 constexpr int SH16_PRM_FLOATS = 3584 + 3072 + 1280;
-constexpr int SH16_SCRATCH_FLOATS = 96 * 256 * 4;     // 80 rows of cos factors (5 layers x 4 batches x 4) + 16 feature rows, 256 uint4 each
+constexpr int SH16_SCRATCH_FLOATS = 48 * SH16_CTHREADS * 4;     // 40 rows of cos factors (5 layers x 4 chunks x 2) + 8 feature rows, 512 uint4 each
 
 struct Seg16 {
     const __half* w;     // weight chunk images
@@ -58,15 +57,28 @@ struct Seg16 {
     uint8_t nchunks;
     uint8_t a_reg, d_reg;// TMEM region of A / D
     uint8_t acc;         // accumulate onto D from the first MMA
-    uint8_t amap;        // 0 / 1: operand column map (see above); 2: the single colour-input chunk at columns 64..95
+    uint8_t cin;         // the single colour-input chunk (gap columns of chunk 0) instead of activation chunks
 };
-__device__ __forceinline__ uint32_t sh16_acol(int amap, int c) {
-    return amap == 0 ? (uint32_t)(128 * (c >> 1) + 32 * (c & 1)) : (amap == 1 ? (uint32_t)(64 * c) : 64u);
-}
 
 __host__ __device__ constexpr size_t shade16_smem_bytes() {
-    // ring | cin[128][36] | params | xs[128][4] | part[2][128][4] | prog | barriers
-    return (size_t)(SH16_NSLOTS * 32768) + (size_t)(UM * 36 + SH16_PRM_FLOATS + UM * 4 + 2 * UM * 4) * 4 + SH16_NSEG * sizeof(Seg16) + 512 + 1024;
+    // ring | cin[128][36] | params | xs[128][4] | part[4][128][4] | prog | barriers
+    return (size_t)(SH16_NSLOTS * 32768) + (size_t)(UM * 36 + SH16_PRM_FLOATS + UM * 4 + 4 * UM * 4) * 4 + SH16_NSEG * sizeof(Seg16) + 512 + 1024;
+}
+
+__device__ __forceinline__ void sh16_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void sh16_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
 __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Shade16 tc, Work w) {
@@ -79,12 +91,12 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
     float (*cin)[36] = reinterpret_cast<float (*)[36]>(ring + SH16_NSLOTS * 32768);
     float* prm = reinterpret_cast<float*>(cin) + UM * 36;
     float (*xs)[4] = reinterpret_cast<float (*)[4]>(prm + SH16_PRM_FLOATS);
-    float (*part)[UM][4] = reinterpret_cast<float (*)[UM][4]>(reinterpret_cast<float*>(xs) + UM * 4);
-    Seg16* prog = reinterpret_cast<Seg16*>(reinterpret_cast<float*>(part) + 2 * UM * 4);
+    float (*part)[UM][4] = reinterpret_cast<float (*)[UM][4]>(reinterpret_cast<float*>(xs) + UM * 4);      // [4][128][4]
+    Seg16* prog = reinterpret_cast<Seg16*>(reinterpret_cast<float*>(part) + 4 * UM * 4);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(prog) + ((SH16_NSEG * sizeof(Seg16) + 15) / 16) * 16);
     uint64_t* full = bars;                       // [5]
     uint64_t* empty = bars + SH16_NSLOTS;        // [5]
-    uint64_t* ready = bars + 2 * SH16_NSLOTS;    // [5] A chunk c written by the 4 warps that own it
+    uint64_t* ready = bars + 2 * SH16_NSLOTS;    // [5] operand chunk j (4: the colour-input chunk) written by all 16 warps
     uint64_t* done_bar = ready + 5;
     uint32_t* tslot = reinterpret_cast<uint32_t*>(done_bar + 1);
     constexpr int P_W0T = 0, P_W6 = 1280, P_W0 = 1536, P_W5 = 2304, P_LF = 3584, P_LG = P_LF + 1536, P_CB = P_LG + 1536;   // P_CB: col_b[0..4] at 0,256,512,640,896
@@ -92,33 +104,29 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
 
     if (tid == 0) {
         for (int i = 0; i < SH16_NSLOTS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 5; ++i) mbar_init(&ready[i], 4);
+        for (int i = 0; i < 5; ++i) mbar_init(&ready[i], SH16_WARPS);
         mbar_init(done_bar, 1);
         mbar_fence_init();
         int s = 0;
-        auto add = [&](const __half* wp, int N, int wbase, int nch, int a, int d, int acc, int amap) {
+        auto add = [&](const __half* wp, int N, int wbase, int nch, int a, int d, int acc, int cinseg) {
             Seg16& g = prog[s++]; g.w = wp; g.N = (uint16_t)N; g.wbase = (uint8_t)wbase; g.nchunks = (uint8_t)nch;
-            g.a_reg = (uint8_t)a; g.d_reg = (uint8_t)d; g.acc = (uint8_t)acc; g.amap = (uint8_t)amap;
+            g.a_reg = (uint8_t)a; g.d_reg = (uint8_t)d; g.acc = (uint8_t)acc; g.cin = (uint8_t)cinseg;
         };
         for (int l = 1; l <= 5; ++l) add(tc.sdf_fwd + (size_t)(l - 1) * 65536, 256, 0, 4, (l - 1) & 1, l & 1, 0, 0);      // A: R0,R1,R0,R1,R0
         for (int l = 5; l >= 1; --l) add(tc.sdf_bwd + (size_t)(l - 1) * 65536, 256, 0, 4, l & 1, (l - 1) & 1, 0, 0);      // A: R1,R0,R1,R0,R1
         add(tc.col0, 256, 0, 4, 1, 0, 0, 0);          // lin0, feature part
-        add(tc.col0, 256, 4, 1, 1, 0, 1, 2);          // lin0, colour-input chunk
+        add(tc.col0, 256, 4, 1, 1, 0, 1, 1);          // lin0, colour-input chunk
         add(tc.col1, 256, 0, 4, 0, 1, 0, 0);
         add(tc.col2, 128, 0, 4, 1, 0, 0, 0);
-        add(tc.col3b, 256, 0, 2, 0, 1, 0, 1);         // lin3, lin2-output part (K = 128)
+        add(tc.col3b, 256, 0, 2, 0, 1, 0, 0);         // lin3, lin2-output part (K = 128: chunks 0, 1)
         add(tc.col3a, 256, 0, 4, 0, 1, 1, 0);         // lin3, feature part
-        add(tc.col3a, 256, 4, 1, 0, 1, 1, 2);         // lin3, colour-input chunk
+        add(tc.col3a, 256, 4, 1, 0, 1, 1, 1);         // lin3, colour-input chunk
         add(tc.col4, 256, 0, 4, 1, 0, 0, 0);
     }
-    if (warp == 0) tmem_alloc(tslot, 512);
+    if (warp == 17) tmem_alloc(tslot, 512);
     for (int i = tid; i < 768; i += SH16_THREADS) { prm[P_W0T + i] = __ldg(tc.sdf_Wt0 + i); prm[P_W0 + i] = __ldg(tc.sdf_W0 + i); prm[P_W5 + i] = __ldg(tc.col_W5 + i); }
     for (int i = tid; i < 256; i += SH16_THREADS) prm[P_W6 + i] = __ldg(tc.sdf_w6 + i);
-    for (int i = tid; i < 1536; i += SH16_THREADS) {
-        // F multiplies the accumulator of the SCALED forward image: fold 1 / s_l in (exact power of two); cos factors use the unscaled F
-        prm[P_LF + i] = __ldg(tc.sdf_F + i);
-        prm[P_LG + i] = __ldg(tc.sdf_G + i);
-    }
+    for (int i = tid; i < 1536; i += SH16_THREADS) { prm[P_LF + i] = __ldg(tc.sdf_F + i); prm[P_LG + i] = __ldg(tc.sdf_G + i); }
     {
         const int cb_off[5] = {0, 256, 512, 640, 896}, cb_n[5] = {256, 256, 128, 256, 256};
         for (int l = 0; l < 5; ++l)
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
     tc_fence_after();
     const uint32_t tbase = *tslot;
 
-    if (warp == 8) {                 // ===== TMA producer =====
+    if (warp == 16) {                // ===== TMA producer =====
         if (lane == 0) {
             uint32_t slot = 0, use = 0;
             for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
         }
         return;
     }
-    if (warp == 9) {                 // ===== MMA issuer =====
+    if (warp == 17) {                // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t slot = 0, use = 0, rpar = 0;
             for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
@@ -156,15 +164,15 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
                     const uint32_t idesc = umma_idesc_f16(UM, g.N);
                     const uint32_t ta = tbase + 256u * g.a_reg, td = tbase + 256u * g.d_reg;
                     for (int c = 0; c < g.nchunks; ++c) {
-                        const int rc = (g.amap == 2) ? 4 : c;                 // which ready barrier guards this operand chunk
+                        const int rc = g.cin ? 4 : c;                         // which ready barrier guards this operand chunk
                         mbar_wait(&ready[rc], (rpar >> rc) & 1u);
                         rpar ^= (1u << rc);
                         mbar_wait(&full[slot], use & 1u);
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(ring + slot * 32768), a_col = ta + sh16_acol(g.amap, c);
+                        const uint32_t b_addr = smem_u32(ring + slot * 32768), a_col = ta + (g.cin ? 8u : 64u * (uint32_t)c);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_f16_ts(td, a_col + 8u * k, umma_smem_desc_sw128(b_addr + 32u * k), idesc, (c > 0 || k > 0) ? 1u : (uint32_t)g.acc);
+                            umma_f16_ts(td, a_col + 16u * k, umma_smem_desc_sw128(b_addr + 32u * k), idesc, (c > 0 || k > 0) ? 1u : (uint32_t)g.acc);
                         umma_commit(&empty[slot]);
                         if (++slot == SH16_NSLOTS) { slot = 0; ++use; }
                     }
@@ -172,79 +180,85 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
                 }
             }
         }
+        __syncwarp();
+        asm volatile("bar.sync 2, 544;" ::: "memory");      // the epilogue warps are out of tensor memory
+        tmem_dealloc(tbase, 512);
         return;
     }
-    // ===== compute / epilogue warps =====
-    const int q = warp & 3, half = warp >> 2;
+    // ===== compute / epilogue warps: q = TMEM lane quarter, u = which 16 columns of every 64-column chunk =====
+    const int q = warp & 3, u = warp >> 2;
     const int r = 32 * q + lane;
     const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
     uint32_t done_par = 0;
+    auto sync_c = [&]() { asm volatile("bar.sync 1, 512;" ::: "memory"); };
     uint4* scr = reinterpret_cast<uint4*>(w.scratch + (size_t)blockIdx.x * SH16_SCRATCH_FLOATS) + tid;
-    // scratch rows: 32 values of one thread as 4 uint4 of packed halfs; row (l, b, i) of the cos factors at (l * 4 + b) * 4 + i,
-    // feature row (b, i) at 80 + 4 b + i; `last`: drop the four 128-byte lines this warp has just read from L2
-    auto pack16 = [&](const float (&v)[32], uint32_t (&p)[16]) {
+    // scratch rows: 16 values of one thread as 2 uint4 of packed halfs; cos factors of (layer l, chunk j) at row (l * 4 + j) * 2,
+    // the feature chunk j at row 40 + 2 j
+    auto pack8 = [&](const float (&v)[16], uint32_t (&p)[8]) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
             const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
             p[i] = *reinterpret_cast<const uint32_t*>(&hh);
         }
     };
-    auto row_put = [&](int row0, const uint32_t (&p)[16]) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) scr[(size_t)(row0 + i) * 256] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+    auto row_put = [&](int row0, const uint32_t (&p)[8]) {
+        scr[(size_t)row0 * SH16_CTHREADS] = make_uint4(p[0], p[1], p[2], p[3]);
+        scr[(size_t)(row0 + 1) * SH16_CTHREADS] = make_uint4(p[4], p[5], p[6], p[7]);
     };
-    auto row_get = [&](int row0, uint32_t (&p)[16]) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint4 u = scr[(size_t)(row0 + i) * 256];
-            p[4 * i] = u.x; p[4 * i + 1] = u.y; p[4 * i + 2] = u.z; p[4 * i + 3] = u.w;
-        }
+    auto row_get = [&](int row0, uint32_t (&p)[8]) {
+        const uint4 a = scr[(size_t)row0 * SH16_CTHREADS], b = scr[(size_t)(row0 + 1) * SH16_CTHREADS];
+        p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
     };
     auto row_discard = [&](int row0) {                          // call after the values have been consumed (warp-converged)
         __syncwarp();
         if ((lane & 7) == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) asm volatile("discard.global.L2 [%0], 128;" ::"l"(scr + (size_t)(row0 + i) * 256) : "memory");
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(scr + (size_t)row0 * SH16_CTHREADS) : "memory");
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(scr + (size_t)(row0 + 1) * SH16_CTHREADS) : "memory");
         }
     };
-    auto cf_put = [&](int l, int b, const float (&v)[32]) { uint32_t p[16]; pack16(v, p); row_put((l * 4 + b) * 4, p); };
-    auto cf_get = [&](int l, int b, float (&v)[32]) {
-        uint32_t p[16];
-        row_get((l * 4 + b) * 4, p);
+    auto cf_get = [&](int l, int j, float (&v)[16]) {
+        uint32_t p[8];
+        row_get((l * 4 + j) * 2, p);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&p[i]));
             v[2 * i] = f.x; v[2 * i + 1] = f.y;
         }
     };
-    // 32 activations -> 16 packed operand columns at `col` of region `reg`
-    auto a_store = [&](int reg, uint32_t col, const float (&v)[32]) {
-        uint32_t p[16];
-        pack16(v, p);
-        tmem_st16(trow + 256u * reg + col, p);
-    };
-    // this warp's share of operand chunk `chunk` is complete
-    auto a_publish = [&](int chunk) {
+    // 16 activations (K = 64 j + 16 u ..) -> the 8 packed columns of K-step u of chunk j in region `reg`
+    auto a_store = [&](int reg, int j, const uint32_t (&p)[8]) { sh16_st8(trow + 256u * reg + (uint32_t)(64 * j + 16 * u), p); };
+    auto a_publish = [&](int chunk) {                           // this warp's share of operand chunk `chunk` is complete
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready[chunk]);
     };
-    // batch b (32 of this thread's 128 columns) of a 256-wide layer: columns 128 half + 32 b -> chunk 2 half + (b >> 1), map 0
-    auto a_put256 = [&](int reg, int b, const float (&v)[32]) {
-        a_store(reg, (uint32_t)(128 * half + 16 * b), v);
-        if (b & 1) a_publish(2 * half + (b >> 1));
+    auto a_put = [&](int reg, int j, const float (&v)[16]) {
+        uint32_t p[8];
+        pack8(v, p);
+        a_store(reg, j, p);
+        a_publish(j);
     };
     // feature vector (packed halfs in scratch) -> operand chunks 0..3 of region `reg`
     auto feat_refill = [&](int reg, bool last) {
 #pragma unroll 1
-        for (int b = 0; b < 4; ++b) {
-            uint32_t p[16];
-            row_get(80 + 4 * b, p);
-            tmem_st16(trow + 256u * reg + (uint32_t)(128 * half + 16 * b), p);
-            if (b & 1) a_publish(2 * half + (b >> 1));
+        for (int j = 0; j < 4; ++j) {
+            uint32_t p[8];
+            row_get(40 + 2 * j, p);
+            a_store(reg, j, p);
+            a_publish(j);
         }
-        if (last) { for (int b = 0; b < 4; ++b) row_discard(80 + 4 * b); }      // (a_publish has waited for the stores)
+        if (last) { for (int j = 0; j < 4; ++j) row_discard(40 + 2 * j); }      // (a_publish has waited for the stores)
+    };
+    // the 33 colour inputs + zero padding = one K-chunk in the gap columns of chunk 0: warp (q, u) writes K-step u
+    auto fill_cin = [&](int reg) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const int k = 16 * u + i; v[i] = (k < 33) ? cin[r][k] : 0.f; }
+        uint32_t p[8];
+        pack8(v, p);
+        sh16_st8(trow + 256u * reg + (uint32_t)(16 * u + 8), p);
+        a_publish(4);
     };
     auto wait_done = [&]() {
         mbar_wait(done_bar, done_par);
@@ -266,23 +280,23 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
         }
         // ================= SDF forward =================
         lp0 = prm + P_LF; lp1 = prm + P_LG;
-        cta_sync_compute();                                       // xs visible
+        sync_c();                                                 // xs visible
         {   // layer 0 (K = 3) on the FP32 pipe -> A1 in R0
             const float x = xs[r][0], y = xs[r][1], z = xs[r][2];
 #pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-                const int col0 = 128 * half + 32 * b;
-                float h[32], c[32];
+            for (int j = 0; j < 4; ++j) {
+                const int col0 = 64 * j + 16 * u;
+                float h[16], c[16];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 16; ++i) {
                     const int cc = col0 + i;
                     const float a = fmaf(prm[P_W0T + 512 + cc], z, fmaf(prm[P_W0T + 256 + cc], y, prm[P_W0T + cc] * x));
                     float s_, c_;
                     __sincosf(fmaf(a, lp0[cc], lp1[cc]), &s_, &c_);
                     h[i] = s_; c[i] = c_ * lp0[cc];
                 }
-                a_put256(0, b, h);
-                cf_put(0, b, c);
+                a_put(0, j, h);
+                { uint32_t p[8]; pack8(c, p); row_put(j * 2, p); }
             }
         }
         pc.mark(0);
@@ -294,32 +308,35 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
             const int dreg = l & 1;
             float dot = 0.f;
 #pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-                const int col0 = 128 * half + 32 * b;
-                float v[32], c[32];
-                tmem_ld32(trow + 256u * dreg + (uint32_t)col0, v);
+            for (int j = 0; j < 4; ++j) {
+                const int col0 = 64 * j + 16 * u;
+                float v[16], c[16];
+                sh16_ld16(trow + 256u * dreg + (uint32_t)col0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 16; ++i) {
                     float s_, c_;
                     __sincosf(fmaf(v[i] * inv, lp0[col0 + i], lp1[col0 + i]), &s_, &c_);
                     v[i] = s_; c[i] = c_ * lp0[col0 + i];
                 }
-                if (l < 5) { cf_put(l, b, c); a_put256(dreg, b, v); }      // in place: D(l) -> A(l+1)
-                else {
-                    { uint32_t p[16]; pack16(v, p); row_put(80 + 4 * b, p); }     // the feature vector of the colour network
+                if (l < 5) {                                      // in place: D(l) -> A(l+1)
+                    a_put(dreg, j, v);
+                    uint32_t p[8]; pack8(c, p); row_put((l * 4 + j) * 2, p);
+                } else {
+                    { uint32_t p[8]; pack8(v, p); row_put(40 + 2 * j, p); }       // the feature vector of the colour network
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) dot = fmaf(v[i], prm[P_W6 + col0 + i], dot);
-                    float g[32];                                  // g_a5 = w6 * cf5, in place in R1 (A of the first reverse GEMM)
+                    for (int i = 0; i < 16; ++i) dot = fmaf(v[i], prm[P_W6 + col0 + i], dot);
+                    float g[16];                                  // g_a5 = w6 * cf5, in place in R1 (A of the first reverse GEMM)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) g[i] = c[i] * prm[P_W6 + col0 + i];
-                    a_put256(1, b, g);
+                    for (int i = 0; i < 16; ++i) g[i] = c[i] * prm[P_W6 + col0 + i];
+                    a_put(1, j, g);
                 }
             }
-            if (l == 5) part[half][r][0] = dot;
+            if (l == 5) part[u][r][0] = dot;
             pc.mark(2);
         }
-        cta_sync_compute();
-        if (tid < UM && sl >= 0 && !w.shade_keep_sdf) w.smp_sdf[sl] = sdf_to_metres(part[0][tid][0] + part[1][tid][0] + __ldg(tc.sdf_b6), fp.cmin, fp.cmax);
+        sync_c();
+        if (tid < UM && sl >= 0 && !w.shade_keep_sdf)
+            w.smp_sdf[sl] = sdf_to_metres(((part[0][tid][0] + part[1][tid][0]) + (part[2][tid][0] + part[3][tid][0])) + __ldg(tc.sdf_b6), fp.cmin, fp.cmax);
         // ================= reverse pass =================
         float g3[3] = {0.f, 0.f, 0.f};
         for (int l = 5; l >= 1; --l) {
@@ -327,34 +344,33 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
             pc.mark(3);
             const int dreg = (l - 1) & 1;
 #pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-                const int col0 = 128 * half + 32 * b;
-                float v[32], c[32];
-                cf_get(l - 1, b, c);
-                tmem_ld32(trow + 256u * dreg + (uint32_t)col0, v);
+            for (int j = 0; j < 4; ++j) {
+                const int col0 = 64 * j + 16 * u;
+                float v[16], c[16];
+                cf_get(l - 1, j, c);
+                sh16_ld16(trow + 256u * dreg + (uint32_t)col0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= c[i];
-                if (l > 1) a_put256(dreg, b, v);
+                for (int i = 0; i < 16; ++i) v[i] *= c[i];
+                if (l > 1) a_put(dreg, j, v);
                 else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
+                    for (int i = 0; i < 16; ++i) {
                         const float* w0 = prm + P_W0 + (col0 + i) * 3;
                         g3[0] = fmaf(v[i], w0[0], g3[0]); g3[1] = fmaf(v[i], w0[1], g3[1]); g3[2] = fmaf(v[i], w0[2], g3[2]);
                     }
                 }
             }
             // last use of the cos factors of layer l - 1: every lane's values have been consumed once the operand stores that
-            // depend on them have completed (a_publish of batch 3 waits for them); layer 0's are dropped further down
-            if (l > 1) { for (int b = 0; b < 4; ++b) row_discard(((l - 1) * 4 + b) * 4); }
+            // depend on them have completed (a_publish waits for them); layer 0's are dropped further down
+            if (l > 1) { for (int j = 0; j < 4; ++j) row_discard(((l - 1) * 4 + j) * 2); }
             pc.mark(4);
         }
         // ---- feature part of colour lin0: A <- feat in R1 (free since reverse GEMM l=1 completed).  Its accumulators go to
         // R0, which the other warps may still be reading (reverse epilogue l=1) -> everyone must be out of R0 first.
-        cta_sync_compute();
+        part[u][r][0] = g3[0]; part[u][r][1] = g3[1]; part[u][r][2] = g3[2];
+        for (int j = 0; j < 4; ++j) row_discard(j * 2);          // layer 0's cos factors (g3 above depends on all of them)
+        sync_c();
         feat_refill(1, false);
-        part[half][r][0] = g3[0]; part[half][r][1] = g3[1]; part[half][r][2] = g3[2];
-        for (int b = 0; b < 4; ++b) row_discard(4 * b);           // layer 0's cos factors (g3 above depends on all of them)
-        cta_sync_compute();
         // ================= colour inputs =================
         if (tid < UM) {
             float v[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
@@ -362,7 +378,9 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
                 const int ray = sl / w.S;
                 const float* T = w.smp_T + 12 * (size_t)sl;
                 const float d[3] = {w.ray_dirs[3 * ray], w.ray_dirs[3 * ray + 1], w.ray_dirs[3 * ray + 2]};
-                const float g[3] = {part[0][tid][0] + part[1][tid][0], part[0][tid][1] + part[1][tid][1], part[0][tid][2] + part[1][tid][2]};
+                float g[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g[k] = (part[0][tid][k] + part[1][tid][k]) + (part[2][tid][k] + part[3][tid][k]);
                 if (fp.cano_view_dirs) {
                     float A3[9], Ai[9];
 #pragma unroll
@@ -392,51 +410,32 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
             c[30] = nrm[0]; c[31] = nrm[1]; c[32] = nrm[2]; c[33] = 0.f; c[34] = 0.f; c[35] = 0.f;
         }
         lp0 = prm + P_CB;
-        cta_sync_compute();                                       // publishes cin
-        // the 33 colour inputs + zero padding = operand chunk 4 (columns 64..95 of the region), written by the warps of half 0
-        auto fill_cin = [&](int reg) {
-            if (half == 0) {
-#pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) { const int k = 32 * c + i; v[i] = (k < 33) ? cin[r][k] : 0.f; }
-                    a_store(reg, 64u + 16u * c, v);
-                }
-                a_publish(4);
-            }
-        };
+        sync_c();                                                 // publishes cin
         auto relu_epilogue = [&](int N, int dreg, bool store) {
-            const int per = N / 2;
             float acc3[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
-            for (int b = 0; b < per / 32; ++b) {
-                const int col0 = per * half + 32 * b;
-                float v[32];
-                tmem_ld32(trow + 256u * dreg + (uint32_t)col0, v);
+            for (int j = 0; j < N / 64; ++j) {
+                const int col0 = 64 * j + 16 * u;
+                float v[16];
+                sh16_ld16(trow + 256u * dreg + (uint32_t)col0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + lp0[col0 + i], 0.f);
-                if (store) {
-                    if (N == 256) a_put256(dreg, b, v);
-                    else {                                        // N = 128 (lin2): columns 64 half + 32 b -> chunk `half`, map 1
-                        a_store(dreg, (uint32_t)(64 * half + 16 * b), v);
-                        if (b & 1) a_publish(half);
-                    }
-                } else {
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + lp0[col0 + i], 0.f);
+                if (store) a_put(dreg, j, v);
+                else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
+                    for (int i = 0; i < 16; ++i) {
                         acc3[0] = fmaf(v[i], prm[P_W5 + col0 + i], acc3[0]);
                         acc3[1] = fmaf(v[i], prm[P_W5 + 256 + col0 + i], acc3[1]);
                         acc3[2] = fmaf(v[i], prm[P_W5 + 512 + col0 + i], acc3[2]);
                     }
                 }
             }
-            if (!store) { part[half][r][0] = acc3[0]; part[half][r][1] = acc3[1]; part[half][r][2] = acc3[2]; }
+            if (!store) { part[u][r][0] = acc3[0]; part[u][r][1] = acc3[1]; part[u][r][2] = acc3[2]; }
         };
         pc.mark(5);
         // ================= colour MLP =================
+        fill_cin(1);                                              // gap columns of R1: free, no need to wait for the feature part
         wait_done();                                              // lin0, feature part done
-        fill_cin(1);
         wait_done();                                              // lin0 complete, D in R0
         relu_epilogue(256, 0, true);
         lp0 = prm + P_CB + 256;
@@ -444,29 +443,28 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
         relu_epilogue(256, 1, true);
         lp0 = prm + P_CB + 512;
         wait_done();                                              // lin2 (N = 128), D in R0[0..127]
-        relu_epilogue(128, 0, true);                              // -> A chunks 0, 1 of R0 (map 1)
+        relu_epilogue(128, 0, true);                              // -> operand chunks 0, 1 of R0
+        fill_cin(0);                                              // gap columns of chunk 0: this warp's own, already consumed accumulators
         lp0 = prm + P_CB + 640;
-        wait_done();                                              // lin3, lin2-output part done -> R0 may be overwritten
+        wait_done();                                              // lin3, lin2-output part done -> R0's chunks may be overwritten
         feat_refill(0, true);
         wait_done();                                              // lin3, feature part done
-        fill_cin(0);
         wait_done();                                              // lin3 complete, D in R1
         relu_epilogue(256, 1, true);
         lp0 = prm + P_CB + 896;
         wait_done();                                              // lin4, D in R0
         relu_epilogue(256, 0, false);                             // lin5 (256 -> 3) folded into the epilogue
-        cta_sync_compute();
+        sync_c();
         if (tid < UM && sl >= 0) {
 #pragma unroll
             for (int j = 0; j < 3; ++j)
-                w.smp_rgb[3 * (size_t)sl + j] = sigmoid_(part[0][tid][j] + part[1][tid][j] + __ldg(tc.col_b[5] + j));
+                w.smp_rgb[3 * (size_t)sl + j] = sigmoid_(((part[0][tid][j] + part[1][tid][j]) + (part[2][tid][j] + part[3][tid][j])) + __ldg(tc.col_b[5] + j));
         }
-        cta_sync_compute();
+        sync_c();
         pc.mark(6);
     }
     tc_fence_before();
-    cta_sync_compute();
-    if (warp == 0) tmem_dealloc(tbase, 512);
+    asm volatile("bar.sync 2, 544;" ::: "memory");
 }
 
 }  // namespace arah
