@@ -173,9 +173,14 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
             const int col0 = 32 * u;
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int cc = col0 + i;
-                v[i] = softplus100_fast(fmaf(sW0[256 + cc], z, fmaf(sW0[128 + cc], y, sW0[cc] * x)) + sb[cc]);
+            for (int i4 = 0; i4 < 8; ++i4) {                            // 128-bit shared-memory loads (LDS shares the MIO queue with MUFU)
+                const int cc = col0 + 4 * i4;
+                const float4 wx = *reinterpret_cast<const float4*>(sW0 + cc), wy = *reinterpret_cast<const float4*>(sW0 + 128 + cc),
+                             wz = *reinterpret_cast<const float4*>(sW0 + 256 + cc), bb = *reinterpret_cast<const float4*>(sb + cc);
+                v[4 * i4 + 0] = softplus100_fast(fmaf(wz.x, z, fmaf(wy.x, y, wx.x * x)) + bb.x);
+                v[4 * i4 + 1] = softplus100_fast(fmaf(wz.y, z, fmaf(wy.y, y, wx.y * x)) + bb.y);
+                v[4 * i4 + 2] = softplus100_fast(fmaf(wz.z, z, fmaf(wy.z, y, wx.z * x)) + bb.z);
+                v[4 * i4 + 3] = softplus100_fast(fmaf(wz.w, z, fmaf(wy.w, y, wx.w * x)) + bb.w);
             }
             emit(v, col0 / 2);
         }
@@ -189,7 +194,13 @@ __global__ void __launch_bounds__(S16_THREADS, 1) k_iso_persist(FrameParams fp, 
                 float v[32];
                 tmem_ld32(trow + 128u + (uint32_t)col0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = softplus100_fast(fmaf(v[i], inv, sb[128 * l + col0 + i]));
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(sb + 128 * l + col0 + 4 * i4);
+                    v[4 * i4 + 0] = softplus100_fast(fmaf(v[4 * i4 + 0], inv, bb.x));
+                    v[4 * i4 + 1] = softplus100_fast(fmaf(v[4 * i4 + 1], inv, bb.y));
+                    v[4 * i4 + 2] = softplus100_fast(fmaf(v[4 * i4 + 2], inv, bb.z));
+                    v[4 * i4 + 3] = softplus100_fast(fmaf(v[4 * i4 + 3], inv, bb.w));
+                }
                 emit(v, col0 / 2);
             }
             publish_sk();

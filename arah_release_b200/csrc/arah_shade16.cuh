@@ -260,6 +260,15 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
         sh16_st8(trow + 256u * reg + (uint32_t)(16 * u + 8), p);
         a_publish(4);
     };
+    // 16 consecutive per-column parameters as four 128-bit shared-memory loads (LDS shares the MIO queue with MUFU; every carve-out
+    // and every column offset 64 j + 16 u is 16-byte aligned)
+    auto lds16 = [&](const float* p, float (&o)[16]) {
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 t = *reinterpret_cast<const float4*>(p + 4 * i4);
+            o[4 * i4] = t.x; o[4 * i4 + 1] = t.y; o[4 * i4 + 2] = t.z; o[4 * i4 + 3] = t.w;
+        }
+    };
     auto wait_done = [&]() {
         mbar_wait(done_bar, done_par);
         done_par ^= 1u;
@@ -286,14 +295,15 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
                 const int col0 = 64 * j + 16 * u;
-                float h[16], c[16];
+                float h[16], c[16], wx[16], wy[16], wz[16], F[16], G[16];
+                lds16(prm + P_W0T + col0, wx); lds16(prm + P_W0T + 256 + col0, wy); lds16(prm + P_W0T + 512 + col0, wz);
+                lds16(lp0 + col0, F); lds16(lp1 + col0, G);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int cc = col0 + i;
-                    const float a = fmaf(prm[P_W0T + 512 + cc], z, fmaf(prm[P_W0T + 256 + cc], y, prm[P_W0T + cc] * x));
+                    const float a = fmaf(wz[i], z, fmaf(wy[i], y, wx[i] * x));
                     float s_, c_;
-                    __sincosf(fmaf(a, lp0[cc], lp1[cc]), &s_, &c_);
-                    h[i] = s_; c[i] = c_ * lp0[cc];
+                    __sincosf(fmaf(a, F[i], G[i]), &s_, &c_);
+                    h[i] = s_; c[i] = c_ * F[i];
                 }
                 a_put(0, j, h);
                 { uint32_t p[8]; pack8(c, p); row_put(j * 2, p); }
@@ -310,24 +320,24 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
                 const int col0 = 64 * j + 16 * u;
-                float v[16], c[16];
+                float v[16], c[16], F[16], G[16];
                 sh16_ld16(trow + 256u * dreg + (uint32_t)col0, v);
+                lds16(lp0 + col0, F); lds16(lp1 + col0, G);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float s_, c_;
-                    __sincosf(fmaf(v[i] * inv, lp0[col0 + i], lp1[col0 + i]), &s_, &c_);
-                    v[i] = s_; c[i] = c_ * lp0[col0 + i];
+                    __sincosf(fmaf(v[i] * inv, F[i], G[i]), &s_, &c_);
+                    v[i] = s_; c[i] = c_ * F[i];
                 }
                 if (l < 5) {                                      // in place: D(l) -> A(l+1)
                     a_put(dreg, j, v);
                     uint32_t p[8]; pack8(c, p); row_put((l * 4 + j) * 2, p);
                 } else {
                     { uint32_t p[8]; pack8(v, p); row_put(40 + 2 * j, p); }       // the feature vector of the colour network
+                    float w6[16], g[16];                          // g_a5 = w6 * cf5, in place in R1 (A of the first reverse GEMM)
+                    lds16(prm + P_W6 + col0, w6);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) dot = fmaf(v[i], prm[P_W6 + col0 + i], dot);
-                    float g[16];                                  // g_a5 = w6 * cf5, in place in R1 (A of the first reverse GEMM)
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) g[i] = c[i] * prm[P_W6 + col0 + i];
+                    for (int i = 0; i < 16; ++i) { dot = fmaf(v[i], w6[i], dot); g[i] = c[i] * w6[i]; }
                     a_put(1, j, g);
                 }
             }
@@ -354,9 +364,11 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
                 if (l > 1) a_put(dreg, j, v);
                 else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float* w0 = prm + P_W0 + (col0 + i) * 3;
-                        g3[0] = fmaf(v[i], w0[0], g3[0]); g3[1] = fmaf(v[i], w0[1], g3[1]); g3[2] = fmaf(v[i], w0[2], g3[2]);
+                    for (int t3 = 0; t3 < 3; ++t3) {              // W0 rows of 16 columns = 48 consecutive floats
+                        float w0[16];
+                        lds16(prm + P_W0 + col0 * 3 + 16 * t3, w0);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) { const int f = 16 * t3 + e; g3[f % 3] = fmaf(v[f / 3], w0[e], g3[f % 3]); }
                     }
                 }
             }
@@ -416,17 +428,19 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
 #pragma unroll 1
             for (int j = 0; j < N / 64; ++j) {
                 const int col0 = 64 * j + 16 * u;
-                float v[16];
+                float v[16], bb[16];
                 sh16_ld16(trow + 256u * dreg + (uint32_t)col0, v);
+                lds16(lp0 + col0, bb);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + lp0[col0 + i], 0.f);
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bb[i], 0.f);
                 if (store) a_put(dreg, j, v);
                 else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        acc3[0] = fmaf(v[i], prm[P_W5 + col0 + i], acc3[0]);
-                        acc3[1] = fmaf(v[i], prm[P_W5 + 256 + col0 + i], acc3[1]);
-                        acc3[2] = fmaf(v[i], prm[P_W5 + 512 + col0 + i], acc3[2]);
+                    for (int t3 = 0; t3 < 3; ++t3) {
+                        float w5[16];
+                        lds16(prm + P_W5 + 256 * t3 + col0, w5);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc3[t3] = fmaf(v[i], w5[i], acc3[t3]);
                     }
                 }
             }
