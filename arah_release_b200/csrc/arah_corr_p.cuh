@@ -283,20 +283,18 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_corr_persist(FrameParams fp, 
     named_sync(bar_tile, 2 * UM);
     bool first_round = true;
     while (true) {
-        // =================== per-point phase ===================
-        // Row r of a lane quarter is visible to both warps of the quarter (h = 0 / 1); each takes the 16 rows with (lane >> 4) == h.
-        // The instruction stream of this phase is one long dependent chain per row (softmax -> blend -> residual -> Broyden update):
-        // two half-filled warps per scheduler hide its latency better than one full warp next to an idle one.
-        const bool mine = (lane >> 4) == h;
-        {
+        // =================== per-point phase (the 128 threads with h == 0 own one row each) ===================
+        // (Measured: letting both warps of a lane quarter take 16 rows each — two half-filled warps to hide the latency of this
+        // dependent chain — doubles the issued instructions next to the other tile's epilogue warps and costs 2 ms.  Reverted.)
+        if (h == 0) {
             int it = __float_as_int(st[CS_IT * UM + r]);
-            bool need = first_round && mine;                            // row wants a new sample
+            bool need = first_round;                                    // row wants a new sample
             float lgv[32];
             if (!first_round) {                                         // warp-uniform: tcgen05.ld is a warp-collective instruction
                 tmem_ld32(tb + 128u, lgv);
                 tc_fence_before();
             }
-            if (!first_round && mine && it != CP_IDLE) {
+            if (!first_round && it != CP_IDLE) {
                 float T12[12], g[3];
                 BroydenState<3> s;
                 {
@@ -404,11 +402,11 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_corr_persist(FrameParams fp, 
                 }
             }
         }
-        if (h == 1 && q == 0) claim_ahead();                             // helper warp: keep the block queue ahead
+        else if (q == 0) claim_ahead();                                  // helper warp: keep the block queue ahead
         first_round = false;
         pc.mark(5);
-        // a tile lives while any of its rows has work (the barrier also publishes xs / the row states to the other warp of the quarter)
-        const bool row_live = mine && (__float_as_int(st[CS_IT * UM + r]) != CP_IDLE);
+        // a tile lives while any of its rows has work (also publishes xs to the h == 1 warps)
+        const bool row_live = (h == 0) && (__float_as_int(st[CS_IT * UM + r]) != CP_IDLE);
         const bool live = named_sync_or(bar_tile, 2 * UM, row_live);
         if (!live) {
             if (tid == T * 2 * UM) tile_dead[T] = 1;
