@@ -1,7 +1,7 @@
 """CPU: the per-element arithmetic of csrc/arah_image.cu (csrc/arah_image_core.h, compiled for the host by
 tests/native/host_image.cpp — test infrastructure, never loaded by the product) against the numpy oracle and the reference's
 golden validation images.  The CUDA kernels call the same functions with the same index expressions, so this pins their
-arithmetic in the build container, which has no GPU; the GPU tests (test_gpu_images.py) then check the kernels themselves.
+arithmetic in the build container, which has no GPU; the GPU tests (test_gpu_zz_images.py) then check the kernels themselves.
 
 Bars: integer outputs (pix_to_face) bit-exact against the oracle; floating point bit-exact against the oracle as well (both
 round every fp32 operation once, in the same order) and 1.2e-7 against the reference's images (see test_images_oracle.py).

@@ -3,7 +3,7 @@
 The build container has no GPU, so the product class cannot run here.  This test swaps the loaded C ABI for a shim with the
 SAME entry-point signatures whose bodies call the host instantiation of the kernels' arithmetic (tests/native/host_image.cpp),
 feeds the product's `FrameImages` methods CPU tensors, and compares with the oracle.  Test infrastructure only: it checks the
-Python mirror's plumbing, not the CUDA kernels (tests/test_gpu_images.py does that on the GPU box).
+Python mirror's plumbing, not the CUDA kernels (tests/test_gpu_zz_images.py does that on the GPU box).
 """
 import ctypes as C
 
