@@ -359,6 +359,8 @@ class ArahRenderer:
     # ------------------------------------------------------------------ canonical mesh
     def sdf_grid(self, N=256):
         """utils/sdf_meshing.py:13-58: the frame's SDF network on the N^3 lattice over [-1,1]^3 -> [N, N, N] (device)."""
+        if not 2 <= int(N) <= 1024:
+            raise _lib.ArahError('lattice side must be in [2, 1024]')
         out = torch.empty(N, N, N, device=self.device)
         check(_lib.lib().arah_sdf_grid(self._h, int(N), _ptr(out), self.stream))
         return out
@@ -368,6 +370,8 @@ class ArahRenderer:
         one fp16 pass over all N^3 points, split precision for the corners of every cell within eps of straddling the level.
         Returns (vol [N, N, N], stats int32[2] = [points refined, refined points whose coarse value was off by more than eps]),
         both on the device; marching_cubes(vol, level) equals marching_cubes(sdf_grid(N), level) bit for bit while stats[1] == 0."""
+        if not 2 <= int(N) <= 1024:
+            raise _lib.ArahError('lattice side must be in [2, 1024]')
         out = torch.empty(N, N, N, device=self.device)
         stats = torch.zeros(2, dtype=torch.int32, device=self.device)
         check(_lib.lib().arah_sdf_grid_banded(self._h, int(N), float(level), float(eps), _ptr(out), _ptr(stats), self.stream))

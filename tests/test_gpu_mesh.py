@@ -73,6 +73,26 @@ def test_banded_lattice_gives_the_full_lattice_mesh(N, level):
     assert torch.equal(f0, f2) and torch.equal(v0, v2) and r.last_band_stats[1] == 0
 
 
+def test_banded_lattice_rejects_what_it_cannot_do():
+    """Error behaviour of arah_sdf_grid_banded: before set_frame, without the fp16 images (root_mode fp32), bad arguments."""
+    from arah_release_b200 import _lib
+    r0 = _renderer()
+    with pytest.raises(_lib.ArahError):
+        r0.sdf_grid_banded(17)                                   # no frame yet
+    fr, _, _ = load_golden('zju377_24x24_s0')
+    net, inputs = _net(fr, 'fp32')
+    r = net._prepare(inputs)
+    with pytest.raises(_lib.ArahError):
+        r.sdf_grid_banded(17)                                    # fp32 root mode packs no fp16 images
+    v, f = r.canonical_mesh(17)                                  # ... and the mirror takes the full-precision lattice by itself
+    assert v.shape[1] == 3 and f.shape[1] == 3
+    net2, inputs2 = _net(fr, '3xtf32')
+    r2 = net2._prepare(inputs2)
+    for bad in (dict(N=1), dict(N=2000), dict(N=17, eps=-1.0), dict(N=17, eps=float('nan'))):
+        with pytest.raises(_lib.ArahError):
+            r2.sdf_grid_banded(**bad)
+
+
 def test_banded_lattice_bound_check_fires():
     """With eps = 0 the coarse values are (almost) never within the bound: the run-time check must report it."""
     fr, _, _ = load_golden('zju377_24x24_s0')
