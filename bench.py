@@ -530,6 +530,18 @@ def stage_table(stats, t_dev, pk, r):
                   2.0 * ((shaded * MAC_SDF if cull_ran else 0.0) + (shaded - culled) * (2 * MAC_SDF + MAC_COL))),
     }
     main = {'trace': 'k_trace_persist', 'iso': 'k_iso_persist', 'sample_corr': 'k_corr_persist', 'shade': 'k_shade16'}
+    # the co-bounding MUFU pipe: EXECUTED transcendental operations of the MLP activations against 16 / clk / SM at the
+    # maximum SM clock — sines of the SDF (1536 per evaluation; + 1536 cosines where the gradient is taken), exp + log of the
+    # skinning MLP's softplus (1024 per evaluation)
+    mufu = {'trace': 1536.0 * S('trace_sdf_evals'),
+            'iso': (1536.0 + 1024.0) * S('iso_g_evals') + S('iso_rays') * 4 * (1536.0 + 2 * 1024.0),
+            'sample_corr': 1024.0 * (S('corr_skin_evals') - S('on_samples')),
+            'shade': 1536.0 * shaded + 2 * 1536.0 * (shaded - culled)}
+    try:
+        import torch
+        mufu_peak = torch.cuda.get_device_properties(0).multi_processor_count * 16 * 1.965e9
+    except Exception:
+        mufu_peak = 148 * 16 * 1.965e9
     out = {}
     for k, (name, msk, alg, ex) in rows.items():
         ms = S(msk)
@@ -537,7 +549,8 @@ def stage_table(stats, t_dev, pk, r):
         out[k] = {'kernel': name, 'main_kernel': main[k], 'ms_per_step': ms / n, 'share_of_step': ms / (1e3 * t_dev),
                   'algorithmic_flops_per_step': alg / n, 'executed_flops_per_step': ex / n,
                   'achieved': alg / max(ms, 1e-9) / 1e9, 'frac': alg / max(ms, 1e-9) / 1e9 / pk['tf_sustained'],
-                  'executed_tflops': ex / max(ms, 1e-9) / 1e9, 'executed_frac': ex / max(ms, 1e-9) / 1e9 / pk['tf_sustained']}
+                  'executed_tflops': ex / max(ms, 1e-9) / 1e9, 'executed_frac': ex / max(ms, 1e-9) / 1e9 / pk['tf_sustained'],
+                  'mufu_ops_per_step': mufu[k] / n, 'mufu_frac_of_16_per_clk_per_sm': mufu[k] / max(ms * 1e-3, 1e-12) / mufu_peak}
     return out
 
 
