@@ -216,9 +216,7 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
             asm volatile("discard.global.L2 [%0], 128;" ::"l"(scr + (size_t)(row0 + 1) * SH16_CTHREADS) : "memory");
         }
     };
-    auto cf_get = [&](int l, int j, float (&v)[16]) {
-        uint32_t p[8];
-        row_get((l * 4 + j) * 2, p);
+    auto unpack8 = [&](const uint32_t (&p)[8], float (&v)[16]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&p[i]));
@@ -241,11 +239,12 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
     };
     // feature vector (packed halfs in scratch) -> operand chunks 0..3 of region `reg`
     auto feat_refill = [&](int reg, bool last) {
-#pragma unroll 1
+        uint32_t p[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) row_get(40 + 2 * j, p[j]);      // all eight loads in flight: one L2 latency instead of four
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
-            uint32_t p[8];
-            row_get(40 + 2 * j, p);
-            a_store(reg, j, p);
+            a_store(reg, j, p[j]);
             a_publish(j);
         }
         if (last) { for (int j = 0; j < 4; ++j) row_discard(40 + 2 * j); }      // (a_publish has waited for the stores)
@@ -350,14 +349,19 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
         // ================= reverse pass =================
         float g3[3] = {0.f, 0.f, 0.f};
         for (int l = 5; l >= 1; --l) {
+            // the cos factors of layer l - 1 (written by this thread in the forward pass) are fetched from L2 while the GEMM runs:
+            // with the loads inside the chunk loop every chunk paid a full L2 latency (the whole reverse epilogue was latency-bound)
+            uint32_t cfp[4][8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) row_get(((l - 1) * 4 + j) * 2, cfp[j]);
             wait_done();                                          // g_h(l-1) = g_a(l) @ W_l in R[(l-1)&1]
             pc.mark(3);
             const int dreg = (l - 1) & 1;
-#pragma unroll 1
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int col0 = 64 * j + 16 * u;
                 float v[16], c[16];
-                cf_get(l - 1, j, c);
+                unpack8(cfp[j], c);
                 sh16_ld16(trow + 256u * dreg + (uint32_t)col0, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] *= c[i];
