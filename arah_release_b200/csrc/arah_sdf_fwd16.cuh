@@ -147,21 +147,30 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_sdf_fwd16(FrameParams fp, Sd
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready[j]);
     };
+    // the query point of row `tid` of a tile; called one tile AHEAD (the two dependent loads shade_list -> smp_xn would otherwise
+    // cost two L2 / HBM latencies at the start of every tile, with all sixteen warps waiting at the barrier behind them)
+    auto fetch = [&](int tile, int& sl, float (&xn)[3]) {
+        sl = -1; xn[0] = 0.f; xn[1] = 0.f; xn[2] = 0.f;
+        const int i = tile * UM + tid;
+        if (tile < ntiles && i < n) {
+            if (g.out) {                                            // lattice coordinates with the reference's arithmetic (sdf_meshing.py:25-38)
+                sl = i;
+                const int iz = i % g.N, iy = (i / g.N) % g.N, ix = i / (g.N * g.N);
+                xn[0] = __fadd_rn(__fmul_rn((float)ix, g.voxel), -1.0f);
+                xn[1] = __fadd_rn(__fmul_rn((float)iy, g.voxel), -1.0f);
+                xn[2] = __fadd_rn(__fmul_rn((float)iz, g.voxel), -1.0f);
+            } else { sl = w.shade_list[i]; xn[0] = w.smp_xn[3 * (size_t)sl]; xn[1] = w.smp_xn[3 * (size_t)sl + 1]; xn[2] = w.smp_xn[3 * (size_t)sl + 2]; }
+        }
+    };
+    int sl_next = -1;
+    float xn_next[3] = {0.f, 0.f, 0.f};
+    if (tid < UM) fetch(blockIdx.x, sl_next, xn_next);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int sl = -1;
         if (tid < UM) {
-            const int i = tile * UM + tid;
-            float xn[3] = {0.f, 0.f, 0.f};
-            if (i < n) {
-                if (g.out) {                                        // lattice coordinates with the reference's arithmetic (sdf_meshing.py:25-38)
-                    sl = i;
-                    const int iz = i % g.N, iy = (i / g.N) % g.N, ix = i / (g.N * g.N);
-                    xn[0] = __fadd_rn(__fmul_rn((float)ix, g.voxel), -1.0f);
-                    xn[1] = __fadd_rn(__fmul_rn((float)iy, g.voxel), -1.0f);
-                    xn[2] = __fadd_rn(__fmul_rn((float)iz, g.voxel), -1.0f);
-                } else { sl = w.shade_list[i]; xn[0] = w.smp_xn[3 * (size_t)sl]; xn[1] = w.smp_xn[3 * (size_t)sl + 1]; xn[2] = w.smp_xn[3 * (size_t)sl + 2]; }
-            }
-            xs[tid][0] = xn[0]; xs[tid][1] = xn[1]; xs[tid][2] = xn[2]; xs[tid][3] = 0.f;
+            sl = sl_next;
+            xs[tid][0] = xn_next[0]; xs[tid][1] = xn_next[1]; xs[tid][2] = xn_next[2]; xs[tid][3] = 0.f;
+            fetch(tile + (int)gridDim.x, sl_next, xn_next);         // in flight while this tile is evaluated
         }
         sync_epi();
         {   // layer 0 (K = 3) on the FP32 pipe -> operand of layer 1 in R0

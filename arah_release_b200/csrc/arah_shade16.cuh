@@ -278,13 +278,29 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
     const float* lp1 = prm + P_LG;
 
     PhaseClk pc; pc.start((tid == 32 && w.phase_clk) ? w.phase_clk + 8 : nullptr);
+    // the sample of row `tid` of a tile, fetched one tile AHEAD (two dependent loads: list entry -> point)
+    auto fetch = [&](int tile, int& sl, float (&xn)[3]) {
+        sl = -1; xn[0] = 0.f; xn[1] = 0.f; xn[2] = 0.f;
+        const int i = tile * UM + tid;
+        if (i < n) { sl = w.shade_list[i]; xn[0] = w.smp_xn[3 * (size_t)sl]; xn[1] = w.smp_xn[3 * (size_t)sl + 1]; xn[2] = w.smp_xn[3 * (size_t)sl + 2]; }
+    };
+    int sl_next = -1;
+    float xn_next[3] = {0.f, 0.f, 0.f};
+    if (tid < UM) fetch(blockIdx.x, sl_next, xn_next);
     for (int tile = blockIdx.x; tile * UM < n; tile += gridDim.x) {
         int sl = -1;
+        float4 Tq[3] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+        float dq[3] = {0.f, 0.f, 0.f};
         if (tid < UM) {
-            const int i = tile * UM + tid;
-            float xn[3] = {0.f, 0.f, 0.f};
-            if (i < n) { sl = w.shade_list[i]; xn[0] = w.smp_xn[3 * (size_t)sl]; xn[1] = w.smp_xn[3 * (size_t)sl + 1]; xn[2] = w.smp_xn[3 * (size_t)sl + 2]; }
-            xs[tid][0] = xn[0]; xs[tid][1] = xn[1]; xs[tid][2] = xn[2]; xs[tid][3] = 0.f;
+            sl = sl_next;
+            xs[tid][0] = xn_next[0]; xs[tid][1] = xn_next[1]; xs[tid][2] = xn_next[2]; xs[tid][3] = 0.f;
+            if (sl >= 0) {                                        // what the colour inputs need, in flight during the SDF passes
+                const float4* Tp = reinterpret_cast<const float4*>(w.smp_T + 12 * (size_t)sl);
+                Tq[0] = Tp[0]; Tq[1] = Tp[1]; Tq[2] = Tp[2];
+                const int ray = sl / w.S;
+                dq[0] = w.ray_dirs[3 * ray]; dq[1] = w.ray_dirs[3 * ray + 1]; dq[2] = w.ray_dirs[3 * ray + 2];
+            }
+            fetch(tile + (int)gridDim.x, sl_next, xn_next);
         }
         // ================= SDF forward =================
         lp0 = prm + P_LF; lp1 = prm + P_LG;
@@ -391,9 +407,8 @@ __global__ void __launch_bounds__(SH16_THREADS, 1) k_shade16(FrameParams fp, Sha
         if (tid < UM) {
             float v[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
             if (sl >= 0) {
-                const int ray = sl / w.S;
-                const float* T = w.smp_T + 12 * (size_t)sl;
-                const float d[3] = {w.ray_dirs[3 * ray], w.ray_dirs[3 * ray + 1], w.ray_dirs[3 * ray + 2]};
+                const float T[12] = {Tq[0].x, Tq[0].y, Tq[0].z, Tq[0].w, Tq[1].x, Tq[1].y, Tq[1].z, Tq[1].w, Tq[2].x, Tq[2].y, Tq[2].z, Tq[2].w};
+                const float d[3] = {dq[0], dq[1], dq[2]};
                 float g[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) g[k] = (part[0][tid][k] + part[1][tid][k]) + (part[2][tid][k] + part[3][tid][k]);
