@@ -189,3 +189,27 @@ def test_fused_loss_has_no_cpu_path_and_validates_arguments():
     assert call() != 0 and b'rgb term' in L.arah_last_error()                    # weight on, inputs missing
     cfg.rgb_weight, cfg.rgb_loss_type = 0.0, 7
     assert call() != 0 and b'rgb_loss_type' in L.arah_last_error()
+
+
+def test_bench_stage_table_rooflines():
+    """bench.stage_table: algorithmic / executed FLOPs of the SURVEY 8d formula and the MUFU co-roofline, from device counters alone."""
+    import bench
+    st = {'rays': 262144, 'trace_sdf_evals': 1766730, 'iso_rays': 49793, 'iso_g_evals': 110738, 'on_samples': 15257069,
+          'corr_skin_evals': 74452293, 'shaded_samples': 15247192, 'culled_samples': 12436792,
+          'ms_trace': 9.2, 'ms_iso': 4.3, 'ms_sample_corr': 31.9, 'ms_shade': 19.4, 'ms_composite': 0.2, 'ms_total': 65.0}
+
+    class R:
+        shade_cull, shade_mode = True, 'tf32'
+    out = bench.stage_table([st, st], 2 * 0.066, {'tf_sustained': 1414.5}, R())
+    assert set(out) == {'trace', 'iso', 'sample_corr', 'shade'}
+    c = out['sample_corr']
+    assert abs(c['algorithmic_flops_per_step'] - 2.0 * 74452293 * bench.MAC_SKIN) < 1.0
+    assert c['executed_flops_per_step'] < c['algorithmic_flops_per_step']          # the kernel evaluates g(x0) once, the reference twice
+    assert abs(c['ms_per_step'] - 31.9) < 1e-9 and 0.0 < c['share_of_step'] < 1.0
+    assert abs(c['frac'] - c['achieved'] / 1414.5) < 1e-12
+    # 1024 exp + log per executed skinning evaluation against 16 / clk / SM
+    assert abs(c['mufu_ops_per_step'] - 1024.0 * (74452293 - 15257069)) < 1.0
+    assert 0.3 < c['mufu_frac_of_16_per_clk_per_sm'] < 0.6
+    s = out['shade']
+    assert s['executed_flops_per_step'] < s['algorithmic_flops_per_step']          # the exact cull removes work the reference does
+    assert s['frac'] > s['executed_frac'] > 0.0
