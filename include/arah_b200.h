@@ -39,8 +39,8 @@ typedef struct ArahConfig {
     int32_t latent_dim;           /* colour-net per-frame latent (128; 0 = none) */
     int32_t n_verts;              /* SMPL vertices (6890) */
     int32_t max_rays;             /* initial workspace size in rays (grown on demand) */
-    int32_t shade_mode;           /* ARAH_SHADE_TF32 (default 0): shading MLPs on tcgen05 tensor cores (gradient + colour: TF32
-                                   * operands; the SDF value compositing uses: fp16 operands), fp32 accumulate;
+    int32_t shade_mode;           /* ARAH_SHADE_TF32 (default 0; the name is historical): shading MLPs on tcgen05 tensor cores with
+                                   * 11-bit-significand operands (fp16 images since round 2, TF32 in round 1), fp32 accumulate;
                                    * ARAH_SHADE_FP32 (1): fp32 FFMA tiles (bit-for-bit the oracle's arithmetic order).
                                    * Independent of root_mode. */
     int32_t root_mode;            /* ARAH_ROOT_3XTF32 (default 0; the name is historical): every MLP of the root-finding stages
