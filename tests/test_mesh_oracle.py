@@ -93,3 +93,46 @@ def test_oracle_level_and_truncation():
     assert v0.shape == v1.shape and np.array_equal(f0, f1) and np.abs(v0 - v1).max() < 1e-5
     ve, fe = orc.marching_cubes(np.ones((8, 8, 8), np.float32))
     assert ve.shape == (0, 3) and fe.shape == (0, 3)
+
+
+def _band_flags(coarse, level, eps):
+    """The refinement rule of arah_sdf_grid_banded (k_grid_band_flag), restated in numpy: a cell whose eight coarse corner values
+    satisfy min - eps <= level <= max + eps marks all its corners."""
+    c = coarse.astype(np.float32)
+    eps = np.float32(eps); level = np.float32(level)
+    corners = [c[dx:c.shape[0] - 1 + dx, dy:c.shape[1] - 1 + dy, dz:c.shape[2] - 1 + dz] for dx in (0, 1) for dy in (0, 1) for dz in (0, 1)]
+    mn, mx = np.minimum.reduce(corners), np.maximum.reduce(corners)
+    cell = (mn - eps <= level) & (level <= mx + eps)
+    flag = np.zeros(c.shape, bool)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                flag[dx:c.shape[0] - 1 + dx, dy:c.shape[1] - 1 + dy, dz:c.shape[2] - 1 + dz] |= cell
+    return flag
+
+
+@pytest.mark.parametrize('level', [0.0, 0.05])
+def test_banded_lattice_argument_holds_for_any_bounded_error(level):
+    """The exactness argument behind arah_sdf_grid_banded, independent of the GPU: perturb a lattice by ANY error of
+    magnitude <= eps, restore the exact values only where the band rule asks for it, and marching cubes cannot tell the result
+    from the exact lattice — vertices and faces bit-identical — even when the error is adversarial (pushes values towards the level)."""
+    from oracle import oracle as orc
+    N, eps = 40, 0.02
+    rng = np.random.default_rng(7)
+    for name, (exact, _, _) in analytic_volumes(N).items():
+        for kind in ('random', 'adversarial'):
+            if kind == 'random':
+                err = rng.uniform(-eps, eps, exact.shape).astype(np.float32)
+            else:
+                err = (-np.sign(exact - level) * eps * 0.999).astype(np.float32)      # every value moved towards / across the level
+            coarse = (exact + err).astype(np.float32)
+            assert np.abs(coarse - exact).max() <= eps
+            flag = _band_flags(coarse, level, eps)
+            banded = np.where(flag, exact, coarse).astype(np.float32)
+            v0, f0 = orc.marching_cubes(exact, level=level)
+            v1, f1 = orc.marching_cubes(banded, level=level)
+            assert np.array_equal(f0, f1) and np.array_equal(v0, v1), (name, kind)
+            # the perturbed lattice alone does give another mesh: the refinement is what makes the difference
+            v2, f2 = orc.marching_cubes(coarse, level=level)
+            assert not (v2.shape == v0.shape and np.array_equal(v2, v0)), (name, kind)
+            assert flag.mean() < 0.5
